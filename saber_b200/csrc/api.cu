@@ -1,0 +1,77 @@
+// saber_b200 — C-ABI plumbing: per-thread error string, version, driver entry point for TMA
+// tensor-map encoding (fetched at run time so the library links against cudart only and loads on a
+// box without a driver — needed by the CPU-side "library loads and exports every symbol" test).
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace {
+thread_local char g_err[1024] = "";
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+}  // namespace
+
+void sb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* sb_last_error(void) { return g_err; }
+
+extern "C" int sb_version(void) { return 100; }
+
+// Number of SMs of the current device (148 on B200); negative on error.
+extern "C" int sb_device_sm_count(void) {
+  int dev = 0, n = 0;
+  SB_CHECK_CUDA(cudaGetDevice(&dev));
+  SB_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return n;
+}
+
+// Fails loudly unless the current device is compute capability 10.x (the kernels are sm_100a-only).
+extern "C" int sb_require_sm100(void) {
+  int dev = 0, major = 0, minor = 0;
+  SB_CHECK_CUDA(cudaGetDevice(&dev));
+  SB_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  SB_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    sb_set_error("saber_b200 requires an sm_100a device (B200); found sm_%d%d", major, minor);
+    return SB_ERR_UNSUPPORTED;
+  }
+  return SB_OK;
+}
+
+int sb_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                         uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      sb_set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s",
+                   cudaGetErrorString(e));
+      return SB_ERR_DRIVER;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sb_set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u",
+                 (int)r, base, (unsigned long long)rows, (unsigned long long)cols,
+                 (unsigned long long)ld_elems, box_rows, box_cols);
+    return SB_ERR_DRIVER;
+  }
+  return SB_OK;
+}

@@ -1,0 +1,454 @@
+// saber_b200 — fused multi-head attention (flash-style online softmax) for the SAM2 path.
+//
+// One kernel covers: Hiera windowed attention with optional 2x2 max-pooled queries and upstream's
+// zero-padding of non-divisible windows (padded tokens carry the QKV bias), Hiera global attention
+// (a single window), and the plain batched attention of the mask decoder / memory attention.
+// Q/K/V are read in place from the projection output (token-major rows, head-major columns), so no
+// window-partition / head-transpose copies are materialised; the output is written token-major.
+// Restates sam2/modeling/backbones/hieradet.py MultiScaleAttention + window_partition/unpartition
+// and sam2/modeling/sam/transformer.py Attention (HF modeling_sam2.py:282-345).
+//
+// v1 math runs on mma.sync.m16n8k16 (bf16 in, fp32 accumulate); softmax statistics are fp32.
+#include "common.cuh"
+
+namespace {
+
+struct AttnParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  long long q_ld, k_ld, v_ld;  // row pitch (elements)
+  __nv_bfloat16* o;
+  long long o_ld;
+  const float* q_bias;  // per-column bias that padded tokens carry (windowed mode), may be null
+  const float* k_bias;
+  const float* v_bias;
+  int heads, hd;
+  float scale_log2;  // softmax scale * log2(e)
+  int mode;          // 0 plain batched, 1 windowed
+  // plain
+  int nq, nk;
+  // windowed: input grid H x W (unpadded), window ws (in key space), q pooling stride (1 or 2),
+  // output grid Ho x Wo (= floor(H/pool), floor(W/pool)), nwx/nwy windows per padded grid.
+  int H, W, ws, pool, Ho, Wo, nwx, nwy;
+  int qtiles;  // q tiles per (batch, window)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb::smem_u32(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                              uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Row index (into the token-major projection buffer) of key j of window `win` in batch b, or -1 for a
+// padded position.
+__device__ __forceinline__ long long key_row(const AttnParams& p, int b, int win, int j) {
+  if (p.mode == 0) return static_cast<long long>(b) * p.nk + j;
+  const int wy = win / p.nwx, wx = win % p.nwx;
+  const int y = wy * p.ws + j / p.ws, x = wx * p.ws + j % p.ws;
+  if (y >= p.H || x >= p.W) return -1;
+  return (static_cast<long long>(b) * p.H + y) * p.W + x;
+}
+
+constexpr int KT = 64;  // keys per tile
+
+template <int HDP, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+flash_attn_kernel(const AttnParams p) {
+  constexpr int PITCH = HDP * 2 + 16;  // bytes; odd multiple of 16 -> conflict-free ldmatrix
+  constexpr int QROWS = 16 * NWARPS;
+  constexpr int NT = NWARPS * 32;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + QROWS * PITCH;
+  uint8_t* sV = sK + 2 * KT * PITCH;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.y;
+  const int qtile = blockIdx.x % p.qtiles;
+  const int bw = blockIdx.x / p.qtiles;
+  int b, win, nq, nk, wq;
+  if (p.mode == 0) {
+    b = bw;
+    win = 0;
+    nq = p.nq;
+    nk = p.nk;
+    wq = 0;
+  } else {
+    const int nwin = p.nwx * p.nwy;
+    b = bw / nwin;
+    win = bw % nwin;
+    wq = p.ws / p.pool;
+    nq = wq * wq;
+    nk = p.ws * p.ws;
+  }
+  const int hd = p.hd;
+  const int chunks = hd >> 3;  // 16-byte chunks per row
+  const int col0 = head * hd;
+
+  // zero the whole staging area once (padded columns must stay 0 / finite)
+  for (int i = tid; i < (QROWS + 4 * KT) * PITCH / 16; i += NT)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  // ---- load the Q tile (with optional 2x2 max pooling; padded tokens = bias) ----
+  const int q0 = qtile * QROWS;
+  for (int idx = tid; idx < QROWS * chunks; idx += NT) {
+    const int r = idx / chunks, c = idx % chunks;
+    const int qi = q0 + r;
+    if (qi >= nq) continue;
+    uint4 val;
+    if (p.mode == 0) {
+      val = *reinterpret_cast<const uint4*>(p.q + (static_cast<long long>(b) * nq + qi) * p.q_ld +
+                                            col0 + c * 8);
+    } else {
+      const int wy = win / p.nwx, wx = win % p.nwx;
+      const int qy = wy * wq + qi / wq, qx = wx * wq + qi % wq;  // pooled padded grid coords
+      __nv_bfloat162 acc[4];
+      bool first = true;
+      for (int dy = 0; dy < p.pool; ++dy)
+        for (int dx = 0; dx < p.pool; ++dx) {
+          const int y = qy * p.pool + dy, x = qx * p.pool + dx;
+          uint4 t;
+          if (y < p.H && x < p.W) {
+            t = *reinterpret_cast<const uint4*>(
+                p.q + ((static_cast<long long>(b) * p.H + y) * p.W + x) * p.q_ld + col0 + c * 8);
+          } else {
+            const float* bq = p.q_bias ? p.q_bias + col0 + c * 8 : nullptr;
+            t.x = bq ? sb::pack_bf16x2(bq[0], bq[1]) : 0u;
+            t.y = bq ? sb::pack_bf16x2(bq[2], bq[3]) : 0u;
+            t.z = bq ? sb::pack_bf16x2(bq[4], bq[5]) : 0u;
+            t.w = bq ? sb::pack_bf16x2(bq[6], bq[7]) : 0u;
+          }
+          const __nv_bfloat162* tv = reinterpret_cast<const __nv_bfloat162*>(&t);
+          if (first) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = tv[e];
+            first = false;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = __hmax2(acc[e], tv[e]);
+          }
+        }
+      val = *reinterpret_cast<uint4*>(acc);
+    }
+    *reinterpret_cast<uint4*>(sQ + r * PITCH + c * 16) = val;
+  }
+
+  // ---- K/V tile loader ----
+  auto load_kv = [&](int t, int stage) {
+    uint8_t* dK = sK + stage * KT * PITCH;
+    uint8_t* dV = sV + stage * KT * PITCH;
+    for (int idx = tid; idx < KT * chunks; idx += NT) {
+      const int r = idx / chunks, c = idx % chunks;
+      const int j = t * KT + r;
+      long long row = (j < nk) ? key_row(p, b, win, j) : -2;
+      if (row >= 0) {
+        cp_async16(dK + r * PITCH + c * 16, p.k + row * p.k_ld + col0 + c * 8);
+        cp_async16(dV + r * PITCH + c * 16, p.v + row * p.v_ld + col0 + c * 8);
+      } else {
+        uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (row == -1) {  // window padding: token is exactly the projection bias
+          if (p.k_bias) {
+            const float* bk = p.k_bias + col0 + c * 8;
+            kk.x = sb::pack_bf16x2(bk[0], bk[1]);
+            kk.y = sb::pack_bf16x2(bk[2], bk[3]);
+            kk.z = sb::pack_bf16x2(bk[4], bk[5]);
+            kk.w = sb::pack_bf16x2(bk[6], bk[7]);
+          }
+          if (p.v_bias) {
+            const float* bv = p.v_bias + col0 + c * 8;
+            vv.x = sb::pack_bf16x2(bv[0], bv[1]);
+            vv.y = sb::pack_bf16x2(bv[2], bv[3]);
+            vv.z = sb::pack_bf16x2(bv[4], bv[5]);
+            vv.w = sb::pack_bf16x2(bv[6], bv[7]);
+          }
+        }
+        *reinterpret_cast<uint4*>(dK + r * PITCH + c * 16) = kk;
+        *reinterpret_cast<uint4*>(dV + r * PITCH + c * 16) = vv;
+      }
+    }
+  };
+
+  const int ntiles = (nk + KT - 1) / KT;
+  load_kv(0, 0);
+  cp_async_commit();
+  __syncthreads();  // Q tile visible
+
+  // Q fragments stay in registers for the whole KV loop
+  uint32_t qf[HDP / 16][4];
+  {
+    const uint32_t base = sb::smem_u32(sQ + (warp * 16 + (lane & 15)) * PITCH + (lane >> 4) * 16);
+#pragma unroll
+    for (int ks = 0; ks < HDP / 16; ++ks)
+      ldsm_x4(base + ks * 32, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  }
+
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int stage = t & 1;
+    if (t + 1 < ntiles) {
+      load_kv(t + 1, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint8_t* tK = sK + stage * KT * PITCH;
+    const uint8_t* tV = sV + stage * KT * PITCH;
+
+    // S = Q K^T  (16 x 64 per warp)
+    float s[KT / 8][4];
+#pragma unroll
+    for (int i = 0; i < KT / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    {
+      const int id = lane >> 3;
+      const uint32_t kbase =
+          sb::smem_u32(tK + ((lane & 7) + (id >> 1) * 8) * PITCH + (id & 1) * 16);
+#pragma unroll
+      for (int ks = 0; ks < HDP / 16; ++ks) {
+#pragma unroll
+        for (int np = 0; np < KT / 16; ++np) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(kbase + np * 16 * PITCH + ks * 32, b0, b1, b2, b3);
+          mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+          mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+        }
+      }
+    }
+    // mask keys beyond nk (only possible in the last tile)
+    const int kbase_idx = t * KT;
+    if (kbase_idx + KT > nk) {
+#pragma unroll
+      for (int i = 0; i < KT / 8; ++i) {
+        const int kk = kbase_idx + i * 8 + (lane & 3) * 2;
+        if (kk >= nk) s[i][0] = s[i][2] = -INFINITY;
+        if (kk + 1 >= nk) s[i][1] = s[i][3] = -INFINITY;
+      }
+    }
+    // online softmax (rows g and g+8 of this warp's 16)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < KT / 8; ++i) {
+      mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = exp2f((m0 - mn0) * p.scale_log2), c1 = exp2f((m1 - mn1) * p.scale_log2);
+    m0 = mn0;
+    m1 = mn1;
+    const float ms0 = mn0 * p.scale_log2, ms1 = mn1 * p.scale_log2;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[KT / 16][4];
+#pragma unroll
+    for (int i = 0; i < KT / 8; ++i) {
+      const float p0 = exp2f(s[i][0] * p.scale_log2 - ms0);
+      const float p1 = exp2f(s[i][1] * p.scale_log2 - ms0);
+      const float p2 = exp2f(s[i][2] * p.scale_log2 - ms1);
+      const float p3 = exp2f(s[i][3] * p.scale_log2 - ms1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pf[i >> 1][(i & 1) * 2 + 0] = sb::pack_bf16x2(p0, p1);
+      pf[i >> 1][(i & 1) * 2 + 1] = sb::pack_bf16x2(p2, p3);
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      o[i][0] *= c0;
+      o[i][1] *= c0;
+      o[i][2] *= c1;
+      o[i][3] *= c1;
+    }
+    // O += P V
+    {
+      const int id = lane >> 3;
+      const uint32_t vbase =
+          sb::smem_u32(tV + ((lane & 7) + (id & 1) * 8) * PITCH + (id >> 1) * 16);
+#pragma unroll
+      for (int kk = 0; kk < KT / 16; ++kk) {
+#pragma unroll
+        for (int np = 0; np < HDP / 16; ++np) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(vbase + kk * 16 * PITCH + np * 32, b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * np], pf[kk], b0, b1);
+          mma_bf16_16816(o[2 * np + 1], pf[kk], b2, b3);
+        }
+      }
+    }
+    __syncthreads();  // all warps done with this stage before it is refilled
+  }
+
+  // finalize: row sums across the quad, normalise, store
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int qi = q0 + warp * 16 + g + half * 8;
+    if (qi >= nq) continue;
+    long long orow;
+    if (p.mode == 0) {
+      orow = static_cast<long long>(b) * nq + qi;
+    } else {
+      const int wy = win / p.nwx, wx = win % p.nwx;
+      const int qy = wy * wq + qi / wq, qx = wx * wq + qi % wq;
+      if (qy >= p.Ho || qx >= p.Wo) continue;  // cropped by window_unpartition
+      orow = (static_cast<long long>(b) * p.Ho + qy) * p.Wo + qx;
+    }
+    __nv_bfloat16* dst = p.o + orow * p.o_ld + col0;
+    const float inv = half ? inv1 : inv0;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      const int d = i * 8 + tq * 2;
+      if (d < hd) {
+        *reinterpret_cast<uint32_t*>(dst + d) =
+            sb::pack_bf16x2(o[i][half * 2] * inv, o[i][half * 2 + 1] * inv);
+      }
+    }
+  }
+}
+
+template <int HDP, int NWARPS>
+int launch_attn(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
+  constexpr int PITCH = HDP * 2 + 16;
+  constexpr int SMEM = (16 * NWARPS + 4 * KT) * PITCH;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HDP, NWARPS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  dim3 grid(static_cast<unsigned>(nblocks_x), static_cast<unsigned>(p.heads), 1);
+  flash_attn_kernel<HDP, NWARPS><<<grid, NWARPS * 32, SMEM, stream>>>(p);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+template <int NWARPS>
+int dispatch_hd(const AttnParams& p, long long nbx, cudaStream_t stream) {
+  const int hd = p.hd;
+  if (hd <= 16) return launch_attn<16, NWARPS>(p, nbx, stream);
+  if (hd <= 32) return launch_attn<32, NWARPS>(p, nbx, stream);
+  if (hd <= 64) return launch_attn<64, NWARPS>(p, nbx, stream);
+  if (hd <= 80) return launch_attn<80, NWARPS>(p, nbx, stream);
+  if (hd <= 96) return launch_attn<96, NWARPS>(p, nbx, stream);
+  if (hd <= 128) return launch_attn<128, NWARPS>(p, nbx, stream);
+  sb_set_error("sb_attention: head_dim %d not supported (max 128)", hd);
+  return SB_ERR_UNSUPPORTED;
+}
+
+int run_attn(AttnParams& p, int batch, int nq_per_window, int nwin, cudaStream_t stream) {
+  SB_REQUIRE((p.hd % 8) == 0, "sb_attention: head_dim must be a multiple of 8 (got %d)", p.hd);
+  SB_REQUIRE((p.q_ld % 8) == 0 && (p.k_ld % 8) == 0 && (p.v_ld % 8) == 0 && (p.o_ld % 2) == 0,
+             "sb_attention: row pitches must be multiples of 8 elements");
+  const int nwarps = nq_per_window <= 16 ? 1 : 4;
+  p.qtiles = (nq_per_window + 16 * nwarps - 1) / (16 * nwarps);
+  const long long nbx = static_cast<long long>(batch) * nwin * p.qtiles;
+  SB_REQUIRE(nbx > 0 && nbx < (1ll << 31), "sb_attention: grid too large");
+  if (nwarps == 1) return dispatch_hd<1>(p, nbx, stream);
+  return dispatch_hd<4>(p, nbx, stream);
+}
+
+}  // namespace
+
+// Plain batched attention: q [B*nq, heads*hd] (pitch q_ld), k/v [B*nk, heads*hd], o [B*nq, heads*hd].
+extern "C" int sb_attention(const void* q, long long q_ld, const void* k, long long k_ld,
+                            const void* v, long long v_ld, void* o, long long o_ld, int batch,
+                            int heads, int hd, int nq, int nk, float scale, void* stream) {
+  SB_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nk > 0, "sb_attention: empty problem");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.q_ld = q_ld;
+  p.k_ld = k_ld;
+  p.v_ld = v_ld;
+  p.o_ld = o_ld;
+  p.heads = heads;
+  p.hd = hd;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.mode = 0;
+  p.nq = nq;
+  p.nk = nk;
+  return run_attn(p, batch, nq, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Hiera attention over a fused QKV buffer [B*H*W, 3*heads*hd] (columns: q | k | v, head-major).
+// ws = window size in the (unpadded) H x W grid (ws >= max(H,W) means global attention), pool = 1 or
+// 2 (queries 2x2 max-pooled after projection). qkv_bias (fp32, 3*heads*hd) is what padded tokens
+// carry when ws does not divide H/W. Output o [B*Ho*Wo, heads*hd], Ho = H/pool, Wo = W/pool.
+extern "C" int sb_window_attention(const void* qkv, const float* qkv_bias, void* o, int batch,
+                                   int H, int W, int heads, int hd, int ws, int pool, float scale,
+                                   void* stream) {
+  SB_REQUIRE(batch > 0 && H > 0 && W > 0 && heads > 0, "sb_window_attention: empty problem");
+  SB_REQUIRE(pool == 1 || pool == 2, "sb_window_attention: pool must be 1 or 2");
+  SB_REQUIRE(ws > 0 && (ws % pool) == 0, "sb_window_attention: ws %% pool != 0");
+  const int C = heads * hd;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+  p.q = base;
+  p.k = base + C;
+  p.v = base + 2 * C;
+  p.q_ld = p.k_ld = p.v_ld = 3ll * C;
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.o_ld = C;
+  if (qkv_bias) {
+    p.q_bias = qkv_bias;
+    p.k_bias = qkv_bias + C;
+    p.v_bias = qkv_bias + 2 * C;
+  }
+  p.heads = heads;
+  p.hd = hd;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.mode = 1;
+  p.H = H;
+  p.W = W;
+  p.ws = ws;
+  p.pool = pool;
+  p.Ho = H / pool;
+  p.Wo = W / pool;
+  p.nwy = (H + ws - 1) / ws;
+  p.nwx = (W + ws - 1) / ws;
+  const int wq = ws / pool;
+  return run_attn(p, batch, wq * wq, p.nwx * p.nwy, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,71 @@
+"""ctypes binding of ``libsaber_b200.so`` — the C ABI declared in ``include/saber_b200.h``.
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or a
+kernel call returns an error code, a ``RuntimeError`` carrying ``sb_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+_LOCK = threading.Lock()
+_LIB = None
+
+c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes (every entry point returns int status unless listed in _SPECIAL)
+SIGNATURES = {
+    "sb_version": [],
+    "sb_device_sm_count": [],
+    "sb_require_sm100": [],
+    "sb_gemm_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p,
+                     c_int, c_void_p, c_ll, c_int, c_int, c_float, c_int, c_void_p],
+    "sb_attention": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
+                     c_int, c_int, c_int, c_float, c_void_p],
+    "sb_window_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_int, c_float, c_void_p],
+    "sb_layernorm": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int,
+                     c_float, c_int, c_void_p],
+    "sb_im2col_k7s4": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sb_maxpool2x2": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "sb_add_upsample2x": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sb_nhwc_to_nchw": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_nchw_to_nhwc": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sb_add_cast": [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p],
+}
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / "libsaber_b200.so"
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the CUDA library. Raises if it cannot be produced."""
+    global _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        path = lib_path()
+        if not path.exists():
+            from . import build as _build
+
+            _build.build()
+        lib = C.CDLL(str(path))
+        lib.sb_last_error.restype = C.c_char_p
+        lib.sb_last_error.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError => missing symbol: fail loudly
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        _LIB = lib
+        return lib
+
+
+def last_error() -> str:
+    return load().sb_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc < 0:
+        raise RuntimeError(f"saber_b200 {what} failed (code {rc}): {last_error()}")
