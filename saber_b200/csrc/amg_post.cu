@@ -1,0 +1,384 @@
+// saber_b200 — integer / indexing stages of automatic mask generation, bit-exact given identical
+// low-res logits: bilinear up-sampling of 256x256 mask logits to the crop size fused with the
+// stability score (two thresholded popcounts), binarisation, bounding box, near-crop-edge test
+// and bit-packing into the full image frame (warp ballots; the fp32 full-res logits that upstream
+// materialises per mask — 805 MB per 64-point batch at 1024^2 — never exist), plus greedy box NMS
+// with torchvision semantics. Restates sam2/utils/amg.py (calculate_stability_score,
+// batched_mask_to_box, is_box_near_crop_edge, uncrop_masks), SAM2Transforms.postprocess_masks and
+// torchvision.ops.nms as driven by sam2/automatic_mask_generator.py::_process_batch/_process_crop
+// (SURVEY §8a U5, Appendix A2). The oracle twin is oracle/amg_post_ref.py.
+#include "common.cuh"
+
+namespace {
+
+// ATen area_pixel_compute_source_index (align_corners=False, not cubic), written without FMA
+// contraction so the GPU and the numpy oracle evaluate the identical fp32 expression tree.
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1,
+                                          float& l0, float& l1) {
+  float s = __fsub_rn(__fmul_rn(scale, __fadd_rn(static_cast<float>(dst), 0.5f)), 0.5f);
+  if (s < 0.f) s = 0.f;
+  i0 = min(static_cast<int>(floorf(s)), in_size - 1);
+  l1 = fminf(fmaxf(__fsub_rn(s, static_cast<float>(i0)), 0.f), 1.f);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l0 = __fsub_rn(1.f, l1);
+}
+
+struct MaskPostParams {
+  const float* planes;     // low-res logit planes, each S x S
+  const int* plane_idx;    // [n] plane index per candidate
+  const float* iou;        // [n] predicted IoU per candidate
+  const int* iou_idx;      // [n] index into iou (nullable -> i)
+  int n, S;
+  int Hc, Wc, x0, y0, H, W, WW;  // crop size / origin, full frame size, words per row
+  float pred_iou_thresh, mask_thresh, stab_offset, stab_thresh, edge_atol;
+  int x1, y1;              // crop box far corner (exclusive)
+  unsigned char* keep;     // [n]
+  float* stability;        // [n]
+  float* iou_out;          // [n]
+  int* bbox;               // [n,4] full-frame xyxy (inclusive max), upstream uncrop_boxes_xyxy applied
+  int* area;               // [n]
+  uint32_t* bits;          // [n, H, WW]
+};
+
+__global__ void __launch_bounds__(256)
+mask_post_kernel(const MaskPostParams p) {
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float iou = p.iou[p.iou_idx ? p.iou_idx[i] : i];
+  uint32_t* bits = p.bits + static_cast<long long>(i) * p.H * p.WW;
+  const bool iou_ok = !(p.pred_iou_thresh > 0.f) || (iou > p.pred_iou_thresh);
+  if (tid == 0) p.iou_out[i] = iou;
+  if (!iou_ok) {
+    if (tid == 0) {
+      p.keep[i] = 0;
+      p.stability[i] = 0.f;
+      p.area[i] = 0;
+      p.bbox[4 * i + 0] = p.bbox[4 * i + 1] = p.bbox[4 * i + 2] = p.bbox[4 * i + 3] = 0;
+    }
+    return;  // block-uniform
+  }
+  const float* plane = p.planes + static_cast<long long>(p.plane_idx[i]) * p.S * p.S;
+  const float scale_h = __fdiv_rn(static_cast<float>(p.S), static_cast<float>(p.Hc));
+  const float scale_w = __fdiv_rn(static_cast<float>(p.S), static_cast<float>(p.Wc));
+  const float hi = __fadd_rn(p.mask_thresh, p.stab_offset), lo = __fsub_rn(p.mask_thresh, p.stab_offset);
+  const bool same = (p.Hc == p.S && p.Wc == p.S);
+
+  int inter = 0, uni = 0, area = 0;
+  int minx = 1 << 30, maxx = -1, miny = 1 << 30, maxy = -1;  // crop-frame coordinates
+  const int total_words = p.H * p.WW;
+  for (int wi = warp; wi < total_words; wi += 8) {
+    const int y = wi / p.WW, wx = wi - y * p.WW;
+    const int x = wx * 32 + lane;
+    const int cy = y - p.y0, cx = x - p.x0;
+    uint32_t word = 0;
+    if (cy >= 0 && cy < p.Hc && wx * 32 + 31 >= p.x0 && wx * 32 < p.x0 + p.Wc) {  // warp-uniform
+      const bool in = (cx >= 0 && cx < p.Wc && x < p.W);
+      float val = -INFINITY;
+      if (in) {
+        if (same) {
+          val = plane[cy * p.S + cx];
+        } else {
+          int y0i, y1i, x0i, x1i;
+          float ly0, ly1, lx0, lx1;
+          src_index(scale_h, cy, p.S, y0i, y1i, ly0, ly1);
+          src_index(scale_w, cx, p.S, x0i, x1i, lx0, lx1);
+          const float v00 = plane[y0i * p.S + x0i], v01 = plane[y0i * p.S + x1i];
+          const float v10 = plane[y1i * p.S + x0i], v11 = plane[y1i * p.S + x1i];
+          const float t0 = __fadd_rn(__fmul_rn(v00, lx0), __fmul_rn(v01, lx1));
+          const float t1 = __fadd_rn(__fmul_rn(v10, lx0), __fmul_rn(v11, lx1));
+          val = __fadd_rn(__fmul_rn(t0, ly0), __fmul_rn(t1, ly1));
+        }
+      }
+      const uint32_t b_hi = __ballot_sync(0xffffffffu, in && val > hi);
+      const uint32_t b_lo = __ballot_sync(0xffffffffu, in && val > lo);
+      word = __ballot_sync(0xffffffffu, in && val > p.mask_thresh);
+      if (lane == 0) {
+        inter += __popc(b_hi);
+        uni += __popc(b_lo);
+        if (word) {
+          area += __popc(word);
+          const int fx = wx * 32 - p.x0;  // crop-frame x of bit 0
+          minx = min(minx, fx + (__ffs(word) - 1));
+          maxx = max(maxx, fx + 31 - __clz(word));
+          miny = min(miny, cy);
+          maxy = max(maxy, cy);
+        }
+      }
+    }
+    if (lane == 0) bits[wi] = word;
+  }
+  __shared__ int s_red[8][7];
+  if (lane == 0) {
+    s_red[warp][0] = inter;
+    s_red[warp][1] = uni;
+    s_red[warp][2] = area;
+    s_red[warp][3] = minx;
+    s_red[warp][4] = maxx;
+    s_red[warp][5] = miny;
+    s_red[warp][6] = maxy;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      inter += s_red[w][0];
+      uni += s_red[w][1];
+      area += s_red[w][2];
+      minx = min(minx, s_red[w][3]);
+      maxx = max(maxx, s_red[w][4]);
+      miny = min(miny, s_red[w][5]);
+      maxy = max(maxy, s_red[w][6]);
+    }
+    // torch: int32 / int32 -> fp32 true division (0/0 = NaN, and NaN >= thr is false)
+    const float stab = __fdiv_rn(static_cast<float>(inter), static_cast<float>(uni));
+    bool keep = true;
+    if (p.stab_thresh > 0.f) keep = stab >= p.stab_thresh;
+    int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;  // empty mask -> [0,0,0,0] (batched_mask_to_box)
+    if (area > 0) {
+      bx0 = minx;
+      by0 = miny;
+      bx1 = maxx;
+      by1 = maxy;
+    }
+    // is_box_near_crop_edge on un-cropped boxes: near the crop box but not near the image box
+    const float fb[4] = {static_cast<float>(bx0 + p.x0), static_cast<float>(by0 + p.y0),
+                         static_cast<float>(bx1 + p.x0), static_cast<float>(by1 + p.y0)};
+    const float cb[4] = {static_cast<float>(p.x0), static_cast<float>(p.y0), static_cast<float>(p.x1),
+                         static_cast<float>(p.y1)};
+    const float ob[4] = {0.f, 0.f, static_cast<float>(p.W), static_cast<float>(p.H)};
+    bool near = false;
+    for (int k = 0; k < 4; ++k) {
+      const bool nc = fabsf(fb[k] - cb[k]) <= p.edge_atol;
+      const bool ni = fabsf(fb[k] - ob[k]) <= p.edge_atol;
+      near = near || (nc && !ni);
+    }
+    keep = keep && !near;
+    p.keep[i] = keep ? 1 : 0;
+    p.stability[i] = stab;
+    p.area[i] = area;
+    p.bbox[4 * i + 0] = bx0 + p.x0;
+    p.bbox[4 * i + 1] = by0 + p.y0;
+    p.bbox[4 * i + 2] = bx1 + p.x0;
+    p.bbox[4 * i + 3] = by1 + p.y0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS (torchvision.ops.nms semantics): stable sort by score descending, suppress iff IoU > thr.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nms_rank_kernel(const float* __restrict__ scores, int n, int* __restrict__ order) {
+  __shared__ float tile[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float si = i < n ? scores[i] : 0.f;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < n ? scores[j] : 0.f;
+    __syncthreads();
+    const int lim = min(256, n - j0);
+    if (i < n) {
+      for (int t = 0; t < lim; ++t) {
+        const float sj = tile[t];
+        rank += (sj > si) || (sj == si && (j0 + t) < i);
+      }
+    }
+    __syncthreads();
+  }
+  if (i < n) order[rank] = i;
+}
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb_ = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb_), inter)) > thr;
+}
+
+// mask[r, cw] bit c = IoU(sorted box r, sorted box cw*64 + c) > thr for c-index > r
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, int n, float thr,
+                unsigned long long* __restrict__ mask, int col_blocks) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;  // only the upper triangle is ever read
+  __shared__ float4 cbox[64];
+  const int csize = min(64, n - cb * 64), rsize = min(64, n - rb * 64);
+  if (threadIdx.x < csize) cbox[threadIdx.x] = boxes[order[cb * 64 + threadIdx.x]];
+  __syncthreads();
+  if (threadIdx.x < rsize) {
+    const int r = rb * 64 + threadIdx.x;
+    const float4 a = boxes[order[r]];
+    unsigned long long t = 0;
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int c = start; c < csize; ++c)
+      if (iou_gt(a, cbox[c], thr)) t |= 1ULL << c;
+    mask[static_cast<long long>(r) * col_blocks + cb] = t;
+  }
+}
+
+// Sequential greedy pass, 64 boxes at a time: one thread resolves the chunk's diagonal block, then
+// all threads OR the kept rows into the running suppression bitmap.
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n,
+                int col_blocks, int* __restrict__ keep_out, int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long remv[];  // col_blocks words
+  __shared__ unsigned long long kept_bits;
+  __shared__ int nkeep;
+  for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) remv[w] = 0;
+  if (threadIdx.x == 0) nkeep = 0;
+  __syncthreads();
+  for (int cb = 0; cb < col_blocks; ++cb) {
+    if (threadIdx.x == 0) {
+      unsigned long long r = remv[cb], kept = 0;
+      const int csize = min(64, n - cb * 64);
+      for (int c = 0; c < csize; ++c) {
+        if (!((r >> c) & 1ULL)) {
+          kept |= 1ULL << c;
+          r |= mask[static_cast<long long>(cb * 64 + c) * col_blocks + cb];
+          keep_out[nkeep++] = order[cb * 64 + c];
+        }
+      }
+      kept_bits = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_bits;
+    for (int w = cb + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
+      unsigned long long acc = remv[w], kb = kept;
+      while (kb) {
+        const int c = __ffsll(static_cast<long long>(kb)) - 1;
+        kb &= kb - 1;
+        acc |= mask[static_cast<long long>(cb * 64 + c) * col_blocks + w];
+      }
+      remv[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *keep_count = nkeep;
+}
+
+// rows[sel[k]] of a packed [n, H, WW] bit volume -> bool bytes [m, H, W]
+__global__ void __launch_bounds__(256)
+unpack_bits_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ sel, int m, int H, int W,
+                   int WW, unsigned char* __restrict__ out) {
+  const long long total = static_cast<long long>(m) * H * W;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const long long t = i / W;
+    const int y = static_cast<int>(t % H);
+    const int k = static_cast<int>(t / H);
+    const int src = sel ? sel[k] : k;
+    const uint32_t w = bits[(static_cast<long long>(src) * H + y) * WW + (x >> 5)];
+    out[i] = (w >> (x & 31)) & 1u;
+  }
+}
+
+// dst[k] = src[sel[k]] for rows of `row_words` 32-bit words (compaction of kept masks / records)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint32_t* __restrict__ src, const int* __restrict__ sel, int m,
+                   long long row_words, uint32_t* __restrict__ dst) {
+  const long long total = static_cast<long long>(m) * row_words;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long k = i / row_words, o = i - k * row_words;
+    dst[i] = src[static_cast<long long>(sel[k]) * row_words + o];
+  }
+}
+
+}  // namespace
+
+extern "C" int sb_amg_mask_post(const float* planes, const int* plane_idx, const float* iou,
+                                const int* iou_idx, int n, int S, int Hc, int Wc, int x0, int y0,
+                                int H, int W, float pred_iou_thresh, float mask_thresh,
+                                float stab_offset, float stab_thresh, unsigned char* keep,
+                                float* stability, float* iou_out, int* bbox, int* area, void* bits,
+                                void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0 && S > 0 && Hc > 0 && Wc > 0 && H >= y0 + Hc && W >= x0 + Wc,
+             "sb_amg_mask_post: bad geometry n=%d S=%d crop=%dx%d+%d+%d frame=%dx%d", n, S, Hc, Wc,
+             x0, y0, H, W);
+  MaskPostParams p;
+  p.planes = planes;
+  p.plane_idx = plane_idx;
+  p.iou = iou;
+  p.iou_idx = iou_idx;
+  p.n = n;
+  p.S = S;
+  p.Hc = Hc;
+  p.Wc = Wc;
+  p.x0 = x0;
+  p.y0 = y0;
+  p.H = H;
+  p.W = W;
+  p.WW = (W + 31) / 32;
+  p.pred_iou_thresh = pred_iou_thresh;
+  p.mask_thresh = mask_thresh;
+  p.stab_offset = stab_offset;
+  p.stab_thresh = stab_thresh;
+  p.edge_atol = 20.0f;
+  p.x1 = x0 + Wc;
+  p.y1 = y0 + Hc;
+  p.keep = keep;
+  p.stability = stability;
+  p.iou_out = iou_out;
+  p.bbox = bbox;
+  p.area = area;
+  p.bits = static_cast<uint32_t*>(bits);
+  mask_post_kernel<<<n, 256, 0, stream>>>(p);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// boxes [n,4] fp32 xyxy, scores [n] fp32. workspace: order [n] int32, mask [n * ceil(n/64)] u64.
+// keep_out [n] int32 receives kept indices in score-descending order, keep_count [1] the count.
+extern "C" int sb_nms(const float* boxes, const float* scores, int n, float iou_thresh, int* order,
+                      void* mask_ws, int* keep_out, int* keep_count, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0, "sb_nms: empty input");
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "sb_nms: boxes must be 16-byte aligned");
+  const int col_blocks = (n + 63) / 64;
+  SB_REQUIRE(col_blocks * 8 <= 200 * 1024, "sb_nms: too many boxes (%d)", n);
+  nms_rank_kernel<<<(n + 255) / 256, 256, 0, stream>>>(scores, n, order);
+  SB_CHECK_LAUNCH();
+  dim3 grid(col_blocks, col_blocks);
+  nms_mask_kernel<<<grid, 64, 0, stream>>>(reinterpret_cast<const float4*>(boxes), order, n,
+                                           iou_thresh, static_cast<unsigned long long*>(mask_ws),
+                                           col_blocks);
+  SB_CHECK_LAUNCH();
+  const size_t smem = static_cast<size_t>(col_blocks) * 8;
+  if (smem > 48 * 1024)
+    SB_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  nms_scan_kernel<<<1, 256, smem, stream>>>(static_cast<const unsigned long long*>(mask_ws), order, n,
+                                            col_blocks, keep_out, keep_count);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_unpack_bits(const void* bits, const int* sel, int m, int H, int W,
+                              unsigned char* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(m > 0 && H > 0 && W > 0, "sb_unpack_bits: empty");
+  const long long total = static_cast<long long>(m) * H * W;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  unpack_bits_kernel<<<static_cast<int>(g), 256, 0, stream>>>(static_cast<const uint32_t*>(bits), sel, m,
+                                                             H, W, (W + 31) / 32, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_gather_rows(const void* src, const int* sel, int m, long long row_words, void* dst,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(m > 0 && row_words > 0, "sb_gather_rows: empty");
+  const long long total = static_cast<long long>(m) * row_words;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  gather_rows_kernel<<<static_cast<int>(g), 256, 0, stream>>>(static_cast<const uint32_t*>(src), sel, m,
+                                                              row_words, static_cast<uint32_t*>(dst));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

@@ -26,8 +26,9 @@ struct AttnParams {
   int heads, hd;
   float scale_log2;  // softmax scale * log2(e)
   int mode;          // 0 plain batched, 1 windowed
-  // plain
+  // plain: q row = b * q_bstride + i, k/v row = b * kv_bstride + j (stride 0 = shared over batch)
   int nq, nk;
+  long long q_bstride, kv_bstride;
   // windowed: input grid H x W (unpadded), window ws (in key space), q pooling stride (1 or 2),
   // output grid Ho x Wo (= floor(H/pool), floor(W/pool)), nwx/nwy windows per padded grid.
   int H, W, ws, pool, Ho, Wo, nwx, nwy;
@@ -67,7 +68,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
 // Row index (into the token-major projection buffer) of key j of window `win` in batch b, or -1 for a
 // padded position.
 __device__ __forceinline__ long long key_row(const AttnParams& p, int b, int win, int j) {
-  if (p.mode == 0) return static_cast<long long>(b) * p.nk + j;
+  if (p.mode == 0) return static_cast<long long>(b) * p.kv_bstride + j;
   const int wy = win / p.nwx, wx = win % p.nwx;
   const int y = wy * p.ws + j / p.ws, x = wx * p.ws + j % p.ws;
   if (y >= p.H || x >= p.W) return -1;
@@ -123,7 +124,7 @@ flash_attn_kernel(const AttnParams p) {
     if (qi >= nq) continue;
     uint4 val;
     if (p.mode == 0) {
-      val = *reinterpret_cast<const uint4*>(p.q + (static_cast<long long>(b) * nq + qi) * p.q_ld +
+      val = *reinterpret_cast<const uint4*>(p.q + (static_cast<long long>(b) * p.q_bstride + qi) * p.q_ld +
                                             col0 + c * 8);
     } else {
       const int wy = win / p.nwx, wx = win % p.nwx;
@@ -389,9 +390,11 @@ int run_attn(AttnParams& p, int batch, int nq_per_window, int nwin, cudaStream_t
 }  // namespace
 
 // Plain batched attention: q [B*nq, heads*hd] (pitch q_ld), k/v [B*nk, heads*hd], o [B*nq, heads*hd].
+// q_shared / kv_shared: the operand has a single batch entry that every batch element reads.
 extern "C" int sb_attention(const void* q, long long q_ld, const void* k, long long k_ld,
                             const void* v, long long v_ld, void* o, long long o_ld, int batch,
-                            int heads, int hd, int nq, int nk, float scale, void* stream) {
+                            int heads, int hd, int nq, int nk, float scale, int q_shared,
+                            int kv_shared, void* stream) {
   SB_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nk > 0, "sb_attention: empty problem");
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -409,6 +412,8 @@ extern "C" int sb_attention(const void* q, long long q_ld, const void* k, long l
   p.mode = 0;
   p.nq = nq;
   p.nk = nk;
+  p.q_bstride = q_shared ? 0 : nq;
+  p.kv_bstride = kv_shared ? 0 : nk;
   return run_attn(p, batch, nq, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 

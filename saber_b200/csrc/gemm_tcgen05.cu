@@ -24,7 +24,7 @@ struct GemmParams {
   long long ldo;
   int out_f32;
   const float* bias;
-  int act;  // 0 none, 1 gelu(erf), 2 relu
+  int act;  // 0 none, 1 gelu(erf), 2 relu, 3 sigmoid
   const void* res;
   long long ldr;
   int res_f32;
@@ -186,6 +186,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         } else if (p.act == 2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        } else if (p.act == 3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 1.0f / (1.0f + expf(-f[j]));
         }
         if (row_ok) {
           if (ncols == 32 && vec_ok) {
@@ -308,7 +311,7 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
   SB_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "sb_gemm_bf16: lda/ldw must be multiples of 8");
   SB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
              "sb_gemm_bf16: A/W must be 16-byte aligned");
-  SB_REQUIRE(act >= 0 && act <= 2, "sb_gemm_bf16: bad act %d", act);
+  SB_REQUIRE(act >= 0 && act <= 3, "sb_gemm_bf16: bad act %d", act);
   if (g_num_sms == 0) {
     int dev = 0;
     SB_CHECK_CUDA(cudaGetDevice(&dev));

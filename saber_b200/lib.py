@@ -22,7 +22,7 @@ SIGNATURES = {
     "sb_gemm_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p,
                      c_int, c_void_p, c_ll, c_int, c_int, c_float, c_int, c_void_p],
     "sb_attention": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
-                     c_int, c_int, c_int, c_float, c_void_p],
+                     c_int, c_int, c_int, c_float, c_int, c_int, c_void_p],
     "sb_window_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_float, c_void_p],
     "sb_layernorm": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int,
@@ -33,6 +33,14 @@ SIGNATURES = {
     "sb_nhwc_to_nchw": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_nchw_to_nhwc": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sb_add_cast": [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p],
+    "sb_prompt_tokens": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_int, c_void_p, c_void_p],
+    "sb_mask_downscale": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_upscale1_post": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                         c_void_p],
+    "sb_upscale2_mask": [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_select_mask": [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
 }
 
 

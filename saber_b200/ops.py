@@ -10,7 +10,7 @@ import torch
 
 from . import lib as _lib
 
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 _BF16, _F32 = torch.bfloat16, torch.float32
 
 launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -96,20 +96,24 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, nq: int,
-              nk: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Plain batched MHA. q [batch*nq, heads*hd], k/v [batch*nk, heads*hd] (bf16, row views allowed)."""
+              nk: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
+              q_shared: bool = False, kv_shared: bool = False) -> torch.Tensor:
+    """Plain batched MHA. q [batch*nq, heads*hd], k/v [batch*nk, heads*hd] (bf16, row views allowed).
+    With q_shared / kv_shared the operand holds one batch entry ([nq|nk, C]) read by every batch element."""
     _chk_cuda(q, k, v, out)
     assert q.dtype == _BF16 and k.dtype == _BF16 and v.dtype == _BF16
     Cc = q.shape[1]
     hd = Cc // heads
-    assert q.shape[0] == batch * nq and k.shape[0] == batch * nk and v.shape[0] == batch * nk
+    assert q.shape[0] == (1 if q_shared else batch) * nq
+    assert k.shape[0] == (1 if kv_shared else batch) * nk and v.shape[0] == k.shape[0]
     if scale is None:
         scale = 1.0 / math.sqrt(hd)
     if out is None:
         out = torch.empty((batch * nq, Cc), dtype=_BF16, device=q.device)
     L = _lib.load()
     rc = L.sb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                        out.data_ptr(), out.stride(0), batch, heads, hd, nq, nk, scale, _stream())
+                        out.data_ptr(), out.stride(0), batch, heads, hd, nq, nk, scale, int(q_shared),
+                        int(kv_shared), _stream())
     _lib.check(rc, "sb_attention")
     _count()
     return out
@@ -215,3 +219,75 @@ def add_cast(a: torch.Tensor, b: Optional[torch.Tensor] = None, out_dtype=_BF16)
                              int(out_dtype == _F32), a.numel(), _stream()), "sb_add_cast")
     _count()
     return out
+
+
+def prompt_tokens(coords: torch.Tensor, labels: torch.Tensor, gauss: torch.Tensor, point_emb: torch.Tensor,
+                  not_a_point: torch.Tensor, out_tokens: torch.Tensor, image_size: int, pad: bool = True) -> torch.Tensor:
+    """Decoder token matrix [B, 6 + Np (+1 pad), 256] fp32: output tokens + point-prompt embeddings."""
+    _chk_cuda(coords, labels, gauss, point_emb, not_a_point, out_tokens)
+    assert coords.dtype == _F32 and coords.is_contiguous() and coords.dim() == 3 and coords.shape[2] == 2
+    assert labels.dtype == torch.int32 and labels.is_contiguous() and labels.shape == coords.shape[:2]
+    B, Np = coords.shape[0], coords.shape[1]
+    Nt = 6 + Np + (1 if pad else 0)
+    tokens = torch.empty((B, Nt, 256), dtype=_F32, device=coords.device)
+    L = _lib.load()
+    _lib.check(L.sb_prompt_tokens(coords.data_ptr(), labels.data_ptr(), B, Np, int(pad), gauss.data_ptr(),
+                                  point_emb.data_ptr(), not_a_point.data_ptr(), out_tokens.data_ptr(), image_size,
+                                  tokens.data_ptr(), _stream()), "sb_prompt_tokens")
+    _count()
+    return tokens
+
+
+def mask_downscale(mask: torch.Tensor, w) -> torch.Tensor:
+    """[B, S, S] fp32 mask prompt -> [B*(S/4)^2, 16] bf16 (mask_downscaling convs 0..5 fused)."""
+    _chk_cuda(mask)
+    assert mask.dtype == _F32 and mask.is_contiguous() and mask.dim() == 3
+    B, S, _ = mask.shape
+    out = torch.empty((B * (S // 4) ** 2, 16), dtype=_BF16, device=mask.device)
+    L = _lib.load()
+    _lib.check(L.sb_mask_downscale(mask.data_ptr(), B, S, *[t.data_ptr() for t in w], out.data_ptr(), _stream()),
+               "sb_mask_downscale")
+    _count()
+    return out
+
+
+def upscale1_post(g1: torch.Tensor, feat_s1: torch.Tensor, s1_batch_stride: int, gamma: torch.Tensor,
+                  beta: torch.Tensor, B: int, h: int, w: int) -> torch.Tensor:
+    _chk_cuda(g1, feat_s1, gamma, beta)
+    assert g1.dtype == _BF16 and g1.is_contiguous() and g1.shape == (B * h * w, 256)
+    assert feat_s1.dtype == _F32 and feat_s1.is_contiguous()
+    u1 = torch.empty((B * 4 * h * w, 64), dtype=_BF16, device=g1.device)
+    L = _lib.load()
+    _lib.check(L.sb_upscale1_post(g1.data_ptr(), feat_s1.data_ptr(), s1_batch_stride, gamma.data_ptr(),
+                                  beta.data_ptr(), B, h, w, u1.data_ptr(), _stream()), "sb_upscale1_post")
+    _count()
+    return u1
+
+
+def upscale2_mask(g2: torch.Tensor, feat_s0: torch.Tensor, s0_batch_stride: int, hyper: torch.Tensor, B: int,
+                  H1: int, W1: int) -> torch.Tensor:
+    _chk_cuda(g2, feat_s0, hyper)
+    assert g2.dtype == _BF16 and g2.is_contiguous() and g2.shape == (B * H1 * W1, 128)
+    assert feat_s0.dtype == _F32 and feat_s0.is_contiguous()
+    assert hyper.dtype == _F32 and hyper.is_contiguous() and hyper.shape == (B, 4, 32)
+    masks = torch.empty((B, 4, 2 * H1, 2 * W1), dtype=_F32, device=g2.device)
+    L = _lib.load()
+    _lib.check(L.sb_upscale2_mask(g2.data_ptr(), feat_s0.data_ptr(), s0_batch_stride, hyper.data_ptr(), B, H1, W1,
+                                  masks.data_ptr(), _stream()), "sb_upscale2_mask")
+    _count()
+    return masks
+
+
+def select_mask(masks: torch.Tensor, ious: torch.Tensor, delta: float, thresh: float):
+    """dynamic_multimask_via_stability: returns (sel_idx int32 [B], sel_iou fp32 [B])."""
+    _chk_cuda(masks, ious)
+    assert masks.dtype == _F32 and masks.is_contiguous() and masks.dim() == 4 and masks.shape[1] == 4
+    assert ious.dtype == _F32 and ious.is_contiguous() and ious.shape == (masks.shape[0], 4)
+    B = masks.shape[0]
+    idx = torch.empty((B,), dtype=torch.int32, device=masks.device)
+    iou = torch.empty((B,), dtype=_F32, device=masks.device)
+    L = _lib.load()
+    _lib.check(L.sb_select_mask(masks.data_ptr(), ious.data_ptr(), B, masks.shape[2] * masks.shape[3], delta, thresh,
+                                idx.data_ptr(), iou.data_ptr(), _stream()), "sb_select_mask")
+    _count()
+    return idx, iou

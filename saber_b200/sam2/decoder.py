@@ -1,0 +1,212 @@
+"""B200 executor of the SAM2 prompt encoder + mask decoder (two-way transformer, transposed-conv
+up-scaling with high-res skips, hyper-network mask heads, IoU and object-score heads).
+
+Token-major layout throughout: decoder tokens ``[B*Nt, 256]`` (fp32 residual stream), image stream
+``[B*4096, 256]``. Constant terms are folded at load time: the image positional encoding is pushed
+through the K/Q projections once (``pe @ W^T + b`` becomes the GEMM's broadcast residual), and the
+first AMG pass — where the dense prompt is the same ``no_mask_embed`` for every point — computes
+the layer-0 image-side projections once per image and shares them across the prompt batch
+(results equal upstream up to fp reassociation; SURVEY §7 "algorithmic redundancy").
+Restates sam2/modeling/sam/{prompt_encoder,mask_decoder,transformer}.py.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import ops
+from . import arch
+
+_BF16, _F32 = torch.bfloat16, torch.float32
+NT_IMG = 4096  # 64 x 64 image tokens
+
+
+def _dense_pe(gauss: torch.Tensor, size: int = 64) -> torch.Tensor:
+    """PositionEmbeddingRandom.forward((64,64)) -> [4096, 256] fp32 (weights-only constant)."""
+    g = gauss.float()
+    grid = torch.ones((size, size), dtype=torch.float32)
+    y = (grid.cumsum(0) - 0.5) / size
+    x = (grid.cumsum(1) - 0.5) / size
+    coords = 2 * torch.stack([x, y], dim=-1) - 1
+    proj = 2 * math.pi * (coords @ g)
+    return torch.cat([proj.sin(), proj.cos()], dim=-1).reshape(size * size, -1)
+
+
+class MaskDecoder:
+    def __init__(self, sd: Dict[str, torch.Tensor], device, dynamic_multimask_via_stability: bool = True):
+        dev = self.device = torch.device(device)
+        md, pe = "sam_mask_decoder.", "sam_prompt_encoder."
+        self.dynamic_multimask_via_stability = dynamic_multimask_via_stability
+        self.stab_delta, self.stab_thresh = 0.05, 0.98
+
+        def w16(t):
+            return t.to(dev, _BF16).contiguous()
+
+        def f32(t):
+            return t.to(dev, _F32).contiguous()
+
+        self.out_tokens = f32(torch.cat([sd[md + "obj_score_token.weight"], sd[md + "iou_token.weight"],
+                                         sd[md + "mask_tokens.weight"]], dim=0))
+        gauss = sd[pe + "pe_layer.positional_encoding_gaussian_matrix"]
+        self.gauss = f32(gauss)
+        self.point_emb = f32(torch.cat([sd[pe + f"point_embeddings.{i}.weight"] for i in range(4)], dim=0))
+        self.not_a_point = f32(sd[pe + "not_a_point_embed.weight"].reshape(-1))
+        self.no_mask_embed = f32(sd[pe + "no_mask_embed.weight"].reshape(-1))
+        self.md_w = [f32(sd[pe + "mask_downscaling.0.weight"].reshape(-1)), f32(sd[pe + "mask_downscaling.0.bias"]),
+                     f32(sd[pe + "mask_downscaling.1.weight"]), f32(sd[pe + "mask_downscaling.1.bias"]),
+                     f32(sd[pe + "mask_downscaling.3.weight"].reshape(-1)), f32(sd[pe + "mask_downscaling.3.bias"]),
+                     f32(sd[pe + "mask_downscaling.4.weight"]), f32(sd[pe + "mask_downscaling.4.bias"])]
+        self.md6_w = w16(sd[pe + "mask_downscaling.6.weight"].reshape(256, 16))
+        self.md6_b = f32(sd[pe + "mask_downscaling.6.bias"])
+        image_pe = _dense_pe(gauss)  # [4096, 256] fp32 on CPU
+        self.image_pe = f32(image_pe)
+
+        def attn_w(prefix):
+            # keys: qw/qb/kw/kb/vw/vb/outw/outb
+            return {f"{k}{p[0]}": sd[f"{prefix}.{k}_proj.{p}"].float()
+                    for k in ("q", "k", "v", "out") for p in ("weight", "bias")}
+
+        self.layers = []
+        for l in range(2):
+            b = f"{md}transformer.layers.{l}."
+            sa, t2i, i2t = attn_w(b + "self_attn"), attn_w(b + "cross_attn_token_to_image"), attn_w(b + "cross_attn_image_to_token")
+            L = {}
+            if l == 0:
+                L["sa_qkv_w"] = w16(torch.cat([sa["qw"], sa["kw"], sa["vw"]], 0))
+                L["sa_qkv_b"] = f32(torch.cat([sa["qb"], sa["kb"], sa["vb"]], 0))
+            else:
+                L["sa_qk_w"] = w16(torch.cat([sa["qw"], sa["kw"]], 0))
+                L["sa_qk_b"] = f32(torch.cat([sa["qb"], sa["kb"]], 0))
+                L["sa_v_w"], L["sa_v_b"] = w16(sa["vw"]), f32(sa["vb"])
+            L["sa_o_w"], L["sa_o_b"] = w16(sa["outw"]), f32(sa["outb"])
+            L["t2i_q_w"], L["t2i_q_b"] = w16(t2i["qw"]), f32(t2i["qb"])
+            L["t2i_kv_w"] = w16(torch.cat([t2i["kw"], t2i["vw"]], 0))
+            L["t2i_kv_res"] = f32(torch.cat([image_pe @ t2i["kw"].t() + t2i["kb"],
+                                             t2i["vb"].expand(NT_IMG, -1)], dim=1))  # [4096, 256]
+            L["t2i_o_w"], L["t2i_o_b"] = w16(t2i["outw"]), f32(t2i["outb"])
+            L["i2t_q_w"] = w16(i2t["qw"])
+            L["i2t_q_res"] = f32(image_pe @ i2t["qw"].t() + i2t["qb"])  # [4096, 128]
+            L["i2t_k_w"], L["i2t_k_b"] = w16(i2t["kw"]), f32(i2t["kb"])
+            L["i2t_v_w"], L["i2t_v_b"] = w16(i2t["vw"]), f32(i2t["vb"])
+            L["i2t_o_w"], L["i2t_o_b"] = w16(i2t["outw"]), f32(i2t["outb"])
+            L["mlp1_w"], L["mlp1_b"] = w16(sd[b + "mlp.layers.0.weight"]), f32(sd[b + "mlp.layers.0.bias"])
+            L["mlp2_w"], L["mlp2_b"] = w16(sd[b + "mlp.layers.1.weight"]), f32(sd[b + "mlp.layers.1.bias"])
+            for k in (1, 2, 3, 4):
+                L[f"n{k}w"], L[f"n{k}b"] = f32(sd[b + f"norm{k}.weight"]), f32(sd[b + f"norm{k}.bias"])
+            self.layers.append(L)
+        fa = attn_w(md + "transformer.final_attn_token_to_image")
+        self.fa_q_w, self.fa_q_b = w16(fa["qw"]), f32(fa["qb"])
+        self.fa_kv_w = w16(torch.cat([fa["kw"], fa["vw"]], 0))
+        self.fa_kv_res = f32(torch.cat([image_pe @ fa["kw"].t() + fa["kb"], fa["vb"].expand(NT_IMG, -1)], dim=1))
+        self.fa_o_w, self.fa_o_b = w16(fa["outw"]), f32(fa["outb"])
+        self.nf_w, self.nf_b = f32(sd[md + "transformer.norm_final_attn.weight"]), f32(sd[md + "transformer.norm_final_attn.bias"])
+        # transposed convs as GEMMs: out column = (dy*2+dx)*Cout + co
+        w1 = sd[md + "output_upscaling.0.weight"].float()  # [ci=256, co=64, 2, 2]
+        self.up1_w = w16(w1.permute(2, 3, 1, 0).reshape(256, 256))
+        self.up1_b = f32(sd[md + "output_upscaling.0.bias"].float().repeat(4))
+        self.up_ln_w, self.up_ln_b = f32(sd[md + "output_upscaling.1.weight"]), f32(sd[md + "output_upscaling.1.bias"])
+        w2 = sd[md + "output_upscaling.3.weight"].float()  # [ci=64, co=32, 2, 2]
+        self.up2_w = w16(w2.permute(2, 3, 1, 0).reshape(128, 64))
+        self.up2_b = f32(sd[md + "output_upscaling.3.bias"].float().repeat(4))
+
+        def mlp3(prefix):
+            return [(w16(sd[f"{prefix}.layers.{k}.weight"]), f32(sd[f"{prefix}.layers.{k}.bias"])) for k in range(3)]
+
+        self.hyper = [mlp3(md + f"output_hypernetworks_mlps.{i}") for i in range(4)]
+        self.iou_head = mlp3(md + "iou_prediction_head")
+        self.obj_head = mlp3(md + "pred_obj_score_head")
+
+    # ------------------------------------------------------------------
+    def prompt_tokens(self, coords: torch.Tensor, labels: torch.Tensor, pad: bool = True) -> torch.Tensor:
+        """coords [B, Np, 2] fp32 in model-input pixels, labels [B, Np] int32 -> tokens [B, Nt, 256] fp32."""
+        return ops.prompt_tokens(coords, labels, self.gauss, self.point_emb, self.not_a_point, self.out_tokens,
+                                 arch.IMAGE_SIZE, pad)
+
+    def _mlp3(self, a: torch.Tensor, head, last_act=ops.ACT_NONE, out: Optional[torch.Tensor] = None):
+        h = ops.gemm(a, head[0][0], head[0][1], act=ops.ACT_RELU)
+        h = ops.gemm(h, head[1][0], head[1][1], act=ops.ACT_RELU)
+        return ops.gemm(h, head[2][0], head[2][1], act=last_act, out_dtype=_F32, out=out)
+
+    def forward(self, image_embed: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, tokens: torch.Tensor,
+                mask_input: Optional[torch.Tensor] = None, multimask_output: bool = True):
+        """image_embed [4096,256] fp32, s0 [65536,32] fp32, s1 [16384,64] fp32 (one image, token-major);
+        tokens [B, Nt, 256] fp32; mask_input [B, 256, 256] fp32 or None.
+
+        Returns dict: masks [B,4,256,256] fp32 (all four tokens), ious [B,4], obj [B,1], hs [B,Nt,256]
+        and, per upstream's output selection, ``sel`` describing which tokens are "the output":
+        multimask -> tokens 1..3; single -> token 0 or the dynamic-stability choice (sel_idx, sel_iou).
+        """
+        B, Nt, _ = tokens.shape
+        query_pe = tokens.reshape(B * Nt, 256)
+        queries = query_pe
+        shared = mask_input is None
+        if shared:
+            keys_f32 = ops.add_cast(image_embed, self.no_mask_embed, _F32)  # [4096,256]
+        else:
+            ds = ops.mask_downscale(mask_input.contiguous(), self.md_w)  # [B*4096,16]
+            keys_f32 = ops.gemm(ds, self.md6_w, self.md6_b, residual=image_embed, res_mod=NT_IMG, out_dtype=_F32)
+        keys = ops.add_cast(keys_f32, None, _BF16)
+        kb = 1 if shared else B  # batch entries of the image stream
+
+        for l, L in enumerate(self.layers):
+            # ---- token self-attention
+            if l == 0:
+                qkv = ops.gemm(ops.add_cast(queries, None, _BF16), L["sa_qkv_w"], L["sa_qkv_b"])
+                a = ops.attention(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt)
+                queries = ops.gemm(a, L["sa_o_w"], L["sa_o_b"], out_dtype=_F32)
+            else:
+                qk = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["sa_qk_w"], L["sa_qk_b"])
+                v = ops.gemm(ops.add_cast(queries, None, _BF16), L["sa_v_w"], L["sa_v_b"])
+                a = ops.attention(qk[:, 0:256], qk[:, 256:512], v, B, 8, Nt, Nt)
+                queries = ops.gemm(a, L["sa_o_w"], L["sa_o_b"], residual=queries, out_dtype=_F32)
+            queries = ops.layernorm(queries, L["n1w"], L["n1b"], 1e-5, _F32)
+            # ---- tokens attend to image
+            q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["t2i_q_w"], L["t2i_q_b"])
+            kv = ops.gemm(keys, L["t2i_kv_w"], None, residual=L["t2i_kv_res"], res_mod=NT_IMG)
+            a = ops.attention(q, kv[:, 0:128], kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))
+            queries = ops.gemm(a, L["t2i_o_w"], L["t2i_o_b"], residual=queries, out_dtype=_F32)
+            queries = ops.layernorm(queries, L["n2w"], L["n2b"], 1e-5, _F32)
+            # ---- token MLP
+            hdn = ops.gemm(ops.add_cast(queries, None, _BF16), L["mlp1_w"], L["mlp1_b"], act=ops.ACT_RELU)
+            queries = ops.gemm(hdn, L["mlp2_w"], L["mlp2_b"], residual=queries, out_dtype=_F32)
+            queries = ops.layernorm(queries, L["n3w"], L["n3b"], 1e-5, _F32)
+            # ---- image attends to tokens
+            kt = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["i2t_k_w"], L["i2t_k_b"])
+            vt = ops.gemm(ops.add_cast(queries, None, _BF16), L["i2t_v_w"], L["i2t_v_b"])
+            qi = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
+            a = ops.attention(qi, kt, vt, B, 8, NT_IMG, Nt, q_shared=(kb == 1))  # [B*4096,128]
+            pre = ops.gemm(a, L["i2t_o_w"], L["i2t_o_b"], residual=keys_f32, res_mod=(NT_IMG if kb == 1 else 0),
+                           out_dtype=_F32)
+            keys = ops.layernorm(pre, L["n4w"], L["n4b"], 1e-5, _BF16)
+            keys_f32 = keys  # bf16 residual from here on (immediately re-normalised)
+            kb = B
+        # ---- final token -> image attention
+        q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), self.fa_q_w, self.fa_q_b)
+        kv = ops.gemm(keys, self.fa_kv_w, None, residual=self.fa_kv_res, res_mod=NT_IMG)
+        a = ops.attention(q, kv[:, 0:128], kv[:, 128:256], B, 8, Nt, NT_IMG)
+        queries = ops.gemm(a, self.fa_o_w, self.fa_o_b, residual=queries, out_dtype=_F32)
+        hs = ops.layernorm(queries, self.nf_w, self.nf_b, 1e-5, _F32)  # [B*Nt,256]
+        # ---- up-scaling + hyper-network masks
+        g1 = ops.gemm(keys, self.up1_w, self.up1_b)  # [B*4096, 4*64]
+        u1 = ops.upscale1_post(g1, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64)  # [B*16384, 64]
+        del g1
+        g2 = ops.gemm(u1, self.up2_w, self.up2_b)  # [B*16384, 4*32]
+        del u1
+        hs16 = ops.add_cast(hs, None, _BF16).view(B, Nt * 256)
+        hyper = torch.empty((B, 4, 32), dtype=_F32, device=self.device)
+        hv = hyper.view(B, 128)
+        for i in range(4):
+            self._mlp3(hs16[:, (2 + i) * 256:(3 + i) * 256], self.hyper[i], out=hv[:, i * 32:(i + 1) * 32])
+        masks = ops.upscale2_mask(g2, s0, 0, hyper, B, 128, 128)  # [B,4,256,256]
+        del g2
+        ious = self._mlp3(hs16[:, 256:512], self.iou_head, last_act=ops.ACT_SIGMOID)  # [B,4]
+        obj = self._mlp3(hs16[:, 0:256], self.obj_head)  # [B,1]
+        out = {"masks": masks, "ious": ious, "obj": obj, "hs": hs.view(B, Nt, 256)}
+        if not multimask_output:
+            if self.dynamic_multimask_via_stability:
+                out["sel_idx"], out["sel_iou"] = ops.select_mask(masks, ious, self.stab_delta, self.stab_thresh)
+            else:
+                out["sel_idx"], out["sel_iou"] = None, None  # token 0
+        return out
