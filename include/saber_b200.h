@@ -1,0 +1,121 @@
+/* saber_b200 — C ABI of libsaber_b200.so (sm_100a CUDA kernels of SABER's SAM2 slice-wise hot path).
+ *
+ * The reference (chanzuckerberg/saber) is pure Python and has no FFI of its own: its plugin seam for this
+ * path is the `sam2` package API (build_sam2 / SAM2ImagePredictor / SAM2AutomaticMaskGenerator, bound at
+ * REF saber/adapters/sam2/automask.py:55-78, REF saber/adapters/sam2/predictor.py:24-26,
+ * REF saber/classifier/models/SAM2.py:45-46). `saber_b200.sam2` re-implements that Python surface; every
+ * arithmetic operation underneath it is one of the entry points below, reached through ctypes
+ * (saber_b200/lib.py). Each entry point names the reference / upstream computation it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all data pointers are DEVICE pointers unless marked [host];
+ *  - the caller owns every buffer (the library allocates nothing persistent), `stream` is a cudaStream_t;
+ *  - launches are asynchronous on `stream`; return value 0 = OK, negative = error (-1 CUDA, -2 bad argument,
+ *    -3 unsupported device, -4 driver entry point); sb_last_error() returns the per-thread message;
+ *  - no global mutable state besides per-process caches of function attributes: safe for SABER's
+ *    one-thread-per-GPU GPUPool (REF saber/utils/parallelization.py:155) and one-process-per-GPU NCCL mode;
+ *  - "bf16" buffers are __nv_bfloat16, row-major with the stated pitch in ELEMENTS.
+ */
+#ifndef SABER_B200_H
+#define SABER_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ---------------------------------------------------------------------------------------- */
+const char* sb_last_error(void);
+int sb_version(void);
+int sb_device_sm_count(void);           /* SM count of the current device (148 on B200) */
+int sb_require_sm100(void);             /* fails unless the current device is compute capability 10.x */
+
+/* ---- tensor-core kernels (tcgen05 / TMEM / TMA) ----------------------------------------------------- */
+/* out[M,N] = act(alpha * A[M,K] @ W[N,K]^T + bias[N]) + residual[m % res_mod (or m), N].
+ * Replaces torch.nn.Linear / 1x1 Conv2d / ConvTranspose2d(k2,s2) (cuBLASLt / cuDNN) inside upstream sam2:
+ * Hiera qkv/proj/mlp (sam2/modeling/backbones/hieradet.py), FpnNeck laterals, mask-decoder projections.
+ * act: 0 none, 1 GELU(erf), 2 ReLU, 3 sigmoid. flags: bit0 out is fp32 (else bf16), bit1 residual is fp32.
+ * force_bn: 0 = choose tile N automatically, else 64 / 128 / 256. */
+int sb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
+                 int K, const float* bias, int act, const void* residual, long long ldr, int res_mod, int flags,
+                 float alpha, int force_bn, void* stream);
+/* Plain batched multi-head attention (mask-decoder two-way transformer: sam2/modeling/sam/transformer.py
+ * Attention.forward -> F.scaled_dot_product_attention). q [batch*nq, heads*hd], k/v [batch*nk, heads*hd]. */
+int sb_attention(const void* q, long long q_ld, const void* k, long long k_ld, const void* v, long long v_ld, void* o,
+                 long long o_ld, int batch, int heads, int hd, int nq, int nk, float scale, int q_shared,
+                 int kv_shared, void* stream);
+/* Hiera MultiScaleAttention over a fused qkv buffer [B*H*W, 3*heads*hd]: window partition (with upstream's zero
+ * padding of ragged windows), optional 2x2 max-pool of q, SDPA, window unpartition — hieradet.py
+ * MultiScaleBlock.forward / MultiScaleAttention.forward. ws >= max(H,W) = global attention. */
+int sb_window_attention(const void* qkv, const float* qkv_bias, void* o, int batch, int H, int W, int heads, int hd,
+                        int ws, int pool, float scale, void* stream);
+
+/* ---- token-major bandwidth kernels of the encoder / decoder ----------------------------------------- */
+int sb_layernorm(const void* in, long long ld_in, int in_f32, void* out, long long ld_out, int out_f32,
+                 const float* gamma, const float* beta, int M, int C, float eps, int act, void* stream);
+int sb_im2col_k7s4(const float* img, void* cols, int B, int Cin, int S, int Kp, void* stream); /* PatchEmbed 7x7 s4 p3 */
+int sb_maxpool2x2(const void* in, void* out, int is_f32, int B, int H, int W, int C, void* stream); /* hieradet do_pool */
+int sb_add_upsample2x(float* dst, const float* src, int B, int H, int W, int C, void* stream);   /* FpnNeck top-down */
+int sb_nhwc_to_nchw(const void* in, int in_f32, void* out, int out_f32, int B, int HW, int C, const float* chan_add,
+                    void* stream);
+int sb_nchw_to_nhwc(const void* in, int in_f32, void* out, int out_f32, int B, int HW, int C, void* stream);
+int sb_add_cast(const void* a, int a_f32, const float* b, long long b_mod, void* out, int out_f32, long long n,
+                void* stream);
+
+/* ---- prompt encoder / mask decoder glue (sam2/modeling/sam/prompt_encoder.py, mask_decoder.py) ------- */
+int sb_prompt_tokens(const float* coords, const int* labels, int B, int Np, int pad, const float* gauss,
+                     const float* point_emb, const float* not_a_point, const float* out_tokens, int image_size,
+                     float* tokens, void* stream);
+/* mask_downscaling[0..5] fused. cpp == 3: `in` is a decoder output [B/3,4,S,S] whose tokens 1..3 are the B mask
+ * prompts (AMG m2m refinement); clampv > 0 clamps to +-clampv (upstream clamps low-res logits to +-32). */
+int sb_mask_downscale(const float* in, int B, int S, int cpp, float clampv, const float* w1, const float* b1,
+                      const float* g1, const float* be1, const float* w2, const float* b2, const float* g2,
+                      const float* be2, void* out, void* stream);
+int sb_upscale1_post(const void* g1, const float* feat_s1, long long s1_batch_stride, const float* gamma,
+                     const float* beta, int B, int h, int w, void* u1, void* stream);
+int sb_upscale2_mask(const void* g2, const float* feat_s0, long long s0_batch_stride, const float* hyper, int B,
+                     int H1, int W1, float* masks, void* stream);
+/* MaskDecoder._dynamic_multimask_via_stability (delta 0.05, thresh 0.98 set by build_sam2(apply_postprocessing)) */
+int sb_select_mask(const float* masks, const float* ious, int B, int HW, float delta, float thresh, int* sel_idx,
+                   float* sel_iou, void* stream);
+
+/* ---- automatic-mask-generation post-processing: integer / indexing, bit-exact ------------------------ */
+/* For n candidates (planes [*,4,S,S], ious4 [*,4]; candidate i = prompt i/cpp, token sel[i] or 1 + i%3 or 0):
+ * bilinear up-sampling to the crop (SAM2Transforms.postprocess_masks), pred-IoU filter, stability score
+ * (sam2/utils/amg.py calculate_stability_score), threshold, box (batched_mask_to_box), near-crop-edge filter
+ * (is_box_near_crop_edge), uncrop + bit-pack into the full frame. Outputs are written at index i. */
+int sb_amg_mask_post(const float* planes, const float* ious4, const int* sel, int cpp, int n, int S, int Hc, int Wc,
+                     int x0, int y0, int H, int W, float pred_iou_thresh, float mask_thresh, float stab_offset,
+                     float stab_thresh, unsigned char* keep, float* stability, float* iou_out, int* bbox, int* area,
+                     void* bits, void* stream);
+int sb_compact_keep(const unsigned char* keep, int base, int n, int* cand, int* count, void* stream);
+/* torchvision.ops.nms semantics (upstream batched_nms per crop and across crops); list lengths are device ints. */
+int sb_nms_dev(const int* bbox, const float* scores, const int* cand, const int* n_ptr, int n_cap, float iou_thresh,
+               int* order, void* mask_ws, int* out_list, int* out_count, void* stream);
+/* pairwise |mask_i & mask_j| for REF saber/segmenters/utils.py:5-86 remove_duplicate_masks */
+int sb_pair_intersections(const void* bits, const int* bbox, const int* area, int m, int H, int W,
+                          double area_ratio_thresh, int* inter, void* stream);
+int sb_unpack_bits(const void* bits, const int* sel, int m, int H, int W, unsigned char* out, void* stream);
+int sb_gather_rows(const void* src, const int* sel, int m, long long row_words, void* dst, void* stream);
+/* REF saber/segmenters/propagation.py:181-186: masks3d[mask] = idx + 1 in list order (later masks win) */
+int sb_stitch_labels(const void* bits, const int* order, int m, int H, int W, void* labels, void* stream);
+/* REF saber/segmenters/utils.py:88-131 separate_masks: 26-connected components (scipy.ndimage.label numbering),
+ * components < min_vol voxels dropped, compact relabel. labels: uint32 [Z,Y,X]; aux: Z*Y*X int32 workspace;
+ * chunk_ws: ceil(Z*Y*X/2048)+1 int32 workspace whose last element receives the component count. */
+int sb_ccl3d_26(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, void* labels, int* aux,
+                int* chunk_ws, void* stream);
+
+/* ---- image-side bandwidth kernels -------------------------------------------------------------------- */
+/* scipy.ndimage.uniform_filter1d(mode='reflect') along one axis — REF saber/utils/preprocessing.py:13-14 */
+int sb_box_filter(const float* in, float* out, int H, int W, int axis, int size, int square, void* stream);
+/* REF saber/utils/preprocessing.py:15-18,36 contrast + clip + min-max; partials: 2048-float workspace */
+int sb_contrast_normalize(const float* img, const float* mean, const float* sq, float* out, long long n,
+                          float cutoff, float* partials, void* stream);
+/* SAM2Transforms: crop -> Resize(S, bilinear, antialias) -> Normalize(mean, std). mean3/std3 are [host]. */
+int sb_resize_normalize(const float* img, int H, int W, int C, const int* crops, int ncrops, int S,
+                        const float* mean3, const float* std3, float* out, void* stream);
+/* F.interpolate(bilinear, align_corners=False): SAM2Transforms.postprocess_masks / video-resolution logits */
+int sb_upsample_bilinear(const float* in, int N, int Hi, int Wi, int Ho, int Wo, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SABER_B200_H */

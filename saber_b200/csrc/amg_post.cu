@@ -11,11 +11,12 @@
 
 namespace {
 
-// ATen area_pixel_compute_source_index (align_corners=False, not cubic), written without FMA
-// contraction so the GPU and the numpy oracle evaluate the identical fp32 expression tree.
+// ATen area_pixel_compute_source_index (align_corners=False, not cubic). The expression tree — including
+// where the fused multiply-adds sit — is the one torch's CPU F.interpolate(bilinear) evaluates (pinned
+// bitwise in tests/test_oracle_pins.py), so the thresholded masks are bit-identical to the reference's CPU path.
 __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1,
                                           float& l0, float& l1) {
-  float s = __fsub_rn(__fmul_rn(scale, __fadd_rn(static_cast<float>(dst), 0.5f)), 0.5f);
+  float s = __fmaf_rn(scale, __fadd_rn(static_cast<float>(dst), 0.5f), -0.5f);
   if (s < 0.f) s = 0.f;
   i0 = min(static_cast<int>(floorf(s)), in_size - 1);
   l1 = fminf(fmaxf(__fsub_rn(s, static_cast<float>(i0)), 0.f), 1.f);
@@ -24,10 +25,10 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 }
 
 struct MaskPostParams {
-  const float* planes;     // low-res logit planes, each S x S
-  const int* plane_idx;    // [n] plane index per candidate
-  const float* iou;        // [n] predicted IoU per candidate
-  const int* iou_idx;      // [n] index into iou (nullable -> i)
+  const float* planes;     // low-res logit planes [B, 4, S, S] (all four mask tokens per prompt)
+  const float* ious4;      // [B, 4] predicted IoU per token
+  const int* sel;          // [n] chosen token per prompt (single-mask / m2m mode), or null
+  int cpp;                 // candidates per prompt: 1 (sel given, or token 0) or 3 (multimask tokens 1..3)
   int n, S;
   int Hc, Wc, x0, y0, H, W, WW;  // crop size / origin, full frame size, words per row
   float pred_iou_thresh, mask_thresh, stab_offset, stab_thresh, edge_atol;
@@ -44,7 +45,10 @@ __global__ void __launch_bounds__(256)
 mask_post_kernel(const MaskPostParams p) {
   const int i = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float iou = p.iou[p.iou_idx ? p.iou_idx[i] : i];
+  const int prompt = i / p.cpp;
+  const int token = p.sel ? p.sel[prompt] : (p.cpp == 3 ? 1 + i % 3 : 0);
+  const int plane_id = prompt * 4 + token;
+  const float iou = p.ious4[plane_id];
   uint32_t* bits = p.bits + static_cast<long long>(i) * p.H * p.WW;
   const bool iou_ok = !(p.pred_iou_thresh > 0.f) || (iou > p.pred_iou_thresh);
   if (tid == 0) p.iou_out[i] = iou;
@@ -57,7 +61,7 @@ mask_post_kernel(const MaskPostParams p) {
     }
     return;  // block-uniform
   }
-  const float* plane = p.planes + static_cast<long long>(p.plane_idx[i]) * p.S * p.S;
+  const float* plane = p.planes + static_cast<long long>(plane_id) * p.S * p.S;
   const float scale_h = __fdiv_rn(static_cast<float>(p.S), static_cast<float>(p.Hc));
   const float scale_w = __fdiv_rn(static_cast<float>(p.S), static_cast<float>(p.Wc));
   const float hi = __fadd_rn(p.mask_thresh, p.stab_offset), lo = __fsub_rn(p.mask_thresh, p.stab_offset);
@@ -84,9 +88,9 @@ mask_post_kernel(const MaskPostParams p) {
           src_index(scale_w, cx, p.S, x0i, x1i, lx0, lx1);
           const float v00 = plane[y0i * p.S + x0i], v01 = plane[y0i * p.S + x1i];
           const float v10 = plane[y1i * p.S + x0i], v11 = plane[y1i * p.S + x1i];
-          const float t0 = __fadd_rn(__fmul_rn(v00, lx0), __fmul_rn(v01, lx1));
-          const float t1 = __fadd_rn(__fmul_rn(v10, lx0), __fmul_rn(v11, lx1));
-          val = __fadd_rn(__fmul_rn(t0, ly0), __fmul_rn(t1, ly1));
+          const float t0 = __fmaf_rn(v00, lx0, __fmul_rn(v01, lx1));
+          const float t1 = __fmaf_rn(v10, lx0, __fmul_rn(v11, lx1));
+          val = __fmaf_rn(t0, ly0, __fmul_rn(t1, ly1));
         }
       }
       const uint32_t b_hi = __ballot_sync(0xffffffffu, in && val > hi);
@@ -164,16 +168,52 @@ mask_post_kernel(const MaskPostParams p) {
 
 // ---------------------------------------------------------------------------------------------
 // NMS (torchvision.ops.nms semantics): stable sort by score descending, suppress iff IoU > thr.
+// Device-resident: candidate lists and their lengths live in device memory, so a whole image's AMG
+// (21 crops + the cross-crop pass) runs without a host synchronisation.
 // ---------------------------------------------------------------------------------------------
+
+// cand[0..*count) = { base + i : keep[base + i] != 0, i < n } in ascending order (single block).
+__global__ void __launch_bounds__(1024)
+compact_keep_kernel(const unsigned char* __restrict__ keep, int base, int n, int* __restrict__ cand,
+                    int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool k = i < n && keep[base + i] != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = running;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (k) cand[off + __popc(bal & ((1u << lane) - 1u))] = base + i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      running += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = running;
+}
+
+// order[rank] = cand[i], rank = #{j : score_j > score_i or (score_j == score_i and j < i)} (stable, desc).
 __global__ void __launch_bounds__(256)
-nms_rank_kernel(const float* __restrict__ scores, int n, int* __restrict__ order) {
+nms_rank_kernel(const float* __restrict__ scores, const int* __restrict__ cand, const int* __restrict__ n_ptr,
+                int* __restrict__ order) {
   __shared__ float tile[256];
+  const int n = *n_ptr;
+  if (blockIdx.x * 256 >= n) return;  // block-uniform
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float si = i < n ? scores[i] : 0.f;
+  const float si = i < n ? scores[cand[i]] : 0.f;
   int rank = 0;
   for (int j0 = 0; j0 < n; j0 += 256) {
     const int j = j0 + threadIdx.x;
-    tile[threadIdx.x] = j < n ? scores[j] : 0.f;
+    tile[threadIdx.x] = j < n ? scores[cand[j]] : 0.f;
     __syncthreads();
     const int lim = min(256, n - j0);
     if (i < n) {
@@ -184,7 +224,13 @@ nms_rank_kernel(const float* __restrict__ scores, int n, int* __restrict__ order
     }
     __syncthreads();
   }
-  if (i < n) order[rank] = i;
+  if (i < n) order[rank] = cand[i];
+}
+
+__device__ __forceinline__ float4 box_f(const int* __restrict__ bbox, int slot) {
+  const int4 b = *reinterpret_cast<const int4*>(bbox + 4 * static_cast<long long>(slot));
+  return make_float4(static_cast<float>(b.x), static_cast<float>(b.y), static_cast<float>(b.z),
+                     static_cast<float>(b.w));
 }
 
 __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
@@ -199,33 +245,39 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
 
 // mask[r, cw] bit c = IoU(sorted box r, sorted box cw*64 + c) > thr for c-index > r
 __global__ void __launch_bounds__(64)
-nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, int n, float thr,
-                unsigned long long* __restrict__ mask, int col_blocks) {
+nms_mask_kernel(const int* __restrict__ bbox, const int* __restrict__ order, const int* __restrict__ n_ptr,
+                float thr, unsigned long long* __restrict__ mask, int col_blocks_cap) {
+  const int n = *n_ptr;
   const int rb = blockIdx.y, cb = blockIdx.x;
-  if (cb < rb) return;  // only the upper triangle is ever read
+  if (cb < rb || cb * 64 >= n || rb * 64 >= n) return;  // only the upper triangle is ever read
   __shared__ float4 cbox[64];
   const int csize = min(64, n - cb * 64), rsize = min(64, n - rb * 64);
-  if (threadIdx.x < csize) cbox[threadIdx.x] = boxes[order[cb * 64 + threadIdx.x]];
+  if (threadIdx.x < csize) cbox[threadIdx.x] = box_f(bbox, order[cb * 64 + threadIdx.x]);
   __syncthreads();
   if (threadIdx.x < rsize) {
     const int r = rb * 64 + threadIdx.x;
-    const float4 a = boxes[order[r]];
+    const float4 a = box_f(bbox, order[r]);
     unsigned long long t = 0;
     const int start = (rb == cb) ? threadIdx.x + 1 : 0;
     for (int c = start; c < csize; ++c)
       if (iou_gt(a, cbox[c], thr)) t |= 1ULL << c;
-    mask[static_cast<long long>(r) * col_blocks + cb] = t;
+    mask[static_cast<long long>(r) * col_blocks_cap + cb] = t;
   }
 }
 
 // Sequential greedy pass, 64 boxes at a time: one thread resolves the chunk's diagonal block, then
-// all threads OR the kept rows into the running suppression bitmap.
+// all threads OR the kept rows into the running suppression bitmap. Kept slots are appended (in
+// score-descending order) to out_list at *out_count, which is then advanced.
 __global__ void __launch_bounds__(256)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n,
-                int col_blocks, int* __restrict__ keep_out, int* __restrict__ keep_count) {
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order,
+                const int* __restrict__ n_ptr, int col_blocks_cap, int* __restrict__ out_list,
+                int* __restrict__ out_count) {
   extern __shared__ unsigned long long remv[];  // col_blocks words
   __shared__ unsigned long long kept_bits;
   __shared__ int nkeep;
+  const int n = *n_ptr;
+  const int col_blocks = (n + 63) / 64;
+  const int out_base = *out_count;
   for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) remv[w] = 0;
   if (threadIdx.x == 0) nkeep = 0;
   __syncthreads();
@@ -236,8 +288,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       for (int c = 0; c < csize; ++c) {
         if (!((r >> c) & 1ULL)) {
           kept |= 1ULL << c;
-          r |= mask[static_cast<long long>(cb * 64 + c) * col_blocks + cb];
-          keep_out[nkeep++] = order[cb * 64 + c];
+          r |= mask[static_cast<long long>(cb * 64 + c) * col_blocks_cap + cb];
+          out_list[out_base + nkeep++] = order[cb * 64 + c];
         }
       }
       kept_bits = kept;
@@ -249,13 +301,53 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       while (kb) {
         const int c = __ffsll(static_cast<long long>(kb)) - 1;
         kb &= kb - 1;
-        acc |= mask[static_cast<long long>(cb * 64 + c) * col_blocks + w];
+        acc |= mask[static_cast<long long>(cb * 64 + c) * col_blocks_cap + w];
       }
       remv[w] = acc;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *keep_count = nkeep;
+  __syncthreads();
+  if (threadIdx.x == 0) *out_count = out_base + nkeep;
+}
+
+// inter[i, j] (i < j) = popcount(mask_i & mask_j) when min(area)/max(area) >= area_ratio_thresh (fp64, as
+// REF saber/segmenters/utils.py:31-45 evaluates it) else -1. Only the rows / words inside both bounding
+// boxes are scanned (bits outside a mask's box are zero). One warp per pair.
+__global__ void __launch_bounds__(256)
+pair_inter_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ bbox, const int* __restrict__ area,
+                  int m, int H, int WW, double area_ratio_thresh, int* __restrict__ inter) {
+  const int lane = threadIdx.x & 31;
+  const long long npairs = static_cast<long long>(m) * m;
+  const long long nwords = static_cast<long long>(H) * WW;
+  for (long long pi = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; pi < npairs;
+       pi += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    const int i = static_cast<int>(pi / m), j = static_cast<int>(pi % m);
+    if (j <= i) continue;
+    const int ai = area[i], aj = area[j];
+    const int amax = max(ai, aj), amin = min(ai, aj);
+    const double ratio = amax > 0 ? static_cast<double>(amin) / static_cast<double>(amax) : 0.0;
+    int result = -1;
+    if (!(ratio < area_ratio_thresh)) {
+      const int x0 = max(bbox[4 * i + 0], bbox[4 * j + 0]), y0 = max(bbox[4 * i + 1], bbox[4 * j + 1]);
+      const int x1 = min(bbox[4 * i + 2], bbox[4 * j + 2]), y1 = min(bbox[4 * i + 3], bbox[4 * j + 3]);
+      int cnt = 0;
+      if (x1 >= x0 && y1 >= y0) {
+        const int w0 = x0 >> 5, w1 = x1 >> 5, nw = w1 - w0 + 1;
+        const int tot = (y1 - y0 + 1) * nw;
+        const uint32_t* bi = bits + static_cast<long long>(i) * nwords;
+        const uint32_t* bj = bits + static_cast<long long>(j) * nwords;
+        for (int t = lane; t < tot; t += 32) {
+          const long long o = static_cast<long long>(y0 + t / nw) * WW + w0 + t % nw;
+          cnt += __popc(bi[o] & bj[o]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      result = cnt;
+    }
+    if (lane == 0) inter[pi] = result;
+  }
 }
 
 // rows[sel[k]] of a packed [n, H, WW] bit volume -> bool bytes [m, H, W]
@@ -289,8 +381,8 @@ gather_rows_kernel(const uint32_t* __restrict__ src, const int* __restrict__ sel
 
 }  // namespace
 
-extern "C" int sb_amg_mask_post(const float* planes, const int* plane_idx, const float* iou,
-                                const int* iou_idx, int n, int S, int Hc, int Wc, int x0, int y0,
+extern "C" int sb_amg_mask_post(const float* planes, const float* ious4, const int* sel, int cpp,
+                                int n, int S, int Hc, int Wc, int x0, int y0,
                                 int H, int W, float pred_iou_thresh, float mask_thresh,
                                 float stab_offset, float stab_thresh, unsigned char* keep,
                                 float* stability, float* iou_out, int* bbox, int* area, void* bits,
@@ -300,10 +392,11 @@ extern "C" int sb_amg_mask_post(const float* planes, const int* plane_idx, const
              "sb_amg_mask_post: bad geometry n=%d S=%d crop=%dx%d+%d+%d frame=%dx%d", n, S, Hc, Wc,
              x0, y0, H, W);
   MaskPostParams p;
+  SB_REQUIRE(cpp == 1 || (cpp == 3 && sel == nullptr), "sb_amg_mask_post: cpp must be 1, or 3 without sel");
   p.planes = planes;
-  p.plane_idx = plane_idx;
-  p.iou = iou;
-  p.iou_idx = iou_idx;
+  p.ious4 = ious4;
+  p.sel = sel;
+  p.cpp = cpp;
   p.n = n;
   p.S = S;
   p.Hc = Hc;
@@ -331,28 +424,54 @@ extern "C" int sb_amg_mask_post(const float* planes, const int* plane_idx, const
   return SB_OK;
 }
 
-// boxes [n,4] fp32 xyxy, scores [n] fp32. workspace: order [n] int32, mask [n * ceil(n/64)] u64.
-// keep_out [n] int32 receives kept indices in score-descending order, keep_count [1] the count.
-extern "C" int sb_nms(const float* boxes, const float* scores, int n, float iou_thresh, int* order,
-                      void* mask_ws, int* keep_out, int* keep_count, void* stream_) {
+// cand[0..count) <- slots base..base+n with keep != 0 (ascending); count is a device int.
+extern "C" int sb_compact_keep(const unsigned char* keep, int base, int n, int* cand, int* count,
+                               void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SB_REQUIRE(n > 0, "sb_nms: empty input");
-  SB_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "sb_nms: boxes must be 16-byte aligned");
-  const int col_blocks = (n + 63) / 64;
-  SB_REQUIRE(col_blocks * 8 <= 200 * 1024, "sb_nms: too many boxes (%d)", n);
-  nms_rank_kernel<<<(n + 255) / 256, 256, 0, stream>>>(scores, n, order);
+  SB_REQUIRE(n >= 0 && base >= 0, "sb_compact_keep: bad range");
+  compact_keep_kernel<<<1, 1024, 0, stream>>>(keep, base, n, cand, count);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// Greedy NMS over the candidate slots cand[0..*n_ptr) (n_cap = host-side upper bound of *n_ptr).
+// bbox [*,4] int32 xyxy and scores [*] fp32 are indexed by slot. Workspace: order [n_cap] int32,
+// mask_ws [n_cap * ceil(n_cap/64)] u64. Kept slots are appended in score-descending order to
+// out_list[*out_count ...] and *out_count advanced (device ints; no host synchronisation).
+extern "C" int sb_nms_dev(const int* bbox, const float* scores, const int* cand, const int* n_ptr, int n_cap,
+                          float iou_thresh, int* order, void* mask_ws, int* out_list, int* out_count,
+                          void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n_cap > 0, "sb_nms_dev: empty capacity");
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(bbox) & 15) == 0, "sb_nms_dev: bbox must be 16-byte aligned");
+  const int col_blocks = (n_cap + 63) / 64;
+  SB_REQUIRE(col_blocks * 8 <= 200 * 1024, "sb_nms_dev: too many boxes (%d)", n_cap);
+  nms_rank_kernel<<<(n_cap + 255) / 256, 256, 0, stream>>>(scores, cand, n_ptr, order);
   SB_CHECK_LAUNCH();
   dim3 grid(col_blocks, col_blocks);
-  nms_mask_kernel<<<grid, 64, 0, stream>>>(reinterpret_cast<const float4*>(boxes), order, n,
-                                           iou_thresh, static_cast<unsigned long long*>(mask_ws),
-                                           col_blocks);
+  nms_mask_kernel<<<grid, 64, 0, stream>>>(bbox, order, n_ptr, iou_thresh,
+                                           static_cast<unsigned long long*>(mask_ws), col_blocks);
   SB_CHECK_LAUNCH();
   const size_t smem = static_cast<size_t>(col_blocks) * 8;
   if (smem > 48 * 1024)
     SB_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-  nms_scan_kernel<<<1, 256, smem, stream>>>(static_cast<const unsigned long long*>(mask_ws), order, n,
-                                            col_blocks, keep_out, keep_count);
+  nms_scan_kernel<<<1, 256, smem, stream>>>(static_cast<const unsigned long long*>(mask_ws), order, n_ptr,
+                                            col_blocks, out_list, out_count);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// Pairwise mask intersections of m packed masks [m, H, ceil(W/32)] (rows i < j of inter [m, m] are written).
+extern "C" int sb_pair_intersections(const void* bits, const int* bbox, const int* area, int m, int H, int W,
+                                     double area_ratio_thresh, int* inter, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(m > 0 && H > 0 && W > 0, "sb_pair_intersections: empty");
+  const long long threads = static_cast<long long>(m) * m * 32;
+  long long g = (threads + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  pair_inter_kernel<<<static_cast<int>(g), 256, 0, stream>>>(static_cast<const uint32_t*>(bits), bbox, area, m, H,
+                                                             (W + 31) / 32, area_ratio_thresh, inter);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

@@ -49,7 +49,8 @@ prompt_tokens_kernel(const float* __restrict__ coords, const int* __restrict__ l
 // Fused mask_downscaling[0..5]: Conv2d(1->4,k2,s2) + LN2d(4) + GELU + Conv2d(4->16,k2,s2) + LN2d(16)
 // + GELU. in: [B, S, S] fp32 (S = 256) -> out: [B*(S/4)^2, 16] bf16 token-major.
 __global__ void __launch_bounds__(256)
-mask_downscale_kernel(const float* __restrict__ in, int B, int S, const float* __restrict__ w1,
+mask_downscale_kernel(const float* __restrict__ in, int B, int S, int cpp, float clampv,
+                      const float* __restrict__ w1,
                       const float* __restrict__ b1, const float* __restrict__ g1,
                       const float* __restrict__ be1, const float* __restrict__ w2,
                       const float* __restrict__ b2, const float* __restrict__ g2,
@@ -74,14 +75,22 @@ mask_downscale_kernel(const float* __restrict__ in, int B, int S, const float* _
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int tx = static_cast<int>(i % T), ty = static_cast<int>((i / T) % T);
     const int b = static_cast<int>(i / (static_cast<long long>(T) * T));
-    const float* src = in + (static_cast<long long>(b) * S + ty * 4) * S + tx * 4;
+    // cpp == 3: mask prompt b is token 1 + b % 3 of prompt b / 3 in a [*, 4, S, S] decoder output (m2m pass)
+    const long long pl = cpp == 3 ? static_cast<long long>(b / 3) * 4 + 1 + b % 3 : b;
+    const float* src = in + (pl * S + ty * 4) * S + tx * 4;
     float h1[2][2][4];  // [py][px][channel] after conv1 + LN + GELU
 #pragma unroll
     for (int py = 0; py < 2; ++py)
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
-        const float a00 = src[(py * 2 + 0) * S + px * 2 + 0], a01 = src[(py * 2 + 0) * S + px * 2 + 1];
-        const float a10 = src[(py * 2 + 1) * S + px * 2 + 0], a11 = src[(py * 2 + 1) * S + px * 2 + 1];
+        float a00 = src[(py * 2 + 0) * S + px * 2 + 0], a01 = src[(py * 2 + 0) * S + px * 2 + 1];
+        float a10 = src[(py * 2 + 1) * S + px * 2 + 0], a11 = src[(py * 2 + 1) * S + px * 2 + 1];
+        if (clampv > 0.f) {  // upstream clamps the low-res logits fed back as mask prompts to +-32
+          a00 = fminf(fmaxf(a00, -clampv), clampv);
+          a01 = fminf(fmaxf(a01, -clampv), clampv);
+          a10 = fminf(fmaxf(a10, -clampv), clampv);
+          a11 = fminf(fmaxf(a11, -clampv), clampv);
+        }
         float c[4], mean = 0.f;
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
@@ -272,14 +281,15 @@ extern "C" int sb_prompt_tokens(const float* coords, const int* labels, int B, i
   return SB_OK;
 }
 
-extern "C" int sb_mask_downscale(const float* in, int B, int S, const float* w1, const float* b1,
+extern "C" int sb_mask_downscale(const float* in, int B, int S, int cpp, float clampv, const float* w1,
+                                 const float* b1,
                                  const float* g1, const float* be1, const float* w2, const float* b2,
                                  const float* g2, const float* be2, void* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SB_REQUIRE(B > 0 && S % 4 == 0, "sb_mask_downscale: bad sizes");
+  SB_REQUIRE(B > 0 && S % 4 == 0 && (cpp == 1 || cpp == 3), "sb_mask_downscale: bad sizes");
   const long long total = static_cast<long long>(B) * (S / 4) * (S / 4);
   mask_downscale_kernel<<<blocks_for(total), 256, 0, stream>>>(
-      in, B, S, w1, b1, g1, be1, w2, b2, g2, be2, static_cast<__nv_bfloat16*>(out));
+      in, B, S, cpp, clampv, w1, b1, g1, be1, w2, b2, g2, be2, static_cast<__nv_bfloat16*>(out));
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

@@ -12,7 +12,7 @@ from pathlib import Path
 _LOCK = threading.Lock()
 _LIB = None
 
-c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+c_void_p, c_int, c_ll, c_float, c_double = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 
 # name -> argtypes (every entry point returns int status unless listed in _SPECIAL)
 SIGNATURES = {
@@ -35,12 +35,28 @@ SIGNATURES = {
     "sb_add_cast": [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p],
     "sb_prompt_tokens": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_int, c_void_p, c_void_p],
-    "sb_mask_downscale": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "sb_mask_downscale": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_upscale1_post": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                          c_void_p],
     "sb_upscale2_mask": [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_select_mask": [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    "sb_amg_mask_post": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_int, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_void_p],
+    "sb_compact_keep": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sb_nms_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                   c_void_p, c_void_p],
+    "sb_pair_intersections": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p],
+    "sb_unpack_bits": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_gather_rows": [c_void_p, c_void_p, c_int, c_ll, c_void_p, c_void_p],
+    "sb_box_filter": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "sb_contrast_normalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p],
+    "sb_resize_normalize": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, C.POINTER(c_float),
+                            C.POINTER(c_float), c_void_p, c_void_p],
+    "sb_upsample_bilinear": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_stitch_labels": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_ccl3d_26": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
 }
 
 

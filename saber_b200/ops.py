@@ -14,6 +14,32 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 _BF16, _F32 = torch.bfloat16, torch.float32
 
 launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+_gemm_profiler = None  # set by GemmProfiler: CUDA events around every GEMM launch (bench.py roofline leg)
+
+
+class GemmProfiler:
+    """Context manager: brackets every ``gemm`` launch with CUDA events on the launching stream and sums the
+    algorithmic FLOPs (2*M*N*K); ``summary()`` gives launches, milliseconds and achieved TFLOP/s."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _gemm_profiler
+        _gemm_profiler = self
+        return self
+
+    def __exit__(self, *exc):
+        global _gemm_profiler
+        _gemm_profiler = None
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for _, a, b in self.records)
+        flops = float(sum(f for f, _, _ in self.records))
+        return {"launches": len(self.records), "ms": ms, "flops": flops,
+                "tflops": (flops / (ms * 1e-3) / 1e12) if ms > 0 else 0.0}
 
 
 def _stream() -> int:
@@ -69,9 +95,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if bias is not None:
         assert bias.dtype == _F32 and bias.numel() == N and bias.is_contiguous()
     L = _lib.load()
+    prof = _gemm_profiler
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = L.sb_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                         out.stride(0), M, N, K, _ptr(bias), act, _ptr(residual), ldr, res_mod,
                         flags, alpha, force_bn, _stream())
+    if prof is not None:
+        ev1.record()
+        prof.records.append((2.0 * M * N * K, ev0, ev1))
     _lib.check(rc, "sb_gemm_bf16")
     _count()
     return out
@@ -238,15 +271,21 @@ def prompt_tokens(coords: torch.Tensor, labels: torch.Tensor, gauss: torch.Tenso
     return tokens
 
 
-def mask_downscale(mask: torch.Tensor, w) -> torch.Tensor:
-    """[B, S, S] fp32 mask prompt -> [B*(S/4)^2, 16] bf16 (mask_downscaling convs 0..5 fused)."""
+def mask_downscale(mask: torch.Tensor, w, clamp: float = 0.0) -> torch.Tensor:
+    """Mask prompts -> [B*(S/4)^2, 16] bf16 (mask_downscaling convs 0..5 fused). ``mask`` is [B, S, S] fp32,
+    or a decoder output [P, 4, S, S] whose multimask tokens 1..3 become B = 3P prompts (AMG m2m pass).
+    clamp > 0 clamps the input to +-clamp first."""
     _chk_cuda(mask)
-    assert mask.dtype == _F32 and mask.is_contiguous() and mask.dim() == 3
-    B, S, _ = mask.shape
+    assert mask.dtype == _F32 and mask.is_contiguous() and mask.dim() in (3, 4)
+    if mask.dim() == 4:
+        assert mask.shape[1] == 4
+        B, S, cpp = mask.shape[0] * 3, mask.shape[2], 3
+    else:
+        B, S, cpp = mask.shape[0], mask.shape[1], 1
     out = torch.empty((B * (S // 4) ** 2, 16), dtype=_BF16, device=mask.device)
     L = _lib.load()
-    _lib.check(L.sb_mask_downscale(mask.data_ptr(), B, S, *[t.data_ptr() for t in w], out.data_ptr(), _stream()),
-               "sb_mask_downscale")
+    _lib.check(L.sb_mask_downscale(mask.data_ptr(), B, S, cpp, clamp, *[t.data_ptr() for t in w], out.data_ptr(),
+                                   _stream()), "sb_mask_downscale")
     _count()
     return out
 
@@ -291,3 +330,194 @@ def select_mask(masks: torch.Tensor, ious: torch.Tensor, delta: float, thresh: f
                                 idx.data_ptr(), iou.data_ptr(), _stream()), "sb_select_mask")
     _count()
     return idx, iou
+
+
+# ---------------------------------------------------------------------------------------------
+# AMG post-processing (integer / indexing stages) and image-side bandwidth kernels
+# ---------------------------------------------------------------------------------------------
+_I32, _U8 = torch.int32, torch.uint8
+
+
+def amg_mask_post(planes: torch.Tensor, ious4: torch.Tensor, sel: Optional[torch.Tensor], cpp: int, n: int,
+                  crop_hw, crop_xy, frame_hw, pred_iou_thresh: float, mask_thresh: float, stab_offset: float,
+                  stab_thresh: float, keep: torch.Tensor, stability: torch.Tensor, iou_out: torch.Tensor,
+                  bbox: torch.Tensor, area: torch.Tensor, bits: torch.Tensor, base: int) -> None:
+    """Stability score / threshold / bbox / near-edge test / bit-packing for ``n`` candidates whose low-res
+    logits are ``planes`` [B,4,S,S]; results land in slots ``base .. base+n`` of the per-image arrays."""
+    _chk_cuda(planes, ious4, sel, keep, stability, iou_out, bbox, area, bits)
+    assert planes.dtype == _F32 and planes.is_contiguous() and planes.dim() == 4 and planes.shape[1] == 4
+    assert ious4.dtype == _F32 and ious4.is_contiguous() and ious4.shape == planes.shape[:2]
+    assert sel is None or (sel.dtype == _I32 and sel.is_contiguous())
+    assert keep.dtype == _U8 and bbox.dtype == _I32 and area.dtype == _I32 and bits.dtype == _I32
+    S = planes.shape[2]
+    (Hc, Wc), (x0, y0), (H, W) = crop_hw, crop_xy, frame_hw
+    WW = (W + 31) // 32
+    assert bits.shape[1:] == (H, WW) and base + n <= bits.shape[0] and n <= planes.shape[0] * cpp
+    L = _lib.load()
+    rc = L.sb_amg_mask_post(planes.data_ptr(), ious4.data_ptr(), _ptr(sel), cpp, n, S, Hc, Wc, x0, y0, H, W,
+                            pred_iou_thresh, mask_thresh, stab_offset, stab_thresh,
+                            keep.data_ptr() + base, stability.data_ptr() + 4 * base, iou_out.data_ptr() + 4 * base,
+                            bbox.data_ptr() + 16 * base, area.data_ptr() + 4 * base,
+                            bits.data_ptr() + 4 * base * H * WW, _stream())
+    _lib.check(rc, "sb_amg_mask_post")
+    _count()
+
+
+def compact_keep(keep: torch.Tensor, base: int, n: int, cand: torch.Tensor, count: torch.Tensor) -> None:
+    _chk_cuda(keep, cand, count)
+    assert keep.dtype == _U8 and cand.dtype == _I32 and count.dtype == _I32 and cand.numel() >= n
+    L = _lib.load()
+    _lib.check(L.sb_compact_keep(keep.data_ptr(), base, n, cand.data_ptr(), count.data_ptr(), _stream()),
+               "sb_compact_keep")
+    _count()
+
+
+def nms_dev(bbox: torch.Tensor, scores: torch.Tensor, cand: torch.Tensor, n_ptr: torch.Tensor, n_cap: int,
+            iou_thresh: float, order_ws: torch.Tensor, mask_ws: torch.Tensor, out_list: torch.Tensor,
+            out_count: torch.Tensor) -> None:
+    """torchvision-semantics greedy NMS over candidate slots; appends kept slots to out_list (device counts)."""
+    _chk_cuda(bbox, scores, cand, n_ptr, order_ws, mask_ws, out_list, out_count)
+    assert bbox.dtype == _I32 and scores.dtype == _F32 and cand.dtype == _I32 and n_ptr.dtype == _I32
+    cb = (n_cap + 63) // 64
+    assert order_ws.numel() >= n_cap and mask_ws.numel() * mask_ws.element_size() >= n_cap * cb * 8
+    L = _lib.load()
+    _lib.check(L.sb_nms_dev(bbox.data_ptr(), scores.data_ptr(), cand.data_ptr(), n_ptr.data_ptr(), n_cap, iou_thresh,
+                            order_ws.data_ptr(), mask_ws.data_ptr(), out_list.data_ptr(), out_count.data_ptr(),
+                            _stream()), "sb_nms_dev")
+    _count(3)
+
+
+def pair_intersections(bits: torch.Tensor, bbox: torch.Tensor, area: torch.Tensor, W: int,
+                       area_ratio_thresh: float) -> torch.Tensor:
+    """inter[i,j] (i<j) = |mask_i & mask_j| or -1 when the area ratio is below the threshold."""
+    _chk_cuda(bits, bbox, area)
+    m, H, WW = bits.shape
+    assert bits.dtype == _I32 and bits.is_contiguous() and WW == (W + 31) // 32
+    assert bbox.dtype == _I32 and bbox.is_contiguous() and bbox.shape == (m, 4)
+    assert area.dtype == _I32 and area.is_contiguous() and area.shape == (m,)
+    inter = torch.full((m, m), -1, dtype=_I32, device=bits.device)
+    L = _lib.load()
+    _lib.check(L.sb_pair_intersections(bits.data_ptr(), bbox.data_ptr(), area.data_ptr(), m, H, W,
+                                       float(area_ratio_thresh), inter.data_ptr(), _stream()), "sb_pair_intersections")
+    _count()
+    return inter
+
+
+def unpack_bits(bits: torch.Tensor, sel: Optional[torch.Tensor], m: int, W: int) -> torch.Tensor:
+    """Packed masks [*, H, ceil(W/32)] -> bool [m, H, W] for rows sel[0..m) (or the first m rows)."""
+    _chk_cuda(bits, sel)
+    H = bits.shape[1]
+    out = torch.empty((m, H, W), dtype=torch.bool, device=bits.device)
+    if m == 0:
+        return out
+    L = _lib.load()
+    _lib.check(L.sb_unpack_bits(bits.data_ptr(), _ptr(sel), m, H, W, out.data_ptr(), _stream()), "sb_unpack_bits")
+    _count()
+    return out
+
+
+def gather_rows(src: torch.Tensor, sel: torch.Tensor, m: int) -> torch.Tensor:
+    """dst[k] = src[sel[k]] for 4-byte-element rows (mask bit planes, records)."""
+    _chk_cuda(src, sel)
+    assert src.is_contiguous() and src.element_size() == 4 and sel.dtype == _I32
+    row_words = src[0].numel()
+    dst = torch.empty((m,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if m == 0:
+        return dst
+    L = _lib.load()
+    _lib.check(L.sb_gather_rows(src.data_ptr(), sel.data_ptr(), m, row_words, dst.data_ptr(), _stream()),
+               "sb_gather_rows")
+    _count()
+    return dst
+
+
+def prepare_slice(img: torch.Tensor, box: int = 500, cutoff: float = 3.0) -> torch.Tensor:
+    """REF saber/utils/preprocessing.py:67-81 ``prepare`` on one [H, W] fp32 slice -> [H, W] fp32 in [0,1]
+    (the three RGB channels SABER feeds SAM2 are identical copies of it)."""
+    _chk_cuda(img)
+    assert img.dtype == _F32 and img.is_contiguous() and img.dim() == 2
+    H, W = img.shape
+    L = _lib.load()
+    t0 = torch.empty_like(img)
+    mean = torch.empty_like(img)
+    sq = torch.empty_like(img)
+    s = _stream()
+    _lib.check(L.sb_box_filter(img.data_ptr(), t0.data_ptr(), H, W, 0, box, 0, s), "sb_box_filter")
+    _lib.check(L.sb_box_filter(t0.data_ptr(), mean.data_ptr(), H, W, 1, box, 0, s), "sb_box_filter")
+    _lib.check(L.sb_box_filter(img.data_ptr(), t0.data_ptr(), H, W, 0, box, 1, s), "sb_box_filter")
+    _lib.check(L.sb_box_filter(t0.data_ptr(), sq.data_ptr(), H, W, 1, box, 0, s), "sb_box_filter")
+    partials = torch.empty((2048,), dtype=_F32, device=img.device)
+    _lib.check(L.sb_contrast_normalize(img.data_ptr(), mean.data_ptr(), sq.data_ptr(), t0.data_ptr(), img.numel(),
+                                       cutoff, partials.data_ptr(), s), "sb_contrast_normalize")
+    _count(6)
+    return t0
+
+
+_MEAN3 = (0.485, 0.456, 0.406)
+_STD3 = (0.229, 0.224, 0.225)
+
+
+def resize_normalize(img: torch.Tensor, crops: torch.Tensor, S: int = 1024, mean=_MEAN3, std=_STD3) -> torch.Tensor:
+    """img [H,W] or [H,W,3] fp32, crops int32 [n,4] (x0,y0,x1,y1) -> [n,3,S,S] fp32 (SAM2Transforms)."""
+    _chk_cuda(img, crops)
+    assert img.dtype == _F32 and img.is_contiguous() and img.dim() in (2, 3)
+    assert crops.dtype == _I32 and crops.is_contiguous() and crops.dim() == 2 and crops.shape[1] == 4
+    H, W = img.shape[:2]
+    Cc = 1 if img.dim() == 2 else img.shape[2]
+    n = crops.shape[0]
+    out = torch.empty((n, 3, S, S), dtype=_F32, device=img.device)
+    import ctypes as _C
+    m3 = (_C.c_float * 3)(*mean)
+    s3 = (_C.c_float * 3)(*std)
+    L = _lib.load()
+    _lib.check(L.sb_resize_normalize(img.data_ptr(), H, W, Cc, crops.data_ptr(), n, S, m3, s3, out.data_ptr(),
+                                     _stream()), "sb_resize_normalize")
+    _count()
+    return out
+
+
+def stitch_labels(bits: torch.Tensor, order: Optional[torch.Tensor], m: int, W: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """labels[y,x] = 1 + max{k : mask order[k] covers (y,x)} (uint16; 0 = background)."""
+    _chk_cuda(bits, order, out)
+    H = bits.shape[1]
+    if out is None:
+        out = torch.empty((H, W), dtype=torch.int16, device=bits.device)  # uint16 payload in int16 storage
+    assert out.dtype in (torch.int16, torch.uint16) and out.is_contiguous() and out.shape == (H, W)
+    L = _lib.load()
+    _lib.check(L.sb_stitch_labels(bits.data_ptr(), _ptr(order), m, H, W, out.data_ptr(), _stream()),
+               "sb_stitch_labels")
+    _count()
+    return out
+
+
+def ccl3d_26(vol: torch.Tensor, min_vol: int):
+    """26-connected components of vol != 0 with components < min_vol voxels dropped and compact raster-order
+    labels (REF saber/segmenters/utils.py:88-131). Returns (labels int32-as-uint32 [Z,Y,X], n_components tensor)."""
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.dim() == 3 and vol.element_size() in (1, 2, 4)
+    Z, Y, X = vol.shape
+    n = vol.numel()
+    labels = torch.empty((Z, Y, X), dtype=_I32, device=vol.device)
+    aux = torch.empty((n,), dtype=_I32, device=vol.device)
+    nchunks = (n + 2047) // 2048
+    chunk_ws = torch.empty((nchunks + 1,), dtype=_I32, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_ccl3d_26(vol.data_ptr(), vol.element_size(), Z, Y, X, int(min_vol), labels.data_ptr(),
+                             aux.data_ptr(), chunk_ws.data_ptr(), _stream()), "sb_ccl3d_26")
+    _count(7)
+    return labels, chunk_ws[nchunks:]
+
+
+def upsample_bilinear(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+    """[..., Hi, Wi] fp32 -> [..., Ho, Wo] fp32 (F.interpolate bilinear, align_corners=False)."""
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.is_contiguous() and x.dim() >= 2
+    Hi, Wi = x.shape[-2:]
+    N = x.numel() // (Hi * Wi)
+    out = torch.empty(tuple(x.shape[:-2]) + (Ho, Wo), dtype=_F32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_upsample_bilinear(x.data_ptr(), N, Hi, Wi, Ho, Wo, out.data_ptr(), _stream()),
+               "sb_upsample_bilinear")
+    _count()
+    return out

@@ -130,9 +130,12 @@ class MaskDecoder:
         return ops.gemm(h, head[2][0], head[2][1], act=last_act, out_dtype=_F32, out=out)
 
     def forward(self, image_embed: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, tokens: torch.Tensor,
-                mask_input: Optional[torch.Tensor] = None, multimask_output: bool = True):
+                mask_input: Optional[torch.Tensor] = None, multimask_output: bool = True,
+                mask_clamp: float = 0.0):
         """image_embed [4096,256] fp32, s0 [65536,32] fp32, s1 [16384,64] fp32 (one image, token-major);
-        tokens [B, Nt, 256] fp32; mask_input [B, 256, 256] fp32 or None.
+        tokens [B, Nt, 256] fp32; mask_input [B, 256, 256] fp32, or a previous decoder output
+        [B/3, 4, 256, 256] whose multimask tokens 1..3 are the B mask prompts (AMG m2m), or None;
+        mask_clamp > 0 clamps the mask prompt to +-mask_clamp (upstream clamps low-res logits to +-32).
 
         Returns dict: masks [B,4,256,256] fp32 (all four tokens), ious [B,4], obj [B,1], hs [B,Nt,256]
         and, per upstream's output selection, ``sel`` describing which tokens are "the output":
@@ -145,7 +148,8 @@ class MaskDecoder:
         if shared:
             keys_f32 = ops.add_cast(image_embed, self.no_mask_embed, _F32)  # [4096,256]
         else:
-            ds = ops.mask_downscale(mask_input.contiguous(), self.md_w)  # [B*4096,16]
+            ds = ops.mask_downscale(mask_input.contiguous(), self.md_w, mask_clamp)  # [B*4096,16]
+            assert ds.shape[0] == B * NT_IMG, (ds.shape, B)
             keys_f32 = ops.gemm(ds, self.md6_w, self.md6_b, residual=image_embed, res_mod=NT_IMG, out_dtype=_F32)
         keys = ops.add_cast(keys_f32, None, _BF16)
         kb = 1 if shared else B  # batch entries of the image stream

@@ -1,0 +1,103 @@
+"""B200 twin of REF saber/segmenters/propagation.py (``propagationSegmenter``, :11-189).
+
+``slice_by_slice`` (REF :164-189) is the slice-wise zero-shot path of BASELINE config 2: per z-slice
+prepare -> AMG -> area filter -> duplicate removal -> sort -> label stitch, then 3-D connected components over
+the whole label volume. Here every stage runs on the device; the volume is uploaded once and only the uint32
+label volume comes back. ``segment`` / ``single_segment`` / ``segment_3d`` need the z-axis memory propagation
+(next §8 row) and raise until it is built.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..adapters.base import AdapterConfig, cfgAMG
+from . import utils
+from .base import saber3D
+
+_I32 = torch.int32
+
+
+class propagationSegmenter(saber3D):
+    def __init__(self, deviceID: int = 0, cfg: Optional[AdapterConfig] = None, amg_cfg: Optional[cfgAMG] = None,
+                 min_mask_area: int = 100, min_rel_box_size: float = 0.025):
+        self.min_rel_box_size = min_rel_box_size
+        super().__init__(deviceID=deviceID, cfg=cfg, amg_cfg=amg_cfg, min_mask_area=min_mask_area)
+        self.ini_depth = 10
+
+    # ------------------------------------------------------------------
+    @torch.inference_mode()
+    def label_slices_device(self, volume: torch.Tensor, labels: torch.Tensor, z0: int = 0, z1: Optional[int] = None):
+        """Slices z0..z1 of a CUDA (Z,Y,X) fp32 volume -> stitched uint16 labels written into labels[z0:z1]
+        (the body of the reference loop, REF :177-187). Returns the number of masks kept per slice."""
+        z1 = volume.shape[0] if z1 is None else z1
+        W = volume.shape[2]
+        counts = []
+        for ii in range(z0, z1):
+            dm, recs = self.segment_image_device(volume[ii])
+            if len(recs) == 0:
+                labels[ii].zero_()
+                counts.append(0)
+                continue
+            order = torch.tensor([r["index"] for r in recs], dtype=_I32, device=volume.device)
+            ops.stitch_labels(dm.bits, order, len(recs), W, out=labels[ii])
+            counts.append(len(recs))
+        return counts
+
+    @torch.inference_mode()
+    def slice_by_slice_device(self, volume: torch.Tensor) -> torch.Tensor:
+        """CUDA (Z,Y,X) fp32 volume -> CUDA int32 (uint32-valued) separated label volume."""
+        assert volume.is_cuda and volume.dim() == 3
+        labels = torch.empty(volume.shape, dtype=torch.int16, device=volume.device)  # uint16 payload
+        self.label_slices_device(volume, labels)
+        return utils.separate_masks_device(labels)
+
+    @torch.inference_mode()
+    def slice_by_slice(self, volume, text_prompt: str = None) -> np.ndarray:
+        """REF :164-189. ``volume``: host (Z,Y,X) array (numpy, or a — preferably pinned — CPU tensor). One H2D copy
+        of the volume, one D2H copy of the uint32 label volume."""
+        if isinstance(volume, np.ndarray):
+            volume = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32))
+        vol = volume.to(self.device, dtype=torch.float32, non_blocking=True)
+        return self.slice_by_slice_device(vol).cpu().numpy().view(np.uint32)
+
+    slice_by_slice_host = slice_by_slice
+
+    # ------------------------------------------------------------------
+    def segment(self, volume, ini_depth, nframes=None, target_class=1, text_prompt=None, display=False):
+        self.ini_depth = ini_depth
+        self.nframes = nframes
+        self.target_class = target_class
+        self.display = display
+        if self.target_class > 0 or self.classifier is None:
+            return self.single_segment(volume, text_prompt=text_prompt)
+        return self.multiclass_segment(volume)
+
+    def segment_3d(self, vol, masks, ann_frame_idx: int = None):
+        if not self._vol_loaded:
+            self.video_predictor.set_volume(vol)
+            self._vol_loaded = True
+        self.masks = masks
+        nx = vol.shape[0]
+        ny, nz = self.masks[0].shape[0], self.masks[0].shape[1]
+        self.ann_frame_idx = ann_frame_idx if ann_frame_idx is not None else nx // 2
+        return self.propagate((nx, ny, nz))
+
+    def single_segment(self, volume, text_prompt=None):
+        final_masks = np.zeros(volume.shape, dtype=np.uint16)
+        for ii in range(2, volume.shape[0], self.ini_depth):
+            masks = self.segment_image(volume[ii], display=False, target_class=self.target_class,
+                                       text_prompt=text_prompt)
+            if len(masks) == 0:
+                continue
+            masks3d = self.segment_3d(volume, [m["segmentation"] for m in masks], ann_frame_idx=ii)
+            if self.target_class > 0:
+                masks3d = (masks3d > 0).astype(np.uint8)
+            np.maximum(final_masks, masks3d, out=final_masks)
+        return utils.separate_masks(final_masks, device=self.device)
+
+    def multiclass_segment(self, volume):
+        raise NotImplementedError("saber_b200: multiclass_segment needs the expert classifier (SURVEY §8a R15/R16)")

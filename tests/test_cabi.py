@@ -1,0 +1,55 @@
+"""The C-ABI library builds, loads without a GPU and exports exactly what include/saber_b200.h declares."""
+import ctypes
+import os
+import re
+
+from saber_b200 import lib as sblib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "saber_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_every_bound_symbol():
+    hdr = set(_header_symbols())
+    bound = set(sblib.SIGNATURES) | {"sb_last_error"}
+    assert hdr == bound, (sorted(hdr - bound), sorted(bound - hdr))
+
+
+def test_library_loads_and_exports_header_symbols():
+    L = sblib.load()  # builds with nvcc if missing; raises on failure
+    for name in _header_symbols():
+        assert hasattr(L, name), f"{name} declared in include/saber_b200.h but not exported"
+    assert L.sb_version() >= 100
+    assert isinstance(sblib.last_error(), str)
+
+
+def test_header_arity_matches_ctypes_signatures():
+    text = open(os.path.join(ROOT, "include", "saber_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, argtypes in sblib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", text, flags=re.S)
+        assert m, name
+        args = m.group(1).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        assert n == len(argtypes), (name, n, len(argtypes))
+
+
+def test_product_fails_loudly_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from saber_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.require_b200()
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    from saber_b200.segmenters.propagation import propagationSegmenter
+    from saber_b200.adapters.base import cfgAMG
+    with pytest.raises(RuntimeError):
+        propagationSegmenter(amg_cfg=cfgAMG(sam2_cfg="tiny"))

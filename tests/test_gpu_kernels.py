@@ -1,0 +1,192 @@
+"""-m gpu: every CUDA kernel against a plain PyTorch fp32 computation of the same op (float kernels, stated
+tolerance) through the C ABI (saber_b200.ops -> ctypes -> libsaber_b200.so)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from saber_b200 import ops as _ops
+    _ops.require_b200()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _ops
+
+
+GEMM_CASES = [
+    dict(M=256, N=128, K=64, bn=128), dict(M=256, N=128, K=128, bn=128), dict(M=128, N=64, K=64, bn=64),
+    dict(M=128, N=256, K=64, bn=256), dict(M=4096, N=1728, K=576), dict(M=4096, N=2304, K=576, act=1, bias=1),
+    dict(M=4096, N=576, K=2304, bias=1, res=1), dict(M=65536, N=432, K=144, bias=1),
+    dict(M=65536, N=144, K=160, bias=1, res=1, res_mod=32768), dict(M=1000, N=100, K=72, bias=1, out_f32=1),
+    dict(M=512, N=4, K=256, bias=1, out_f32=1), dict(M=777, N=136, K=200, bias=1, act=2),
+    dict(M=64, N=4, K=256, bias=1, act=3, out_f32=1), dict(M=1, N=256, K=256, bias=1),
+]
+
+
+@pytest.mark.parametrize("kw", GEMM_CASES, ids=lambda k: "x".join(str(k[c]) for c in "MNK"))
+def test_gemm_bf16(ops, kw):
+    """bf16 operands, fp32 accumulate: tolerance 2e-2 relative (BASELINE north_star) vs fp32 matmul of the same
+    bf16-rounded operands; observed ~3e-3."""
+    torch.manual_seed(0)
+    M, N, K = kw["M"], kw["N"], kw["K"]
+    a = torch.randn(M, K, device="cuda").to(BF16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF16)
+    bias = torch.randn(N, device="cuda") if kw.get("bias") else None
+    res_mod = kw.get("res_mod", 0)
+    res = torch.randn(res_mod if res_mod else M, N, device="cuda") if kw.get("res") else None
+    out = ops.gemm(a, w, bias, kw.get("act", 0), res, res_mod, F32 if kw.get("out_f32") else BF16,
+                   force_bn=kw.get("bn", 0))
+    ref = a.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    ref = {0: lambda x: x, 1: F.gelu, 2: F.relu, 3: torch.sigmoid}[kw.get("act", 0)](ref)
+    if res is not None:
+        ref = ref + (res.repeat(M // res.shape[0], 1) if res_mod else res)
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-2 * max(1.0, ref.abs().max().item()) if out.dtype == BF16 else 1e-4 * max(1.0, ref.abs().max().item())
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("M,C,in_f32,act", [(4096, 576, 0, 0), (1000, 144, 1, 0), (333, 256, 1, 1), (7, 64, 1, 0)])
+def test_layernorm(ops, M, C, in_f32, act):
+    torch.manual_seed(1)
+    x = torch.randn(M, C, device="cuda") * 3 + 1
+    xi = x if in_f32 else x.to(BF16)
+    g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    out = ops.layernorm(xi, g, b, 1e-6, F32, act=act)
+    ref = F.layer_norm(xi.float(), (C,), g, b, 1e-6)
+    if act:
+        ref = F.gelu(ref)
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+def _sdpa_ref(q, k, v, B, heads, nq, nk):
+    hd = q.shape[1] // heads
+    qh = q.float().view(B, nq, heads, hd).transpose(1, 2)
+    kh = k.float().view(B, nk, heads, hd).transpose(1, 2)
+    vh = v.float().view(B, nk, heads, hd).transpose(1, 2)
+    o = F.scaled_dot_product_attention(qh, kh, vh)
+    return o.transpose(1, 2).reshape(B * nq, heads * hd)
+
+
+@pytest.mark.parametrize("B,heads,hd,nq,nk", [(2, 8, 72, 4096, 4096), (3, 8, 16, 7, 4096), (3, 8, 16, 4096, 7),
+                                              (3, 8, 32, 8, 8), (2, 1, 64, 100, 333), (1, 1, 128, 64, 200)])
+def test_attention(ops, B, heads, hd, nq, nk):
+    torch.manual_seed(2)
+    C = heads * hd
+    q = torch.randn(B * nq, C, device="cuda").to(BF16)
+    k = torch.randn(B * nk, C, device="cuda").to(BF16)
+    v = torch.randn(B * nk, C, device="cuda").to(BF16)
+    out = ops.attention(q, k, v, B, heads, nq, nk)
+    ref = _sdpa_ref(q, k, v, B, heads, nq, nk)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+def _window_ref(qkv, bias, B, H, W, heads, hd, ws, pool):
+    """Hiera MultiScaleAttention on an already-projected qkv (padding tokens carry the bias), fp32."""
+    C = heads * hd
+    x = qkv.float().view(B, H, W, 3 * C)
+    if ws > 0:
+        ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
+        if ph or pw:
+            pad = bias.float().view(1, 1, 1, 3 * C).expand(B, H + ph, W + pw, 3 * C).clone()
+            pad[:, :H, :W] = x
+            x = pad
+        Hp, Wp = H + ph, W + pw
+        x = x.view(B, Hp // ws, ws, Wp // ws, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws, ws, 3 * C)
+    else:
+        Hp, Wp, ws = H, W, max(H, W)
+        x = x.reshape(B, H, W, 3 * C)
+    nW, hh, ww = x.shape[0], x.shape[1], x.shape[2]
+    q, k, v = x.reshape(nW, hh * ww, 3, heads, hd).unbind(2)
+    if pool == 2:
+        qq = q.reshape(nW, hh, ww, C).permute(0, 3, 1, 2)
+        qq = F.max_pool2d(qq, 2, 2)
+        hq, wq = qq.shape[2:]
+        q = qq.permute(0, 2, 3, 1).reshape(nW, hq * wq, heads, hd)
+    else:
+        hq, wq = hh, ww
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+    o = o.transpose(1, 2).reshape(nW, hq, wq, C)
+    if nW != B:
+        nwh, nww = Hp // (hh), Wp // (ww)
+        o = o.view(B, nwh, nww, hq, wq, C).permute(0, 1, 3, 2, 4, 5).reshape(B, nwh * hq, nww * wq, C)
+    Ho, Wo = H // pool, W // pool
+    return o[:, :Ho, :Wo].reshape(B * Ho * Wo, C)
+
+
+@pytest.mark.parametrize("B,H,W,heads,hd,ws,pool", [(2, 64, 64, 8, 72, 16, 1), (2, 256, 256, 2, 72, 8, 1),
+                                                    (1, 256, 256, 4, 72, 8, 2), (1, 64, 64, 4, 96, 14, 1),
+                                                    (1, 64, 64, 8, 96, 14, 2), (1, 64, 64, 8, 72, 0, 1),
+                                                    (1, 32, 32, 16, 72, 8, 1), (1, 128, 128, 4, 56, 4, 1)])
+def test_window_attention(ops, B, H, W, heads, hd, ws, pool):
+    torch.manual_seed(3)
+    C = heads * hd
+    qkv = torch.randn(B * H * W, 3 * C, device="cuda").to(BF16)
+    bias = torch.randn(3 * C, device="cuda") * 0.5
+    out = ops.window_attention(qkv, bias, B, H, W, heads, ws, pool)
+    ref = _window_ref(qkv, bias.to(BF16), B, H, W, heads, hd, ws, pool)
+    assert out.shape == ref.shape
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+def test_relayout_and_pointwise(ops):
+    torch.manual_seed(4)
+    img = torch.randn(2, 3, 64, 64, device="cuda")
+    cols = ops.im2col_k7s4(img, 160)
+    ref = F.unfold(img, 7, padding=3, stride=4).transpose(1, 2).reshape(-1, 147)
+    assert torch.equal(cols[:, :147].float(), ref.to(BF16).float()) and cols[:, 147:].abs().max().item() == 0
+    x = torch.randn(2 * 16 * 16, 40, device="cuda")
+    mp = ops.maxpool2x2(x, 2, 16, 16)
+    ref = F.max_pool2d(x.view(2, 16, 16, 40).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 40)
+    assert torch.equal(mp, ref)
+    dst = torch.randn(2 * 8 * 8, 24, device="cuda")
+    src = torch.randn(2 * 4 * 4, 24, device="cuda")
+    ref = dst + F.interpolate(src.view(2, 4, 4, 24).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).reshape(-1, 24)
+    assert torch.equal(ops.add_upsample2x_(dst.clone(), src, 2, 8, 8), ref)
+    t = torch.randn(2 * 100, 48, device="cuda")
+    add = torch.randn(48, device="cuda")
+    nchw = ops.nhwc_to_nchw(t, 2, 100, F32, add)
+    assert torch.equal(nchw, (t + add).view(2, 100, 48).transpose(1, 2).contiguous())
+    back = ops.nchw_to_nhwc(nchw, F32)
+    assert torch.equal(back, t + add)
+    ac = ops.add_cast(t, add, BF16)
+    assert torch.equal(ac, (t + add).to(BF16))
+
+
+@pytest.mark.parametrize("hw,crop", [((1024, 1024), (0, 0, 1024, 1024)), ((1024, 1024), (341, 0, 1024, 683)),
+                                     ((512, 512), (0, 0, 512, 512)), ((600, 640), (10, 20, 400, 300)),
+                                     ((2048, 1536), (0, 0, 1536, 2048))])
+def test_resize_normalize_vs_torch_antialias(ops, hw, crop):
+    """SAM2Transforms: fp32, tolerance 1e-4 (north_star fp32 validation mode) vs F.interpolate(antialias=True)."""
+    torch.manual_seed(5)
+    H, W = hw
+    img = torch.rand(H, W, 3, device="cuda")
+    x0, y0, x1, y1 = crop
+    out = ops.resize_normalize(img, torch.tensor([crop], dtype=torch.int32, device="cuda"), 1024)
+    c = img[y0:y1, x0:x1].permute(2, 0, 1)[None].cpu()
+    ref = F.interpolate(c, (1024, 1024), mode="bilinear", align_corners=False, antialias=True)[0]
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    ref = (ref - mean) / std
+    assert (out[0].cpu() - ref).abs().max().item() < 1e-4
+    gray = ops.resize_normalize(img[..., 0].contiguous(), torch.tensor([crop], dtype=torch.int32, device="cuda"), 1024)
+    ref_g = (F.interpolate(c[:, :1], (1024, 1024), mode="bilinear", align_corners=False, antialias=True)[0] - mean) / std
+    assert (gray[0].cpu() - ref_g).abs().max().item() < 1e-4
+
+
+def test_prepare_slice_vs_oracle(ops):
+    """REF saber/utils/preprocessing.prepare: fp32, tolerance 1e-4 absolute on a [0,1] output."""
+    from oracle import saber_ref
+    from saber_b200 import synth
+    img = synth.make_tomogram((1, 600, 640), seed=3, n_ellipsoids=12)[0]
+    out = ops.prepare_slice(img.cuda()).cpu().numpy()
+    ref = saber_ref.prepare(img.numpy(), to_rgb=True)[..., 0]
+    assert abs(out - ref).max() < 1e-4
+    assert out.min() == 0.0 and abs(out.max() - 1.0) < 1e-6
