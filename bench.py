@@ -52,7 +52,7 @@ def parse_args():
 def workload_name(args):
     return (f"SAM2.1 hiera-{args.cfg} slice-wise zero-shot segmentation of a {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} synthetic "
             f"tomogram (BASELINE configs[1]); AMG at SABER defaults (32 pts/side, 2 crop layers, multimask + m2m)"
-            + ("" if args.thresholds == "default" else "; thresholds opened (pred_iou 0.3, stability 0.5)"))
+            + ("" if args.thresholds == "default" else "; thresholds opened (pred_iou 0.3, stability filter off)"))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,7 +134,7 @@ def cpu_reference_sample(cfg: str, thresholds: str, n_points: int = 16):
         st["img"] = synth.make_tomogram(SHAPE, seed=0, z_range=(100, 101))[0].numpy()
     model, img = st["model"], st["img"]
     thr = dict(pred_iou_thresh=0.7, stability_score_thresh=0.92) if thresholds == "default" else \
-        dict(pred_iou_thresh=0.3, stability_score_thresh=0.5)
+        dict(pred_iou_thresh=0.3, stability_score_thresh=0.0)
     gen = OracleAMG(model, points_per_side=32, points_per_batch=64, stability_score_offset=0.7, crop_n_layers=2,
                     box_nms_thresh=0.7, crop_n_points_downscale_factor=2, use_m2m=True, multimask_output=True, **thr)
     t0 = time.perf_counter()
@@ -207,7 +207,7 @@ def run_b200(args):
     sam_cfg = {"large": "large", "base_plus": "base", "small": "small", "tiny": "tiny"}[args.cfg]
     amg_kw = dict(sam2_cfg=sam_cfg)
     if args.thresholds == "open":
-        amg_kw.update(pred_iou_thresh=0.3, stability_score_thresh=0.5)
+        amg_kw.update(pred_iou_thresh=0.3, stability_score_thresh=0.0)
     seg = propagationSegmenter(deviceID=local, cfg=SAM2AdapterConfig(cfg=sam_cfg, amg_cfg=cfgAMG(**amg_kw),
                                                                     min_mask_area=100), min_mask_area=100)
     S = args.slices_per_step
@@ -284,6 +284,10 @@ def run_b200(args):
             step(args.warmup + args.steps)
         torch.cuda.synchronize()
         r = prof.summary()
+        if os.environ.get("SB_GEMM_SHAPES"):
+            with open(os.environ["SB_GEMM_SHAPES"], "w") as fh:
+                for tag, n, ms_, tf in prof.by_shape(40):
+                    fh.write(f"{ms_:9.3f} ms  n={n:5d}  {tf:8.1f} TFLOP/s  {tag}\n")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -37,6 +37,20 @@ int sb_require_sm100(void);             /* fails unless the current device is co
 int sb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
                  int K, const float* bias, int act, const void* residual, long long ldr, int res_mod, int flags,
                  float alpha, int force_bn, void* stream);
+/* out[M,N] = LayerNorm_N(A @ W^T + bias + residual) * gamma + beta in one kernel (N <= 256, N % 16 == 0): the
+ * "keys = norm4(keys + cross_attn_image_to_token(...))" step of sam2/modeling/sam/transformer.py TwoWayAttentionBlock. */
+int sb_gemm_ln(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N, int K,
+               const float* bias, const void* residual, long long ldr, int res_mod, int flags, const float* gamma,
+               const float* beta, float eps, void* stream);
+/* mask_decoder.py output_upscaling[0..2]: ConvTranspose2d(256->64,k2,s2) + feat_s1 skip + LayerNorm2d + GELU, fused */
+int sb_gemm_upscale1(const void* A, long long lda, const void* W, long long ldw, int B, int gh, int gw,
+                     const float* bias, const float* feat_s1, long long skip_bstride, const float* gamma,
+                     const float* beta, float eps, void* u1, void* stream);
+/* output_upscaling[3..4] + (hyper_in @ upscaled_embedding): ConvTranspose2d(64->32,k2,s2) + feat_s0 + GELU + dot with the
+ * prompt's 4 hyper-network vectors -> masks [B,4,2gh,2gw] fp32, fused */
+int sb_gemm_upscale2(const void* A, long long lda, const void* W, long long ldw, int B, int gh, int gw,
+                     const float* bias, const float* feat_s0, long long skip_bstride, const float* hyper, float* masks,
+                     void* stream);
 /* Plain batched multi-head attention (mask-decoder two-way transformer: sam2/modeling/sam/transformer.py
  * Attention.forward -> F.scaled_dot_product_attention). q [batch*nq, heads*hd], k/v [batch*nk, heads*hd]. */
 int sb_attention(const void* q, long long q_ld, const void* k, long long k_ld, const void* v, long long v_ld, void* o,

@@ -41,6 +41,20 @@ class GemmProfiler:
         return {"launches": len(self.records), "ms": ms, "flops": flops,
                 "tflops": (flops / (ms * 1e-3) / 1e12) if ms > 0 else 0.0}
 
+    def by_shape(self, top: int = 25):
+        """Aggregate (tag, launches, ms, TFLOP/s) per GEMM shape, sorted by time."""
+        torch.cuda.synchronize()
+        agg = {}
+        for rec in self.records:
+            f, a, b = rec[0], rec[1], rec[2]
+            tag = rec[3] if len(rec) > 3 else "?"
+            e = agg.setdefault(tag, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+            e[2] += f
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
+        return [(t, n, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0) for t, (n, ms, fl) in rows]
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -104,10 +118,87 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                         flags, alpha, force_bn, _stream())
     if prof is not None:
         ev1.record()
-        prof.records.append((2.0 * M * N * K, ev0, ev1))
+        prof.records.append((2.0 * M * N * K, ev0, ev1, f"std M={M} N={N} K={K} {'f32' if out.dtype == _F32 else 'bf16'}"
+                             f"{' +res' if residual is not None else ''}"))
     _lib.check(rc, "sb_gemm_bf16")
     _count()
     return out
+
+
+def _prof_begin():
+    if _gemm_profiler is None:
+        return None
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    return ev0
+
+
+def _prof_end(ev0, flops):
+    if ev0 is not None and _gemm_profiler is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        _gemm_profiler.records.append((flops, ev0, ev1))
+
+
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+            gamma: torch.Tensor, beta: torch.Tensor, eps: float, res_mod: int = 0, out_dtype=_BF16) -> torch.Tensor:
+    """out = LayerNorm(a @ w^T + bias + residual[m % res_mod or m]) * gamma + beta, fused in the GEMM epilogue."""
+    _chk_cuda(a, w, bias, residual, gamma, beta)
+    assert a.dtype == _BF16 and w.dtype == _BF16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and N <= 256 and N % 16 == 0
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    flags = 1 if out_dtype == _F32 else 0
+    ldr = 0
+    if residual is not None:
+        assert residual.dim() == 2 and residual.stride(1) == 1 and residual.shape[1] == N
+        flags |= 2 if residual.dtype == _F32 else 0
+        ldr = residual.stride(0)
+    L = _lib.load()
+    ev = _prof_begin()
+    rc = L.sb_gemm_ln(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+                      _ptr(bias), _ptr(residual), ldr, res_mod, flags, gamma.data_ptr(), beta.data_ptr(), eps, _stream())
+    _prof_end(ev, 2.0 * M * N * K)
+    _lib.check(rc, "sb_gemm_ln")
+    _count()
+    return out
+
+
+def gemm_upscale1(keys: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_s1: torch.Tensor, s1_bstride: int,
+                  gamma: torch.Tensor, beta: torch.Tensor, B: int, gh: int, gw: int, eps: float = 1e-6) -> torch.Tensor:
+    """keys [B*gh*gw,256] bf16 -> u1 [B*2gh*2gw, 64] bf16 (transposed conv + skip + LayerNorm2d + GELU fused)."""
+    _chk_cuda(keys, w, bias, feat_s1, gamma, beta)
+    assert keys.dtype == _BF16 and keys.shape == (B * gh * gw, 256) and keys.stride(1) == 1
+    assert w.dtype == _BF16 and w.shape == (256, 256) and bias.numel() == 256 and feat_s1.dtype == _F32
+    u1 = torch.empty((B * 4 * gh * gw, 64), dtype=_BF16, device=keys.device)
+    L = _lib.load()
+    ev = _prof_begin()
+    rc = L.sb_gemm_upscale1(keys.data_ptr(), keys.stride(0), w.data_ptr(), w.stride(0), B, gh, gw, bias.data_ptr(),
+                            feat_s1.data_ptr(), s1_bstride, gamma.data_ptr(), beta.data_ptr(), eps, u1.data_ptr(),
+                            _stream())
+    _prof_end(ev, 2.0 * B * gh * gw * 256 * 256)
+    _lib.check(rc, "sb_gemm_upscale1")
+    _count()
+    return u1
+
+
+def gemm_upscale2(u1: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_s0: torch.Tensor, s0_bstride: int,
+                  hyper: torch.Tensor, B: int, gh: int, gw: int) -> torch.Tensor:
+    """u1 [B*gh*gw,64] bf16 -> masks [B,4,2gh,2gw] fp32 (transposed conv + skip + GELU + hyper-network dot fused)."""
+    _chk_cuda(u1, w, bias, feat_s0, hyper)
+    assert u1.dtype == _BF16 and u1.shape == (B * gh * gw, 64) and (gh * gw) % 128 == 0
+    assert w.dtype == _BF16 and w.shape == (128, 64) and bias.numel() == 128 and feat_s0.dtype == _F32
+    assert hyper.dtype == _F32 and hyper.is_contiguous() and hyper.shape == (B, 4, 32)
+    masks = torch.empty((B, 4, 2 * gh, 2 * gw), dtype=_F32, device=u1.device)
+    L = _lib.load()
+    ev = _prof_begin()
+    rc = L.sb_gemm_upscale2(u1.data_ptr(), u1.stride(0), w.data_ptr(), w.stride(0), B, gh, gw, bias.data_ptr(),
+                            feat_s0.data_ptr(), s0_bstride, hyper.data_ptr(), masks.data_ptr(), _stream())
+    _prof_end(ev, 2.0 * B * gh * gw * 128 * 64)
+    _lib.check(rc, "sb_gemm_upscale2")
+    _count()
+    return masks
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,

@@ -181,9 +181,9 @@ class MaskDecoder:
             vt = ops.gemm(ops.add_cast(queries, None, _BF16), L["i2t_v_w"], L["i2t_v_b"])
             qi = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
             a = ops.attention(qi, kt, vt, B, 8, NT_IMG, Nt, q_shared=(kb == 1))  # [B*4096,128]
-            pre = ops.gemm(a, L["i2t_o_w"], L["i2t_o_b"], residual=keys_f32, res_mod=(NT_IMG if kb == 1 else 0),
-                           out_dtype=_F32)
-            keys = ops.layernorm(pre, L["n4w"], L["n4b"], 1e-5, _BF16)
+            # keys = norm4(keys + out_proj(attn)) fused in the GEMM epilogue (no fp32 round trip of the image stream)
+            keys = ops.gemm_ln(a, L["i2t_o_w"], L["i2t_o_b"], keys_f32, L["n4w"], L["n4b"], 1e-5,
+                               res_mod=(NT_IMG if kb == 1 else 0))
             keys_f32 = keys  # bf16 residual from here on (immediately re-normalised)
             kb = B
         # ---- final token -> image attention
@@ -193,18 +193,14 @@ class MaskDecoder:
         queries = ops.gemm(a, self.fa_o_w, self.fa_o_b, residual=queries, out_dtype=_F32)
         hs = ops.layernorm(queries, self.nf_w, self.nf_b, 1e-5, _F32)  # [B*Nt,256]
         # ---- up-scaling + hyper-network masks
-        g1 = ops.gemm(keys, self.up1_w, self.up1_b)  # [B*4096, 4*64]
-        u1 = ops.upscale1_post(g1, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64)  # [B*16384, 64]
-        del g1
-        g2 = ops.gemm(u1, self.up2_w, self.up2_b)  # [B*16384, 4*32]
-        del u1
+        u1 = ops.gemm_upscale1(keys, self.up1_w, self.up1_b, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64)
         hs16 = ops.add_cast(hs, None, _BF16).view(B, Nt * 256)
         hyper = torch.empty((B, 4, 32), dtype=_F32, device=self.device)
         hv = hyper.view(B, 128)
         for i in range(4):
             self._mlp3(hs16[:, (2 + i) * 256:(3 + i) * 256], self.hyper[i], out=hv[:, i * 32:(i + 1) * 32])
-        masks = ops.upscale2_mask(g2, s0, 0, hyper, B, 128, 128)  # [B,4,256,256]
-        del g2
+        masks = ops.gemm_upscale2(u1, self.up2_w, self.up2_b, s0, 0, hyper, B, 128, 128)  # [B,4,256,256]
+        del u1
         ious = self._mlp3(hs16[:, 256:512], self.iou_head, last_act=ops.ACT_SIGMOID)  # [B,4]
         obj = self._mlp3(hs16[:, 0:256], self.obj_head)  # [B,1]
         out = {"masks": masks, "ious": ious, "obj": obj, "hs": hs.view(B, Nt, 256)}

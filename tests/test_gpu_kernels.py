@@ -190,3 +190,63 @@ def test_prepare_slice_vs_oracle(ops):
     ref = saber_ref.prepare(img.numpy(), to_rgb=True)[..., 0]
     assert abs(out - ref).max() < 1e-4
     assert out.min() == 0.0 and abs(out.max() - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K,res", [(4096, 256, 128, "f32mod"), (8192, 256, 128, "bf16"), (300, 256, 256, None),
+                                       (1000, 128, 64, "f32"), (513, 64, 192, "bf16")])
+def test_gemm_ln_fused(ops, M, N, K, res):
+    """GEMM + residual + LayerNorm fused epilogue vs fp32 torch (bf16 tolerance 2e-2 on an O(1) output)."""
+    torch.manual_seed(6)
+    a = torch.randn(M, K, device="cuda").to(BF16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF16)
+    bias = torch.randn(N, device="cuda")
+    g, b = 1 + 0.1 * torch.randn(N, device="cuda"), 0.1 * torch.randn(N, device="cuda")
+    r, res_mod = None, 0
+    if res == "f32mod":
+        res_mod = 1024
+        r = torch.randn(res_mod, N, device="cuda")
+    elif res == "f32":
+        r = torch.randn(M, N, device="cuda")
+    elif res == "bf16":
+        r = torch.randn(M, N, device="cuda").to(BF16)
+    out = ops.gemm_ln(a, w, bias, r, g, b, 1e-5, res_mod=res_mod)
+    x = a.float() @ w.float().t() + bias
+    if r is not None:
+        x = x + (r.float().repeat(M // res_mod, 1) if res_mod else r.float())
+    ref = F.layer_norm(x, (N,), g, b, 1e-5)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    out32 = ops.gemm_ln(a, w, bias, r, g, b, 1e-5, res_mod=res_mod, out_dtype=F32)
+    assert (out32 - ref).abs().max().item() < 2e-3
+
+
+def test_gemm_upscale_fused(ops):
+    """The two fused transposed-conv stages of the mask decoder vs torch ConvTranspose2d / LayerNorm2d / GELU."""
+    torch.manual_seed(7)
+    B, gh, gw = 3, 16, 16
+    keys = torch.randn(B * gh * gw, 256, device="cuda").to(BF16)
+    w1 = torch.randn(256, 64, 2, 2, device="cuda") / 16
+    b1 = torch.randn(64, device="cuda") * 0.1
+    s1 = torch.randn(4 * gh * gw, 64, device="cuda")
+    g, be = 1 + 0.1 * torch.randn(64, device="cuda"), 0.1 * torch.randn(64, device="cuda")
+    w1g = w1.permute(2, 3, 1, 0).reshape(256, 256).to(BF16).contiguous()
+    u1 = ops.gemm_upscale1(keys, w1g, b1.repeat(4).contiguous(), s1, 0, g, be, B, gh, gw)
+    x = keys.float().view(B, gh, gw, 256).permute(0, 3, 1, 2)
+    y = F.conv_transpose2d(x, w1.to(BF16).float(), b1, stride=2) + s1.view(1, 2 * gh, 2 * gw, 64).permute(0, 3, 1, 2)
+    mu = y.mean(1, keepdim=True)
+    var = (y - mu).pow(2).mean(1, keepdim=True)
+    y = F.gelu((y - mu) / torch.sqrt(var + 1e-6) * g.view(1, -1, 1, 1) + be.view(1, -1, 1, 1))
+    ref1 = y.permute(0, 2, 3, 1).reshape(-1, 64)
+    assert (u1.float() - ref1).abs().max().item() < 3e-2
+    # stage 2 (needs gh*gw % 128 == 0): input = u1 on the 32x32 grid
+    w2 = torch.randn(64, 32, 2, 2, device="cuda") / 8
+    b2 = torch.randn(32, device="cuda") * 0.1
+    s0 = torch.randn(16 * gh * gw, 32, device="cuda")
+    hyper = torch.randn(B, 4, 32, device="cuda")
+    w2g = w2.permute(2, 3, 1, 0).reshape(128, 64).to(BF16).contiguous()
+    masks = ops.gemm_upscale2(u1, w2g, b2.repeat(4).contiguous(), s0, 0, hyper, B, 2 * gh, 2 * gw)
+    x2 = u1.float().view(B, 2 * gh, 2 * gw, 64).permute(0, 3, 1, 2)
+    y2 = F.gelu(F.conv_transpose2d(x2, w2.to(BF16).float(), b2, stride=2)
+                + s0.view(1, 4 * gh, 4 * gw, 32).permute(0, 3, 1, 2))
+    ref2 = torch.einsum("bmc,bchw->bmhw", hyper, y2)
+    assert masks.shape == ref2.shape
+    assert (masks - ref2).abs().max().item() < 3e-2 * max(1.0, ref2.abs().max().item())
