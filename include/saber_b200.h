@@ -95,11 +95,13 @@ int sb_select_mask(const float* masks, const float* ious, int B, int HW, float d
 /* For n candidates (planes [*,4,S,S], ious4 [*,4]; candidate i = prompt i/cpp, token sel[i] or 1 + i%3 or 0):
  * bilinear up-sampling to the crop (SAM2Transforms.postprocess_masks), pred-IoU filter, stability score
  * (sam2/utils/amg.py calculate_stability_score), threshold, box (batched_mask_to_box), near-crop-edge filter
- * (is_box_near_crop_edge), uncrop + bit-pack into the full frame. Outputs are written at index i. */
+ * (is_box_near_crop_edge), uncrop + bit-pack into the full frame. Outputs are written at index i. geom_dev (optional,
+ * device int[5] = {Hc, Wc, x0, y0, base}) overrides the crop geometry and offsets the outputs by `base` entries, so a
+ * captured CUDA graph can be replayed for every crop / prompt batch. */
 int sb_amg_mask_post(const float* planes, const float* ious4, const int* sel, int cpp, int n, int S, int Hc, int Wc,
                      int x0, int y0, int H, int W, float pred_iou_thresh, float mask_thresh, float stab_offset,
                      float stab_thresh, unsigned char* keep, float* stability, float* iou_out, int* bbox, int* area,
-                     void* bits, void* stream);
+                     void* bits, const int* geom_dev, void* stream);
 int sb_compact_keep(const unsigned char* keep, int base, int n, int* cand, int* count, void* stream);
 /* torchvision.ops.nms semantics (upstream batched_nms per crop and across crops); list lengths are device ints. */
 int sb_nms_dev(const int* bbox, const float* scores, const int* cand, const int* n_ptr, int n_cap, float iou_thresh,

@@ -39,10 +39,27 @@ struct MaskPostParams {
   int* bbox;               // [n,4] full-frame xyxy (inclusive max), upstream uncrop_boxes_xyxy applied
   int* area;               // [n]
   uint32_t* bits;          // [n, H, WW]
+  const int* geom;         // optional device-side {Hc, Wc, x0, y0, base}: overrides the crop geometry and offsets the
+                           // outputs by `base` slots (lets one captured CUDA graph serve every crop / batch)
 };
 
 __global__ void __launch_bounds__(256)
-mask_post_kernel(const MaskPostParams p) {
+mask_post_kernel(MaskPostParams p) {
+  if (p.geom) {
+    p.Hc = p.geom[0];
+    p.Wc = p.geom[1];
+    p.x0 = p.geom[2];
+    p.y0 = p.geom[3];
+    p.x1 = p.x0 + p.Wc;
+    p.y1 = p.y0 + p.Hc;
+    const long long base = p.geom[4];
+    p.keep += base;
+    p.stability += base;
+    p.iou_out += base;
+    p.bbox += 4 * base;
+    p.area += base;
+    p.bits += base * p.H * p.WW;
+  }
   const int i = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int prompt = i / p.cpp;
@@ -386,9 +403,9 @@ extern "C" int sb_amg_mask_post(const float* planes, const float* ious4, const i
                                 int H, int W, float pred_iou_thresh, float mask_thresh,
                                 float stab_offset, float stab_thresh, unsigned char* keep,
                                 float* stability, float* iou_out, int* bbox, int* area, void* bits,
-                                void* stream_) {
+                                const int* geom_dev, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SB_REQUIRE(n > 0 && S > 0 && Hc > 0 && Wc > 0 && H >= y0 + Hc && W >= x0 + Wc,
+  SB_REQUIRE(geom_dev != nullptr || (n > 0 && S > 0 && Hc > 0 && Wc > 0 && H >= y0 + Hc && W >= x0 + Wc),
              "sb_amg_mask_post: bad geometry n=%d S=%d crop=%dx%d+%d+%d frame=%dx%d", n, S, Hc, Wc,
              x0, y0, H, W);
   MaskPostParams p;
@@ -419,6 +436,7 @@ extern "C" int sb_amg_mask_post(const float* planes, const float* ious4, const i
   p.bbox = bbox;
   p.area = area;
   p.bits = static_cast<uint32_t*>(bits);
+  p.geom = geom_dev;
   mask_post_kernel<<<n, 256, 0, stream>>>(p);
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -49,7 +49,7 @@ SIGNATURES = {
     "sb_select_mask": [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
     "sb_amg_mask_post": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
-                         c_void_p, c_void_p, c_void_p],
+                         c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_compact_keep": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sb_nms_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
                    c_void_p, c_void_p],

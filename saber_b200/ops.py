@@ -36,8 +36,8 @@ class GemmProfiler:
 
     def summary(self):
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for _, a, b in self.records)
-        flops = float(sum(f for f, _, _ in self.records))
+        ms = sum(r[1].elapsed_time(r[2]) for r in self.records)
+        flops = float(sum(r[0] for r in self.records))
         return {"launches": len(self.records), "ms": ms, "flops": flops,
                 "tflops": (flops / (ms * 1e-3) / 1e12) if ms > 0 else 0.0}
 
@@ -133,11 +133,11 @@ def _prof_begin():
     return ev0
 
 
-def _prof_end(ev0, flops):
+def _prof_end(ev0, flops, tag="fused"):
     if ev0 is not None and _gemm_profiler is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
-        _gemm_profiler.records.append((flops, ev0, ev1))
+        _gemm_profiler.records.append((flops, ev0, ev1, tag))
 
 
 def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
@@ -159,7 +159,7 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resi
     ev = _prof_begin()
     rc = L.sb_gemm_ln(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K,
                       _ptr(bias), _ptr(residual), ldr, res_mod, flags, gamma.data_ptr(), beta.data_ptr(), eps, _stream())
-    _prof_end(ev, 2.0 * M * N * K)
+    _prof_end(ev, 2.0 * M * N * K, f"ln M={M} N={N} K={K}")
     _lib.check(rc, "sb_gemm_ln")
     _count()
     return out
@@ -177,7 +177,7 @@ def gemm_upscale1(keys: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_
     rc = L.sb_gemm_upscale1(keys.data_ptr(), keys.stride(0), w.data_ptr(), w.stride(0), B, gh, gw, bias.data_ptr(),
                             feat_s1.data_ptr(), s1_bstride, gamma.data_ptr(), beta.data_ptr(), eps, u1.data_ptr(),
                             _stream())
-    _prof_end(ev, 2.0 * B * gh * gw * 256 * 256)
+    _prof_end(ev, 2.0 * B * gh * gw * 256 * 256, f"up1 M={B * gh * gw} N=256 K=256")
     _lib.check(rc, "sb_gemm_upscale1")
     _count()
     return u1
@@ -195,7 +195,7 @@ def gemm_upscale2(u1: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_s0
     ev = _prof_begin()
     rc = L.sb_gemm_upscale2(u1.data_ptr(), u1.stride(0), w.data_ptr(), w.stride(0), B, gh, gw, bias.data_ptr(),
                             feat_s0.data_ptr(), s0_bstride, hyper.data_ptr(), masks.data_ptr(), _stream())
-    _prof_end(ev, 2.0 * B * gh * gw * 128 * 64)
+    _prof_end(ev, 2.0 * B * gh * gw * 128 * 64, f"up2 M={B * gh * gw} N=128 K=64")
     _lib.check(rc, "sb_gemm_upscale2")
     _count()
     return masks
@@ -432,9 +432,12 @@ _I32, _U8 = torch.int32, torch.uint8
 def amg_mask_post(planes: torch.Tensor, ious4: torch.Tensor, sel: Optional[torch.Tensor], cpp: int, n: int,
                   crop_hw, crop_xy, frame_hw, pred_iou_thresh: float, mask_thresh: float, stab_offset: float,
                   stab_thresh: float, keep: torch.Tensor, stability: torch.Tensor, iou_out: torch.Tensor,
-                  bbox: torch.Tensor, area: torch.Tensor, bits: torch.Tensor, base: int) -> None:
+                  bbox: torch.Tensor, area: torch.Tensor, bits: torch.Tensor, base: int,
+                  geom_dev: Optional[torch.Tensor] = None) -> None:
     """Stability score / threshold / bbox / near-edge test / bit-packing for ``n`` candidates whose low-res
-    logits are ``planes`` [B,4,S,S]; results land in slots ``base .. base+n`` of the per-image arrays."""
+    logits are ``planes`` [B,4,S,S]; results land in slots ``base .. base+n`` of the per-image arrays. With
+    ``geom_dev`` (device int32 [5] = Hc, Wc, x0, y0, base) the geometry and slot base are read on the device instead
+    (crop_hw / crop_xy / base arguments are ignored) — used under CUDA-graph replay."""
     _chk_cuda(planes, ious4, sel, keep, stability, iou_out, bbox, area, bits)
     assert planes.dtype == _F32 and planes.is_contiguous() and planes.dim() == 4 and planes.shape[1] == 4
     assert ious4.dtype == _F32 and ious4.is_contiguous() and ious4.shape == planes.shape[:2]
@@ -444,12 +447,15 @@ def amg_mask_post(planes: torch.Tensor, ious4: torch.Tensor, sel: Optional[torch
     (Hc, Wc), (x0, y0), (H, W) = crop_hw, crop_xy, frame_hw
     WW = (W + 31) // 32
     assert bits.shape[1:] == (H, WW) and base + n <= bits.shape[0] and n <= planes.shape[0] * cpp
+    if geom_dev is not None:
+        assert geom_dev.dtype == _I32 and geom_dev.numel() >= 5 and geom_dev.is_cuda
+        base = 0
     L = _lib.load()
     rc = L.sb_amg_mask_post(planes.data_ptr(), ious4.data_ptr(), _ptr(sel), cpp, n, S, Hc, Wc, x0, y0, H, W,
                             pred_iou_thresh, mask_thresh, stab_offset, stab_thresh,
                             keep.data_ptr() + base, stability.data_ptr() + 4 * base, iou_out.data_ptr() + 4 * base,
                             bbox.data_ptr() + 16 * base, area.data_ptr() + 4 * base,
-                            bits.data_ptr() + 4 * base * H * WW, _stream())
+                            bits.data_ptr() + 4 * base * H * WW, _ptr(geom_dev), _stream())
     _lib.check(rc, "sb_amg_mask_post")
     _count()
 

@@ -71,6 +71,7 @@ class _CropPlan:
     points_full: torch.Tensor   # [n,2] fp32 host: uncrop_points
     in_points: torch.Tensor     # [n,1,2] fp32 device: model-input pixel coordinates
     labels: torch.Tensor        # [n,1] int32 device (ones)
+    geom_dev: torch.Tensor = None  # [n_batches, 8] int32 device: (Hc, Wc, x0, y0, slot base of the batch, 0, 0, 0)
 
 
 @dataclass
@@ -134,6 +135,8 @@ class SAM2AutomaticMaskGenerator:
         self.m2m_batch = 3 * points_per_batch
         # test hook: when a list, every post-processing call appends (crop, base, n, cpp, planes, ious4, sel) host copies
         self.capture: Optional[list] = None
+        self.use_cuda_graph = True
+        self._graphs: Dict[Tuple[int, int], Any] = {}
         self._plans: Dict[Tuple[int, int], _ImagePlan] = {}
         self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
 
@@ -162,9 +165,11 @@ class SAM2AutomaticMaskGenerator:
             inp = inp * res
             full = pts + torch.tensor([[x0, y0]])
             n = pts.shape[0]
+            ppb = self.points_per_batch
+            geom = torch.tensor([[hc, wc, x0, y0, base + b0 * cpp, 0, 0, 0] for b0 in range(0, n, ppb)], dtype=_I32)
             crops.append(_CropPlan(tuple(box), layer, base, n, pts, full,
                                    inp[:, None, :].contiguous().to(dev),
-                                   torch.ones((n, 1), dtype=_I32, device=dev)))
+                                   torch.ones((n, 1), dtype=_I32, device=dev), geom.to(dev)))
             base += n * cpp
         cb = torch.tensor(boxes, dtype=_F32)
         crop_score = 1 / ((cb[:, 2] - cb[:, 0]) * (cb[:, 3] - cb[:, 1]))
@@ -215,33 +220,22 @@ class SAM2AutomaticMaskGenerator:
             emb = tok["embed"][k * 4096:(k + 1) * 4096]
             s0 = tok["s0"][k * 65536:(k + 1) * 65536]
             s1 = tok["s1"][k * 16384:(k + 1) * 16384]
+            graph = self._batch_graph(plan, ws) if (self.use_cuda_graph and self.capture is None) else None
+            if graph is not None:
+                graph["emb"].copy_(emb)
+                graph["s0"].copy_(s0)
+                graph["s1"].copy_(s1)
             for p0 in range(0, crop.n_points, ppb):
                 pb = min(ppb, crop.n_points - p0)
-                coords = crop.in_points[p0:p0 + pb]
-                tokens = dec.prompt_tokens(coords, crop.labels[p0:p0 + pb])
-                out = dec.forward(emb, s0, s1, tokens, None, multimask_output=self.multimask_output)
                 base = crop.base + p0 * plan.cpp
-                geom = ((y1 - y0, x1 - x0), (x0, y0), hw, self.pred_iou_thresh, self.mask_threshold,
-                        self.stability_score_offset, self.stability_score_thresh, ws["keep"], ws["stab"], ws["iou"],
-                        ws["bbox"], ws["area"], ws["bits"])
-                if self.use_m2m:
-                    # every candidate mask of the first pass is refined with itself as the mask prompt
-                    if self.multimask_output:
-                        tokens2 = tokens.repeat_interleave(3, dim=0)
-                        mask_in, step = out["masks"], max(3, self.m2m_batch - self.m2m_batch % 3)
-                    else:
-                        tokens2 = tokens
-                        mask_in, step = self._select_planes(out, pb), max(1, self.m2m_batch)
-                    ncand = tokens2.shape[0]
-                    for c0 in range(0, ncand, step):
-                        cbn = min(step, ncand - c0)
-                        mi = mask_in[c0 // 3:(c0 + cbn) // 3] if self.multimask_output else mask_in[c0:c0 + cbn]
-                        out2 = dec.forward(emb, s0, s1, tokens2[c0:c0 + cbn].contiguous(), mi,
-                                           multimask_output=False, mask_clamp=32.0)
-                        self._post(k, out2["masks"], out2["ious"], out2.get("sel_idx"), 1, cbn, geom, base + c0)
+                if graph is not None and pb == ppb:
+                    graph["coords"].copy_(crop.in_points[p0:p0 + pb])
+                    graph["geom"].copy_(crop.geom_dev[p0 // ppb])
+                    graph["g"].replay()
+                    ops.launch_count += graph["launches"]
                 else:
-                    sel = None if self.multimask_output else out.get("sel_idx")
-                    self._post(k, out["masks"], out["ious"], sel, plan.cpp, pb * plan.cpp, geom, base)
+                    self._process_batch(k, crop.in_points[p0:p0 + pb], crop.labels[p0:p0 + pb], emb, s0, s1, plan, ws,
+                                        crop.box, base, None)
             n_crop = crop.n_points * plan.cpp
             ops.compact_keep(ws["keep"], crop.base, n_crop, ws["cand"], n_cand)
             ops.nms_dev(ws["bbox"], ws["iou"], ws["cand"], n_cand, n_crop, self.box_nms_thresh, ws["order"],
@@ -259,8 +253,77 @@ class SAM2AutomaticMaskGenerator:
                            ops.gather_rows(ws["iou"].view(_I32), slots, m).view(_F32),
                            ops.gather_rows(ws["stab"].view(_I32), slots, m).view(_F32), plan)
 
-    def _post(self, crop_idx, planes, ious4, sel, cpp, n, geom, base):
-        ops.amg_mask_post(planes, ious4, sel, cpp, n, *geom, base)
+    def _process_batch(self, k, coords, labels, emb, s0, s1, plan, ws, box, base, geom_dev):
+        """One batch of point prompts of crop k: decoder (+ m2m refinement) + integer post-processing into the
+        image-level slot arrays. With ``geom_dev`` the crop geometry / slot base are read on the device (graph replay)."""
+        dec = self.predictor.model.decoder
+        x0, y0, x1, y1 = box
+        pb = coords.shape[0]
+        tokens = dec.prompt_tokens(coords, labels)
+        out = dec.forward(emb, s0, s1, tokens, None, multimask_output=self.multimask_output)
+        geom = ((y1 - y0, x1 - x0), (x0, y0), plan.hw, self.pred_iou_thresh, self.mask_threshold,
+                self.stability_score_offset, self.stability_score_thresh, ws["keep"], ws["stab"], ws["iou"],
+                ws["bbox"], ws["area"], ws["bits"])
+        if self.use_m2m:
+            # every candidate mask of the first pass is refined with itself as the mask prompt
+            if self.multimask_output:
+                tokens2 = tokens.repeat_interleave(3, dim=0)
+                mask_in, step = out["masks"], max(3, self.m2m_batch - self.m2m_batch % 3)
+            else:
+                tokens2 = tokens
+                mask_in, step = self._select_planes(out, pb), max(1, self.m2m_batch)
+            ncand = tokens2.shape[0]
+            for c0 in range(0, ncand, step):
+                cbn = min(step, ncand - c0)
+                mi = mask_in[c0 // 3:(c0 + cbn) // 3] if self.multimask_output else mask_in[c0:c0 + cbn]
+                out2 = dec.forward(emb, s0, s1, tokens2[c0:c0 + cbn].contiguous(), mi, multimask_output=False,
+                                   mask_clamp=32.0)
+                self._post(k, out2["masks"], out2["ious"], out2.get("sel_idx"), 1, cbn, geom, base + c0,
+                           geom_dev, c0)
+        else:
+            sel = None if self.multimask_output else out.get("sel_idx")
+            self._post(k, out["masks"], out["ious"], sel, plan.cpp, pb * plan.cpp, geom, base, geom_dev, 0)
+
+    def _batch_graph(self, plan, ws):
+        """CUDA graph of one full prompt batch (points_per_batch points): the ~250 small launches of the two decoder
+        passes are replayed with one host call; crop features, point coordinates and crop geometry are graph inputs."""
+        key = plan.hw
+        if key in self._graphs:
+            return self._graphs[key]
+        dev, ppb = self.device, self.points_per_batch
+        if self.use_m2m and self.m2m_batch < (3 if self.multimask_output else 1) * ppb:
+            self._graphs[key] = None  # m2m split into several post calls with different bases: keep it eager
+            return None
+        st = dict(emb=torch.zeros((4096, 256), dtype=_F32, device=dev), s0=torch.zeros((65536, 32), dtype=_F32, device=dev),
+                  s1=torch.zeros((16384, 64), dtype=_F32, device=dev), coords=torch.zeros((ppb, 1, 2), dtype=_F32, device=dev),
+                  labels=torch.ones((ppb, 1), dtype=_I32, device=dev), geom=torch.zeros((8,), dtype=_I32, device=dev))
+        crop0 = plan.crops[0]
+        st["geom"].copy_(crop0.geom_dev[0])
+        st["coords"].copy_(crop0.in_points[:ppb])
+
+        def body():
+            self._process_batch(0, st["coords"], st["labels"], st["emb"], st["s0"], st["s1"], plan, ws, crop0.box, 0,
+                                st["geom"])
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()  # warm-up: sets function attributes, loads modules
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        st["launches"] = ops.launch_count - n0
+        ops.launch_count = n0
+        st["g"] = g
+        self._graphs[key] = st
+        return st
+
+    def _post(self, crop_idx, planes, ious4, sel, cpp, n, geom, base, geom_dev=None, sub_base=0):
+        assert geom_dev is None or sub_base == 0
+        ops.amg_mask_post(planes, ious4, sel, cpp, n, *geom, base, geom_dev)
         if self.capture is not None:
             self.capture.append(dict(crop=crop_idx, base=base, n=n, cpp=cpp, planes=planes.cpu().numpy(),
                                      ious4=ious4.cpu().numpy(), sel=None if sel is None else sel.cpu().numpy()))

@@ -147,11 +147,14 @@ class MaskDecoder:
         shared = mask_input is None
         if shared:
             keys_f32 = ops.add_cast(image_embed, self.no_mask_embed, _F32)  # [4096,256]
+            keys = ops.add_cast(keys_f32, None, _BF16)
         else:
             ds = ops.mask_downscale(mask_input.contiguous(), self.md_w, mask_clamp)  # [B*4096,16]
             assert ds.shape[0] == B * NT_IMG, (ds.shape, B)
-            keys_f32 = ops.gemm(ds, self.md6_w, self.md6_b, residual=image_embed, res_mod=NT_IMG, out_dtype=_F32)
-        keys = ops.add_cast(keys_f32, None, _BF16)
+            # per-prompt image stream (image_embed + dense mask embedding) kept in bf16: it is re-normalised by
+            # norm4 right after the first block, and an fp32 copy would be 805 MB per 192 prompts
+            keys = ops.gemm(ds, self.md6_w, self.md6_b, residual=image_embed, res_mod=NT_IMG, out_dtype=_BF16)
+            keys_f32 = keys
         kb = 1 if shared else B  # batch entries of the image stream
 
         for l, L in enumerate(self.layers):

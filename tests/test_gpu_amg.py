@@ -158,3 +158,23 @@ def test_slice_by_slice_given_identical_masks(tiny):
     got2 = seg.segment_image(vol[0], display=False)
     want2 = saber_ref.apply_classifier_none(seg.adapter.segment_image_2d(vol[0]), 50)
     assert [m["area"] for m in got2] == [m["area"] for m in want2]
+
+
+def test_amg_cuda_graph_replay_equals_eager(tiny):
+    """The CUDA-graph replay of a prompt batch (device-side crop geometry / slot base) must give exactly the eager
+    result, run twice to cover graph reuse across images."""
+    from saber_b200 import synth
+    from saber_b200.sam2.automatic_mask_generator import SAM2AutomaticMaskGenerator
+    from saber_b200.utils import preprocessing as prep
+    _, model, _ = tiny
+    kw = dict(AMG_KW, pred_iou_thresh=0.3, stability_score_thresh=0.2, use_m2m=True, multimask_output=True,
+              points_per_batch=16)
+    eager = SAM2AutomaticMaskGenerator(model, **kw)
+    eager.use_cuda_graph = False
+    graph = SAM2AutomaticMaskGenerator(model, **kw)
+    for seed in (2, 3):
+        img = prep.prepare(synth.make_tomogram((1, 300, 517), seed=seed, n_ellipsoids=10)[0].numpy(), to_rgb=True)
+        a, b = eager.generate(img), graph.generate(img)
+        assert graph._graphs[(300, 517)] is not None
+        assert_mask_lists_equal(a, b)
+        assert len(a) > 0
