@@ -278,11 +278,17 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel: one extra instrumented step, CUDA events around every GEMM launch
     roofline = None
+    phases = None
     if not args.no_roofline and rank == 0:
+        gen = seg.adapter._amg().base_generator
+        gen.phase_ms = {}
         prof = ops.GemmProfiler()
         with prof:
             step(args.warmup + args.steps)
         torch.cuda.synchronize()
+        n_img = max(1, gen.phase_ms.get("images", 1))
+        phases = {k: v / n_img for k, v in gen.phase_ms.items() if k != "images"}
+        gen.phase_ms = None
         r = prof.summary()
         if os.environ.get("SB_GEMM_SHAPES"):
             with open(os.environ["SB_GEMM_SHAPES"], "w") as fh:
@@ -313,7 +319,8 @@ def run_b200(args):
                 "config": {"workload": workload_name(args), "slices_per_step": S, "sharding": f"z-slab x{world}",
                            "voxels_per_s": value * SHAPE[1] * SHAPE[2], "masks_kept_per_slice": kept / max(1, S * args.steps),
                            "l2": "256 MiB flush write between timed steps; per-step activations (>10 GB) exceed L2",
-                           "weights": "random-init (seed 0) of the named architecture"},
+                           "weights": "random-init (seed 0) of the named architecture",
+                           "phase_ms_per_slice": phases},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -54,13 +54,16 @@ struct GemmParams {
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int MAX_STAGES = 8;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+constexpr int SMEM_MAX = 227 * 1024;
+constexpr int BAR_BYTES = 1024;           // barriers + tmem pointer, at the (1024-aligned) start of dynamic smem
+constexpr int STG_BYTES = 32 * 128;       // one staging tile: 32 rows x 128 B
+constexpr int NEPI_WARPS = 8;
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 1) return sb::gelu_erf(x);
@@ -69,191 +72,232 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// residual chunk (16 columns) -> up to 4 x uint4 registers
-__device__ __forceinline__ void load_res(const GemmParams& p, long long rrow, int n0, uint4* r) {
-  if (p.res_f32) {
-    const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + rrow * p.ldr + n0);
+// ---- per-warp staging tiles (32 rows x RB bytes, RB = 128 or 64), XOR-swizzled in 16-byte chunks so that both the
+// "one thread = one row" accesses of the TMEM epilogue and the "8 (4) lanes = one row" coalesced global accesses are
+// bank-conflict free. All global traffic of the epilogue goes through them: per-thread-row LDG/STG.128 would cost
+// one L1 wavefront per 16 bytes, the cooperative form moves 64-128 bytes per wavefront. -----------------------------
+template <int RB>
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+  return RB == 128 ? static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4))
+                   : static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Asynchronous cooperative gather of 32 rows x `valid` bytes (valid <= RB, multiple of 16) into a staging tile.
+// Lane r owns row r: its source is gbase + off16 * 16 bytes (off16 < 0 = row not loaded).
+template <int RB>
+__device__ __forceinline__ void gather_async(uint32_t stg, const uint8_t* gbase, int off16, int valid, int lane) {
+  constexpr int PPR = RB / 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) r[j] = __ldg(g + j);
-  } else {
-    const uint4* g =
-        reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow * p.ldr + n0);
-    r[0] = __ldg(g);
-    r[1] = __ldg(g + 1);
+  for (int t = 0; t < PPR; ++t) {
+    const int id = t * 32 + lane;
+    const int row = id / PPR, ch = id % PPR;
+    const int o = __shfl_sync(0xffffffffu, off16, row);
+    if (o >= 0 && ch * 16 < valid) cp_async16(stg + swz<RB>(row, ch), gbase + (static_cast<long long>(o) + ch) * 16);
+  }
+  cp_async_commit();
+}
+// Cooperative coalesced store of a staging tile: row r goes to gbase + off16 * 16 bytes (off16 < 0 = skip).
+template <int RB>
+__device__ __forceinline__ void scatter_store(uint32_t stg, uint8_t* gbase, int off16, int valid, int lane) {
+  constexpr int PPR = RB / 16;
+#pragma unroll
+  for (int t = 0; t < PPR; ++t) {
+    const int id = t * 32 + lane;
+    const int row = id / PPR, ch = id % PPR;
+    const int o = __shfl_sync(0xffffffffu, off16, row);
+    if (o >= 0 && ch * 16 < valid) {
+      const uint4 v = lds128(stg + swz<RB>(row, ch));
+      *reinterpret_cast<uint4*>(gbase + (static_cast<long long>(o) + ch) * 16) = v;
+    }
   }
 }
-__device__ __forceinline__ void add_res(const GemmParams& p, const uint4* r, float* f) {
-  if (p.res_f32) {
+
+struct EpiSmem {
+  uint32_t out_stg;     // shared-space address of this warp's output staging tile
+  uint32_t res_stg[2];  // residual / skip staging tiles (res_stg[1] == res_stg[0] when single-buffered)
+  int nres;             // number of distinct residual staging tiles (0, 1 or 2)
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 r, float* f) {
+  f[0] = sb::bf16_lo(r.x);
+  f[1] = sb::bf16_hi(r.x);
+  f[2] = sb::bf16_lo(r.y);
+  f[3] = sb::bf16_hi(r.y);
+  f[4] = sb::bf16_lo(r.z);
+  f[5] = sb::bf16_hi(r.z);
+  f[6] = sb::bf16_lo(r.w);
+  f[7] = sb::bf16_hi(r.w);
+}
+
+// Residual group (32 columns of this thread's row) staging -> f[32] += residual
+template <bool RES_F32>
+__device__ __forceinline__ void add_res_from_stg(uint32_t stg, int lane, int ncols, float* f) {
+  if (RES_F32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j * 4 < ncols) {
+        const uint4 r = lds128(stg + swz<128>(lane, j));
+        f[4 * j + 0] += __uint_as_float(r.x);
+        f[4 * j + 1] += __uint_as_float(r.y);
+        f[4 * j + 2] += __uint_as_float(r.z);
+        f[4 * j + 3] += __uint_as_float(r.w);
+      }
+    }
+  } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      f[4 * j + 0] += __uint_as_float(r[j].x);
-      f[4 * j + 1] += __uint_as_float(r[j].y);
-      f[4 * j + 2] += __uint_as_float(r[j].z);
-      f[4 * j + 3] += __uint_as_float(r[j].w);
-    }
-  } else {
+      if (j * 8 < ncols) {
+        float t[8];
+        unpack_bf16x8(lds128(stg + swz<64>(lane, j)), t);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      f[8 * j + 0] += sb::bf16_lo(r[j].x);
-      f[8 * j + 1] += sb::bf16_hi(r[j].x);
-      f[8 * j + 2] += sb::bf16_lo(r[j].y);
-      f[8 * j + 3] += sb::bf16_hi(r[j].y);
-      f[8 * j + 4] += sb::bf16_lo(r[j].z);
-      f[8 * j + 5] += sb::bf16_hi(r[j].z);
-      f[8 * j + 6] += sb::bf16_lo(r[j].w);
-      f[8 * j + 7] += sb::bf16_hi(r[j].w);
+        for (int e = 0; e < 8; ++e) f[8 * j + e] += t[e];
+      }
     }
   }
 }
-__device__ __forceinline__ void store16(void* out, int out_f32, long long off, const float* f) {
+
+// this thread's 32 results of the current group -> output staging (fp32: 128-byte rows, bf16: 64-byte rows)
+__device__ __forceinline__ void stage_out(uint32_t stg, int lane, int out_f32, const float* f) {
   if (out_f32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    for (int j = 0; j < 8; ++j)
+      sts128(stg + swz<128>(lane, j), make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                                  __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
   } else {
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + off);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint4 t;
-      t.x = sb::pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-      t.y = sb::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-      t.z = sb::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-      t.w = sb::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-      o[j] = t;
-    }
+    for (int j = 0; j < 4; ++j)
+      sts128(stg + swz<64>(lane, j),
+             make_uint4(sb::pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), sb::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                        sb::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), sb::pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
   }
 }
 
-// ---- STD epilogue of one 128 x BN tile (this warp: 32 rows) -------------------------------------------
-template <int BN>
-__device__ __forceinline__ void epilogue_std(const GemmParams& p, uint32_t tmem_acc, int m_idx, int n_idx, int q,
-                                             int lane) {
-  constexpr int NCH = BN / CH;
-  const int row = m_idx + q * 32 + lane;
-  const bool row_ok = row < p.M;
-  const long long rrow = p.res_mod > 0 ? (row % p.res_mod) : row;
-  const bool vec_ok = ((p.ldo & 7) == 0) && (!p.res || (p.ldr & 7) == 0) && ((p.N & 15) == 0);
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  const bool use_res = p.res != nullptr && row_ok && vec_ok;
-  uint32_t v[2][CH];
-  uint4 rb[2][4];
-  sb::tmem_ld_32x16(taddr, v[0]);
-  if (use_res && n_idx < p.N) load_res(p, rrow, n_idx, rb[0]);
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int n0 = n_idx + c * CH;
-    if (n0 >= p.N) break;  // warp-uniform
-    sb::tmem_ld_wait();
-    if (c + 1 < NCH && n0 + CH < p.N) {
-      sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * CH), v[(c + 1) & 1]);
-      if (use_res) load_res(p, rrow, n0 + CH, rb[(c + 1) & 1]);
-    }
-    float f[CH];
-#pragma unroll
-    for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[c & 1][j]) * p.alpha;
-    if (vec_ok) {
-      if (p.bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 t = __ldg(b4 + j);
-          f[4 * j + 0] += t.x;
-          f[4 * j + 1] += t.y;
-          f[4 * j + 2] += t.z;
-          f[4 * j + 3] += t.w;
-        }
-      }
-      if (p.act) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act);
-      }
-      if (row_ok) {
-        if (p.res) add_res(p, rb[c & 1], f);
-        store16(p.out, p.out_f32, static_cast<long long>(row) * p.ldo + n0, f);
-      }
-    } else {
-      const int ncols = min(CH, p.N - n0);
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        if (j < ncols && row_ok) {
-          float x = f[j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
-          x = apply_act(x, p.act);
-          if (p.res) {
-            x += p.res_f32 ? reinterpret_cast<const float*>(p.res)[rrow * p.ldr + n0 + j]
-                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[rrow * p.ldr + n0 + j]);
-          }
-          if (p.out_f32)
-            reinterpret_cast<float*>(p.out)[static_cast<long long>(row) * p.ldo + n0 + j] = x;
-          else
-            reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(row) * p.ldo + n0 + j] = __float2bfloat16(x);
-        }
-      }
-    }
-  }
+__device__ __forceinline__ void issue_res_gather(const GemmParams& p, uint32_t stg, int res_off16_row, int n0,
+                                                 int ncols, int lane) {
+  // res_off16_row: 16-byte offset of this lane's residual row start (or < 0); group starts n0 columns in
+  if (p.res_f32)
+    gather_async<128>(stg, reinterpret_cast<const uint8_t*>(p.res), res_off16_row < 0 ? -1 : res_off16_row + n0 / 4,
+                      ncols * 4, lane);
+  else
+    gather_async<64>(stg, reinterpret_cast<const uint8_t*>(p.res), res_off16_row < 0 ? -1 : res_off16_row + n0 / 8,
+                     ncols * 2, lane);
 }
 
-// ---- LN epilogue: the tile spans the whole row (N <= BN, N % 16 == 0) ----------------------------------
-template <int BN>
-__device__ __forceinline__ void epilogue_ln(const GemmParams& p, uint32_t tmem_acc, int m_idx, int q, int lane) {
-  constexpr int NCH = BN / CH;
+// ---- STD / LN epilogue of one 128 x BN tile (this warp: 32 rows), 32-column groups ---------------------
+// LN: two passes over the row (statistics, then normalise); the tile spans the whole row (N <= BN).
+template <int BN, bool LN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
+                                              int n_idx, int q, int lane) {
+  constexpr int NG = BN / 32;
   const int row = m_idx + q * 32 + lane;
   const bool row_ok = row < p.M;
   const long long rrow = p.res_mod > 0 ? (row % p.res_mod) : row;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  const bool use_res = p.res != nullptr && row_ok;
-  float sum = 0.f, sumsq = 0.f;
-  float mean = 0.f, rstd = 0.f;
+  const bool has_res = p.res != nullptr;
+  // 16-byte offsets of this lane's rows (all pitches are multiples of 16 bytes on this path)
+  const int res_off16 = (has_res && row_ok) ? static_cast<int>(rrow * p.ldr / (p.res_f32 ? 4 : 8)) : -1;
+  const int out_off16 = row_ok ? static_cast<int>(static_cast<long long>(row) * p.ldo / (p.out_f32 ? 4 : 8)) : -1;
+  float sum = 0.f, sumsq = 0.f, mean = 0.f, rstd = 0.f;
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    uint32_t v[2][CH];
-    uint4 rb[2][4];
-    sb::tmem_ld_32x16(taddr, v[0]);
-    if (use_res) load_res(p, rrow, 0, rb[0]);
+  for (int pass = 0; pass < (LN ? 2 : 1); ++pass) {
+    if (has_res && n_idx < p.N) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {
+      const int n0 = n_idx + g * 32;
+      if (n0 >= p.N) break;  // warp-uniform
+      const int ncols = min(32, p.N - n0);  // 16 or 32
+      uint32_t v[32];
+      sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(g * 32), v);
+      if (ncols > 16) sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(g * 32 + 16), v + 16);
+      float f[32];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int n0 = c * CH;
-      if (n0 >= p.N) break;
+      for (int j = 0; j < 32; ++j) f[j] = 0.f;
+      if (has_res) {
+        const bool more = (n0 + 32 < p.N) && (g + 1 < NG);
+        if (es.nres == 2 && more) {  // double-buffered: the next group's gather is in flight while this one is consumed
+          issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
+          cp_async_wait_1();
+        } else {
+          cp_async_wait_all();
+        }
+        __syncwarp();
+        if (p.res_f32)
+          add_res_from_stg<true>(es.res_stg[g & 1], lane, ncols, f);
+        else
+          add_res_from_stg<false>(es.res_stg[g & 1], lane, ncols, f);
+        __syncwarp();
+        if (es.nres != 2 && more)
+          issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
+      }
       sb::tmem_ld_wait();
-      if (c + 1 < NCH && n0 + CH < p.N) {
-        sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * CH), v[(c + 1) & 1]);
-        if (use_res) load_res(p, rrow, n0 + CH, rb[(c + 1) & 1]);
-      }
-      float f[CH];
+      if (!LN) {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[c & 1][j]);
-      if (p.bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+        for (int j = 0; j < 8; ++j) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && j * 4 < ncols) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+          // act(alpha * acc + bias) + residual
+          f[4 * j + 0] += apply_act(fmaf(__uint_as_float(v[4 * j + 0]), p.alpha, b.x), p.act);
+          f[4 * j + 1] += apply_act(fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b.y), p.act);
+          f[4 * j + 2] += apply_act(fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b.z), p.act);
+          f[4 * j + 3] += apply_act(fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b.w), p.act);
+        }
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 t = __ldg(b4 + j);
-          f[4 * j + 0] += t.x;
-          f[4 * j + 1] += t.y;
-          f[4 * j + 2] += t.z;
-          f[4 * j + 3] += t.w;
+        for (int j = 0; j < 8; ++j) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && j * 4 < ncols) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+          f[4 * j + 0] += __uint_as_float(v[4 * j + 0]) + b.x;
+          f[4 * j + 1] += __uint_as_float(v[4 * j + 1]) + b.y;
+          f[4 * j + 2] += __uint_as_float(v[4 * j + 2]) + b.z;
+          f[4 * j + 3] += __uint_as_float(v[4 * j + 3]) + b.w;
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              sum += f[j];
+              sumsq += f[j] * f[j];
+            }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j * 4 < ncols) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + n0) + j);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + n0) + j);
+            f[4 * j + 0] = (f[4 * j + 0] - mean) * rstd * ga.x + be.x;
+            f[4 * j + 1] = (f[4 * j + 1] - mean) * rstd * ga.y + be.y;
+            f[4 * j + 2] = (f[4 * j + 2] - mean) * rstd * ga.z + be.z;
+            f[4 * j + 3] = (f[4 * j + 3] - mean) * rstd * ga.w + be.w;
+          }
         }
       }
-      if (use_res) add_res(p, rb[c & 1], f);
-      if (pass == 0) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          sum += f[j];
-          sumsq += f[j] * f[j];
-        }
-      } else if (row_ok) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.gamma + n0);
-        const float4* be4 = reinterpret_cast<const float4*>(p.beta + n0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 g = __ldg(g4 + j), b = __ldg(be4 + j);
-          f[4 * j + 0] = (f[4 * j + 0] - mean) * rstd * g.x + b.x;
-          f[4 * j + 1] = (f[4 * j + 1] - mean) * rstd * g.y + b.y;
-          f[4 * j + 2] = (f[4 * j + 2] - mean) * rstd * g.z + b.z;
-          f[4 * j + 3] = (f[4 * j + 3] - mean) * rstd * g.w + b.w;
-        }
-        store16(p.out, p.out_f32, static_cast<long long>(row) * p.ldo + n0, f);
-      }
+      stage_out(es.out_stg, lane, p.out_f32, f);
+      __syncwarp();
+      if (p.out_f32)
+        scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 4,
+                           ncols * 4, lane);
+      else
+        scatter_store<64>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 8,
+                          ncols * 2, lane);
+      __syncwarp();
     }
-    if (pass == 0) {
+    if (LN && pass == 0) {
       mean = sum / static_cast<float>(p.N);
       const float var = fmaxf(sumsq / static_cast<float>(p.N) - mean * mean, 0.f);
       rstd = rsqrtf(var + p.eps);
@@ -261,48 +305,81 @@ __device__ __forceinline__ void epilogue_ln(const GemmParams& p, uint32_t tmem_a
   }
 }
 
+// ---- scalar fallback for shapes the staged path cannot take (N % 16 != 0 or pitches not multiples of 16 bytes) -----
+template <int BN>
+__device__ __forceinline__ void epilogue_scalar(const GemmParams& p, uint32_t tmem_acc, int m_idx, int n_idx, int q,
+                                                int lane) {
+  constexpr int NCH = BN / CH;
+  const int row = m_idx + q * 32 + lane;
+  const bool row_ok = row < p.M;
+  const long long rrow = p.res_mod > 0 ? (row % p.res_mod) : row;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int n0 = n_idx + c * CH;
+    if (n0 >= p.N) break;  // warp-uniform
+    uint32_t v[CH];
+    sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(c * CH), v);
+    sb::tmem_ld_wait();
+    const int ncols = min(CH, p.N - n0);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (j < ncols && row_ok) {
+        float x = __uint_as_float(v[j]) * p.alpha + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+        x = apply_act(x, p.act);
+        if (p.res) {
+          x += p.res_f32 ? reinterpret_cast<const float*>(p.res)[rrow * p.ldr + n0 + j]
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[rrow * p.ldr + n0 + j]);
+        }
+        if (p.out_f32)
+          reinterpret_cast<float*>(p.out)[static_cast<long long>(row) * p.ldo + n0 + j] = x;
+        else
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(row) * p.ldo + n0 + j] = __float2bfloat16(x);
+      }
+    }
+  }
+}
+
 // ---- UP1 epilogue: N = 4 groups x 64 channels; row m = (b, y, x) of the gh x gw token grid ---------------
-__device__ __forceinline__ void epilogue_up1(const GemmParams& p, uint32_t tmem_acc, int m_idx, int q, int lane) {
+__device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
+                                             int q, int lane) {
   const int row = m_idx + q * 32 + lane;
   const bool row_ok = row < p.M;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int x = row % p.gw, y = (row / p.gw) % p.gh;
   const long long b = row / (p.gw * p.gh);
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const uint8_t* skip = reinterpret_cast<const uint8_t*>(p.skip);
 #pragma unroll 1
   for (int d = 0; d < 4; ++d) {
     const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
     const long long pix = static_cast<long long>(oy) * (2 * p.gw) + ox;
-    const float4* s4 = reinterpret_cast<const float4*>(p.skip + (row_ok ? b * p.skip_bstride + pix * 64 : 0));
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + d * 64);
+    // skip row: 64 fp32 = 256 bytes = 16 x 16 B ; output row: 64 bf16 = 128 bytes = 8 x 16 B
+    const int skip_off16 = row_ok ? static_cast<int>((b * p.skip_bstride + pix * 64) / 4) : -1;
+    const int out_off16 = row_ok ? static_cast<int>(((b * (2 * p.gh) + oy) * (2 * p.gw) + ox) * 8) : -1;
     float f[64];
     float sum = 0.f;
-    uint32_t v[2][CH];
-    float4 sk[2][4];
-    sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 64), v[0]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sk[0][j] = __ldg(s4 + j);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int h = 0; h < 2; ++h) {
+      gather_async<128>(es.res_stg[0], skip, skip_off16 < 0 ? -1 : skip_off16 + h * 8, 128, lane);
+      uint32_t v[32];
+      sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 64 + h * 32), v);
+      sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 64 + h * 32 + 16), v + 16);
+      cp_async_wait_all();
+      __syncwarp();
       sb::tmem_ld_wait();
-      if (c + 1 < 4) {
-        sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 64 + (c + 1) * CH), v[(c + 1) & 1]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sk[(c + 1) & 1][j] = __ldg(s4 + (c + 1) * 4 + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 bb = __ldg(b4 + c * 4 + j);
-        const float4 kk = sk[c & 1][j];
-        const int e = c * CH + 4 * j;
-        f[e + 0] = __uint_as_float(v[c & 1][4 * j + 0]) + bb.x + kk.x;
-        f[e + 1] = __uint_as_float(v[c & 1][4 * j + 1]) + bb.y + kk.y;
-        f[e + 2] = __uint_as_float(v[c & 1][4 * j + 2]) + bb.z + kk.z;
-        f[e + 3] = __uint_as_float(v[c & 1][4 * j + 3]) + bb.w + kk.w;
+      for (int j = 0; j < 8; ++j) {
+        const uint4 sk = lds128(es.res_stg[0] + swz<128>(lane, j));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + d * 64 + h * 32) + j);
+        const int e = h * 32 + 4 * j;
+        f[e + 0] = __uint_as_float(v[4 * j + 0]) + bb.x + __uint_as_float(sk.x);
+        f[e + 1] = __uint_as_float(v[4 * j + 1]) + bb.y + __uint_as_float(sk.y);
+        f[e + 2] = __uint_as_float(v[4 * j + 2]) + bb.z + __uint_as_float(sk.z);
+        f[e + 3] = __uint_as_float(v[4 * j + 3]) + bb.w + __uint_as_float(sk.w);
         sum += f[e + 0] + f[e + 1] + f[e + 2] + f[e + 3];
       }
+      __syncwarp();
     }
-    if (!row_ok) continue;
     const float mean = sum * (1.f / 64.f);
     float vs = 0.f;
 #pragma unroll
@@ -311,25 +388,24 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, uint32_t tmem_
       vs += dd * dd;
     }
     const float rstd = rsqrtf(vs * (1.f / 64.f) + p.eps);
-    uint4* o = reinterpret_cast<uint4*>(out + ((b * (2 * p.gh) + oy) * (2 * p.gw) + ox) * 64);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float g[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         g[e] = sb::gelu_erf((f[8 * j + e] - mean) * rstd * __ldg(p.gamma + 8 * j + e) + __ldg(p.beta + 8 * j + e));
-      uint4 t;
-      t.x = sb::pack_bf16x2(g[0], g[1]);
-      t.y = sb::pack_bf16x2(g[2], g[3]);
-      t.z = sb::pack_bf16x2(g[4], g[5]);
-      t.w = sb::pack_bf16x2(g[6], g[7]);
-      o[j] = t;
+      sts128(es.out_stg + swz<128>(lane, j), make_uint4(sb::pack_bf16x2(g[0], g[1]), sb::pack_bf16x2(g[2], g[3]),
+                                                         sb::pack_bf16x2(g[4], g[5]), sb::pack_bf16x2(g[6], g[7])));
     }
+    __syncwarp();
+    scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16, 128, lane);
+    __syncwarp();
   }
 }
 
 // ---- UP2 epilogue: N = 4 groups x 32 channels -> 4 mask logits per output pixel --------------------------
-__device__ __forceinline__ void epilogue_up2(const GemmParams& p, uint32_t tmem_acc, int m_idx, int q, int lane) {
+__device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
+                                             int q, int lane) {
   const int row = m_idx + q * 32 + lane;
   const bool row_ok = row < p.M;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
@@ -337,57 +413,66 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, uint32_t tmem_
   const long long b = row / (p.gw * p.gh);
   const int H2 = 2 * p.gh, W2 = 2 * p.gw;
   float* masks = reinterpret_cast<float*>(p.out);
-  const float4* hy = reinterpret_cast<const float4*>(p.hyper + b * 128);
+  const float4* hy = reinterpret_cast<const float4*>(p.hyper + (row_ok ? b : 0) * 128);
+  const uint8_t* skip = reinterpret_cast<const uint8_t*>(p.skip);
+  // skip row of (d): 32 fp32 = 128 bytes
+  auto skip_off = [&](int d) -> int {
+    const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
+    return row_ok ? static_cast<int>((b * p.skip_bstride + (static_cast<long long>(oy) * W2 + ox) * 32) / 4) : -1;
+  };
+  gather_async<128>(es.res_stg[0], skip, skip_off(0), 128, lane);
 #pragma unroll 1
   for (int d = 0; d < 4; ++d) {
     const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
     uint32_t v[32];
     sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 32), v);
     sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 32 + CH), v + CH);
-    float4 sk[8];
-    if (row_ok) {
-      const float4* s4 = reinterpret_cast<const float4*>(p.skip + b * p.skip_bstride +
-                                                          (static_cast<long long>(oy) * W2 + ox) * 32);
+    cp_async_wait_all();
+    __syncwarp();
+    uint4 sk[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sk[j] = __ldg(s4 + j);
-    }
+    for (int j = 0; j < 8; ++j) sk[j] = lds128(es.res_stg[d & 1] + swz<128>(lane, j));
+    __syncwarp();
+    if (d + 1 < 4) gather_async<128>(es.res_stg[(d + 1) & 1], skip, skip_off(d + 1), 128, lane);
     sb::tmem_ld_wait();
-    if (!row_ok) continue;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + d * 32) + j);
-      const float g0 = sb::gelu_erf(__uint_as_float(v[4 * j + 0]) + bb.x + sk[j].x);
-      const float g1 = sb::gelu_erf(__uint_as_float(v[4 * j + 1]) + bb.y + sk[j].y);
-      const float g2 = sb::gelu_erf(__uint_as_float(v[4 * j + 2]) + bb.z + sk[j].z);
-      const float g3 = sb::gelu_erf(__uint_as_float(v[4 * j + 3]) + bb.w + sk[j].w);
+      const float g0 = sb::gelu_erf(__uint_as_float(v[4 * j + 0]) + bb.x + __uint_as_float(sk[j].x));
+      const float g1 = sb::gelu_erf(__uint_as_float(v[4 * j + 1]) + bb.y + __uint_as_float(sk[j].y));
+      const float g2 = sb::gelu_erf(__uint_as_float(v[4 * j + 2]) + bb.z + __uint_as_float(sk[j].z));
+      const float g3 = sb::gelu_erf(__uint_as_float(v[4 * j + 3]) + bb.w + __uint_as_float(sk[j].w));
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const float4 h = __ldg(hy + m * 8 + j);  // warp-uniform address: one broadcast transaction
         acc[m] += g0 * h.x + g1 * h.y + g2 * h.z + g3 * h.w;
       }
     }
+    if (row_ok) {
 #pragma unroll
-    for (int m = 0; m < 4; ++m) masks[((b * 4 + m) * H2 + oy) * W2 + ox] = acc[m];
+      for (int m = 0; m < 4; ++m) masks[((b * 4 + m) * H2 + oy) * W2 + ox] = acc[m];
+    }
   }
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
+                         const GemmParams p, const int stages, const int res_bufs, const int staged) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::STAGES;
-  uint64_t* tfull_bar = bars + 2 * C::STAGES;
-  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* empty_bar = bars + C::MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * C::MAX_STAGES;
+  uint64_t* tempty_bar = bars + 2 * C::MAX_STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::MAX_STAGES + 4);
+  uint8_t* sA = smem + BAR_BYTES;
+  uint8_t* sB = sA + stages * C::A_BYTES;
+  uint8_t* sEpi = sA + stages * C::STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -403,7 +488,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     sb::tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::STAGES; ++i) {
+    for (int i = 0; i < stages; ++i) {
       sb::mbar_init(&full_bar[i], 1);
       sb::mbar_init(&empty_bar[i], 1);
     }
@@ -435,7 +520,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           sb::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           sb::tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_idx);
           sb::tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_idx);
-          if (++stage == C::STAGES) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -466,7 +551,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                           static_cast<uint32_t>((kb | k) != 0));
           }
           sb::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == C::STAGES) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -482,6 +567,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===================== epilogue: set s = (warp - 4) / 4 drains accumulator stage s =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int set = (warp - 4) >> 2;
+    EpiSmem es;
+    {
+      uint8_t* mine = sEpi + (warp - 4) * (1 + res_bufs) * STG_BYTES;
+      es.out_stg = sb::smem_u32(mine);
+      es.res_stg[0] = sb::smem_u32(mine + (res_bufs > 0 ? STG_BYTES : 0));
+      es.res_stg[1] = sb::smem_u32(mine + (res_bufs > 1 ? 2 * STG_BYTES : (res_bufs > 0 ? STG_BYTES : 0)));
+      es.nres = res_bufs;
+    }
     uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -491,14 +584,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       sb::mbar_wait(&tfull_bar[set], acc_phase);
       sb::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(set * BN);
-      if (EPI == EPI_STD)
-        epilogue_std<BN>(p, tmem_acc, m_idx, n_idx, q, lane);
-      else if (EPI == EPI_LN)
-        epilogue_ln<BN>(p, tmem_acc, m_idx, q, lane);
-      else if (EPI == EPI_UP1)
-        epilogue_up1(p, tmem_acc, m_idx, q, lane);
-      else
-        epilogue_up2(p, tmem_acc, m_idx, q, lane);
+      if (EPI == EPI_STD) {
+        if (staged)
+          epilogue_rows<BN, false>(p, es, tmem_acc, m_idx, n_idx, q, lane);
+        else
+          epilogue_scalar<BN>(p, tmem_acc, m_idx, n_idx, q, lane);
+      } else if (EPI == EPI_LN) {
+        epilogue_rows<BN, true>(p, es, tmem_acc, m_idx, 0, q, lane);
+      } else if (EPI == EPI_UP1) {
+        epilogue_up1(p, es, tmem_acc, m_idx, q, lane);
+      } else {
+        epilogue_up2(p, es, tmem_acc, m_idx, q, lane);
+      }
       sb::tc_fence_before();
       __syncwarp();
       if (lane == 0) sb::mbar_arrive(&tempty_bar[set]);
@@ -521,14 +618,38 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   static bool attr_done = false;
   if (!attr_done) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     attr_done = true;
   }
+  // staged (coalesced) epilogue needs 16-byte-aligned pitches and N % 16 == 0
+  int staged = 1;
+  if (EPI == EPI_STD) {
+    const long long ob = p.ldo * (p.out_f32 ? 4 : 2), rb = p.ldr * (p.res_f32 ? 4 : 2);
+    staged = ((p.N & 15) == 0) && (ob % 16 == 0) && (!p.res || rb % 16 == 0) &&
+             ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) &&
+             (p.res_mod == 0 || (p.res_mod % 32) == 0) &&
+             (static_cast<long long>(p.M) * ob < (1ll << 35)) && (!p.res || static_cast<long long>(p.M) * rb < (1ll << 35));
+  }
+  const bool needs_res = (EPI == EPI_UP1 || EPI == EPI_UP2) || (p.res != nullptr);
+  int res_bufs = needs_res ? 2 : 0;
+  const int num_kb = (p.K + BK - 1) / BK;
+  auto stages_for = [&](int rbufs) {
+    const int epi = NEPI_WARPS * (1 + rbufs) * STG_BYTES;
+    return (SMEM_MAX - 1024 - BAR_BYTES - epi) / C::STAGE_BYTES;
+  };
+  int stages = stages_for(res_bufs);
+  if (needs_res && stages < 3 && EPI != EPI_UP2) {  // BN = 256: trade the second residual buffer for a pipeline stage
+    res_bufs = 1;
+    stages = stages_for(res_bufs);
+  }
+  if (stages > C::MAX_STAGES) stages = C::MAX_STAGES;
+  if (stages > num_kb + 2) stages = num_kb + 2 > 2 ? num_kb + 2 : 2;
+  const int smem_bytes = 1024 + BAR_BYTES + stages * C::STAGE_BYTES + NEPI_WARPS * (1 + res_bufs) * STG_BYTES;
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, NTHREADS, smem_bytes, stream>>>(tmA, tmB, p, stages, res_bufs, staged);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

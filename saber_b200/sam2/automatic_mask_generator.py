@@ -136,6 +136,7 @@ class SAM2AutomaticMaskGenerator:
         # test hook: when a list, every post-processing call appends (crop, base, n, cpp, planes, ious4, sel) host copies
         self.capture: Optional[list] = None
         self.use_cuda_graph = True
+        self.phase_ms: Optional[Dict[str, float]] = None  # set to {} to accumulate encode / decode+post / total ms
         self._graphs: Dict[Tuple[int, int], Any] = {}
         self._plans: Dict[Tuple[int, int], _ImagePlan] = {}
         self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
@@ -212,7 +213,12 @@ class SAM2AutomaticMaskGenerator:
         counts = ws["counts"]
         counts.zero_()
         n_cand, n_l1, n_l2 = counts[0:1], counts[1:2], counts[2:3]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.phase_ms is not None else None
+        if ev:
+            ev[0].record()
         feats = pred.encode_crops(img, plan.crops_dev)
+        if ev:
+            ev[1].record()
         tok = feats.tok
         ppb = self.points_per_batch
         for k, crop in enumerate(plan.crops):
@@ -246,7 +252,13 @@ class SAM2AutomaticMaskGenerator:
             final_list, final_count = ws["list2"], n_l2
         else:
             final_list, final_count = ws["list1"], n_l1
+        if ev:
+            ev[2].record()
         m = int(final_count.item())  # the one host synchronisation of the image
+        if ev:
+            self.phase_ms["encode"] = self.phase_ms.get("encode", 0.0) + ev[0].elapsed_time(ev[1])
+            self.phase_ms["decode_post_nms"] = self.phase_ms.get("decode_post_nms", 0.0) + ev[1].elapsed_time(ev[2])
+            self.phase_ms["images"] = self.phase_ms.get("images", 0) + 1
         slots = final_list[:m].clone()
         return DeviceMasks(hw, m, slots, ops.gather_rows(ws["bits"], slots, m),
                            ops.gather_rows(ws["bbox"], slots, m), ops.gather_rows(ws["area"], slots, m),
