@@ -210,6 +210,8 @@ def run_b200(args):
         amg_kw.update(pred_iou_thresh=0.3, stability_score_thresh=0.0)
     seg = propagationSegmenter(deviceID=local, cfg=SAM2AdapterConfig(cfg=sam_cfg, amg_cfg=cfgAMG(**amg_kw),
                                                                     min_mask_area=100), min_mask_area=100)
+    if os.environ.get("SB_NO_GRAPH"):
+        seg.adapter._amg().base_generator.use_cuda_graph = False
     S = args.slices_per_step
     Z = SHAPE[0]
     # z-slab sharding: rank r owns slices [r*Z/world, (r+1)*Z/world); each step takes the next S slices of the slab

@@ -143,44 +143,40 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 r, float* f) {
   f[7] = sb::bf16_hi(r.w);
 }
 
-// Residual group (32 columns of this thread's row) staging -> f[32] += residual
+// Residual of 16 columns (half `h` of the current 32-column group) of this thread's row: staging -> f[16] += residual
 template <bool RES_F32>
-__device__ __forceinline__ void add_res_from_stg(uint32_t stg, int lane, int ncols, float* f) {
+__device__ __forceinline__ void add_res_from_stg(uint32_t stg, int lane, int h, float* f) {
   if (RES_F32) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j * 4 < ncols) {
-        const uint4 r = lds128(stg + swz<128>(lane, j));
-        f[4 * j + 0] += __uint_as_float(r.x);
-        f[4 * j + 1] += __uint_as_float(r.y);
-        f[4 * j + 2] += __uint_as_float(r.z);
-        f[4 * j + 3] += __uint_as_float(r.w);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const uint4 r = lds128(stg + swz<128>(lane, h * 4 + j));
+      f[4 * j + 0] += __uint_as_float(r.x);
+      f[4 * j + 1] += __uint_as_float(r.y);
+      f[4 * j + 2] += __uint_as_float(r.z);
+      f[4 * j + 3] += __uint_as_float(r.w);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j * 8 < ncols) {
-        float t[8];
-        unpack_bf16x8(lds128(stg + swz<64>(lane, j)), t);
+    for (int j = 0; j < 2; ++j) {
+      float t[8];
+      unpack_bf16x8(lds128(stg + swz<64>(lane, h * 2 + j)), t);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[8 * j + e] += t[e];
-      }
+      for (int e = 0; e < 8; ++e) f[8 * j + e] += t[e];
     }
   }
 }
 
-// this thread's 32 results of the current group -> output staging (fp32: 128-byte rows, bf16: 64-byte rows)
-__device__ __forceinline__ void stage_out(uint32_t stg, int lane, int out_f32, const float* f) {
+// this thread's 16 results (half `h` of the group) -> output staging (fp32: 128-byte rows, bf16: 64-byte rows)
+__device__ __forceinline__ void stage_out(uint32_t stg, int lane, int h, int out_f32, const float* f) {
   if (out_f32) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sts128(stg + swz<128>(lane, j), make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                                  __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+    for (int j = 0; j < 4; ++j)
+      sts128(stg + swz<128>(lane, h * 4 + j), make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                                          __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      sts128(stg + swz<64>(lane, j),
+    for (int j = 0; j < 2; ++j)
+      sts128(stg + swz<64>(lane, h * 2 + j),
              make_uint4(sb::pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), sb::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                         sb::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), sb::pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
   }
@@ -197,7 +193,8 @@ __device__ __forceinline__ void issue_res_gather(const GemmParams& p, uint32_t s
                      ncols * 2, lane);
 }
 
-// ---- STD / LN epilogue of one 128 x BN tile (this warp: 32 rows), 32-column groups ---------------------
+// ---- STD / LN epilogue of one 128 x BN tile (this warp: 32 rows). Arithmetic runs on 16-column chunks (TMEM loads
+// one chunk ahead), global IO on 32-column groups through the staging tiles.
 // LN: two passes over the row (statistics, then normalise); the tile spans the whole row (N <= BN).
 template <int BN, bool LN>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
@@ -214,18 +211,15 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
   float sum = 0.f, sumsq = 0.f, mean = 0.f, rstd = 0.f;
 #pragma unroll 1
   for (int pass = 0; pass < (LN ? 2 : 1); ++pass) {
-    if (has_res && n_idx < p.N) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
+    if (n_idx >= p.N) break;
+    if (has_res) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
+    uint32_t v[2][CH];
+    sb::tmem_ld_32x16(taddr, v[0]);
 #pragma unroll 1
     for (int g = 0; g < NG; ++g) {
       const int n0 = n_idx + g * 32;
       if (n0 >= p.N) break;  // warp-uniform
       const int ncols = min(32, p.N - n0);  // 16 or 32
-      uint32_t v[32];
-      sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(g * 32), v);
-      if (ncols > 16) sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(g * 32 + 16), v + 16);
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = 0.f;
       if (has_res) {
         const bool more = (n0 + 32 < p.N) && (g + 1 < NG);
         if (es.nres == 2 && more) {  // double-buffered: the next group's gather is in flight while this one is consumed
@@ -235,67 +229,70 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
           cp_async_wait_all();
         }
         __syncwarp();
-        if (p.res_f32)
-          add_res_from_stg<true>(es.res_stg[g & 1], lane, ncols, f);
-        else
-          add_res_from_stg<false>(es.res_stg[g & 1], lane, ncols, f);
-        __syncwarp();
-        if (es.nres != 2 && more)
-          issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
       }
-      sb::tmem_ld_wait();
-      if (!LN) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+      for (int h = 0; h < 2; ++h) {
+        if (h * CH >= ncols) break;  // warp-uniform
+        const int c0 = n0 + h * CH;
+        sb::tmem_ld_wait();
+        if (c0 + CH < p.N && (g * 2 + h + 1) < 2 * NG)  // next chunk of this tile row
+          sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((g * 2 + h + 1) * CH), v[(h + 1) & 1]);
+        float f[CH];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && j * 4 < ncols) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-          // act(alpha * acc + bias) + residual
-          f[4 * j + 0] += apply_act(fmaf(__uint_as_float(v[4 * j + 0]), p.alpha, b.x), p.act);
-          f[4 * j + 1] += apply_act(fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b.y), p.act);
-          f[4 * j + 2] += apply_act(fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b.z), p.act);
-          f[4 * j + 3] += apply_act(fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b.w), p.act);
+          if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+          if (!LN) {  // act(alpha * acc + bias)
+            f[4 * j + 0] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 0]), p.alpha, b.x), p.act);
+            f[4 * j + 1] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 1]), p.alpha, b.y), p.act);
+            f[4 * j + 2] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 2]), p.alpha, b.z), p.act);
+            f[4 * j + 3] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 3]), p.alpha, b.w), p.act);
+          } else {
+            f[4 * j + 0] = __uint_as_float(v[h][4 * j + 0]) + b.x;
+            f[4 * j + 1] = __uint_as_float(v[h][4 * j + 1]) + b.y;
+            f[4 * j + 2] = __uint_as_float(v[h][4 * j + 2]) + b.z;
+            f[4 * j + 3] = __uint_as_float(v[h][4 * j + 3]) + b.w;
+          }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && j * 4 < ncols) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-          f[4 * j + 0] += __uint_as_float(v[4 * j + 0]) + b.x;
-          f[4 * j + 1] += __uint_as_float(v[4 * j + 1]) + b.y;
-          f[4 * j + 2] += __uint_as_float(v[4 * j + 2]) + b.z;
-          f[4 * j + 3] += __uint_as_float(v[4 * j + 3]) + b.w;
+        if (has_res) {
+          if (p.res_f32)
+            add_res_from_stg<true>(es.res_stg[g & 1], lane, h, f);
+          else
+            add_res_from_stg<false>(es.res_stg[g & 1], lane, h, f);
         }
-        if (pass == 0) {
+        if (LN) {
+          if (pass == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
+            for (int j = 0; j < CH; ++j) {
               sum += f[j];
               sumsq += f[j] * f[j];
             }
+            continue;
           }
-          continue;
-        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j * 4 < ncols) {
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + n0) + j);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + n0) + j);
+          for (int j = 0; j < 4; ++j) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c0) + j);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0) + j);
             f[4 * j + 0] = (f[4 * j + 0] - mean) * rstd * ga.x + be.x;
             f[4 * j + 1] = (f[4 * j + 1] - mean) * rstd * ga.y + be.y;
             f[4 * j + 2] = (f[4 * j + 2] - mean) * rstd * ga.z + be.z;
             f[4 * j + 3] = (f[4 * j + 3] - mean) * rstd * ga.w + be.w;
           }
         }
+        stage_out(es.out_stg, lane, h, p.out_f32, f);
       }
-      stage_out(es.out_stg, lane, p.out_f32, f);
-      __syncwarp();
-      if (p.out_f32)
-        scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 4,
-                           ncols * 4, lane);
-      else
-        scatter_store<64>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 8,
-                          ncols * 2, lane);
-      __syncwarp();
+      __syncwarp();  // residual tile fully consumed, output tile fully written
+      if (has_res && es.nres != 2 && (n0 + 32 < p.N) && (g + 1 < NG))
+        issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
+      if (!(LN && pass == 0)) {
+        if (p.out_f32)
+          scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 4,
+                             ncols * 4, lane);
+        else
+          scatter_store<64>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 8,
+                            ncols * 2, lane);
+        __syncwarp();
+      }
     }
     if (LN && pass == 0) {
       mean = sum / static_cast<float>(p.N);
