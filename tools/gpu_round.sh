@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, ncu launch list of one bench step, full capture of the GEMM.
+# usage: tools/gpu_round.sh <tag> [tests|bench|launches|full ...]
+TAG=${1:-run}; shift
+WHAT=${@:-tests bench launches}
+mkdir -p gpurun_out
+for w in $WHAT; do
+case $w in
+tests) timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/${TAG}_tests.log;;
+smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/${TAG}_smoke.log;;
+bench) SB_GEMM_SHAPES=gpurun_out/${TAG}_gemm_shapes.txt timeout 1200 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err;;
+launches) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_launches.log 2>&1; echo "launches rc=$?"; wc -l gpurun_out/${TAG}_launches.csv;;
+full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 3000 -c 3 -o gpurun_out/${TAG}_gemm python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_full.log 2>&1; echo "full rc=$?";;
+diag) timeout 900 python tools/kernel_diag.py > gpurun_out/${TAG}_kernel_diag.log 2>&1; tail -40 gpurun_out/${TAG}_kernel_diag.log;;
+esac
+done
