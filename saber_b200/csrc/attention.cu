@@ -75,11 +75,12 @@ __device__ __forceinline__ long long key_row(const AttnParams& p, int b, int win
   return (static_cast<long long>(b) * p.H + y) * p.W + x;
 }
 
-constexpr int KT = 64;  // keys per tile
-
-template <int HDP, int NWARPS>
+// KT = keys per tile. HDP > 128 (memory attention: one head of 256) keeps the Q fragments in shared memory instead of
+// registers (the fp32 output accumulator alone is 128 registers per thread) and uses 32-key tiles.
+template <int HDP, int NWARPS, int KT>
 __global__ void __launch_bounds__(NWARPS * 32)
 flash_attn_kernel(const AttnParams p) {
+  constexpr bool Q_IN_REGS = HDP <= 128;
   constexpr int PITCH = HDP * 2 + 16;  // bytes; odd multiple of 16 -> conflict-free ldmatrix
   constexpr int QROWS = 16 * NWARPS;
   constexpr int NT = NWARPS * 32;
@@ -201,12 +202,12 @@ flash_attn_kernel(const AttnParams p) {
   __syncthreads();  // Q tile visible
 
   // Q fragments stay in registers for the whole KV loop
-  uint32_t qf[HDP / 16][4];
-  {
-    const uint32_t base = sb::smem_u32(sQ + (warp * 16 + (lane & 15)) * PITCH + (lane >> 4) * 16);
+  uint32_t qf[Q_IN_REGS ? HDP / 16 : 1][4];
+  const uint32_t qbase = sb::smem_u32(sQ + (warp * 16 + (lane & 15)) * PITCH + (lane >> 4) * 16);
+  if constexpr (Q_IN_REGS) {
 #pragma unroll
     for (int ks = 0; ks < HDP / 16; ++ks)
-      ldsm_x4(base + ks * 32, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      ldsm_x4(qbase + ks * 32, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
   }
 
   float o[HDP / 8][4];
@@ -237,12 +238,15 @@ flash_attn_kernel(const AttnParams p) {
           sb::smem_u32(tK + ((lane & 7) + (id >> 1) * 8) * PITCH + (id & 1) * 16);
 #pragma unroll
       for (int ks = 0; ks < HDP / 16; ++ks) {
+        uint32_t qs[4];
+        if constexpr (!Q_IN_REGS) ldsm_x4(qbase + ks * 32, qs[0], qs[1], qs[2], qs[3]);
+        const uint32_t* qa = Q_IN_REGS ? qf[Q_IN_REGS ? ks : 0] : qs;
 #pragma unroll
         for (int np = 0; np < KT / 16; ++np) {
           uint32_t b0, b1, b2, b3;
           ldsm_x4(kbase + np * 16 * PITCH + ks * 32, b0, b1, b2, b3);
-          mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
-          mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+          mma_bf16_16816(s[2 * np], qa, b0, b1);
+          mma_bf16_16816(s[2 * np + 1], qa, b2, b3);
         }
       }
     }
@@ -348,16 +352,17 @@ flash_attn_kernel(const AttnParams p) {
 
 template <int HDP, int NWARPS>
 int launch_attn(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
+  constexpr int KT = HDP > 128 ? 32 : 64;
   constexpr int PITCH = HDP * 2 + 16;
   constexpr int SMEM = (16 * NWARPS + 4 * KT) * PITCH;
   static bool attr_done = false;
   if (!attr_done) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HDP, NWARPS>,
+    SB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HDP, NWARPS, KT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
   dim3 grid(static_cast<unsigned>(nblocks_x), static_cast<unsigned>(p.heads), 1);
-  flash_attn_kernel<HDP, NWARPS><<<grid, NWARPS * 32, SMEM, stream>>>(p);
+  flash_attn_kernel<HDP, NWARPS, KT><<<grid, NWARPS * 32, SMEM, stream>>>(p);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
@@ -371,7 +376,8 @@ int dispatch_hd(const AttnParams& p, long long nbx, cudaStream_t stream) {
   if (hd <= 80) return launch_attn<80, NWARPS>(p, nbx, stream);
   if (hd <= 96) return launch_attn<96, NWARPS>(p, nbx, stream);
   if (hd <= 128) return launch_attn<128, NWARPS>(p, nbx, stream);
-  sb_set_error("sb_attention: head_dim %d not supported (max 128)", hd);
+  if (hd <= 256) return launch_attn<256, NWARPS>(p, nbx, stream);
+  sb_set_error("sb_attention: head_dim %d not supported (max 256)", hd);
   return SB_ERR_UNSUPPORTED;
 }
 

@@ -20,6 +20,7 @@
 // concurrently and overlap the main loop of the following tiles. Inside an epilogue the TMEM load and the residual
 // loads of column chunk c+1 are issued before chunk c is processed.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -50,6 +51,7 @@ struct GemmParams {
   long long skip_bstride;     // elements between batch entries of skip (0 = shared by all prompts)
   const float* hyper;         // UP2: [B, 4, 32] fp32
   int gh, gw;                 // input token grid of the transposed conv (rows m = (b, y, x), y < gh, x < gw)
+  int dbg;                    // diagnostics (env SB_GEMM_DBG): bit0 skip global stores, bit1 skip TMEM loads, bit2 skip math
 };
 
 template <int BN>
@@ -214,7 +216,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
     if (n_idx >= p.N) break;
     if (has_res) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
     uint32_t v[2][CH];
-    sb::tmem_ld_32x16(taddr, v[0]);
+    const bool dbg_nold = p.dbg & 2, dbg_nost = p.dbg & 1, dbg_nomath = p.dbg & 4;
+    if (dbg_nold) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[0][j] = v[1][j] = 0u;
+    }
+    if (!dbg_nold) sb::tmem_ld_32x16(taddr, v[0]);
 #pragma unroll 1
     for (int g = 0; g < NG; ++g) {
       const int n0 = n_idx + g * 32;
@@ -234,10 +241,16 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
       for (int h = 0; h < 2; ++h) {
         if (h * CH >= ncols) break;  // warp-uniform
         const int c0 = n0 + h * CH;
-        sb::tmem_ld_wait();
-        if (c0 + CH < p.N && (g * 2 + h + 1) < 2 * NG)  // next chunk of this tile row
-          sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((g * 2 + h + 1) * CH), v[(h + 1) & 1]);
+        if (!dbg_nold) {
+          sb::tmem_ld_wait();
+          if (c0 + CH < p.N && (g * 2 + h + 1) < 2 * NG)  // next chunk of this tile row
+            sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((g * 2 + h + 1) * CH), v[(h + 1) & 1]);
+        }
         float f[CH];
+        if (dbg_nomath) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[h][j]);
+        } else
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -284,7 +297,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
       __syncwarp();  // residual tile fully consumed, output tile fully written
       if (has_res && es.nres != 2 && (n0 + 32 < p.N) && (g + 1 < NG))
         issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
-      if (!(LN && pass == 0)) {
+      if (!(LN && pass == 0) && !dbg_nost) {
         if (p.out_f32)
           scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 4,
                              ncols * 4, lane);
@@ -699,6 +712,14 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
   p.res_f32 = (flags & 2) ? 1 : 0;
   p.res_mod = res_mod;
   p.alpha = alpha;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("SB_GEMM_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
 
   // Tile-N choice: minimise waves x tile cost (BN as proxy for per-tile time).
   int bn = force_bn;

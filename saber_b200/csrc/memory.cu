@@ -1,0 +1,579 @@
+// saber_b200 — z-axis propagation (SAM2 video predictor) glue kernels: everything of the memory-attention /
+// memory-encoder / tracking step that is not a GEMM, LayerNorm or attention:
+//   * axial RoPE on projected q / k (sam2/modeling/position_encoding.py apply_rotary_enc, rope_k_repeat, object-pointer
+//     tokens excluded),
+//   * the mask down-sampler's 3x3 stride-2 convs + LayerNorm2d + GELU (memory_encoder.py MaskDownSampler) with the
+//     sigmoid*20-10 / binarise input transform of SAM2Base._encode_new_memory, and its im2col for the last (GEMM) stage,
+//   * CXBlock's 7x7 depth-wise conv fused with its LayerNorm (memory_encoder.py CXBlock),
+//   * occlusion embedding + bf16 cast of the memory features (SAM2Base._encode_new_memory, sam2_video_predictor.py
+//     `maskmem_features.to(torch.bfloat16)`),
+//   * best-IoU mask / token selection with the object-score gate (SAM2Base._forward_sam_heads), object-pointer mixing,
+//   * hole filling of low-res mask scores (sam2/utils/misc.py fill_holes_in_mask_scores; 8-connected, area <= 8),
+//   * mask prompt helpers (binarise, SAM2Base.mask_downsample 4x4/s4 conv),
+//   * the per-frame label stitch of REF saber/adapters/sam2/predictor.py:289-297 (threshold > 0, nearest resize to the
+//     tomogram's (H, W) as skimage.transform.resize(order=0), higher object id wins).
+// Reached from REF saber/adapters/sam2/predictor.py:164-169,196-202,232-348.
+#include "common.cuh"
+
+namespace {
+
+inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE. x: [rows, C] (fp32 or bf16, pitch ld_in), rows = batch * rows_per_batch. Row r of a batch entry is rotated with
+// the frequencies of token r % ntok when r < n_rope, copied otherwise. cs: [ntok, C/2, 2] fp32 (cos, sin).
+// Pair (2i, 2i+1) is one complex number: (a + ib)(cos + i sin).
+// ------------------------------------------------------------------------------------------------
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+rope_kernel(const TIN* __restrict__ x, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
+            long long rows, int C, int rows_per_batch, int n_rope, int ntok, const float2* __restrict__ cs) {
+  const int half = C / 2;
+  const long long total = rows * half;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(t % half);
+    const long long r = t / half;
+    const int rb = static_cast<int>(r % rows_per_batch);
+    float a, b;
+    if constexpr (sizeof(TIN) == 4) {
+      const float2 v = *reinterpret_cast<const float2*>(x + r * ld_in + 2 * i);
+      a = v.x;
+      b = v.y;
+    } else {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(x + r * ld_in + 2 * i);
+      a = sb::bf16_lo(u);
+      b = sb::bf16_hi(u);
+    }
+    if (rb < n_rope) {
+      const float2 f = cs[static_cast<long long>(rb % ntok) * half + i];
+      const float ra = a * f.x - b * f.y;
+      const float rbv = a * f.y + b * f.x;
+      a = ra;
+      b = rbv;
+    }
+    *reinterpret_cast<uint32_t*>(out + r * ld_out + 2 * i) = sb::pack_bf16x2(a, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Conv2d(CIN -> COUT, k3, s2, p1) + LayerNorm2d(COUT, eps) + GELU on NHWC activations; one thread per output pixel.
+// in: [B, Hi, Wi, CIN] (fp32, or bf16 when IN_BF16); w: [COUT, CIN, 3, 3] fp32; out: [B, Ho, Wo, COUT] bf16.
+// in_xf (CIN == 1 only): 0 none, 1 v -> sigmoid(v)*20-10, 2 v -> (v > 0 ? 1 : 0)*20-10.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, bool IN_BF16>
+__global__ void __launch_bounds__(128)
+conv3x3s2_ln_gelu_kernel(const void* __restrict__ in_, int B, int Hi, int Wi, const float* __restrict__ w,
+                         const float* __restrict__ bias, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, int in_xf, float xf_scale, float xf_bias,
+                         __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sw[];  // [9][CIN][COUT] + bias/gamma/beta
+  float* sbias = sw + 9 * CIN * COUT;
+  float* sg = sbias + COUT;
+  float* sbe = sg + COUT;
+  for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % CIN, k = i / (COUT * CIN);
+    sw[i] = w[(co * CIN + ci) * 9 + k];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    sbias[i] = bias[i];
+    sg[i] = gamma[i];
+    sbe[i] = beta[i];
+  }
+  __syncthreads();
+  const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(t % Wo), oy = static_cast<int>((t / Wo) % Ho);
+    const long long b = t / (static_cast<long long>(Wo) * Ho);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = sbias[co];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy - 1 + ky;
+      if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox - 1 + kx;
+        if (ix < 0 || ix >= Wi) continue;
+        const long long pix = (b * Hi + iy) * Wi + ix;
+        const float* wk = sw + (ky * 3 + kx) * CIN * COUT;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          float v;
+          if (IN_BF16)
+            v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in_)[pix * CIN + ci]);
+          else
+            v = reinterpret_cast<const float*>(in_)[pix * CIN + ci];
+          if (CIN == 1) {
+            if (in_xf == 1) v = (1.f / (1.f + expf(-v))) * xf_scale + xf_bias;
+            if (in_xf == 2) v = (v > 0.f ? 1.f : 0.f) * xf_scale + xf_bias;
+          }
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(wk[ci * COUT + co], v, acc[co]);
+        }
+      }
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) mean += acc[co];
+    mean *= (1.f / COUT);
+    float var = 0.f;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) var += (acc[co] - mean) * (acc[co] - mean);
+    const float rstd = rsqrtf(var * (1.f / COUT) + eps);
+    __nv_bfloat16* dst = out + t * COUT;
+#pragma unroll
+    for (int co = 0; co < COUT; co += 2) {
+      const float a = sb::gelu_erf((acc[co] - mean) * rstd * sg[co] + sbe[co]);
+      const float c = sb::gelu_erf((acc[co + 1] - mean) * rstd * sg[co + 1] + sbe[co + 1]);
+      *reinterpret_cast<uint32_t*>(dst + co) = sb::pack_bf16x2(a, c);
+    }
+  }
+}
+
+// im2col for Conv2d(k3, s2, p1) on NHWC bf16: in [B, Hi, Wi, C] -> cols [B*Ho*Wo, 9*C], column = (ky*3+kx)*C + c.
+__global__ void __launch_bounds__(256)
+im2col_3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int B, int Hi, int Wi, int C,
+                    __nv_bfloat16* __restrict__ cols) {
+  const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  const int c8 = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * c8;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(t % c8);
+    const int k = static_cast<int>((t / c8) % 9);
+    const long long pix = t / (9ll * c8);
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+    const long long b = pix / (static_cast<long long>(Wo) * Ho);
+    const int iy = 2 * oy - 1 + k / 3, ix = 2 * ox - 1 + k % 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi)
+      v = *reinterpret_cast<const uint4*>(in + ((b * Hi + iy) * Wi + ix) * C + cc * 8);
+    *reinterpret_cast<uint4*>(cols + pix * 9 * C + k * C + cc * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CXBlock front half: depth-wise Conv2d(C, C, k7, p3, groups=C) + LayerNorm(C, eps) on NHWC fp32 [B, H, W, C];
+// one warp per pixel, C = 256 (8 channels per lane). w: [C, 49] fp32. out: bf16 [B*H*W, C].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv7_ln_kernel(const float* __restrict__ in, int B, int H, int W, const float* __restrict__ w,
+                  const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, __nv_bfloat16* __restrict__ out) {
+  constexpr int C = 256;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long total = static_cast<long long>(B) * H * W;
+  const int c0 = lane * 8;
+  for (long long pix = warp; pix < total; pix += nwarps) {
+    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias[c0 + e];
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = y - 3 + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = x - 3 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float* src = in + ((b * H + iy) * W + ix) * C + c0;
+        const float4 v0 = *reinterpret_cast<const float4*>(src);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const int k = ky * 7 + kx;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(__ldg(w + (c0 + e) * 49 + k), vv[e], acc[e]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += acc[e];
+    const float mean = sb::warp_sum(s) * (1.f / C);
+    float vs = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vs += (acc[e] - mean) * (acc[e] - mean);
+    const float rstd = rsqrtf(sb::warp_sum(vs) * (1.f / C) + eps);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (acc[e] - mean) * rstd * gamma[c0 + e] + beta[c0 + e];
+    *reinterpret_cast<uint4*>(out + pix * C + c0) =
+        make_uint4(sb::pack_bf16x2(o[0], o[1]), sb::pack_bf16x2(o[2], o[3]), sb::pack_bf16x2(o[4], o[5]),
+                   sb::pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// out[b, r, c] = bf16(x[b, r, c] + (score[b] > 0 ? 0 : vec[c])): occlusion embedding + the bf16 storage cast.
+__global__ void __launch_bounds__(256)
+add_vec_cond_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ vec,
+                    long long rows_per_batch, int C, long long total, __nv_bfloat16* __restrict__ out) {
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(t % C);
+    const long long b = t / (rows_per_batch * C);
+    const float add = score[b] > 0.f ? 0.f : vec[c];
+    out[t] = __float2bfloat16(x[t] + add);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SAM heads of a tracking step. masks [B,4,S,S], ious [B,4], obj [B], hs [B,Nt,256].
+// multimask != 0: best = argmax(ious[b,1:4]) (first maximum), plane 1+best, token hs[b, 3+best];
+// else sel (nullable) picks the plane (dynamic multimask via stability) and the token is hs[b, 2].
+// low_res[b] = obj[b] > 0 ? plane : -1024 ; token[b] = chosen token ; best_out[b] = plane index.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+track_select_kernel(const float* __restrict__ masks, const float* __restrict__ ious, const float* __restrict__ obj,
+                    const float* __restrict__ hs, const int* __restrict__ sel, int multimask, int Nt, int SS,
+                    float* __restrict__ low_res, float* __restrict__ token, int* __restrict__ best_out) {
+  const int b = blockIdx.y;
+  int plane, tok;
+  if (multimask) {
+    const float i1 = ious[b * 4 + 1], i2 = ious[b * 4 + 2], i3 = ious[b * 4 + 3];
+    int best = 0;
+    float m = i1;
+    if (i2 > m) { m = i2; best = 1; }
+    if (i3 > m) { m = i3; best = 2; }
+    plane = 1 + best;
+    tok = 3 + best;
+  } else {
+    plane = sel ? sel[b] : 0;
+    tok = 2;
+  }
+  const bool appear = obj[b] > 0.f;
+  const float* src = masks + (static_cast<long long>(b) * 4 + plane) * SS;
+  float* dst = low_res + static_cast<long long>(b) * SS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SS; i += gridDim.x * blockDim.x)
+    dst[i] = appear ? src[i] : -1024.f;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < 256; c += blockDim.x)
+      token[b * 256 + c] = hs[(static_cast<long long>(b) * Nt + tok) * 256 + c];
+    if (threadIdx.x == 0) best_out[b] = plane;
+  }
+}
+
+// ptr[b, c] = cond[b] > 0 ? ptr[b, c] : no_obj_ptr[c]   (lambda * ptr + (1 - lambda) * no_obj_ptr with lambda in {0,1})
+__global__ void __launch_bounds__(256)
+objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ cond, const float* __restrict__ no_obj_ptr, int B,
+                  int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  if (!(cond[b] > 0.f)) ptr[i] = no_obj_ptr[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill_holes_in_mask_scores: background (score <= 0) 8-connected components with area <= max_area get +0.1.
+// One CTA per S x S mask (S <= 256): union-find over the background pixels in shared memory (uint16 parents with
+// S*S <= 65536 ... stored as int for atomics), iterated hooking until stable, then per-root areas.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int* parent, int i) {
+  while (true) {
+    const int p = parent[i];
+    if (p == i) return i;
+    i = p;
+  }
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }  // a > b : hook a under b
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+fill_holes_kernel(const float* __restrict__ in, float* __restrict__ out, int S, int max_area, int* __restrict__ ws) {
+  // ws: per-mask workspace of 2*S*S ints (parents, areas) in global memory (L2-resident; 512 KB per 256^2 mask)
+  const int n = S * S;
+  const float* src = in + static_cast<long long>(blockIdx.x) * n;
+  float* dst = out + static_cast<long long>(blockIdx.x) * n;
+  int* parent = ws + static_cast<long long>(blockIdx.x) * 2 * n;
+  int* area = parent + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    parent[i] = (src[i] <= 0.f) ? i : -1;
+    area[i] = 0;
+  }
+  __syncthreads();
+  // hook every background pixel to its 4 raster-preceding 8-neighbours (W, NW, N, NE)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (parent[i] < 0) continue;
+    const int y = i / S, x = i % S;
+    if (x > 0 && parent[i - 1] >= 0) uf_union(parent, i, i - 1);
+    if (y > 0) {
+      if (parent[i - S] >= 0) uf_union(parent, i, i - S);
+      if (x > 0 && parent[i - S - 1] >= 0) uf_union(parent, i, i - S - 1);
+      if (x < S - 1 && parent[i - S + 1] >= 0) uf_union(parent, i, i - S + 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (parent[i] < 0) continue;
+    const int r = uf_find(parent, i);
+    parent[i] = r;  // roots are fixed now: compression is race-free (root[r] == r)
+    atomicAdd(&area[r], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = src[i];
+    const int p = parent[i];
+    dst[i] = (p >= 0 && area[p] <= max_area) ? 0.1f : v;
+  }
+}
+
+// out = (in >= thr ? 1 : 0) * scale + bias
+__global__ void __launch_bounds__(256)
+threshold_affine_kernel(const float* __restrict__ in, float thr, float scale, float bias, long long n,
+                        float* __restrict__ out) {
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
+       t += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[t] = (in[t] >= thr ? 1.f : 0.f) * scale + bias;
+}
+
+// SAM2Base.mask_downsample: Conv2d(1, 1, k4, s4) on [B, S, S] fp32 -> [B, S/4, S/4]
+__global__ void __launch_bounds__(256)
+conv4x4s4_kernel(const float* __restrict__ in, int B, int S, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ out) {
+  const int T = S / 4;
+  const long long total = static_cast<long long>(B) * T * T;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(t % T), oy = static_cast<int>((t / T) % T);
+    const long long b = t / (static_cast<long long>(T) * T);
+    const float* src = in + (b * S + oy * 4) * S + ox * 4;
+    float acc = bias[0];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float4 v = *reinterpret_cast<const float4*>(src + ky * S);
+      acc = fmaf(w[ky * 4 + 0], v.x, acc);
+      acc = fmaf(w[ky * 4 + 1], v.y, acc);
+      acc = fmaf(w[ky * 4 + 2], v.z, acc);
+      acc = fmaf(w[ky * 4 + 3], v.w, acc);
+    }
+    out[t] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-frame label stitch (REF saber/adapters/sam2/predictor.py:289-297): for objects i = 0..N-1 in order,
+// labels[y, x] = ids[i] where logits_i[sy, sx] > 0, with (sy, sx) = floor((y + 0.5) * Sv / H) (skimage order-0 resize
+// of the Sv x Sv mask to (H, W); identity when H == W == Sv). logits: [N, Sv, Sv] fp32. labels: uint16 [H, W],
+// updated in place (pixels no object claims keep their value).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stitch_objects_kernel(const float* __restrict__ logits, const int* __restrict__ ids, int N, int Sv, int H, int W,
+                      unsigned short* __restrict__ labels) {
+  const long long total = static_cast<long long>(H) * W;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(t % W), y = static_cast<int>(t / W);
+    // scipy.ndimage.zoom(order=0, grid_mode=True) evaluates c = (i + 0.5) * (in / out) - 0.5 in double and rounds to
+    // nearest (floor(c + 0.5)); exact ties land either side of the integer by rounding error, so the same double
+    // expression (no FMA contraction) is evaluated here to stay bit-identical with the reference's skimage resize.
+    const double zy = __ddiv_rn(static_cast<double>(Sv), static_cast<double>(H));
+    const double zx = __ddiv_rn(static_cast<double>(Sv), static_cast<double>(W));
+    const double cy = __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(y), 0.5), zy), -0.5);
+    const double cx = __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(x), 0.5), zx), -0.5);
+    const int sy = max(0, min(static_cast<int>(floor(__dadd_rn(cy, 0.5))), Sv - 1));
+    const int sx = max(0, min(static_cast<int>(floor(__dadd_rn(cx, 0.5))), Sv - 1));
+    int lab = -1;
+    for (int i = 0; i < N; ++i)
+      if (logits[(static_cast<long long>(i) * Sv + sy) * Sv + sx] > 0.f) lab = ids[i];
+    if (lab >= 0) labels[t] = static_cast<unsigned short>(lab);
+  }
+}
+
+// any[z] = 1 if slice z of a uint16 [Z, n] volume has a non-zero voxel
+__global__ void __launch_bounds__(256)
+slice_any_kernel(const unsigned short* __restrict__ vol, long long n, unsigned char* __restrict__ any) {
+  const unsigned short* s = vol + static_cast<long long>(blockIdx.x) * n;
+  int found = 0;
+  for (long long i = threadIdx.x; i < n && !found; i += blockDim.x) found |= (s[i] != 0);
+  found = __syncthreads_or(found);
+  if (threadIdx.x == 0) any[blockIdx.x] = found ? 1 : 0;
+}
+
+// labels[i] = 0 where labels[i] == id (presence-score filtering of one object in one slice)
+__global__ void __launch_bounds__(256)
+erase_label_kernel(unsigned short* __restrict__ labels, long long n, int id) {
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
+       t += static_cast<long long>(gridDim.x) * blockDim.x)
+    if (labels[t] == id) labels[t] = 0;
+}
+
+template <int CIN, int COUT, bool IN_BF16>
+int launch_conv(const void* in, int B, int Hi, int Wi, const float* w, const float* bias, const float* gamma,
+                const float* beta, float eps, int in_xf, float xf_scale, float xf_bias, void* out,
+                cudaStream_t stream) {
+  const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  const int smem = (9 * CIN * COUT + 3 * COUT) * static_cast<int>(sizeof(float));
+  static bool attr_done = false;
+  if (!attr_done && smem > 48 * 1024) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(conv3x3s2_ln_gelu_kernel<CIN, COUT, IN_BF16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  conv3x3s2_ln_gelu_kernel<CIN, COUT, IN_BF16>
+      <<<grid_for(static_cast<long long>(B) * Ho * Wo, 128, 148 * 32), 128, smem, stream>>>(
+          in, B, Hi, Wi, w, bias, gamma, beta, eps, in_xf, xf_scale, xf_bias, static_cast<__nv_bfloat16*>(out));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+}  // namespace
+
+extern "C" int sb_rope_apply(const void* x, long long ld_in, int in_f32, void* out, long long ld_out, long long rows,
+                             int C, int rows_per_batch, int n_rope, int ntok, const float* cos_sin, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(rows > 0 && C > 0 && (C % 2) == 0 && rows_per_batch > 0 && ntok > 0 && n_rope >= 0 &&
+                 n_rope <= rows_per_batch && (rows % rows_per_batch) == 0,
+             "sb_rope_apply: bad arguments");
+  SB_REQUIRE((ld_in % 2) == 0 && (ld_out % 2) == 0, "sb_rope_apply: pitches must be even");
+  const long long total = rows * (C / 2);
+  const float2* cs = reinterpret_cast<const float2*>(cos_sin);
+  if (in_f32)
+    rope_kernel<float><<<grid_for(total), 256, 0, stream>>>(static_cast<const float*>(x), ld_in,
+                                                            static_cast<__nv_bfloat16*>(out), ld_out, rows, C,
+                                                            rows_per_batch, n_rope, ntok, cs);
+  else
+    rope_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld_in,
+                                                                    static_cast<__nv_bfloat16*>(out), ld_out, rows, C,
+                                                                    rows_per_batch, n_rope, ntok, cs);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// stage: 0 = 1->4 (fp32 in, input transform in_xf), 1 = 4->16, 2 = 16->64 (bf16 in). Output bf16 NHWC.
+extern "C" int sb_conv3x3s2_ln_gelu(const void* in, int stage, int B, int Hi, int Wi, const float* w, const float* bias,
+                                    const float* gamma, const float* beta, float eps, int in_xf, float xf_scale,
+                                    float xf_bias, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && Hi > 0 && Wi > 0 && in && w && bias && gamma && beta && out, "sb_conv3x3s2_ln_gelu: bad arguments");
+  if (stage == 0) return launch_conv<1, 4, false>(in, B, Hi, Wi, w, bias, gamma, beta, eps, in_xf, xf_scale, xf_bias, out, stream);
+  if (stage == 1) return launch_conv<4, 16, true>(in, B, Hi, Wi, w, bias, gamma, beta, eps, 0, 0.f, 0.f, out, stream);
+  if (stage == 2) return launch_conv<16, 64, true>(in, B, Hi, Wi, w, bias, gamma, beta, eps, 0, 0.f, 0.f, out, stream);
+  sb_set_error("sb_conv3x3s2_ln_gelu: stage %d not supported", stage);
+  return SB_ERR_ARG;
+}
+
+extern "C" int sb_im2col_3x3s2(const void* in, int B, int Hi, int Wi, int C, void* cols, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && Hi > 0 && Wi > 0 && C > 0 && (C % 8) == 0, "sb_im2col_3x3s2: bad arguments");
+  const long long total = static_cast<long long>(B) * ((Hi + 1) / 2) * ((Wi + 1) / 2) * 9 * (C / 8);
+  im2col_3x3s2_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), B, Hi, Wi, C,
+                                                           static_cast<__nv_bfloat16*>(cols));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_dwconv7_ln(const float* in, int B, int H, int W, int C, const float* w, const float* bias,
+                             const float* gamma, const float* beta, float eps, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && H > 0 && W > 0 && C == 256, "sb_dwconv7_ln: C must be 256 (got %d)", C);
+  const long long total = static_cast<long long>(B) * H * W;
+  dwconv7_ln_kernel<<<grid_for(total * 32), 256, 0, stream>>>(in, B, H, W, w, bias, gamma, beta, eps,
+                                                              static_cast<__nv_bfloat16*>(out));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_add_vec_cond(const float* x, const float* score, const float* vec, int B, long long rows_per_batch,
+                               int C, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && rows_per_batch > 0 && C > 0, "sb_add_vec_cond: bad arguments");
+  const long long total = static_cast<long long>(B) * rows_per_batch * C;
+  add_vec_cond_kernel<<<grid_for(total), 256, 0, stream>>>(x, score, vec, rows_per_batch, C, total,
+                                                           static_cast<__nv_bfloat16*>(out));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_track_select(const float* masks, const float* ious, const float* obj, const float* hs, const int* sel,
+                               int multimask, int B, int Nt, int S, float* low_res, float* token, int* best,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && Nt >= 6 && S > 0, "sb_track_select: bad arguments");
+  dim3 grid(16, B);
+  track_select_kernel<<<grid, 256, 0, stream>>>(masks, ious, obj, hs, sel, multimask, Nt, S * S, low_res, token, best);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_objptr_mix(float* ptr, const float* cond, const float* no_obj_ptr, int B, int C, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && C > 0, "sb_objptr_mix: bad arguments");
+  objptr_mix_kernel<<<(B * C + 255) / 256, 256, 0, stream>>>(ptr, cond, no_obj_ptr, B, C);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// ws: B * 2 * S * S int32 workspace
+extern "C" int sb_fill_holes(const float* in, float* out, int B, int S, int max_area, int* ws, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && S > 0 && max_area > 0 && ws, "sb_fill_holes: bad arguments");
+  fill_holes_kernel<<<B, 1024, 0, stream>>>(in, out, S, max_area, ws);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_threshold_affine(const float* in, float thr, float scale, float bias, long long n, float* out,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0, "sb_threshold_affine: empty");
+  threshold_affine_kernel<<<grid_for(n), 256, 0, stream>>>(in, thr, scale, bias, n, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_conv4x4s4(const float* in, int B, int S, const float* w, const float* bias, float* out,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && S > 0 && (S % 4) == 0, "sb_conv4x4s4: bad arguments");
+  conv4x4s4_kernel<<<grid_for(static_cast<long long>(B) * (S / 4) * (S / 4)), 256, 0, stream>>>(in, B, S, w, bias, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_stitch_objects(const float* logits, const int* ids, int N, int Sv, int H, int W, void* labels,
+                                 void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(N > 0 && Sv > 0 && H > 0 && W > 0, "sb_stitch_objects: bad arguments");
+  stitch_objects_kernel<<<grid_for(static_cast<long long>(H) * W), 256, 0, stream>>>(
+      logits, ids, N, Sv, H, W, static_cast<unsigned short*>(labels));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_slice_any(const void* vol, int Z, long long n, unsigned char* any, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && n > 0, "sb_slice_any: bad arguments");
+  slice_any_kernel<<<Z, 256, 0, stream>>>(static_cast<const unsigned short*>(vol), n, any);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_erase_label(void* labels, long long n, int id, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0, "sb_erase_label: empty");
+  erase_label_kernel<<<grid_for(n), 256, 0, stream>>>(static_cast<unsigned short*>(labels), n, id);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
