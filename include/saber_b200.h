@@ -131,6 +131,39 @@ int sb_resize_normalize(const float* img, int H, int W, int C, const int* crops,
 /* F.interpolate(bilinear, align_corners=False): SAM2Transforms.postprocess_masks / video-resolution logits */
 int sb_upsample_bilinear(const float* in, int N, int Hi, int Wi, int Ho, int Wo, float* out, void* stream);
 
+/* ---- z-axis propagation: memory attention / memory encoder / tracking glue (upstream sam2_video_predictor.py, ----
+ * modeling/{memory_attention,memory_encoder,sam2_base}.py, reached from REF saber/adapters/sam2/predictor.py:164-202) */
+/* axial RoPE (position_encoding.py apply_rotary_enc): rows r < n_rope of each batch entry are rotated with the
+ * frequencies of token r % ntok (rope_k_repeat), the rest (object-pointer tokens) are copied. cos_sin: [ntok, C/2, 2]. */
+int sb_rope_apply(const void* x, long long ld_in, int in_f32, void* out, long long ld_out, long long rows, int C,
+                  int rows_per_batch, int n_rope, int ntok, const float* cos_sin, void* stream);
+/* MaskDownSampler stage: Conv2d(k3,s2,p1) + LayerNorm2d + GELU on NHWC; stage 0: 1->4 (fp32 in; in_xf 1 = sigmoid(v)*
+ * xf_scale+xf_bias, 2 = (v>0)*xf_scale+xf_bias: SAM2Base._encode_new_memory), 1: 4->16, 2: 16->64 (bf16 in). bf16 out. */
+int sb_conv3x3s2_ln_gelu(const void* in, int stage, int B, int Hi, int Wi, const float* w, const float* bias,
+                         const float* gamma, const float* beta, float eps, int in_xf, float xf_scale, float xf_bias,
+                         void* out, void* stream);
+int sb_im2col_3x3s2(const void* in, int B, int Hi, int Wi, int C, void* cols, void* stream);
+/* CXBlock: depth-wise Conv2d(256,k7,p3) + LayerNorm on NHWC fp32 -> bf16 */
+int sb_dwconv7_ln(const float* in, int B, int H, int W, int C, const float* w, const float* bias, const float* gamma,
+                  const float* beta, float eps, void* out, void* stream);
+/* maskmem_features + (score <= 0) * no_obj_embed_spatial, stored as bf16 (sam2_video_predictor.py) */
+int sb_add_vec_cond(const float* x, const float* score, const float* vec, int B, long long rows_per_batch, int C,
+                    void* out, void* stream);
+/* SAM2Base._forward_sam_heads: best-IoU multimask choice (or `sel`), object-score gate (-1024), output token */
+int sb_track_select(const float* masks, const float* ious, const float* obj, const float* hs, const int* sel,
+                    int multimask, int B, int Nt, int S, float* low_res, float* token, int* best, void* stream);
+int sb_objptr_mix(float* ptr, const float* cond, const float* no_obj_ptr, int B, int C, void* stream);
+/* sam2/utils/misc.py fill_holes_in_mask_scores (8-connected background components of area <= max_area -> +0.1).
+ * ws: B*2*S*S int32 workspace */
+int sb_fill_holes(const float* in, float* out, int B, int S, int max_area, int* ws, void* stream);
+int sb_threshold_affine(const float* in, float thr, float scale, float bias, long long n, float* out, void* stream);
+int sb_conv4x4s4(const float* in, int B, int S, const float* w, const float* bias, float* out, void* stream); /* SAM2Base.mask_downsample */
+/* REF saber/adapters/sam2/predictor.py:289-297: per-frame label stitch (threshold > 0, skimage order-0 resize to (H,W),
+ * later objects overwrite earlier ones). logits [N,Sv,Sv] fp32, ids int32 [N], labels uint16 [H,W] updated in place. */
+int sb_stitch_objects(const float* logits, const int* ids, int N, int Sv, int H, int W, void* labels, void* stream);
+int sb_slice_any(const void* vol, int Z, long long n, unsigned char* any, void* stream);     /* REF :321 `.any()` */
+int sb_erase_label(void* labels, long long n, int id, void* stream);                          /* REF :345-346 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,6 @@
 // concurrently and overlap the main loop of the following tiles. Inside an epilogue the TMEM load and the residual
 // loads of column chunk c+1 are issued before chunk c is processed.
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace {
 
@@ -51,7 +50,6 @@ struct GemmParams {
   long long skip_bstride;     // elements between batch entries of skip (0 = shared by all prompts)
   const float* hyper;         // UP2: [B, 4, 32] fp32
   int gh, gw;                 // input token grid of the transposed conv (rows m = (b, y, x), y < gh, x < gw)
-  int dbg;                    // diagnostics (env SB_GEMM_DBG): bit0 skip global stores, bit1 skip TMEM loads, bit2 skip math
 };
 
 template <int BN>
@@ -66,12 +64,27 @@ constexpr int SMEM_MAX = 227 * 1024;
 constexpr int BAR_BYTES = 1024;           // barriers + tmem pointer, at the (1024-aligned) start of dynamic smem
 constexpr int STG_BYTES = 32 * 128;       // one staging tile: 32 rows x 128 B
 constexpr int NEPI_WARPS = 8;
+constexpr int VEC_FLOATS = 3 * 256;        // per epilogue set: bias | gamma (or hyper) | beta of the current tile's columns
+constexpr int VEC_BYTES = 2 * VEC_FLOATS * 4;
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == 1) return sb::gelu_erf(x);
-  if (act == 2) return fmaxf(x, 0.0f);
-  if (act == 3) return 1.0f / (1.0f + expf(-x));
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == 1) return sb::gelu_erf(x);
+  if (ACT == 2) return fmaxf(x, 0.0f);
+  if (ACT == 3) return __fdividef(1.0f, 1.0f + __expf(-x));
   return x;
+}
+// named barrier among the 4 warps of one epilogue set (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void set_barrier(int set) {
+  asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory");
+}
+// Cooperative (128 threads of a set) staging of n floats src[0..n) -> dst (zero beyond `valid` / null src); n % 4 == 0.
+__device__ __forceinline__ void stage_vec(float* dst, const float* src, int n, int valid, int tid128) {
+  for (int c = tid128 * 4; c < n; c += 512) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src != nullptr && c < valid) v = __ldg(reinterpret_cast<const float4*>(src + c));
+    *reinterpret_cast<float4*>(dst + c) = v;
+  }
 }
 
 // ---- per-warp staging tiles (32 rows x RB bytes, RB = 128 or 64), XOR-swizzled in 16-byte chunks so that both the
@@ -132,6 +145,7 @@ struct EpiSmem {
   uint32_t out_stg;     // shared-space address of this warp's output staging tile
   uint32_t res_stg[2];  // residual / skip staging tiles (res_stg[1] == res_stg[0] when single-buffered)
   int nres;             // number of distinct residual staging tiles (0, 1 or 2)
+  const float* vec;     // this set's staged vectors: [0,256) bias, [256,512) gamma / hyper, [512,768) beta
 };
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4 r, float* f) {
@@ -198,7 +212,7 @@ __device__ __forceinline__ void issue_res_gather(const GemmParams& p, uint32_t s
 // ---- STD / LN epilogue of one 128 x BN tile (this warp: 32 rows). Arithmetic runs on 16-column chunks (TMEM loads
 // one chunk ahead), global IO on 32-column groups through the staging tiles.
 // LN: two passes over the row (statistics, then normalise); the tile spans the whole row (N <= BN).
-template <int BN, bool LN>
+template <int BN, bool LN, int ACT>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
                                               int n_idx, int q, int lane) {
   constexpr int NG = BN / 32;
@@ -216,12 +230,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
     if (n_idx >= p.N) break;
     if (has_res) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
     uint32_t v[2][CH];
-    const bool dbg_nold = p.dbg & 2, dbg_nost = p.dbg & 1, dbg_nomath = p.dbg & 4;
-    if (dbg_nold) {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) v[0][j] = v[1][j] = 0u;
-    }
-    if (!dbg_nold) sb::tmem_ld_32x16(taddr, v[0]);
+    sb::tmem_ld_32x16(taddr, v[0]);
 #pragma unroll 1
     for (int g = 0; g < NG; ++g) {
       const int n0 = n_idx + g * 32;
@@ -241,25 +250,18 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
       for (int h = 0; h < 2; ++h) {
         if (h * CH >= ncols) break;  // warp-uniform
         const int c0 = n0 + h * CH;
-        if (!dbg_nold) {
-          sb::tmem_ld_wait();
-          if (c0 + CH < p.N && (g * 2 + h + 1) < 2 * NG)  // next chunk of this tile row
-            sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((g * 2 + h + 1) * CH), v[(h + 1) & 1]);
-        }
+        sb::tmem_ld_wait();
+        if (c0 + CH < p.N && (g * 2 + h + 1) < 2 * NG)  // next chunk of this tile row
+          sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((g * 2 + h + 1) * CH), v[(h + 1) & 1]);
         float f[CH];
-        if (dbg_nomath) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[h][j]);
-        } else
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+          const float4 b = *reinterpret_cast<const float4*>(es.vec + (c0 - n_idx) + 4 * j);  // staged bias (LDS broadcast)
           if (!LN) {  // act(alpha * acc + bias)
-            f[4 * j + 0] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 0]), p.alpha, b.x), p.act);
-            f[4 * j + 1] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 1]), p.alpha, b.y), p.act);
-            f[4 * j + 2] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 2]), p.alpha, b.z), p.act);
-            f[4 * j + 3] = apply_act(fmaf(__uint_as_float(v[h][4 * j + 3]), p.alpha, b.w), p.act);
+            f[4 * j + 0] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 0]), p.alpha, b.x));
+            f[4 * j + 1] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 1]), p.alpha, b.y));
+            f[4 * j + 2] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 2]), p.alpha, b.z));
+            f[4 * j + 3] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 3]), p.alpha, b.w));
           } else {
             f[4 * j + 0] = __uint_as_float(v[h][4 * j + 0]) + b.x;
             f[4 * j + 1] = __uint_as_float(v[h][4 * j + 1]) + b.y;
@@ -284,8 +286,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c0) + j);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0) + j);
+            const float4 ga = *reinterpret_cast<const float4*>(es.vec + 256 + c0 + 4 * j);
+            const float4 be = *reinterpret_cast<const float4*>(es.vec + 512 + c0 + 4 * j);
             f[4 * j + 0] = (f[4 * j + 0] - mean) * rstd * ga.x + be.x;
             f[4 * j + 1] = (f[4 * j + 1] - mean) * rstd * ga.y + be.y;
             f[4 * j + 2] = (f[4 * j + 2] - mean) * rstd * ga.z + be.z;
@@ -297,7 +299,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
       __syncwarp();  // residual tile fully consumed, output tile fully written
       if (has_res && es.nres != 2 && (n0 + 32 < p.N) && (g + 1 < NG))
         issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
-      if (!(LN && pass == 0) && !dbg_nost) {
+      if (!(LN && pass == 0)) {
         if (p.out_f32)
           scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16 < 0 ? -1 : out_off16 + n0 / 4,
                              ncols * 4, lane);
@@ -316,7 +318,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
 }
 
 // ---- scalar fallback for shapes the staged path cannot take (N % 16 != 0 or pitches not multiples of 16 bytes) -----
-template <int BN>
+template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_scalar(const GemmParams& p, uint32_t tmem_acc, int m_idx, int n_idx, int q,
                                                 int lane) {
   constexpr int NCH = BN / CH;
@@ -336,7 +338,7 @@ __device__ __forceinline__ void epilogue_scalar(const GemmParams& p, uint32_t tm
     for (int j = 0; j < CH; ++j) {
       if (j < ncols && row_ok) {
         float x = __uint_as_float(v[j]) * p.alpha + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
-        x = apply_act(x, p.act);
+        x = apply_act<ACT>(x);
         if (p.res) {
           x += p.res_f32 ? reinterpret_cast<const float*>(p.res)[rrow * p.ldr + n0 + j]
                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[rrow * p.ldr + n0 + j]);
@@ -380,7 +382,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint4 sk = lds128(es.res_stg[0] + swz<128>(lane, j));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + d * 64 + h * 32) + j);
+        const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 64 + h * 32 + 4 * j);
         const int e = h * 32 + 4 * j;
         f[e + 0] = __uint_as_float(v[4 * j + 0]) + bb.x + __uint_as_float(sk.x);
         f[e + 1] = __uint_as_float(v[4 * j + 1]) + bb.y + __uint_as_float(sk.y);
@@ -403,7 +405,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
       float g[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        g[e] = sb::gelu_erf((f[8 * j + e] - mean) * rstd * __ldg(p.gamma + 8 * j + e) + __ldg(p.beta + 8 * j + e));
+        g[e] = sb::gelu_erf((f[8 * j + e] - mean) * rstd * es.vec[256 + 8 * j + e] + es.vec[512 + 8 * j + e]);
       sts128(es.out_stg + swz<128>(lane, j), make_uint4(sb::pack_bf16x2(g[0], g[1]), sb::pack_bf16x2(g[2], g[3]),
                                                          sb::pack_bf16x2(g[4], g[5]), sb::pack_bf16x2(g[6], g[7])));
     }
@@ -423,7 +425,7 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
   const long long b = row / (p.gw * p.gh);
   const int H2 = 2 * p.gh, W2 = 2 * p.gw;
   float* masks = reinterpret_cast<float*>(p.out);
-  const float4* hy = reinterpret_cast<const float4*>(p.hyper + (row_ok ? b : 0) * 128);
+  const float4* hy = reinterpret_cast<const float4*>(es.vec + 256);  // this tile's prompt: staged hyper-network vectors
   const uint8_t* skip = reinterpret_cast<const uint8_t*>(p.skip);
   // skip row of (d): 32 fp32 = 128 bytes
   auto skip_off = [&](int d) -> int {
@@ -448,14 +450,14 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + d * 32) + j);
+      const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 32 + 4 * j);
       const float g0 = sb::gelu_erf(__uint_as_float(v[4 * j + 0]) + bb.x + __uint_as_float(sk[j].x));
       const float g1 = sb::gelu_erf(__uint_as_float(v[4 * j + 1]) + bb.y + __uint_as_float(sk[j].y));
       const float g2 = sb::gelu_erf(__uint_as_float(v[4 * j + 2]) + bb.z + __uint_as_float(sk[j].z));
       const float g3 = sb::gelu_erf(__uint_as_float(v[4 * j + 3]) + bb.w + __uint_as_float(sk[j].w));
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const float4 h = __ldg(hy + m * 8 + j);  // warp-uniform address: one broadcast transaction
+        const float4 h = hy[m * 8 + j];  // warp-uniform shared-memory address: broadcast
         acc[m] += g0 * h.x + g1 * h.y + g2 * h.z + g3 * h.w;
       }
     }
@@ -466,7 +468,7 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p, const int stages, const int res_bufs, const int staged) {
@@ -482,7 +484,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::MAX_STAGES + 4);
   uint8_t* sA = smem + BAR_BYTES;
   uint8_t* sB = sA + stages * C::A_BYTES;
-  uint8_t* sEpi = sA + stages * C::STAGE_BYTES;
+  float* sVec = reinterpret_cast<float*>(sA + stages * C::STAGE_BYTES);
+  uint8_t* sEpi = reinterpret_cast<uint8_t*>(sVec) + VEC_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -584,23 +587,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       es.res_stg[0] = sb::smem_u32(mine + (res_bufs > 0 ? STG_BYTES : 0));
       es.res_stg[1] = sb::smem_u32(mine + (res_bufs > 1 ? 2 * STG_BYTES : (res_bufs > 0 ? STG_BYTES : 0)));
       es.nres = res_bufs;
+      es.vec = sVec + set * VEC_FLOATS;
     }
+    float* myvec = sVec + set * VEC_FLOATS;
+    const int tid128 = (warp & 3) * 32 + lane;
     uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != set) continue;
       const int m_idx = (tile / n_tiles) * BM;
       const int n_idx = (tile % n_tiles) * BN;
+      // stage this tile's per-column vectors once per set: every read in the epilogues is a shared-memory broadcast
+      // (per-chunk __ldg of bias / gamma / hyper was the epilogue's critical path: ~4x the main loop at K = 576)
+      set_barrier(set);  // the previous tile's readers are done
+      if (EPI == EPI_STD) {
+        stage_vec(myvec, p.bias ? p.bias + n_idx : nullptr, BN, ((p.N - n_idx) + 3) & ~3, tid128);
+      } else if (EPI == EPI_LN) {
+        stage_vec(myvec, p.bias, BN, p.N, tid128);
+        stage_vec(myvec + 256, p.gamma, BN, p.N, tid128);
+        stage_vec(myvec + 512, p.beta, BN, p.N, tid128);
+      } else if (EPI == EPI_UP1) {
+        stage_vec(myvec, p.bias, 256, 256, tid128);
+        stage_vec(myvec + 256, p.gamma, 64, 64, tid128);
+        stage_vec(myvec + 512, p.beta, 64, 64, tid128);
+      } else {
+        stage_vec(myvec, p.bias, 128, 128, tid128);
+        stage_vec(myvec + 256, p.hyper + static_cast<long long>(m_idx / (p.gh * p.gw)) * 128, 128, 128, tid128);
+      }
+      set_barrier(set);
       sb::mbar_wait(&tfull_bar[set], acc_phase);
       sb::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(set * BN);
       if (EPI == EPI_STD) {
         if (staged)
-          epilogue_rows<BN, false>(p, es, tmem_acc, m_idx, n_idx, q, lane);
+          epilogue_rows<BN, false, ACT>(p, es, tmem_acc, m_idx, n_idx, q, lane);
         else
-          epilogue_scalar<BN>(p, tmem_acc, m_idx, n_idx, q, lane);
+          epilogue_scalar<BN, ACT>(p, tmem_acc, m_idx, n_idx, q, lane);
       } else if (EPI == EPI_LN) {
-        epilogue_rows<BN, true>(p, es, tmem_acc, m_idx, 0, q, lane);
+        epilogue_rows<BN, true, 0>(p, es, tmem_acc, m_idx, 0, q, lane);
       } else if (EPI == EPI_UP1) {
         epilogue_up1(p, es, tmem_acc, m_idx, q, lane);
       } else {
@@ -621,13 +645,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int ACT = 0>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                 cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>,
+    SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, ACT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     attr_done = true;
   }
@@ -644,7 +668,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   int res_bufs = needs_res ? 2 : 0;
   const int num_kb = (p.K + BK - 1) / BK;
   auto stages_for = [&](int rbufs) {
-    const int epi = NEPI_WARPS * (1 + rbufs) * STG_BYTES;
+    const int epi = NEPI_WARPS * (1 + rbufs) * STG_BYTES + VEC_BYTES;
     return (SMEM_MAX - 1024 - BAR_BYTES - epi) / C::STAGE_BYTES;
   };
   int stages = stages_for(res_bufs);
@@ -654,12 +678,13 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   }
   if (stages > C::MAX_STAGES) stages = C::MAX_STAGES;
   if (stages > num_kb + 2) stages = num_kb + 2 > 2 ? num_kb + 2 : 2;
-  const int smem_bytes = 1024 + BAR_BYTES + stages * C::STAGE_BYTES + NEPI_WARPS * (1 + res_bufs) * STG_BYTES;
+  const int smem_bytes =
+      1024 + BAR_BYTES + stages * C::STAGE_BYTES + VEC_BYTES + NEPI_WARPS * (1 + res_bufs) * STG_BYTES;
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, NTHREADS, smem_bytes, stream>>>(tmA, tmB, p, stages, res_bufs, staged);
+  gemm_bf16_tcgen05_kernel<BN, EPI, ACT><<<grid, NTHREADS, smem_bytes, stream>>>(tmA, tmB, p, stages, res_bufs, staged);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
@@ -712,14 +737,6 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
   p.res_f32 = (flags & 2) ? 1 : 0;
   p.res_mod = res_mod;
   p.alpha = alpha;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("SB_GEMM_DBG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.dbg = dbg;
-  }
 
   // Tile-N choice: minimise waves x tile cost (BN as proxy for per-tile time).
   int bn = force_bn;
@@ -746,9 +763,17 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, M, N, K, bn, &tmA, &tmB);
   if (rc != SB_OK) return rc;
-  if (bn == 256) return launch_gemm<256, EPI_STD>(tmA, tmB, p, g_num_sms, stream);
-  if (bn == 128) return launch_gemm<128, EPI_STD>(tmA, tmB, p, g_num_sms, stream);
-  return launch_gemm<64, EPI_STD>(tmA, tmB, p, g_num_sms, stream);
+#define SB_DISPATCH_ACT(BN_)                                                        \
+  switch (act) {                                                                   \
+    case 1: return launch_gemm<BN_, EPI_STD, 1>(tmA, tmB, p, g_num_sms, stream);   \
+    case 2: return launch_gemm<BN_, EPI_STD, 2>(tmA, tmB, p, g_num_sms, stream);   \
+    case 3: return launch_gemm<BN_, EPI_STD, 3>(tmA, tmB, p, g_num_sms, stream);   \
+    default: return launch_gemm<BN_, EPI_STD, 0>(tmA, tmB, p, g_num_sms, stream);  \
+  }
+  if (bn == 256) { SB_DISPATCH_ACT(256) }
+  if (bn == 128) { SB_DISPATCH_ACT(128) }
+  SB_DISPATCH_ACT(64)
+#undef SB_DISPATCH_ACT
 }
 
 // out[M,N] = LayerNorm_N(A @ W^T + bias + residual[m % res_mod or m]) * gamma + beta, N in {64,128,256} x (N%16==0).

@@ -63,6 +63,22 @@ SIGNATURES = {
     "sb_upsample_bilinear": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_stitch_labels": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_ccl3d_26": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_rope_apply": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_conv3x3s2_ln_gelu": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                             c_int, c_float, c_float, c_void_p, c_void_p],
+    "sb_im2col_3x3s2": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_dwconv7_ln": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                      c_void_p],
+    "sb_add_vec_cond": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "sb_track_select": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                        c_void_p, c_void_p, c_void_p],
+    "sb_objptr_mix": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "sb_fill_holes": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_threshold_affine": [c_void_p, c_float, c_float, c_float, c_ll, c_void_p, c_void_p],
+    "sb_conv4x4s4": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_stitch_objects": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_slice_any": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
+    "sb_erase_label": [c_void_p, c_ll, c_int, c_void_p],
 }
 
 

@@ -618,3 +618,176 @@ def upsample_bilinear(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
                "sb_upsample_bilinear")
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# z-axis propagation: memory attention / memory encoder / tracking glue (csrc/memory.cu)
+# ---------------------------------------------------------------------------------------------
+def rope_apply(x: torch.Tensor, cos_sin: torch.Tensor, rows_per_batch: int, n_rope: Optional[int] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Axial RoPE on a projected q / k matrix [batch*rows_per_batch, C] (fp32 or bf16 view) -> bf16. Rows
+    r < n_rope of each batch entry use token r % ntok's frequencies; the rest are copied. cos_sin [ntok, C/2, 2] fp32."""
+    _chk_cuda(x, cos_sin, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (_BF16, _F32)
+    rows, Cc = x.shape
+    assert cos_sin.dtype == _F32 and cos_sin.is_contiguous() and cos_sin.shape[1:] == (Cc // 2, 2)
+    if n_rope is None:
+        n_rope = rows_per_batch
+    if out is None:
+        out = torch.empty((rows, Cc), dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_rope_apply(x.data_ptr(), x.stride(0), int(x.dtype == _F32), out.data_ptr(), out.stride(0), rows, Cc,
+                               rows_per_batch, n_rope, cos_sin.shape[0], cos_sin.data_ptr(), _stream()), "sb_rope_apply")
+    _count()
+    return out
+
+
+def conv3x3s2_ln_gelu(x: torch.Tensor, stage: int, w, bias, gamma, beta, eps: float = 1e-6, in_xf: int = 0,
+                      xf_scale: float = 20.0, xf_bias: float = -10.0) -> torch.Tensor:
+    """One MaskDownSampler stage on NHWC input [B, H, W, Cin] -> bf16 [B, H/2, W/2, Cout]."""
+    _chk_cuda(x, w, bias, gamma, beta)
+    cin, cout = ((1, 4), (4, 16), (16, 64))[stage]
+    assert x.is_contiguous() and x.dim() == 4 and x.shape[3] == cin and x.dtype == (_F32 if stage == 0 else _BF16)
+    assert w.dtype == _F32 and w.is_contiguous() and w.numel() == cout * cin * 9
+    B, H, W = x.shape[:3]
+    out = torch.empty((B, (H + 1) // 2, (W + 1) // 2, cout), dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_conv3x3s2_ln_gelu(x.data_ptr(), stage, B, H, W, w.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+                                      beta.data_ptr(), eps, in_xf, xf_scale, xf_bias, out.data_ptr(), _stream()),
+               "sb_conv3x3s2_ln_gelu")
+    _count()
+    return out
+
+
+def im2col_3x3s2(x: torch.Tensor) -> torch.Tensor:
+    """NHWC bf16 [B, H, W, C] -> [B*(H/2)*(W/2), 9*C] patches of a 3x3 stride-2 pad-1 conv (column = (ky*3+kx)*C + c)."""
+    _chk_cuda(x)
+    assert x.dtype == _BF16 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    cols = torch.empty((B * ((H + 1) // 2) * ((W + 1) // 2), 9 * Cc), dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_im2col_3x3s2(x.data_ptr(), B, H, W, Cc, cols.data_ptr(), _stream()), "sb_im2col_3x3s2")
+    _count()
+    return cols
+
+
+def dwconv7_ln(x: torch.Tensor, B: int, H: int, W: int, w, bias, gamma, beta, eps: float = 1e-6) -> torch.Tensor:
+    """CXBlock front half on token-major fp32 [B*H*W, 256] -> bf16."""
+    _chk_cuda(x, w, bias, gamma, beta)
+    assert x.dtype == _F32 and x.is_contiguous() and x.shape == (B * H * W, 256)
+    out = torch.empty((B * H * W, 256), dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_dwconv7_ln(x.data_ptr(), B, H, W, 256, w.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+                               beta.data_ptr(), eps, out.data_ptr(), _stream()), "sb_dwconv7_ln")
+    _count()
+    return out
+
+
+def add_vec_cond(x: torch.Tensor, score: torch.Tensor, vec: torch.Tensor, B: int) -> torch.Tensor:
+    """bf16(x[b] + (score[b] <= 0) * vec) for x fp32 [B*rows, C]."""
+    _chk_cuda(x, score, vec)
+    assert x.dtype == _F32 and x.is_contiguous() and score.dtype == _F32 and score.numel() == B
+    rows = x.shape[0] // B
+    out = torch.empty(x.shape, dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_add_vec_cond(x.data_ptr(), score.data_ptr(), vec.data_ptr(), B, rows, x.shape[1], out.data_ptr(),
+                                 _stream()), "sb_add_vec_cond")
+    _count()
+    return out
+
+
+def track_select(masks: torch.Tensor, ious: torch.Tensor, obj: torch.Tensor, hs: torch.Tensor,
+                 sel: Optional[torch.Tensor], multimask: bool):
+    """-> (low_res [B,S,S] fp32 gated by the object score, token [B,256] fp32, plane index int32 [B])."""
+    _chk_cuda(masks, ious, obj, hs, sel)
+    B, _, S, _ = masks.shape
+    Nt = hs.shape[1]
+    assert masks.dtype == _F32 and masks.is_contiguous() and ious.is_contiguous() and hs.is_contiguous() and hs.dtype == _F32
+    low = torch.empty((B, S, S), dtype=_F32, device=masks.device)
+    tok = torch.empty((B, 256), dtype=_F32, device=masks.device)
+    best = torch.empty((B,), dtype=_I32, device=masks.device)
+    L = _lib.load()
+    _lib.check(L.sb_track_select(masks.data_ptr(), ious.data_ptr(), obj.data_ptr(), hs.data_ptr(), _ptr(sel),
+                                 int(multimask), B, Nt, S, low.data_ptr(), tok.data_ptr(), best.data_ptr(), _stream()),
+               "sb_track_select")
+    _count()
+    return low, tok, best
+
+
+def objptr_mix_(ptr: torch.Tensor, cond: torch.Tensor, no_obj_ptr: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(ptr, cond, no_obj_ptr)
+    assert ptr.dtype == _F32 and ptr.is_contiguous() and cond.dtype == _F32
+    L = _lib.load()
+    _lib.check(L.sb_objptr_mix(ptr.data_ptr(), cond.data_ptr(), no_obj_ptr.data_ptr(), ptr.shape[0], ptr.shape[1],
+                               _stream()), "sb_objptr_mix")
+    _count()
+    return ptr
+
+
+def fill_holes(masks: torch.Tensor, max_area: int) -> torch.Tensor:
+    """[B, S, S] fp32 mask scores -> holes (8-connected background components, area <= max_area) set to 0.1."""
+    _chk_cuda(masks)
+    assert masks.dtype == _F32 and masks.is_contiguous() and masks.dim() == 3 and masks.shape[1] == masks.shape[2]
+    B, S, _ = masks.shape
+    out = torch.empty_like(masks)
+    ws = torch.empty((B * 2 * S * S,), dtype=_I32, device=masks.device)
+    L = _lib.load()
+    _lib.check(L.sb_fill_holes(masks.data_ptr(), out.data_ptr(), B, S, int(max_area), ws.data_ptr(), _stream()),
+               "sb_fill_holes")
+    _count()
+    return out
+
+
+def threshold_affine(x: torch.Tensor, thr: float, scale: float, bias: float) -> torch.Tensor:
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.is_contiguous()
+    out = torch.empty_like(x)
+    L = _lib.load()
+    _lib.check(L.sb_threshold_affine(x.data_ptr(), thr, scale, bias, x.numel(), out.data_ptr(), _stream()),
+               "sb_threshold_affine")
+    _count()
+    return out
+
+
+def conv4x4s4(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """SAM2Base.mask_downsample on [B, S, S] fp32 -> [B, S/4, S/4]."""
+    _chk_cuda(x, w, bias)
+    assert x.dtype == _F32 and x.is_contiguous() and x.dim() == 3
+    B, S, _ = x.shape
+    out = torch.empty((B, S // 4, S // 4), dtype=_F32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_conv4x4s4(x.data_ptr(), B, S, w.data_ptr(), bias.data_ptr(), out.data_ptr(), _stream()), "sb_conv4x4s4")
+    _count()
+    return out
+
+
+def stitch_objects_(logits: torch.Tensor, ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """labels (uint16-in-int16 [H, W], in place) <- ids[i] where object i's video-resolution logits are > 0."""
+    _chk_cuda(logits, ids, labels)
+    assert logits.dtype == _F32 and logits.is_contiguous() and logits.dim() == 3 and logits.shape[1] == logits.shape[2]
+    assert ids.dtype == _I32 and ids.numel() == logits.shape[0] and labels.is_contiguous() and labels.element_size() == 2
+    H, W = labels.shape
+    L = _lib.load()
+    _lib.check(L.sb_stitch_objects(logits.data_ptr(), ids.data_ptr(), logits.shape[0], logits.shape[1], H, W,
+                                   labels.data_ptr(), _stream()), "sb_stitch_objects")
+    _count()
+    return labels
+
+
+def slice_any(vol: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.element_size() == 2 and vol.dim() == 3
+    out = torch.empty((vol.shape[0],), dtype=_U8, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_slice_any(vol.data_ptr(), vol.shape[0], vol.shape[1] * vol.shape[2], out.data_ptr(), _stream()),
+               "sb_slice_any")
+    _count()
+    return out
+
+
+def erase_label_(labels: torch.Tensor, obj_id: int) -> None:
+    _chk_cuda(labels)
+    assert labels.is_contiguous() and labels.element_size() == 2
+    L = _lib.load()
+    _lib.check(L.sb_erase_label(labels.data_ptr(), labels.numel(), int(obj_id), _stream()), "sb_erase_label")
+    _count()

@@ -19,7 +19,7 @@ def main():
     only = [int(x) for x in sys.argv[1:]]
     torch.manual_seed(0)
     dev = "cuda"
-    print("SB_GEMM_DBG =", os.environ.get("SB_GEMM_DBG", "0"))
+    
     for idx, (M, N, K, act, res, of32, bn) in enumerate(SHAPES):
         if only and idx not in only:
             continue

@@ -6,13 +6,14 @@ WHAT=${@:-tests bench launches}
 mkdir -p gpurun_out
 for w in $WHAT; do
 case $w in
-tests) timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/${TAG}_tests.log;;
+tests) timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/${TAG}_tests.log;;
 smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/${TAG}_smoke.log;;
 bench) SB_GEMM_SHAPES=gpurun_out/${TAG}_gemm_shapes.txt timeout 1200 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err;;
 launches) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_launches.log 2>&1; echo "launches rc=$?"; wc -l gpurun_out/${TAG}_launches.csv;;
 full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 3000 -c 3 -o gpurun_out/${TAG}_gemm python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_full.log 2>&1; echo "full rc=$?";;
-gprobe) for d in 0 1 2 4 7; do SB_GEMM_DBG=$d timeout 300 python tools/gemm_probe.py >> gpurun_out/${TAG}_gemm_probe.log 2>&1; done; cat gpurun_out/${TAG}_gemm_probe.log;;
+gprobe) timeout 300 python tools/gemm_probe.py > gpurun_out/${TAG}_gemm_probe.log 2>&1; cat gpurun_out/${TAG}_gemm_probe.log;;
 gncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 2 -o gpurun_out/${TAG}_gemm1 python tools/gemm_probe.py 0 > gpurun_out/${TAG}_gncu.log 2>&1; echo "gncu rc=$?"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 2 -o gpurun_out/${TAG}_gemm2 python tools/gemm_probe.py 11 >> gpurun_out/${TAG}_gncu.log 2>&1;;
+dprobe) timeout 600 python tools/decoder_probe.py > gpurun_out/${TAG}_decoder_probe.log 2>&1; cat gpurun_out/${TAG}_decoder_probe.log; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_dec_launches.csv python tools/decoder_probe.py --once > gpurun_out/${TAG}_dprobe_ncu.log 2>&1; echo "dprobe ncu rc=$?";;
 diag) timeout 900 python tools/kernel_diag.py > gpurun_out/${TAG}_kernel_diag.log 2>&1; tail -40 gpurun_out/${TAG}_kernel_diag.log;;
 esac
 done
