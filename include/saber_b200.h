@@ -164,6 +164,21 @@ int sb_stitch_objects(const float* logits, const int* ids, int N, int Sv, int H,
 int sb_slice_any(const void* vol, int Z, long long n, unsigned char* any, void* stream);     /* REF :321 `.any()` */
 int sb_erase_label(void* labels, long long n, int id, void* stream);                          /* REF :345-346 */
 
+/* ---- whole-tomogram bandwidth kernels of the 3-D path (REF saber/adapters/preprocessing.py, saber/filters/gaussian.py) */
+int sb_minmax(const float* in, long long n, float* mm, float* partials, void* stream);  /* mm[0]=min, mm[1]=max (device) */
+/* out = ((in - mm[0]) / ((mm[1] - mm[0]) + eps)) * a + b: normalize_tomogram (REF adapters/preprocessing.py:72-76: eps 0,
+ * a 2, b -1) and preprocessing.normalize (REF utils/preprocessing.py:20-37: eps 1e-8, a 1, b 0) */
+int sb_minmax_affine(const float* in, long long n, const float* mm, float eps, float a, float b, float* out, void* stream);
+/* skimage.transform.resize(order=1, mode='reflect') of each z-slice = scipy zoom(grid_mode, mirror), then a*v+b
+ * (REF adapters/preprocessing.py:21,59) */
+int sb_zoom_linear_mirror(const float* in, int Z, int Hi, int Wi, int Ho, int Wo, float a, float b, float* out,
+                          void* stream);
+/* the anti-aliasing Gaussian skimage applies before down-sampling (scipy gaussian_filter, mode='mirror'); axis 1=y, 2=x */
+int sb_gauss1d_mirror(const float* in, int Z, int H, int W, int axis, const double* weights, int r, float* out,
+                      void* stream);
+int sb_gaussian_z(const float* in, int Z, long long plane, const float* w, int ks, float* out, void* stream); /* REF filters/gaussian.py:17-74 */
+int sb_mean_z(const float* in, long long plane, int z0, int z1, float* out, void* stream); /* REF utils/preprocessing.py:39-66 */
+
 #ifdef __cplusplus
 }
 #endif

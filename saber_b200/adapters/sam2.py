@@ -139,7 +139,8 @@ class SAM2Adapter(BaseAdapter):
         out_rgb = True if image.ndim == 2 else False
         if image.ndim != 2:
             raise NotImplementedError("saber_b200: segment_image_2d takes a grayscale (H,W) slice")
-        x = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.device)
+        x = (image.to(self.device, torch.float32) if isinstance(image, torch.Tensor) else
+             torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.device))
         x = prep.prepare(x, to_rgb=out_rgb)
         return self._amg().generate(x)
 
@@ -150,12 +151,176 @@ class SAM2Adapter(BaseAdapter):
         x = prep.prepare_device(image)
         return self._amg().generate_device(x)
 
-    # ------------------------------------------------------------------ 3-D (memory propagation) — next §8 row
-    def _no3d(self, *a, **k):
-        raise NotImplementedError("saber_b200: z-axis memory propagation is not built yet (SURVEY §8a U6-U9)")
+    # ------------------------------------------------------------------ 3-D (z-axis memory propagation)
+    def _video(self):
+        """Video predictor built on first use (REF saber/adapters/sam2/predictor.py:24-34 builds it in __init__; the
+        slice-wise path never needs it). maskmem_tpos_enc is truncated and num_maskmem set exactly as the reference."""
+        if self.predictor is None:
+            from ..sam2.sam2_video_predictor import build_sam2_video_predictor
+            p = build_sam2_video_predictor(_CFG_TO_ARCH[self._config.cfg], self._config.checkpoint, device=self.device,
+                                           vos_optimized=False, seed=self._config.seed)
+            maskmem = p.maskmem_tpos_enc[:self._config.num_maskmem]
+            p.maskmem_tpos_enc = torch.nn.Parameter(maskmem, requires_grad=False)
+            p.num_maskmem = self._config.num_maskmem
+            self.predictor = p
+        return self.predictor
 
-    set_volume = add_new_mask = add_new_points_or_box = propagate_in_video = segment_volume = _no3d
+    @torch.inference_mode()
+    def set_volume(self, tomogram, offload_video_to_cpu: bool = False) -> None:
+        """REF :76-84. `tomogram`: numpy (Z,Y,X) or a CUDA tensor (stays on the device)."""
+        self._vol_shape = tuple(tomogram.shape)
+        self.frame_metrics = {}
+        self.inference_state = self.create_inference_state_from_tomogram(tomogram)
+
+    @torch.inference_mode()
+    def create_inference_state_from_tomogram(self, tomogram, offload_video_to_cpu: bool = False,
+                                             offload_state_to_cpu: bool = False) -> Dict[str, Any]:
+        """REF :90-116 with TomogramPreprocessor (REF saber/adapters/preprocessing.py:16-76) on the device:
+        global min-max to [-1,1], per-slice skimage-style resize to 1024^2, `2x - 1`. The three RGB channels are
+        identical, so `images` is a stride-0 view [Z,3,S,S] of one [Z,S,S] plane stack (3x less HBM than the
+        reference's materialised tensor). Every frame is encoded here, once, in batches (Phase A)."""
+        from .. import ops
+        p = self._video()
+        vol = (tomogram if isinstance(tomogram, torch.Tensor) else
+               torch.from_numpy(np.ascontiguousarray(tomogram, dtype=np.float32)))
+        vol = vol.to(self.device, dtype=torch.float32).contiguous()
+        mm = ops.minmax(vol)
+        vol = ops.minmax_affine(vol, mm, 0.0, 2.0, -1.0)  # normalize_tomogram
+        S = p.image_size
+        planes = ops.skimage_resize_stack(vol, S, 2.0, -1.0)  # load_grayscale_image_array: resize, then 2*x - 1
+        del vol
+        images = planes[:, None].expand(-1, 3, -1, -1)
+        state = self._create_empty_inference_state(images, S, S, offload_video_to_cpu, offload_state_to_cpu)
+        p.encode_frames(state)
+        return state
+
+    def _create_empty_inference_state(self, images, video_height, video_width, offload_video_to_cpu=False,
+                                      offload_state_to_cpu=False) -> Dict[str, Any]:
+        """REF :118-154 (same keys)."""
+        from collections import OrderedDict
+        dev = self.device
+        st = {"images": images, "num_frames": len(images), "offload_video_to_cpu": offload_video_to_cpu,
+              "offload_state_to_cpu": offload_state_to_cpu, "video_height": video_height, "video_width": video_width,
+              "device": dev, "storage_device": dev, "point_inputs_per_obj": {}, "mask_inputs_per_obj": {},
+              "cached_features": {}, "constants": {}, "obj_id_to_idx": OrderedDict(), "obj_idx_to_id": OrderedDict(),
+              "obj_ids": [], "output_dict_per_obj": {}, "temp_output_dict_per_obj": {}, "frames_tracked_per_obj": {}}
+        self._video()._get_image_feature(st, frame_idx=0, batch_size=1)
+        return st
+
+    def add_new_mask(self, frame_idx: int, obj_id: int, mask, inference_state=None):
+        state = inference_state or self.inference_state
+        return self._video().add_new_mask(inference_state=state, frame_idx=frame_idx, obj_id=obj_id, mask=mask)
+
+    def add_new_points_or_box(self, frame_idx: int, obj_id: int, inference_state=None, **kwargs):
+        state = inference_state or self.inference_state
+        return self._video().add_new_points_or_box(inference_state=state, frame_idx=frame_idx, obj_id=obj_id, **kwargs)
+
+    @torch.inference_mode()
+    def propagate_in_video(self, start_frame_idx, max_frame_num_to_track=None, reverse=False, inference_state=None):
+        """REF :186-206: yields (frame_idx, obj_ids, low_res_masks, video_res_masks, obj_scores=None)."""
+        state = inference_state or self.inference_state
+        for frame_idx, obj_ids, logits in self._video().propagate_in_video(
+                state, start_frame_idx=start_frame_idx, max_frame_num_to_track=max_frame_num_to_track, reverse=reverse):
+            yield frame_idx, obj_ids, logits, logits, None
+
+    @staticmethod
+    def _normalize_masks(masks) -> List[Any]:
+        """REF :208-230; CUDA tensors are kept on the device (the seed masks of the resident path)."""
+        if masks is None:
+            return []
+        if isinstance(masks, torch.Tensor):
+            return [masks[i].squeeze() for i in range(masks.shape[0])]
+        if isinstance(masks, np.ndarray) and masks.ndim >= 3:
+            return [np.squeeze(masks[i]).astype(np.float32) for i in range(masks.shape[0])]
+        out = []
+        for m in masks:
+            if isinstance(m, dict):
+                m = m["segmentation"]
+            out.append(m.squeeze() if isinstance(m, torch.Tensor) else np.squeeze(np.asarray(m)).astype(np.float32))
+        return out
+
+    @torch.inference_mode()
+    def segment_volume_device(self, start_frame_idx: int, masks=None, vol_shape=None, max_frame_num_to_track=None,
+                              min_presence_score: float = 0.5, inference_state=None) -> torch.Tensor:
+        """REF :232-348 with the label volume kept on the device: returns CUDA int16 (uint16 payload) [Z,H,W]."""
+        from .. import ops
+        from ..filters import estimate_thickness
+        state = inference_state or self.inference_state
+        if state is None:
+            raise RuntimeError("Call set_volume() before segment_volume().")
+        if vol_shape is None:
+            vol_shape = self._vol_shape
+        if vol_shape is None:
+            raise RuntimeError("vol_shape required when inference_state is passed explicitly.")
+        Z, H, W = vol_shape
+        p = self._video()
+        mask_list = self._normalize_masks(masks)
+        for obj_id, mask in enumerate(mask_list, start=1):
+            if float(mask.max()) == 0:
+                continue
+            self.add_new_mask(frame_idx=start_frame_idx, obj_id=obj_id, mask=mask, inference_state=state)
+        self._current_frame = None
+        captured: Dict[Any, list] = {}
+
+        def _hook(module, inputs, output):
+            logits = output[3].detach().cpu().to(torch.float32).numpy()
+            captured.setdefault(self._current_frame, []).append(logits)
+
+        handle = p.sam_mask_decoder.register_forward_hook(_hook)
+        self.frame_metrics = {}
+        vol_masks = torch.zeros((Z, H, W), dtype=torch.int16, device=self.device)
+
+        def _apply(frame_idx, obj_ids, mask_logits):
+            ids = torch.tensor([int(o) for o in obj_ids], dtype=torch.int32, device=self.device)
+            ops.stitch_objects_(mask_logits[:, 0].contiguous(), ids, vol_masks[frame_idx])
+
+        for frame_idx, obj_ids, mask_logits, _, _ in self.propagate_in_video(
+                start_frame_idx=start_frame_idx, max_frame_num_to_track=max_frame_num_to_track, reverse=False,
+                inference_state=state):
+            self._current_frame = frame_idx
+            _apply(frame_idx, obj_ids, mask_logits)
+        nonempty = ops.slice_any(vol_masks).cpu().numpy()  # one D2H of Z bytes: which slices the forward pass filled
+        for frame_idx, obj_ids, mask_logits, _, _ in self.propagate_in_video(
+                start_frame_idx=start_frame_idx, max_frame_num_to_track=max_frame_num_to_track, reverse=True,
+                inference_state=state):
+            self._current_frame = frame_idx
+            if not nonempty[frame_idx]:
+                _apply(frame_idx, obj_ids, mask_logits)
+        handle.remove()
+        nMasks = len(mask_list)
+        self.frame_scores = np.zeros([Z, nMasks])
+        if nMasks > 0:
+            for fidx, scores in captured.items():
+                if fidx is None:
+                    continue
+                vals = np.concatenate([s.flatten() for s in scores])
+                n = min(len(vals), nMasks)
+                self.frame_scores[fidx, :n] = vals[:n]
+            bounds = estimate_thickness.fit_organelle_boundaries(self.frame_scores, plot=False)
+            for fidx in range(Z):
+                self.frame_metrics[fidx] = {}
+                for mi in range(nMasks):
+                    ps = float(bounds[fidx, mi])
+                    self.frame_metrics[fidx][mi + 1] = {"presence_score": ps}
+                    if ps < min_presence_score:
+                        ops.erase_label_(vol_masks[fidx], mi + 1)
+        return vol_masks
+
+    @torch.inference_mode()
+    def segment_volume(self, start_frame_idx: int, masks=None, vol_shape=None, max_frame_num_to_track=None,
+                       min_presence_score: float = 0.5, inference_state=None) -> np.ndarray:
+        """REF :232-348: bidirectional propagation with hook-captured presence scores -> (Z,H,W) uint16."""
+        v = self.segment_volume_device(start_frame_idx, masks, vol_shape, max_frame_num_to_track, min_presence_score,
+                                       inference_state)
+        return v.cpu().numpy().view(np.uint16)
 
     def reset_state(self, inference_state=None) -> None:
-        self.inference_state = None
-        self.frame_metrics = {}
+        state = inference_state or self.inference_state
+        if state is not None and self.predictor is not None:
+            self.predictor.reset_state(state)
+
+    def clear_all_prompts_in_frame(self, *args, **kwargs):
+        return self._video().clear_all_prompts_in_frame(*args, **kwargs)
+
+    def remove_object(self, *args, **kwargs):
+        return self._video().remove_object(*args, **kwargs)

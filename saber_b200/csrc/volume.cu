@@ -1,0 +1,226 @@
+// saber_b200 — whole-tomogram bandwidth kernels on the 3-D propagation path:
+//   * global min / max and the affine min-max normalisations of REF saber/adapters/preprocessing.py:72-76
+//     (normalize_tomogram) and REF saber/utils/preprocessing.py:20-37 (normalize), device-side scalars (no host sync);
+//   * skimage.transform.resize(order=1, mode='reflect', anti_aliasing=True) of every z-slice to the model input size
+//     (REF saber/adapters/preprocessing.py:16-28), i.e. scipy.ndimage.zoom(grid_mode=True, mode='mirror') preceded by a
+//     mirror-mode Gaussian when down-sampling, fused with the `2x - 1` of :59;
+//   * the 15-tap z-axis Gaussian of REF saber/filters/gaussian.py:17-74 (zero padding);
+//   * the z-slab mean of REF saber/utils/preprocessing.py:39-66 (project_tomogram).
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+__global__ void __launch_bounds__(256)
+minmax_partial_kernel(const float* __restrict__ in, long long n, float* __restrict__ partials) {
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  const long long n4 = n / 4;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = in4[i];
+    mn = fminf(fminf(mn, v.x), fminf(fminf(v.y, v.z), v.w));
+    mx = fmaxf(fmaxf(mx, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      mn = fminf(mn, in[i]);
+      mx = fmaxf(mx, in[i]);
+    }
+  __shared__ float smn[8], smx[8];
+  mn = -sb::warp_max(-mn);
+  mx = sb::warp_max(mx);
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      mn = fminf(mn, smn[w]);
+      mx = fmaxf(mx, smx[w]);
+    }
+    partials[2 * blockIdx.x] = mn;
+    partials[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+__global__ void minmax_final_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out) {
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    mn = fminf(mn, partials[2 * i]);
+    mx = fmaxf(mx, partials[2 * i + 1]);
+  }
+  mn = -sb::warp_max(-mn);
+  mx = sb::warp_max(mx);
+  if (threadIdx.x == 0) {
+    out[0] = mn;
+    out[1] = mx;
+  }
+}
+
+// y = ((x - mn) / ((mx - mn) + eps)) * a + b, every step rounded to fp32 as numpy evaluates it (no FMA contraction)
+__global__ void __launch_bounds__(256)
+minmax_affine_kernel(const float* __restrict__ in, long long n, const float* __restrict__ mm, float eps, float a,
+                     float b, float* __restrict__ out) {
+  const float mn = mm[0];
+  const float den = __fadd_rn(__fsub_rn(mm[1], mn), eps);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float t = __fdiv_rn(__fsub_rn(in[i], mn), den);
+    out[i] = __fadd_rn(__fmul_rn(t, a), b);
+  }
+}
+
+__device__ __forceinline__ int mirror_idx(int i, int n) {
+  // scipy 'mirror' (whole-sample symmetric): d c b | a b c d | c b a
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  int j = i % period;
+  if (j < 0) j += period;
+  return j < n ? j : period - j;
+}
+
+// scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True) of each [Hi, Wi] slice to [Ho, Wo]; coordinates and the
+// linear blend are evaluated in double (scipy's spline path), the result is rounded to fp32, then out = a * v + b.
+__global__ void __launch_bounds__(256)
+zoom_linear_mirror_kernel(const float* __restrict__ in, int Z, int Hi, int Wi, int Ho, int Wo, float a, float b,
+                          float* __restrict__ out) {
+  const double zy = static_cast<double>(Hi) / static_cast<double>(Ho);
+  const double zx = static_cast<double>(Wi) / static_cast<double>(Wo);
+  const long long total = static_cast<long long>(Z) * Ho * Wo;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(t % Wo), oy = static_cast<int>((t / Wo) % Ho);
+    const long long z = t / (static_cast<long long>(Wo) * Ho);
+    const double cy = (static_cast<double>(oy) + 0.5) * zy - 0.5;
+    const double cx = (static_cast<double>(ox) + 0.5) * zx - 0.5;
+    const double fy = floor(cy), fx = floor(cx);
+    const double wy1 = cy - fy, wx1 = cx - fx;
+    const int y0 = mirror_idx(static_cast<int>(fy), Hi), y1 = mirror_idx(static_cast<int>(fy) + 1, Hi);
+    const int x0 = mirror_idx(static_cast<int>(fx), Wi), x1 = mirror_idx(static_cast<int>(fx) + 1, Wi);
+    const float* p = in + z * Hi * Wi;
+    const double v00 = p[y0 * Wi + x0], v01 = p[y0 * Wi + x1], v10 = p[y1 * Wi + x0], v11 = p[y1 * Wi + x1];
+    const double v = (1.0 - wy1) * ((1.0 - wx1) * v00 + wx1 * v01) + wy1 * ((1.0 - wx1) * v10 + wx1 * v11);
+    out[t] = __fadd_rn(__fmul_rn(static_cast<float>(v), a), b);
+  }
+}
+
+// scipy.ndimage.correlate1d(mode='mirror') with a Gaussian kernel (weights [2r+1], double) along axis 1 (rows, y) or
+// 2 (columns, x) of a [Z, H, W] fp32 stack; double accumulation, fp32 storage between passes as scipy does.
+__global__ void __launch_bounds__(256)
+gauss1d_mirror_kernel(const float* __restrict__ in, int Z, int H, int W, int axis, const double* __restrict__ wts,
+                      int r, float* __restrict__ out) {
+  const long long total = static_cast<long long>(Z) * H * W;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(t % W), y = static_cast<int>((t / W) % H);
+    const long long z = t / (static_cast<long long>(W) * H);
+    const float* p = in + z * H * W;
+    double acc = 0.0;
+    for (int k = -r; k <= r; ++k) {
+      const float v = axis == 1 ? p[mirror_idx(y + k, H) * W + x] : p[y * W + mirror_idx(x + k, W)];
+      acc += wts[k + r] * static_cast<double>(v);
+    }
+    out[t] = static_cast<float>(acc);
+  }
+}
+
+// out[z, i] = sum_k w[k] * in[z + k - r, i] with zero padding (F.conv1d(padding = ks/2) along z)
+__global__ void __launch_bounds__(256)
+gaussian_z_kernel(const float* __restrict__ in, int Z, long long plane, const float* __restrict__ w, int ks,
+                  float* __restrict__ out) {
+  const int r = ks / 2;
+  const long long total = static_cast<long long>(Z) * plane;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = t % plane;
+    const int z = static_cast<int>(t / plane);
+    float acc = 0.f;
+    for (int k = 0; k < ks; ++k) {
+      const int zz = z + k - r;
+      if (zz >= 0 && zz < Z) acc = fmaf(w[k], in[static_cast<long long>(zz) * plane + i], acc);
+    }
+    out[t] = acc;
+  }
+}
+
+// out[i] = mean_{z0 <= z < z1} in[z, i]
+__global__ void __launch_bounds__(256)
+mean_z_kernel(const float* __restrict__ in, long long plane, int z0, int z1, float* __restrict__ out) {
+  const float inv = 1.f / static_cast<float>(z1 - z0);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < plane;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int z = z0; z < z1; ++z) acc += in[static_cast<long long>(z) * plane + i];
+    out[i] = acc * inv;
+  }
+}
+
+}  // namespace
+
+// mm[0] = min, mm[1] = max of n floats; partials: 2 * 1024 float workspace. No host synchronisation.
+extern "C" int sb_minmax(const float* in, long long n, float* mm, float* partials, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0 && in && mm && partials, "sb_minmax: bad arguments");
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "sb_minmax: input must be 16-byte aligned");
+  const int nb = grid_for(n / 4 + 1, 256, 1024);
+  minmax_partial_kernel<<<nb, 256, 0, stream>>>(in, n, partials);
+  SB_CHECK_LAUNCH();
+  minmax_final_kernel<<<1, 32, 0, stream>>>(partials, nb, mm);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// out = ((in - mm[0]) / ((mm[1] - mm[0]) + eps)) * a + b   (mm on the device)
+extern "C" int sb_minmax_affine(const float* in, long long n, const float* mm, float eps, float a, float b, float* out,
+                                void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0 && in && mm && out, "sb_minmax_affine: bad arguments");
+  minmax_affine_kernel<<<grid_for(n), 256, 0, stream>>>(in, n, mm, eps, a, b, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_zoom_linear_mirror(const float* in, int Z, int Hi, int Wi, int Ho, int Wo, float a, float b, float* out,
+                                     void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "sb_zoom_linear_mirror: bad arguments");
+  zoom_linear_mirror_kernel<<<grid_for(static_cast<long long>(Z) * Ho * Wo), 256, 0, stream>>>(in, Z, Hi, Wi, Ho, Wo, a,
+                                                                                                b, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// axis: 1 = along y, 2 = along x. weights: device double [2r+1].
+extern "C" int sb_gauss1d_mirror(const float* in, int Z, int H, int W, int axis, const double* weights, int r, float* out,
+                                 void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && H > 0 && W > 0 && (axis == 1 || axis == 2) && r >= 0 && weights, "sb_gauss1d_mirror: bad arguments");
+  gauss1d_mirror_kernel<<<grid_for(static_cast<long long>(Z) * H * W), 256, 0, stream>>>(in, Z, H, W, axis, weights, r, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_gaussian_z(const float* in, int Z, long long plane, const float* w, int ks, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && plane > 0 && ks > 0 && (ks & 1) && w, "sb_gaussian_z: bad arguments");
+  gaussian_z_kernel<<<grid_for(static_cast<long long>(Z) * plane), 256, 0, stream>>>(in, Z, plane, w, ks, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_mean_z(const float* in, long long plane, int z0, int z1, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(plane > 0 && z1 > z0 && z0 >= 0, "sb_mean_z: bad arguments");
+  mean_z_kernel<<<grid_for(plane), 256, 0, stream>>>(in, plane, z0, z1, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

@@ -79,6 +79,12 @@ SIGNATURES = {
     "sb_stitch_objects": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_slice_any": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
     "sb_erase_label": [c_void_p, c_ll, c_int, c_void_p],
+    "sb_minmax": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
+    "sb_minmax_affine": [c_void_p, c_ll, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p],
+    "sb_zoom_linear_mirror": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p],
+    "sb_gauss1d_mirror": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "sb_gaussian_z": [c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p, c_void_p],
+    "sb_mean_z": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
 }
 
 

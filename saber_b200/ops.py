@@ -791,3 +791,78 @@ def erase_label_(labels: torch.Tensor, obj_id: int) -> None:
     L = _lib.load()
     _lib.check(L.sb_erase_label(labels.data_ptr(), labels.numel(), int(obj_id), _stream()), "sb_erase_label")
     _count()
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-tomogram bandwidth kernels of the 3-D path (csrc/volume.cu)
+# ---------------------------------------------------------------------------------------------
+def minmax(x: torch.Tensor) -> torch.Tensor:
+    """-> device fp32 [2] = (min, max) of x (no host synchronisation)."""
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.is_contiguous()
+    mm = torch.empty((2,), dtype=_F32, device=x.device)
+    partials = torch.empty((2048,), dtype=_F32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_minmax(x.data_ptr(), x.numel(), mm.data_ptr(), partials.data_ptr(), _stream()), "sb_minmax")
+    _count(2)
+    return mm
+
+
+def minmax_affine(x: torch.Tensor, mm: torch.Tensor, eps: float, a: float, b: float) -> torch.Tensor:
+    """((x - mm[0]) / ((mm[1] - mm[0]) + eps)) * a + b with mm on the device."""
+    _chk_cuda(x, mm)
+    assert x.dtype == _F32 and x.is_contiguous() and mm.dtype == _F32 and mm.numel() == 2
+    out = torch.empty_like(x)
+    L = _lib.load()
+    _lib.check(L.sb_minmax_affine(x.data_ptr(), x.numel(), mm.data_ptr(), eps, a, b, out.data_ptr(), _stream()),
+               "sb_minmax_affine")
+    _count()
+    return out
+
+
+def skimage_resize_stack(vol: torch.Tensor, S: int, a: float = 1.0, b: float = 0.0) -> torch.Tensor:
+    """skimage.transform.resize(slice, (S, S), anti_aliasing=True) for every slice of vol [Z,H,W] fp32, then a*v + b."""
+    _chk_cuda(vol)
+    assert vol.dtype == _F32 and vol.is_contiguous() and vol.dim() == 3
+    Z, H, W = vol.shape
+    L = _lib.load()
+    src = vol
+    for axis, n in ((1, H), (2, W)):  # scipy.ndimage.gaussian_filter filters axis 0 of the slice first, then axis 1
+        sigma = max(0.0, (n / S - 1) / 2)
+        if sigma > 0:
+            r = int(4.0 * sigma + 0.5)
+            xs = torch.arange(-r, r + 1, dtype=torch.float64)
+            w = torch.exp(-0.5 / (sigma * sigma) * xs ** 2)
+            w = (w / w.sum()).to(vol.device)
+            dst = torch.empty_like(src)
+            _lib.check(L.sb_gauss1d_mirror(src.data_ptr(), Z, H, W, axis, w.data_ptr(), r, dst.data_ptr(), _stream()),
+                       "sb_gauss1d_mirror")
+            _count()
+            src = dst
+    out = torch.empty((Z, S, S), dtype=_F32, device=vol.device)
+    _lib.check(L.sb_zoom_linear_mirror(src.data_ptr(), Z, H, W, S, S, a, b, out.data_ptr(), _stream()),
+               "sb_zoom_linear_mirror")
+    _count()
+    return out
+
+
+def gaussian_z(vol: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """Zero-padded 1-D correlation along z of vol [Z,Y,X] fp32 with `weights` (odd length, fp32, device)."""
+    _chk_cuda(vol, weights)
+    assert vol.dtype == _F32 and vol.is_contiguous() and vol.dim() == 3 and weights.dtype == _F32
+    out = torch.empty_like(vol)
+    L = _lib.load()
+    _lib.check(L.sb_gaussian_z(vol.data_ptr(), vol.shape[0], vol.shape[1] * vol.shape[2], weights.data_ptr(),
+                               weights.numel(), out.data_ptr(), _stream()), "sb_gaussian_z")
+    _count()
+    return out
+
+
+def mean_z(vol: torch.Tensor, z0: int, z1: int) -> torch.Tensor:
+    _chk_cuda(vol)
+    assert vol.dtype == _F32 and vol.is_contiguous() and vol.dim() == 3 and 0 <= z0 < z1 <= vol.shape[0]
+    out = torch.empty(vol.shape[1:], dtype=_F32, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_mean_z(vol.data_ptr(), vol.shape[1] * vol.shape[2], z0, z1, out.data_ptr(), _stream()), "sb_mean_z")
+    _count()
+    return out

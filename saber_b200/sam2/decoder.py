@@ -132,7 +132,9 @@ class MaskDecoder:
     def forward(self, image_embed: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, tokens: torch.Tensor,
                 mask_input: Optional[torch.Tensor] = None, multimask_output: bool = True,
                 mask_clamp: float = 0.0):
-        """image_embed [4096,256] fp32, s0 [65536,32] fp32, s1 [16384,64] fp32 (one image, token-major);
+        """image_embed [4096,256] fp32 (one image shared by the B prompts) or [B*4096,256] fp32 (one conditioned
+        embedding per prompt: the video predictor's memory-attention output), s0 [65536,32] fp32, s1 [16384,64] fp32
+        (one image, token-major);
         tokens [B, Nt, 256] fp32; mask_input [B, 256, 256] fp32, or a previous decoder output
         [B/3, 4, 256, 256] whose multimask tokens 1..3 are the B mask prompts (AMG m2m), or None;
         mask_clamp > 0 clamps the mask prompt to +-mask_clamp (upstream clamps low-res logits to +-32).
@@ -144,11 +146,14 @@ class MaskDecoder:
         B, Nt, _ = tokens.shape
         query_pe = tokens.reshape(B * Nt, 256)
         queries = query_pe
-        shared = mask_input is None
-        if shared:
-            keys_f32 = ops.add_cast(image_embed, self.no_mask_embed, _F32)  # [4096,256]
+        per_prompt = image_embed.shape[0] != NT_IMG
+        assert image_embed.shape[0] == (B * NT_IMG if per_prompt else NT_IMG)
+        shared = mask_input is None and not per_prompt
+        if mask_input is None:
+            keys_f32 = ops.add_cast(image_embed, self.no_mask_embed, _F32)  # [4096,256] or [B*4096,256]
             keys = ops.add_cast(keys_f32, None, _BF16)
         else:
+            assert not per_prompt, "mask prompts with per-prompt image embeddings are not on the path"
             ds = ops.mask_downscale(mask_input.contiguous(), self.md_w, mask_clamp)  # [B*4096,16]
             assert ds.shape[0] == B * NT_IMG, (ds.shape, B)
             # per-prompt image stream (image_embed + dense mask embedding) kept in bf16: it is re-normalised by

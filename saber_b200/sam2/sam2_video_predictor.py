@@ -1,0 +1,427 @@
+"""Drop-in for ``sam2.sam2_video_predictor.SAM2VideoPredictor`` (as returned by ``build_sam2_video_predictor``) on the
+B200 kernels — the surface REF saber/adapters/sam2/predictor.py binds:
+
+  ``maskmem_tpos_enc`` (re-assigned, REF :31-32), ``num_maskmem`` (REF :33-34), ``image_size`` (:101), ``device``,
+  ``sam_mask_decoder.register_forward_hook`` (hook reads ``output[3]``, REF :278,284),
+  ``_get_image_feature(state, frame_idx=, batch_size=)`` (:114,152), ``add_new_mask`` (:164-169),
+  ``propagate_in_video`` -> ``(frame_idx, obj_ids, logits [N,1,Hv,Wv])`` (:196-202), ``reset_state``.
+  The inference-state dict is the one SABER builds itself (REF :130-150).
+
+B200 design (SURVEY §7 "device-resident batched state machine"): all objects tracked in a frame run as ONE batch
+through memory attention -> mask decoder -> memory encoder (upstream loops objects with batch 1); the per-object
+memory bank (bf16 ``[4096,64]`` features, fp32 object pointers, low-res scores) never leaves the device; every frame is
+encoded once and its features stay cached (upstream keeps one frame and re-encodes the volume for every pass). The
+forward hook still fires once per object per frame with ``output[3]`` shaped ``[1,1]``.
+Restates sam2/sam2_video_predictor.py + sam2/modeling/sam2_base.py.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from . import arch
+from .build_sam import SAM2Model, _load_state_dict
+from .memory import MemoryAttention, MemoryEncoder, sine_pe_1d
+
+_BF16, _F32, _I32 = torch.bfloat16, torch.float32, torch.int32
+NT = 4096
+NO_OBJ_SCORE = -1024.0
+
+
+class _HookHandle:
+    def __init__(self, hooks: list, fn):
+        self._hooks, self._fn = hooks, fn
+
+    def remove(self):
+        if self._fn in self._hooks:
+            self._hooks.remove(self._fn)
+
+
+class _DecoderModule:
+    """``predictor.sam_mask_decoder``: the B200 mask-decoder executor behind torch's forward-hook interface."""
+
+    def __init__(self, exec_):
+        self.exec = exec_
+        self._hooks: List[Callable] = []
+
+    def register_forward_hook(self, fn):
+        self._hooks.append(fn)
+        return _HookHandle(self._hooks, fn)
+
+    def fire(self, masks, ious, tokens, obj_scores):
+        """One hook call per batch entry with upstream's output tuple (masks, iou_pred, sam_tokens_out,
+        object_score_logits); the scores are brought to the host once for the whole batch."""
+        if not self._hooks:
+            return
+        host = obj_scores.detach().reshape(-1, 1).cpu()
+        for i in range(host.shape[0]):
+            out = (masks[i:i + 1], ious[i:i + 1], tokens[i:i + 1], host[i:i + 1])
+            for fn in list(self._hooks):
+                fn(self, (), out)
+
+
+class SAM2VideoPredictor(SAM2Model):
+    def __init__(self, cfg, state_dict, device="cuda", dynamic_multimask_via_stability=True, num_maskmem=7,
+                 fill_hole_area=8, binarize_mask_from_pts_for_mem_enc=True):
+        self.fill_hole_area = fill_hole_area
+        self.binarize_mask_from_pts_for_mem_enc = binarize_mask_from_pts_for_mem_enc
+        self.max_obj_ptrs_in_encoder = 16
+        self.mem_attn: Optional[MemoryAttention] = None
+        self.mem_enc: Optional[MemoryEncoder] = None
+        self.sam_mask_decoder: Optional[_DecoderModule] = None
+        self._const_cache: Dict[Any, Any] = {}
+        self.max_encode_batch = 8
+        super().__init__(cfg, state_dict, device=device, dynamic_multimask_via_stability=dynamic_multimask_via_stability,
+                         num_maskmem=num_maskmem)
+
+    # ---- attributes SABER re-assigns: `maskmem_tpos_enc` is a registered nn.Parameter (REF saber/adapters/sam2/
+    # predictor.py:31-32 slices it and assigns a new torch.nn.Parameter) and `num_maskmem` a plain attribute (:33-34);
+    # every constant derived from them is cached under a key that includes both.
+    def _tpos(self) -> torch.Tensor:
+        return self._parameters["maskmem_tpos_enc"].detach().cpu().float()
+
+    def _tpos_key(self):
+        p = self._parameters["maskmem_tpos_enc"]
+        return (p.data_ptr(), tuple(p.shape), int(self.num_maskmem))
+
+    def _build_executors(self, dev):
+        super()._build_executors(dev)
+        sd = {k: v.cpu() for k, v in self.upstream_state_dict().items()}
+        with torch.cuda.device(dev):
+            self.mem_attn = MemoryAttention(sd, dev)
+            self.mem_enc = MemoryEncoder(sd, dev)
+            self.sam_mask_decoder = _DecoderModule(self.decoder)
+            self.k_no_obj_ptr = sd["no_obj_ptr"].reshape(-1).to(dev, _F32).contiguous()
+            self.objptr_mlp = [(sd[f"obj_ptr_proj.layers.{k}.weight"].to(dev, _BF16).contiguous(),
+                                sd[f"obj_ptr_proj.layers.{k}.bias"].to(dev, _F32).contiguous()) for k in range(3)]
+            self.mask_ds_w = sd["mask_downsample.weight"].reshape(16).to(dev, _F32).contiguous()
+            self.mask_ds_b = sd["mask_downsample.bias"].reshape(1).to(dev, _F32).contiguous()
+            self._tpos_proj = (sd["obj_ptr_tpos_proj.weight"].float(), sd["obj_ptr_tpos_proj.bias"].float())
+        self._const_cache.clear()
+
+    # ---- constants that depend on (re-assignable) maskmem_tpos_enc / num_maskmem ------------------
+    def _spatial_key_pos(self, t_pos: int) -> List[torch.Tensor]:
+        """Per layer [4096,256]: k_proj(maskmem_pos_enc + maskmem_tpos_enc[num_maskmem - t_pos - 1]) positional term."""
+        key = ("spatial", t_pos, self._tpos_key())
+        if key not in self._const_cache:
+            tpos = self._tpos()[self.num_maskmem - t_pos - 1].reshape(1, -1)  # [1,64]
+            self._const_cache[key] = self.mem_attn.key_pos_term(self.mem_enc.pos + tpos)
+        return self._const_cache[key]
+
+    def _ptr_key_pos(self, t_diffs: Tuple[int, ...], num_frames: int) -> List[torch.Tensor]:
+        """Per layer [4*len(t_diffs), 256]: positional term of the object-pointer tokens (signed temporal distance)."""
+        key = ("ptr", t_diffs, num_frames)
+        if key not in self._const_cache:
+            t_diff_max = min(num_frames, self.max_obj_ptrs_in_encoder) - 1
+            pos = torch.tensor(t_diffs, dtype=torch.float32)
+            pe = sine_pe_1d(pos / t_diff_max, arch.HIDDEN)
+            w, b = self._tpos_proj
+            pe = pe @ w.t() + b  # [n,64]
+            pe = pe.repeat_interleave(arch.HIDDEN // arch.MEM_DIM, dim=0)
+            self._const_cache[key] = self.mem_attn.key_pos_term(pe)
+        return self._const_cache[key]
+
+    # ---- frame features ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_frames(self, inference_state, frame_ids=None) -> None:
+        """Phase A: encode frames in batches and keep their features resident (bf16 is not needed: a
+        300-slice tomogram is 5 GB of fp32 features in 180 GB of HBM)."""
+        self._require_gpu()
+        st = inference_state
+        ids = [f for f in (range(st["num_frames"]) if frame_ids is None else frame_ids) if f not in st["cached_features"]]
+        for k0 in range(0, len(ids), self.max_encode_batch):
+            chunk = ids[k0:k0 + self.max_encode_batch]
+            x = torch.stack([st["images"][f] for f in chunk]).to(self.device, _F32).contiguous()
+            out = self.encoder.forward(x)
+            for j, f in enumerate(chunk):
+                st["cached_features"][f] = {
+                    "feat": out["feat"][j * NT:(j + 1) * NT], "s1": out["s1"][j * 16384:(j + 1) * 16384],
+                    "s0": out["s0"][j * 65536:(j + 1) * 65536]}
+
+    def _frame(self, st, frame_idx) -> Dict[str, torch.Tensor]:
+        c = st["cached_features"].get(frame_idx)
+        if c is None or "feat" not in c:
+            self.encode_frames(st, [frame_idx])
+            c = st["cached_features"][frame_idx]
+        if "pix_proj" not in c:
+            c["pix_proj"] = self.mem_enc.project_pix(c["feat"])
+        return c
+
+    @torch.no_grad()
+    def _get_image_feature(self, inference_state, frame_idx=0, batch_size=1):
+        """Upstream returns (image, backbone_out, vision_feats, vision_pos, feat_sizes); SABER discards the result
+        (REF :114,152) — this warms the feature cache and returns the token-major features of the frame."""
+        c = self._frame(inference_state, frame_idx)
+        return c
+
+    # ---- object bookkeeping (upstream dict layout) ---------------------------------------------------------
+    def _obj_id_to_idx(self, st, obj_id):
+        idx = st["obj_id_to_idx"].get(obj_id, None)
+        if idx is not None:
+            return idx
+        idx = len(st["obj_id_to_idx"])
+        st["obj_id_to_idx"][obj_id] = idx
+        st["obj_idx_to_id"][idx] = obj_id
+        st["obj_ids"] = list(st["obj_id_to_idx"])
+        st["point_inputs_per_obj"][idx] = {}
+        st["mask_inputs_per_obj"][idx] = {}
+        st["output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        st["temp_output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        st["frames_tracked_per_obj"][idx] = {}
+        return idx
+
+    def _get_obj_num(self, st):
+        return len(st["obj_idx_to_id"])
+
+    # ---- prompting -------------------------------------------------------------------------------------------
+    def _mask_to_model_res(self, mask) -> torch.Tensor:
+        """bool/float (H,W) mask -> [1024,1024] fp32 {0,1} on the device (bilinear-antialias resize + >= 0.5)."""
+        if isinstance(mask, torch.Tensor):
+            m = mask.to(self.device)
+        else:
+            m = torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)
+        m = (m != 0).to(_F32).contiguous()  # torch.tensor(mask, dtype=torch.bool).float()
+        assert m.dim() == 2
+        H, W = m.shape
+        S = self.image_size
+        if (H, W) != (S, S):
+            crops = torch.tensor([[0, 0, W, H]], dtype=_I32, device=self.device)
+            r = ops.resize_normalize(m, crops, S, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0))[0, 0].contiguous()
+            m = ops.threshold_affine(r, 0.5, 1.0, 0.0)
+        return m
+
+    @torch.no_grad()
+    def add_new_mask(self, inference_state, frame_idx, obj_id, mask):
+        self._require_gpu()
+        st = inference_state
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        mi = self._mask_to_model_res(mask)  # [S,S] {0,1}
+        st["mask_inputs_per_obj"][obj_idx][frame_idx] = mi
+        st["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        tracked = st["frames_tracked_per_obj"][obj_idx]
+        is_init_cond_frame = frame_idx not in tracked
+        key = "cond_frame_outputs" if is_init_cond_frame else "non_cond_frame_outputs"
+        st["temp_output_dict_per_obj"][obj_idx][key][frame_idx] = self._use_mask_as_output(st, frame_idx, mi)
+        # consolidated video-resolution scores of every object on this frame (upstream's return value)
+        B = self._get_obj_num(st)
+        vh, vw = st["video_height"], st["video_width"]
+        low = torch.full((B, 256, 256), NO_OBJ_SCORE, dtype=_F32, device=self.device)
+        for i in range(B):
+            out = st["temp_output_dict_per_obj"][i][key].get(frame_idx)
+            if out is None:
+                out = st["output_dict_per_obj"][i]["cond_frame_outputs"].get(frame_idx)
+            if out is None:
+                out = st["output_dict_per_obj"][i]["non_cond_frame_outputs"].get(frame_idx)
+            if out is not None:
+                low[i] = out["pred_masks"].view(256, 256)
+        video_res = ops.upsample_bilinear(low, vh, vw).view(B, 1, vh, vw)
+        return frame_idx, st["obj_ids"], video_res
+
+    def _use_mask_as_output(self, st, frame_idx, mask_inputs: torch.Tensor) -> Dict[str, Any]:
+        """SAM2Base._use_mask_as_output for one object: scores = mask*20-10, low-res = antialiased x1/4, pointer from a
+        decoder call prompted with mask_downsample(mask); memory is encoded later (preflight)."""
+        S = self.image_size
+        c = self._frame(st, frame_idx)
+        hi = ops.threshold_affine(mask_inputs, 0.5, 20.0, -10.0)  # mask in {0,1} -> {-10, +10}
+        crops = torch.tensor([[0, 0, S, S]], dtype=_I32, device=self.device)
+        low = ops.resize_normalize(hi, crops, S // 4, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0))[0, 0:1].contiguous()
+        prompt = ops.conv4x4s4(mask_inputs.view(1, S, S), self.mask_ds_w, self.mask_ds_b)  # [1,256,256]
+        dec = self.decoder
+        coords = torch.zeros((1, 1, 2), dtype=_F32, device=self.device)
+        labels = torch.full((1, 1), -1, dtype=_I32, device=self.device)
+        tokens = dec.prompt_tokens(coords, labels)
+        out = dec.forward(c["feat"], c["s0"], c["s1"], tokens, prompt, multimask_output=False)
+        self.sam_mask_decoder.fire(out["masks"][:, 0:1], out["ious"][:, 0:1], out["hs"][:, 2:3], out["obj"])
+        _, tok, _ = ops.track_select(out["masks"], out["ious"], out["obj"].reshape(-1).contiguous(), out["hs"].contiguous(),
+                                     out.get("sel_idx"), False)
+        ptr = self._obj_ptr(tok, out["obj"].reshape(-1).contiguous())
+        # torch.any(mask > 0) on a {0,1} mask == any non-zero bit pattern
+        appear = ops.slice_any(mask_inputs.view(torch.int16).view(1, S, 2 * S)).to(_F32)
+        score = ops.threshold_affine(appear, 0.5, 20.0, -10.0)
+        ptr = ops.objptr_mix_(ptr, score, self.k_no_obj_ptr)
+        if self.fill_hole_area > 0:  # sam2_video_predictor._run_single_frame_inference fills holes on every path
+            low = ops.fill_holes(low, self.fill_hole_area)
+        return {"maskmem_features": None, "maskmem_pos_enc": None, "pred_masks": low.view(1, 1, S // 4, S // 4),
+                "obj_ptr": ptr, "object_score_logits": score.view(1, 1)}
+
+    def _obj_ptr(self, token: torch.Tensor, obj_scores: torch.Tensor) -> torch.Tensor:
+        h = ops.gemm(ops.add_cast(token.contiguous(), None, _BF16), *self.objptr_mlp[0], act=ops.ACT_RELU)
+        h = ops.gemm(h, *self.objptr_mlp[1], act=ops.ACT_RELU)
+        ptr = ops.gemm(h, *self.objptr_mlp[2], out_dtype=_F32)
+        return ops.objptr_mix_(ptr, obj_scores, self.k_no_obj_ptr)
+
+    # ---- propagation ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def propagate_in_video_preflight(self, inference_state):
+        st = inference_state
+        B = self._get_obj_num(st)
+        if B == 0:
+            raise RuntimeError("No input points or masks are provided for any object; please add inputs first.")
+        for i in range(B):
+            obj_out = st["output_dict_per_obj"][i]
+            obj_tmp = st["temp_output_dict_per_obj"][i]
+            for is_cond in (False, True):
+                key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+                for frame_idx, out in obj_tmp[key].items():
+                    if out["maskmem_features"] is None:
+                        c = self._frame(st, frame_idx)
+                        out["maskmem_features"] = self.mem_enc.forward(
+                            c["pix_proj"], out["pred_masks"].view(1, 256, 256), out["object_score_logits"].reshape(-1),
+                            binarize=self.binarize_mask_from_pts_for_mem_enc)
+                        out["maskmem_pos_enc"] = True
+                    obj_out[key][frame_idx] = out
+                obj_tmp[key].clear()
+            if len(obj_out["cond_frame_outputs"]) == 0:
+                raise RuntimeError(f"No input points or masks are provided for object id {st['obj_idx_to_id'][i]}; "
+                                   "please add inputs first.")
+            for frame_idx in obj_out["cond_frame_outputs"]:
+                obj_out["non_cond_frame_outputs"].pop(frame_idx, None)
+
+    def _memory_plan(self, obj_out, frame_idx, num_frames, reverse):
+        """Which stored outputs form the memory of `frame_idx` for one object (SAM2Base._prepare_memory_conditioned_
+        features): returns (signature, spatial [(t_pos, out)], pointers [(t_diff, out)])."""
+        cond = obj_out["cond_frame_outputs"]
+        spatial = [(0, f, out) for f, out in cond.items()]
+        for t_pos in range(1, self.num_maskmem):
+            t_rel = self.num_maskmem - t_pos
+            if t_rel == 1:
+                prev = frame_idx + t_rel if reverse else frame_idx - t_rel
+            elif not reverse:
+                prev = (frame_idx - 2) - (t_rel - 2)
+            else:
+                prev = (frame_idx + 2) + (t_rel - 2)
+            out = obj_out["non_cond_frame_outputs"].get(prev)
+            if out is not None:
+                spatial.append((t_pos, prev, out))
+        sign = -1 if reverse else 1
+        ptrs = [((frame_idx - f) * sign, f, out) for f, out in cond.items() if (f >= frame_idx if reverse else f <= frame_idx)]
+        for t_diff in range(1, min(num_frames, self.max_obj_ptrs_in_encoder)):
+            t = frame_idx + t_diff if reverse else frame_idx - t_diff
+            if t < 0 or t >= num_frames:
+                break
+            out = obj_out["non_cond_frame_outputs"].get(t)
+            if out is not None:
+                ptrs.append((t_diff, t, out))
+        sig = (tuple(tp for tp, _, _ in spatial), tuple(td for td, _, _ in ptrs))
+        return sig, spatial, ptrs
+
+    def _track_group(self, st, frame_idx, objs: List[int], sig, plans, reverse) -> Dict[int, Dict[str, Any]]:
+        """One tracking step for a batch of objects that share the memory layout `sig`."""
+        B = len(objs)
+        c = self._frame(st, frame_idx)
+        t_pos_list, t_diff_list = sig
+        n_ptr_tok = 4 * len(t_diff_list)
+        Nk = NT * len(t_pos_list) + n_ptr_tok
+        memory = torch.empty((B, Nk, 64), dtype=_BF16, device=self.device)
+        for bi, i in enumerate(objs):
+            _, spatial, ptrs = plans[i]
+            off = 0
+            for _, _, out in spatial:
+                memory[bi, off:off + NT] = out["maskmem_features"]
+                off += NT
+            for _, _, out in ptrs:
+                memory[bi, off:off + 4] = out["obj_ptr"].view(4, 64)  # fp32 -> bf16 storage cast
+                off += 4
+        # key positional term: spatial slots + pointer tokens (weights-only constants, cached per layout)
+        ck = ("layout", sig, st["num_frames"], self._tpos_key())
+        if ck not in self._const_cache:
+            parts = [self._spatial_key_pos(tp) for tp in t_pos_list]
+            if t_diff_list:
+                parts.append(self._ptr_key_pos(tuple(t_diff_list), st["num_frames"]))
+            self._const_cache[ck] = [torch.cat([p[l] for p in parts], 0).contiguous() for l in range(4)]
+        pos_k = self._const_cache[ck]
+        pix = self.mem_attn.forward(c["feat"], memory.view(B * Nk, 64), pos_k, n_ptr_tok, B)  # [B*4096,256]
+        del memory
+        dec = self.decoder
+        coords = torch.zeros((B, 1, 2), dtype=_F32, device=self.device)
+        labels = torch.full((B, 1), -1, dtype=_I32, device=self.device)
+        tokens = dec.prompt_tokens(coords, labels)
+        out = dec.forward(pix, c["s0"], c["s1"], tokens, None, multimask_output=True)
+        self.sam_mask_decoder.fire(out["masks"][:, 1:4], out["ious"][:, 1:4], out["hs"][:, 3:6], out["obj"])
+        obj = out["obj"].reshape(-1).contiguous()
+        low, tok, _ = ops.track_select(out["masks"], out["ious"], obj, out["hs"].contiguous(), None, True)
+        ptr = self._obj_ptr(tok, obj)
+        mem = self.mem_enc.forward(c["pix_proj"], low, obj, binarize=False)  # is_mask_from_pts = False
+        pred = ops.fill_holes(low, self.fill_hole_area) if self.fill_hole_area > 0 else low
+        res = {}
+        for bi, i in enumerate(objs):
+            res[i] = {"maskmem_features": mem[bi * NT:(bi + 1) * NT], "maskmem_pos_enc": True,
+                      "pred_masks": pred[bi].view(1, 1, 256, 256), "obj_ptr": ptr[bi:bi + 1],
+                      "object_score_logits": obj[bi].view(1, 1)}
+        return res
+
+    @torch.no_grad()
+    def propagate_in_video(self, inference_state, start_frame_idx=None, max_frame_num_to_track=None, reverse=False):
+        self._require_gpu()
+        st = inference_state
+        self.propagate_in_video_preflight(st)
+        obj_ids = st["obj_ids"]
+        num_frames = st["num_frames"]
+        B = self._get_obj_num(st)
+        if start_frame_idx is None:
+            start_frame_idx = min(t for d in st["output_dict_per_obj"].values() for t in d["cond_frame_outputs"])
+        if max_frame_num_to_track is None:
+            max_frame_num_to_track = num_frames
+        if reverse:
+            end = max(start_frame_idx - max_frame_num_to_track, 0)
+            order = range(start_frame_idx, end - 1, -1) if start_frame_idx > 0 else []
+        else:
+            end = min(start_frame_idx + max_frame_num_to_track, num_frames - 1)
+            order = range(start_frame_idx, end + 1)
+        vh, vw = st["video_height"], st["video_width"]
+        for frame_idx in order:
+            low = torch.empty((B, 256, 256), dtype=_F32, device=self.device)
+            groups: Dict[Any, List[int]] = {}
+            plans = {}
+            for i in range(B):
+                obj_out = st["output_dict_per_obj"][i]
+                if frame_idx in obj_out["cond_frame_outputs"]:
+                    low[i] = obj_out["cond_frame_outputs"][frame_idx]["pred_masks"].view(256, 256)
+                else:
+                    plans[i] = self._memory_plan(obj_out, frame_idx, num_frames, reverse)
+                    groups.setdefault(plans[i][0], []).append(i)
+            for sig, objs in groups.items():
+                res = self._track_group(st, frame_idx, objs, sig, plans, reverse)
+                for i in objs:
+                    st["output_dict_per_obj"][i]["non_cond_frame_outputs"][frame_idx] = res[i]
+                    low[i] = res[i]["pred_masks"].view(256, 256)
+            for i in range(B):
+                st["frames_tracked_per_obj"][i][frame_idx] = {"reverse": reverse}
+            video_res = ops.upsample_bilinear(low, vh, vw).view(B, 1, vh, vw)
+            yield frame_idx, obj_ids, video_res
+
+    # ---- state ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def reset_state(self, inference_state):
+        s = inference_state
+        for k in ("obj_id_to_idx", "obj_idx_to_id", "obj_ids", "point_inputs_per_obj", "mask_inputs_per_obj",
+                  "output_dict_per_obj", "temp_output_dict_per_obj", "frames_tracked_per_obj"):
+            s[k].clear()
+
+    def add_new_points_or_box(self, *a, **k):
+        raise NotImplementedError("saber_b200: point / box prompts of the video predictor are not on SABER's segmenter "
+                                  "path (REF saber/segmenters/* seed with masks only)")
+
+    def clear_all_prompts_in_frame(self, *a, **k):
+        raise NotImplementedError("saber_b200: clear_all_prompts_in_frame is not on SABER's segmenter path")
+
+    def remove_object(self, *a, **k):
+        raise NotImplementedError("saber_b200: remove_object is not on SABER's segmenter path")
+
+
+def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_overrides_extra=None,
+                               apply_postprocessing=True, vos_optimized=False, seed: int = 0, state_dict=None,
+                               **kwargs) -> SAM2VideoPredictor:
+    """Same call shape as upstream ``sam2.build_sam.build_sam2_video_predictor`` (REF saber/adapters/sam2/
+    predictor.py:24-26); applies upstream's overrides: binarize_mask_from_pts_for_mem_enc, fill_hole_area=8 and (with
+    apply_postprocessing) dynamic multimask via stability."""
+    cfg = arch.resolve(config_file)
+    sd = state_dict if state_dict is not None else _load_state_dict(cfg, ckpt_path, seed)
+    model = SAM2VideoPredictor(cfg, sd, device=device, dynamic_multimask_via_stability=bool(apply_postprocessing),
+                               fill_hole_area=8, binarize_mask_from_pts_for_mem_enc=True)
+    if mode == "eval":
+        model.eval()
+    return model

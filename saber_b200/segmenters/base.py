@@ -146,7 +146,7 @@ class saber3D(saber2D):
     def propagate(self, mask_shape, target_class: Optional[int] = 1):
         mask_arrays = [m["segmentation"] for m in self.masks] if isinstance(self.masks[0], dict) else self.masks
         vol_masks = self.video_predictor.segment_volume(
-            start_frame_idx=self.ann_frame_idx, masks=mask_arrays, vol_shape=mask_shape,
+            start_frame_idx=self.ann_frame_idx, masks=mask_arrays, vol_shape=tuple(int(v) for v in mask_shape),
             max_frame_num_to_track=self.nframes, min_presence_score=self.filter_threshold)
         self.video_predictor.reset_state()
         return vol_masks

@@ -3,8 +3,8 @@
 ``slice_by_slice`` (REF :164-189) is the slice-wise zero-shot path of BASELINE config 2: per z-slice
 prepare -> AMG -> area filter -> duplicate removal -> sort -> label stitch, then 3-D connected components over
 the whole label volume. Here every stage runs on the device; the volume is uploaded once and only the uint32
-label volume comes back. ``segment`` / ``single_segment`` / ``segment_3d`` need the z-axis memory propagation
-(next §8 row) and raise until it is built.
+label volume comes back. ``segment`` / ``single_segment`` / ``segment_3d`` (REF :41-130) drive the z-axis memory
+propagation of the adapter (``segment_volume``).
 """
 from __future__ import annotations
 

@@ -72,3 +72,20 @@ def test_sliding_windows_match_reference_formula():
     assert w[0] == (0, 0, 256, 256) and all((y2 - y1) >= 128 and (x2 - x1) >= 128 for y1, x1, y2, x2 in w)
     assert (384, 576, 600, 700) not in w  # 124-px wide remainder is skipped
     assert s._to_global_bbox([1, 2, 3, 4], 10, 20) == [21, 12, 3, 4]
+
+
+def test_estimate_thickness_twin_matches_reference_golden(golden_dir):
+    """saber_b200.filters.estimate_thickness (host scipy, R8) reproduces the reference-run golden vector."""
+    import os
+    import numpy as np
+    from saber_b200.filters import estimate_thickness
+    g = np.load(os.path.join(golden_dir, "saber3d_fit_boundaries.npz"))
+    out = estimate_thickness.fit_organelle_boundaries(g["frame_scores"].copy())
+    np.testing.assert_allclose(out, g["out"], rtol=1e-9, atol=1e-12)
+
+
+def test_gaussian_kernel_twin():
+    import numpy as np
+    from oracle import saber_ref
+    from saber_b200.filters.gaussian import make_gaussian_kernel
+    np.testing.assert_array_equal(make_gaussian_kernel(5).numpy(), saber_ref.make_gaussian_kernel(5))
