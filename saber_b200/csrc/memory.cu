@@ -277,9 +277,11 @@ objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ cond, const
 // One CTA per S x S mask (S <= 256): union-find over the background pixels in shared memory (uint16 parents with
 // S*S <= 65536 ... stored as int for atomics), iterated hooking until stable, then per-root areas.
 // ------------------------------------------------------------------------------------------------
+// parent[] is updated with atomics (resolved in L2) by other threads of the CTA: every read bypasses the
+// (non-coherent) L1 with ld.global.cg, otherwise a stale "root" splits a component and its area is under-counted.
 __device__ __forceinline__ int uf_find(const int* parent, int i) {
   while (true) {
-    const int p = parent[i];
+    const int p = __ldcg(parent + i);
     if (p == i) return i;
     i = p;
   }
@@ -315,27 +317,28 @@ fill_holes_kernel(const float* __restrict__ in, float* __restrict__ out, int S, 
   __syncthreads();
   // hook every background pixel to its 4 raster-preceding 8-neighbours (W, NW, N, NE)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (parent[i] < 0) continue;
+    if (!(src[i] <= 0.f)) continue;
     const int y = i / S, x = i % S;
-    if (x > 0 && parent[i - 1] >= 0) uf_union(parent, i, i - 1);
+    if (x > 0 && src[i - 1] <= 0.f) uf_union(parent, i, i - 1);
     if (y > 0) {
-      if (parent[i - S] >= 0) uf_union(parent, i, i - S);
-      if (x > 0 && parent[i - S - 1] >= 0) uf_union(parent, i, i - S - 1);
-      if (x < S - 1 && parent[i - S + 1] >= 0) uf_union(parent, i, i - S + 1);
+      if (src[i - S] <= 0.f) uf_union(parent, i, i - S);
+      if (x > 0 && src[i - S - 1] <= 0.f) uf_union(parent, i, i - S - 1);
+      if (x < S - 1 && src[i - S + 1] <= 0.f) uf_union(parent, i, i - S + 1);
     }
   }
   __syncthreads();
+  // roots are final after the barrier: count areas per root, then classify every background pixel by its root's area
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (parent[i] < 0) continue;
+    if (!(src[i] <= 0.f)) continue;
     const int r = uf_find(parent, i);
-    parent[i] = r;  // roots are fixed now: compression is race-free (root[r] == r)
     atomicAdd(&area[r], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float v = src[i];
-    const int p = parent[i];
-    dst[i] = (p >= 0 && area[p] <= max_area) ? 0.1f : v;
+    bool hole = false;
+    if (v <= 0.f) hole = __ldcg(area + uf_find(parent, i)) <= max_area;
+    dst[i] = hole ? 0.1f : v;
   }
 }
 

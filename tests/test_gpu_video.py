@@ -39,6 +39,19 @@ def setup():
     cfg = SAM2AdapterConfig(cfg="tiny", amg_cfg=cfgAMG(sam2_cfg="tiny"), num_maskmem=2, seed=0)
     ad = SAM2Adapter(cfg, device="cuda:0")
     sd = arch.random_state_dict("tiny", seed=0)
+    # Random-init heads give three near-identical IoU predictions (argmax decided by bf16 noise) and mask logits of
+    # ~1e-1: give the mask logits a realistic dynamic range and separate the IoU / object-score outputs so that the
+    # discrete choices (best multimask token, object present) are well-conditioned on both sides.
+    for k in list(sd):
+        if "output_hypernetworks_mlps" in k and ".layers.2." in k:
+            sd[k] = sd[k] * 30.0
+    sd["sam_mask_decoder.iou_prediction_head.layers.2.bias"] = torch.tensor([0.0, -1.0, 1.0, 0.0])
+    sd["sam_mask_decoder.pred_obj_score_head.layers.2.bias"] = torch.tensor([1.5])
+    from saber_b200.sam2.sam2_video_predictor import build_sam2_video_predictor
+    vp = build_sam2_video_predictor("tiny", None, device="cuda:0", state_dict=sd)
+    vp.maskmem_tpos_enc = torch.nn.Parameter(vp.maskmem_tpos_enc[:2], requires_grad=False)  # as SAM2Adapter._video()
+    vp.num_maskmem = 2
+    ad.predictor = vp
     # ---- oracle: reference preprocessing + upstream state machine, fp32 on the host
     orc = oracle_build("tiny", None, device="cpu", state_dict=sd)
     orc.maskmem_tpos_enc = torch.nn.Parameter(orc.maskmem_tpos_enc[:2])  # REF saber/adapters/sam2/predictor.py:31-34
@@ -67,6 +80,11 @@ def test_propagation_logits_match_oracle(setup):
         ad.set_volume(setup["vol"])
     p, st = ad._video(), ad.inference_state
     p.reset_state(st)
+    # Hole filling (area <= 8 background components -> +0.1) is discontinuous in the logits: on the noise-like masks of
+    # random-init weights a 1e-3 perturbation re-wires which specks count as holes. It is checked bit-exactly on
+    # identical inputs (test_gpu_memory_kernels.py::test_fill_holes_bit_exact and the replay test below) and switched
+    # off on both sides here so that this test measures the float path.
+    p.fill_hole_area, orc.fill_hole_area = 0, 0
     got_scores, want_scores = [], []
     h1 = p.sam_mask_decoder.register_forward_hook(lambda m, i, o: got_scores.append(float(o[3].reshape(-1)[0])))
     h2 = orc.sam_mask_decoder.register_forward_hook(lambda m, i, o: want_scores.append(float(o[3].reshape(-1)[0])))
@@ -91,6 +109,7 @@ def test_propagation_logits_match_oracle(setup):
             assert agree > 0.995
     h1.remove()
     h2.remove()
+    p.fill_hole_area, orc.fill_hole_area = 8, 8
     assert len(got_scores) == len(want_scores) > 0
     np.testing.assert_allclose(got_scores, want_scores, rtol=2e-2, atol=5e-2)
     print("worst rel", worst)
