@@ -56,6 +56,17 @@ int sb_gemm_upscale2(const void* A, long long lda, const void* W, long long ldw,
 int sb_attention(const void* q, long long q_ld, const void* k, long long k_ld, const void* v, long long v_ld, void* o,
                  long long o_ld, int batch, int heads, int hd, int nq, int nk, float scale, int q_shared,
                  int kv_shared, void* stream);
+/* sb_attention with an additive key term shared by all batch entries (scores = q (k[b] + k_add)^T): the mask decoder's
+ * token -> image attention, k_add = image_pe @ Wk^T + bk ([nk, heads*hd] bf16) */
+int sb_attention_kadd(const void* q, long long q_ld, const void* k, long long k_ld, const void* k_add, long long k_add_ld,
+                      const void* v, long long v_ld, void* o, long long o_ld, int batch, int heads, int hd, int nq,
+                      int nk, float scale, int kv_shared, void* stream);
+/* Mask-decoder image -> token attention (TwoWayAttentionBlock.cross_attn_image_to_token; 8 heads x 16, <= 16 keys per
+ * prompt) as a stream over the query matrix; q_add [nq,128] fp32 (nullable) is the query projection's positional term
+ * (image_pe @ Wq^T + bq), shared by all prompts, added before the scores. */
+int sb_attention_few_keys(const void* q, long long q_ld, const float* q_add, const void* k, long long k_ld, const void* v,
+                          long long v_ld, void* o, long long o_ld, int batch, int nq, int nk, float scale, int q_shared,
+                          void* stream);
 /* Hiera MultiScaleAttention over a fused qkv buffer [B*H*W, 3*heads*hd]: window partition (with upstream's zero
  * padding of ragged windows), optional 2x2 max-pool of q, SDPA, window unpartition — hieradet.py
  * MultiScaleBlock.forward / MultiScaleAttention.forward. ws >= max(H,W) = global attention. */
@@ -83,6 +94,10 @@ int sb_prompt_tokens(const float* coords, const int* labels, int B, int Np, int 
 int sb_mask_downscale(const float* in, int B, int S, int cpp, float clampv, const float* w1, const float* b1,
                       const float* g1, const float* be1, const float* w2, const float* b2, const float* g2,
                       const float* be2, void* out, void* stream);
+/* mask_downscaling[6] (1x1 conv 16->256) + `src = image_embeddings + dense_prompt_embeddings` of the mask decoder:
+ * keys[b*T+t] = bf16(image_embed[t] + bias + ds[b*T+t] @ w^T); ds [ntok,16] bf16, w [256,16] fp32, image_embed [T,256] */
+int sb_mask_embed_keys(const void* ds, const float* w, const float* bias, const float* image_embed, int T, long long ntok,
+                       void* keys, void* stream);
 int sb_upscale1_post(const void* g1, const float* feat_s1, long long s1_batch_stride, const float* gamma,
                      const float* beta, int B, int h, int w, void* u1, void* stream);
 int sb_upscale2_mask(const void* g2, const float* feat_s0, long long s0_batch_stride, const float* hyper, int B,

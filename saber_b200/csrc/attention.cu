@@ -33,6 +33,11 @@ struct AttnParams {
   // output grid Ho x Wo (= floor(H/pool), floor(W/pool)), nwx/nwy windows per padded grid.
   int H, W, ws, pool, Ho, Wo, nwx, nwy;
   int qtiles;  // q tiles per (batch, window)
+  // plain mode only: optional additive key term shared by all batch entries, k_eff[j] = k[b, j] + k_add[j]
+  // ([nk, heads*hd] bf16). Applied as a second MMA (S = Q K^T + Q k_add^T), so the producer of k needs no
+  // broadcast-residual epilogue (mask decoder: k_add = image_pe @ Wk^T + bk).
+  const __nv_bfloat16* k_add;
+  long long k_add_ld;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -88,6 +93,8 @@ flash_attn_kernel(const AttnParams p) {
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + QROWS * PITCH;
   uint8_t* sV = sK + 2 * KT * PITCH;
+  uint8_t* sR = sV + 2 * KT * PITCH;  // only allocated / touched when p.k_add != nullptr
+  const bool has_kadd = p.k_add != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y;
@@ -113,7 +120,7 @@ flash_attn_kernel(const AttnParams p) {
   const int col0 = head * hd;
 
   // zero the whole staging area once (padded columns must stay 0 / finite)
-  for (int i = tid; i < (QROWS + 4 * KT) * PITCH / 16; i += NT)
+  for (int i = tid; i < (QROWS + (has_kadd ? 6 : 4) * KT) * PITCH / 16; i += NT)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
@@ -172,6 +179,8 @@ flash_attn_kernel(const AttnParams p) {
       if (row >= 0) {
         cp_async16(dK + r * PITCH + c * 16, p.k + row * p.k_ld + col0 + c * 8);
         cp_async16(dV + r * PITCH + c * 16, p.v + row * p.v_ld + col0 + c * 8);
+        if (has_kadd)
+          cp_async16(sR + stage * KT * PITCH + r * PITCH + c * 16, p.k_add + static_cast<long long>(j) * p.k_add_ld + col0 + c * 8);
       } else {
         uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
         if (row == -1) {  // window padding: token is exactly the projection bias
@@ -247,6 +256,22 @@ flash_attn_kernel(const AttnParams p) {
           ldsm_x4(kbase + np * 16 * PITCH + ks * 32, b0, b1, b2, b3);
           mma_bf16_16816(s[2 * np], qa, b0, b1);
           mma_bf16_16816(s[2 * np + 1], qa, b2, b3);
+        }
+      }
+      if (has_kadd) {  // S += Q k_add^T
+        const uint32_t rbase = kbase + static_cast<uint32_t>(sR - sK);  // same stage / lane offsets, R region
+#pragma unroll
+        for (int ks = 0; ks < HDP / 16; ++ks) {
+          uint32_t qs[4];
+          if constexpr (!Q_IN_REGS) ldsm_x4(qbase + ks * 32, qs[0], qs[1], qs[2], qs[3]);
+          const uint32_t* qa = Q_IN_REGS ? qf[Q_IN_REGS ? ks : 0] : qs;
+#pragma unroll
+          for (int np = 0; np < KT / 16; ++np) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(rbase + np * 16 * PITCH + ks * 32, b0, b1, b2, b3);
+            mma_bf16_16816(s[2 * np], qa, b0, b1);
+            mma_bf16_16816(s[2 * np + 1], qa, b2, b3);
+          }
         }
       }
     }
@@ -350,17 +375,123 @@ flash_attn_kernel(const AttnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Attention with a handful of keys (mask decoder "image attends to tokens": 4096 image queries per prompt, 7-9 token
+// keys, 8 heads x 16). The flash kernel above pads the keys to a 64-wide MMA tile and spends a CTA-wide pipeline on
+// 8 keys; here the op is what it is — a stream over the query matrix (32 B in, 32 B out per (row, head)) with the
+// prompt's K / V held in shared memory as fp32. One thread per (query row, head); HBM-bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int FK_MAX_KEYS = 16;
+constexpr int FK_ROWS = 32;  // query rows per block iteration (256 threads = 32 rows x 8 heads)
+
+__global__ void __launch_bounds__(256)
+fewkeys_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld, long long q_bstride,
+                    const float* __restrict__ q_add /* [nq, 128] fp32 added to every batch entry's q, or null */,
+                    const __nv_bfloat16* __restrict__ k, long long k_ld, const __nv_bfloat16* __restrict__ v,
+                    long long v_ld, __nv_bfloat16* __restrict__ o, long long o_ld, int nq, int nk, float scale_log2,
+                    int rows_per_block) {
+  constexpr int C = 128;
+  // per key: 8 heads x (16 values + 4 pad floats). The 8 lanes of a quarter-warp read the 8 heads of one row with
+  // LDS.128; a head pitch of 20 floats spreads them over all 32 banks (16 would be a 4-way conflict).
+  constexpr int HP = 20, KP = 8 * HP;
+  __shared__ __align__(16) float sK[FK_MAX_KEYS * KP];
+  __shared__ __align__(16) float sV[FK_MAX_KEYS * KP];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < nk * C; i += blockDim.x) {
+    const int j = i / C, c = i % C;
+    sK[j * KP + (c >> 4) * HP + (c & 15)] = __bfloat162float(k[(static_cast<long long>(b) * nk + j) * k_ld + c]);
+    sV[j * KP + (c >> 4) * HP + (c & 15)] = __bfloat162float(v[(static_cast<long long>(b) * nk + j) * v_ld + c]);
+  }
+  __syncthreads();
+  const int head = threadIdx.x & 7, rsub = threadIdx.x >> 3;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(nq, r_begin + rows_per_block);
+  for (int r0 = r_begin; r0 < r_end; r0 += FK_ROWS) {
+    const int r = r0 + rsub;
+    if (r >= r_end) continue;
+    const __nv_bfloat16* qp = q + (static_cast<long long>(b) * q_bstride + r) * q_ld + head * 16;
+    const uint4 qa = *reinterpret_cast<const uint4*>(qp);
+    const uint4 qb = *reinterpret_cast<const uint4*>(qp + 8);
+    float qf[16];
+    qf[0] = sb::bf16_lo(qa.x); qf[1] = sb::bf16_hi(qa.x); qf[2] = sb::bf16_lo(qa.y); qf[3] = sb::bf16_hi(qa.y);
+    qf[4] = sb::bf16_lo(qa.z); qf[5] = sb::bf16_hi(qa.z); qf[6] = sb::bf16_lo(qa.w); qf[7] = sb::bf16_hi(qa.w);
+    qf[8] = sb::bf16_lo(qb.x); qf[9] = sb::bf16_hi(qb.x); qf[10] = sb::bf16_lo(qb.y); qf[11] = sb::bf16_hi(qb.y);
+    qf[12] = sb::bf16_lo(qb.z); qf[13] = sb::bf16_hi(qb.z); qf[14] = sb::bf16_lo(qb.w); qf[15] = sb::bf16_hi(qb.w);
+    if (q_add != nullptr) {  // positional term of the query projection (shared by all prompts, L2-resident)
+      const float4* ap = reinterpret_cast<const float4*>(q_add + static_cast<long long>(r) * C + head * 16);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 a4 = __ldg(ap + t);
+        // the GEMM this replaces rounded (acc + residual) to bf16 once; keep that rounding point
+        qf[4 * t + 0] = __bfloat162float(__float2bfloat16(qf[4 * t + 0] + a4.x));
+        qf[4 * t + 1] = __bfloat162float(__float2bfloat16(qf[4 * t + 1] + a4.y));
+        qf[4 * t + 2] = __bfloat162float(__float2bfloat16(qf[4 * t + 2] + a4.z));
+        qf[4 * t + 3] = __bfloat162float(__float2bfloat16(qf[4 * t + 3] + a4.w));
+      }
+    }
+    float sc[FK_MAX_KEYS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < FK_MAX_KEYS; ++j) {
+      if (j < nk) {
+        const float4* kp = reinterpret_cast<const float4*>(sK + j * KP + head * HP);
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 kk = kp[t];
+          acc = fmaf(qf[4 * t + 0], kk.x, acc);
+          acc = fmaf(qf[4 * t + 1], kk.y, acc);
+          acc = fmaf(qf[4 * t + 2], kk.z, acc);
+          acc = fmaf(qf[4 * t + 3], kk.w, acc);
+        }
+        sc[j] = acc * scale_log2;
+        mx = fmaxf(mx, sc[j]);
+      }
+    }
+    float l = 0.f;
+    float out[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) out[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < FK_MAX_KEYS; ++j) {
+      if (j < nk) {
+        const float pj = exp2f(sc[j] - mx);  // ex2.approx
+        l += pj;
+        const float4* vp = reinterpret_cast<const float4*>(sV + j * KP + head * HP);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 vv = vp[t];
+          out[4 * t + 0] = fmaf(pj, vv.x, out[4 * t + 0]);
+          out[4 * t + 1] = fmaf(pj, vv.y, out[4 * t + 1]);
+          out[4 * t + 2] = fmaf(pj, vv.z, out[4 * t + 2]);
+          out[4 * t + 3] = fmaf(pj, vv.w, out[4 * t + 3]);
+        }
+      }
+    }
+    const float inv = __fdividef(1.f, l);
+    __nv_bfloat16* op = o + (static_cast<long long>(b) * nq + r) * o_ld + head * 16;
+    *reinterpret_cast<uint4*>(op) =
+        make_uint4(sb::pack_bf16x2(out[0] * inv, out[1] * inv), sb::pack_bf16x2(out[2] * inv, out[3] * inv),
+                   sb::pack_bf16x2(out[4] * inv, out[5] * inv), sb::pack_bf16x2(out[6] * inv, out[7] * inv));
+    *reinterpret_cast<uint4*>(op + 8) =
+        make_uint4(sb::pack_bf16x2(out[8] * inv, out[9] * inv), sb::pack_bf16x2(out[10] * inv, out[11] * inv),
+                   sb::pack_bf16x2(out[12] * inv, out[13] * inv), sb::pack_bf16x2(out[14] * inv, out[15] * inv));
+  }
+}
+
 template <int HDP, int NWARPS>
 int launch_attn(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
   constexpr int KT = HDP > 128 ? 32 : 64;
   constexpr int PITCH = HDP * 2 + 16;
-  constexpr int SMEM = (16 * NWARPS + 4 * KT) * PITCH;
+  constexpr int SMEM_MAX_ = (16 * NWARPS + 6 * KT) * PITCH;
+  const int SMEM = (16 * NWARPS + (p.k_add ? 6 : 4) * KT) * PITCH;
   static bool attr_done = false;
   if (!attr_done) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HDP, NWARPS, KT>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_ > 227 * 1024 ? 227 * 1024 : SMEM_MAX_));
     attr_done = true;
   }
+  SB_REQUIRE(SMEM <= 227 * 1024, "sb_attention: k_add does not fit in shared memory at head_dim %d", p.hd);
   dim3 grid(static_cast<unsigned>(nblocks_x), static_cast<unsigned>(p.heads), 1);
   flash_attn_kernel<HDP, NWARPS, KT><<<grid, NWARPS * 32, SMEM, stream>>>(p);
   SB_CHECK_LAUNCH();
@@ -420,6 +551,65 @@ extern "C" int sb_attention(const void* q, long long q_ld, const void* k, long l
   p.nk = nk;
   p.q_bstride = q_shared ? 0 : nq;
   p.kv_bstride = kv_shared ? 0 : nk;
+  // few keys, 8 heads x 16, many queries: the streaming kernel (see fewkeys_attn_kernel)
+  if (nk <= FK_MAX_KEYS && heads == 8 && hd == 16 && !kv_shared && nq >= 1024 && (q_ld % 8) == 0 && (o_ld % 8) == 0 &&
+      ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+    const int rows_per_block = 256;
+    dim3 grid((nq + rows_per_block - 1) / rows_per_block, batch);
+    fewkeys_attn_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        p.q, q_ld, p.q_bstride, nullptr, p.k, k_ld, p.v, v_ld, p.o, o_ld, nq, nk, p.scale_log2, rows_per_block);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+  }
+  return run_attn(p, batch, nq, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Mask-decoder image -> token attention with the query's positional term folded in: q_eff = bf16(q + q_add[row]),
+// 8 heads x 16, nk <= 16 keys per prompt. q [batch*nq (or nq when q_shared), 128] bf16, q_add [nq, 128] fp32 or null.
+extern "C" int sb_attention_few_keys(const void* q, long long q_ld, const float* q_add, const void* k, long long k_ld,
+                                     const void* v, long long v_ld, void* o, long long o_ld, int batch, int nq, int nk,
+                                     float scale, int q_shared, void* stream) {
+  SB_REQUIRE(batch > 0 && nq > 0 && nk > 0 && nk <= FK_MAX_KEYS, "sb_attention_few_keys: nk must be in 1..%d", FK_MAX_KEYS);
+  SB_REQUIRE((q_ld % 8) == 0 && (o_ld % 8) == 0 &&
+                 ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(q_add)) & 15) == 0,
+             "sb_attention_few_keys: q / o / q_add must be 16-byte aligned with pitches that are multiples of 8");
+  const int rows_per_block = 256;
+  dim3 grid((nq + rows_per_block - 1) / rows_per_block, batch);
+  fewkeys_attn_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(q), q_ld, q_shared ? 0 : nq, q_add, static_cast<const __nv_bfloat16*>(k), k_ld,
+      static_cast<const __nv_bfloat16*>(v), v_ld, static_cast<__nv_bfloat16*>(o), o_ld, nq, nk,
+      scale * 1.4426950408889634f, rows_per_block);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// sb_attention with an additive key term shared by all batch entries: scores = q (k[b] + k_add)^T (k_add [nk, heads*hd]
+// bf16, pitch k_add_ld). Mask decoder token -> image attention: the image positional term of the key projection.
+extern "C" int sb_attention_kadd(const void* q, long long q_ld, const void* k, long long k_ld, const void* k_add,
+                                 long long k_add_ld, const void* v, long long v_ld, void* o, long long o_ld, int batch,
+                                 int heads, int hd, int nq, int nk, float scale, int kv_shared, void* stream) {
+  SB_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nk > 0 && k_add, "sb_attention_kadd: bad arguments");
+  SB_REQUIRE((k_add_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(k_add) & 15) == 0, "sb_attention_kadd: k_add alignment");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.q_ld = q_ld;
+  p.k_ld = k_ld;
+  p.v_ld = v_ld;
+  p.o_ld = o_ld;
+  p.heads = heads;
+  p.hd = hd;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.mode = 0;
+  p.nq = nq;
+  p.nk = nk;
+  p.q_bstride = nq;
+  p.kv_bstride = kv_shared ? 0 : nk;
+  p.k_add = static_cast<const __nv_bfloat16*>(k_add);
+  p.k_add_ld = k_add_ld;
   return run_attn(p, batch, nq, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 

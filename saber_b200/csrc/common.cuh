@@ -207,6 +207,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+// 32 lanes x 16 columns of fp32 back into TMEM (thread i writes lane base_lane + i)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- small math -----------------------------------------------------------------------------
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. below fp32
 // rounding of the result for |x| < 8): 1 MUFU.RCP + 1 MUFU.EX2 + 8 FMA/MUL instead of the ~30-instruction erff().

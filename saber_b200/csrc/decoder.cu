@@ -138,6 +138,60 @@ mask_downscale_kernel(const float* __restrict__ in, int B, int S, int cpp, float
   }
 }
 
+
+// keys[b*T + t, n] = bf16(image_embed[t, n] + bias[n] + sum_c ds[b*T + t, c] * w[n, c])   (n < 256, c < 16):
+// mask_downscaling[6] (1x1 conv 16 -> 256) plus the dense-prompt add of the mask decoder (src = image_embeddings +
+// dense_prompt_embeddings), i.e. the per-prompt image stream of the m2m pass, written once. A K = 16 contraction is
+// not tensor-core work: one warp per token, 8 channels per lane with their 8 x 16 weights in registers; the kernel
+// is bound by the 512 B it stores per token.
+__global__ void __launch_bounds__(128)
+mask_embed_keys_kernel(const __nv_bfloat16* __restrict__ ds, const float* __restrict__ w /*[256,16]*/,
+                       const float* __restrict__ bias, const float* __restrict__ image_embed /*[T,256]*/, int T,
+                       long long ntok, __nv_bfloat16* __restrict__ keys) {
+  // two warps per token (4 channels per lane: 64 weight registers), two tokens per iteration with all loads issued
+  // before the math, so enough bytes are in flight per SM to cover the latency of the streaming store / L2 loads
+  const int lane = threadIdx.x & 31;
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int c0 = static_cast<int>(gw & 1) * 128 + lane * 4;
+  float wr[4][16];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) wr[e][c] = w[(c0 + e) * 16 + c];
+  const float4 br = *reinterpret_cast<const float4*>(bias + c0);
+  // 32-bit token arithmetic (ntok < 2^31 is checked by the launcher): a 64-bit modulo per token costs more
+  // instructions than the 64 FMAs of the contraction
+  const unsigned npairs = (gridDim.x * blockDim.x) >> 6;  // warp pairs in the grid
+  const unsigned n = static_cast<unsigned>(ntok), uT = static_cast<unsigned>(T);
+  for (unsigned t0 = static_cast<unsigned>(gw >> 1) * 2; t0 < n; t0 += npairs * 2) {
+    uint4 d[2][2];
+    float4 ie[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned tok = t0 + u < n ? t0 + u : t0;
+      d[u][0] = *reinterpret_cast<const uint4*>(ds + static_cast<size_t>(tok) * 16);
+      d[u][1] = *reinterpret_cast<const uint4*>(ds + static_cast<size_t>(tok) * 16 + 8);
+      ie[u] = __ldg(reinterpret_cast<const float4*>(image_embed + static_cast<size_t>(tok % uT) * 256 + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (t0 + u >= n) break;
+      float dv[16];
+      dv[0] = sb::bf16_lo(d[u][0].x); dv[1] = sb::bf16_hi(d[u][0].x); dv[2] = sb::bf16_lo(d[u][0].y); dv[3] = sb::bf16_hi(d[u][0].y);
+      dv[4] = sb::bf16_lo(d[u][0].z); dv[5] = sb::bf16_hi(d[u][0].z); dv[6] = sb::bf16_lo(d[u][0].w); dv[7] = sb::bf16_hi(d[u][0].w);
+      dv[8] = sb::bf16_lo(d[u][1].x); dv[9] = sb::bf16_hi(d[u][1].x); dv[10] = sb::bf16_lo(d[u][1].y); dv[11] = sb::bf16_hi(d[u][1].y);
+      dv[12] = sb::bf16_lo(d[u][1].z); dv[13] = sb::bf16_hi(d[u][1].z); dv[14] = sb::bf16_lo(d[u][1].w); dv[15] = sb::bf16_hi(d[u][1].w);
+      float acc[4] = {ie[u].x + br.x, ie[u].y + br.y, ie[u].z + br.z, ie[u].w + br.w};
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = fmaf(dv[c], wr[e][c], acc[e]);
+      *reinterpret_cast<uint2*>(keys + static_cast<size_t>(t0 + u) * 256 + c0) =
+          make_uint2(sb::pack_bf16x2(acc[0], acc[1]), sb::pack_bf16x2(acc[2], acc[3]));
+    }
+  }
+}
+
 // Stage 1 of output_upscaling after the ConvTranspose2d(256->64,k2,s2) GEMM:
 // g1 [B*h*w, 4*64] (col = (dy*2+dx)*64 + co, bias included) -> pixel shuffle -> + feat_s1 ->
 // LayerNorm2d(64) -> GELU -> u1 [B*(2h)*(2w), 64] bf16. One warp per (token, dydx).
@@ -290,6 +344,19 @@ extern "C" int sb_mask_downscale(const float* in, int B, int S, int cpp, float c
   const long long total = static_cast<long long>(B) * (S / 4) * (S / 4);
   mask_downscale_kernel<<<blocks_for(total), 256, 0, stream>>>(
       in, B, S, cpp, clampv, w1, b1, g1, be1, w2, b2, g2, be2, static_cast<__nv_bfloat16*>(out));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_mask_embed_keys(const void* ds, const float* w, const float* bias, const float* image_embed, int T,
+                                  long long ntok, void* keys, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(ds && w && bias && image_embed && keys && T > 0 && ntok > 0 && ntok < (1ll << 31),
+             "sb_mask_embed_keys: bad arguments");
+  long long blocks = (ntok + 3) / 4;  // 4 warps = 2 warp pairs = 4 tokens per block iteration
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mask_embed_keys_kernel<<<static_cast<int>(blocks), 128, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(ds), w, bias, image_embed, T, ntok, static_cast<__nv_bfloat16*>(keys));
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

@@ -228,7 +228,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
 #pragma unroll 1
   for (int pass = 0; pass < (LN ? 2 : 1); ++pass) {
     if (n_idx >= p.N) break;
-    if (has_res) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
+    // LN: pass 0 computes acc + bias + residual, accumulates the row statistics and parks the sums back in TMEM
+    // (tcgen05.st); pass 1 only re-reads TMEM — the residual stream is gathered once.
+    const bool use_res = has_res && !(LN && pass == 1);
+    if (use_res) issue_res_gather(p, es.res_stg[0], res_off16, n_idx, min(32, p.N - n_idx), lane);
     uint32_t v[2][CH];
     sb::tmem_ld_32x16(taddr, v[0]);
 #pragma unroll 1
@@ -236,7 +239,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
       const int n0 = n_idx + g * 32;
       if (n0 >= p.N) break;  // warp-uniform
       const int ncols = min(32, p.N - n0);  // 16 or 32
-      if (has_res) {
+      if (use_res) {
         const bool more = (n0 + 32 < p.N) && (g + 1 < NG);
         if (es.nres == 2 && more) {  // double-buffered: the next group's gather is in flight while this one is consumed
           issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
@@ -262,14 +265,19 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
             f[4 * j + 1] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 1]), p.alpha, b.y));
             f[4 * j + 2] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 2]), p.alpha, b.z));
             f[4 * j + 3] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 3]), p.alpha, b.w));
-          } else {
+          } else if (pass == 0) {
             f[4 * j + 0] = __uint_as_float(v[h][4 * j + 0]) + b.x;
             f[4 * j + 1] = __uint_as_float(v[h][4 * j + 1]) + b.y;
             f[4 * j + 2] = __uint_as_float(v[h][4 * j + 2]) + b.z;
             f[4 * j + 3] = __uint_as_float(v[h][4 * j + 3]) + b.w;
+          } else {
+            f[4 * j + 0] = __uint_as_float(v[h][4 * j + 0]);
+            f[4 * j + 1] = __uint_as_float(v[h][4 * j + 1]);
+            f[4 * j + 2] = __uint_as_float(v[h][4 * j + 2]);
+            f[4 * j + 3] = __uint_as_float(v[h][4 * j + 3]);
           }
         }
-        if (has_res) {
+        if (use_res) {
           if (p.res_f32)
             add_res_from_stg<true>(es.res_stg[g & 1], lane, h, f);
           else
@@ -282,6 +290,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
               sum += f[j];
               sumsq += f[j] * f[j];
             }
+            sb::tmem_st_32x16(taddr + static_cast<uint32_t>((g * 2 + h) * CH), reinterpret_cast<const uint32_t*>(f));
             continue;
           }
 #pragma unroll
@@ -297,7 +306,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
         stage_out(es.out_stg, lane, h, p.out_f32, f);
       }
       __syncwarp();  // residual tile fully consumed, output tile fully written
-      if (has_res && es.nres != 2 && (n0 + 32 < p.N) && (g + 1 < NG))
+      if (use_res && es.nres != 2 && (n0 + 32 < p.N) && (g + 1 < NG))
         issue_res_gather(p, es.res_stg[(g + 1) & 1], res_off16, n0 + 32, min(32, p.N - n0 - 32), lane);
       if (!(LN && pass == 0)) {
         if (p.out_f32)
@@ -310,6 +319,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
       }
     }
     if (LN && pass == 0) {
+      sb::tmem_st_wait();
       mean = sum / static_cast<float>(p.N);
       const float var = fmaxf(sumsq / static_cast<float>(p.N) - mean * mean, 0.f);
       rstd = rsqrtf(var + p.eps);

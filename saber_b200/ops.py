@@ -243,6 +243,60 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     return out
 
 
+def attention_kadd(q: torch.Tensor, k: torch.Tensor, k_add: torch.Tensor, v: torch.Tensor, batch: int, heads: int, nq: int,
+                   nk: int, kv_shared: bool = False, scale: Optional[float] = None) -> torch.Tensor:
+    """attention() with scores = q (k[b] + k_add)^T; k_add [nk, heads*hd] bf16 is shared by all batch entries."""
+    _chk_cuda(q, k, k_add, v)
+    assert q.dtype == _BF16 and k.dtype == _BF16 and v.dtype == _BF16 and k_add.dtype == _BF16
+    Cc = q.shape[1]
+    hd = Cc // heads
+    assert q.shape[0] == batch * nq and k.shape[0] == (1 if kv_shared else batch) * nk and v.shape[0] == k.shape[0]
+    assert k_add.shape == (nk, Cc) and k_add.stride(1) == 1
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    out = torch.empty((batch * nq, Cc), dtype=_BF16, device=q.device)
+    L = _lib.load()
+    _lib.check(L.sb_attention_kadd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), k_add.data_ptr(), k_add.stride(0),
+                                   v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0), batch, heads, hd, nq, nk,
+                                   scale, int(kv_shared), _stream()), "sb_attention_kadd")
+    _count()
+    return out
+
+
+def attention_few_keys(q: torch.Tensor, q_add: Optional[torch.Tensor], k: torch.Tensor, v: torch.Tensor, batch: int,
+                       nq: int, nk: int, q_shared: bool = False, scale: Optional[float] = None) -> torch.Tensor:
+    """Image -> token attention of the mask decoder (8 heads x 16, nk <= 16): out[b, i] = softmax((q[b,i] + q_add[i]) k_b^T)
+    v_b. q [batch*nq (nq when q_shared), 128] bf16 (row views allowed), q_add [nq,128] fp32 or None."""
+    _chk_cuda(q, q_add, k, v)
+    assert q.dtype == _BF16 and k.dtype == _BF16 and v.dtype == _BF16 and q.shape[1] == 128 and q.stride(1) == 1
+    assert q.shape[0] == (1 if q_shared else batch) * nq and k.shape == (batch * nk, 128) and v.shape == k.shape
+    assert q_add is None or (q_add.dtype == _F32 and q_add.is_contiguous() and q_add.shape == (nq, 128))
+    if scale is None:
+        scale = 0.25
+    out = torch.empty((batch * nq, 128), dtype=_BF16, device=q.device)
+    L = _lib.load()
+    _lib.check(L.sb_attention_few_keys(q.data_ptr(), q.stride(0), _ptr(q_add), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                       v.stride(0), out.data_ptr(), out.stride(0), batch, nq, nk, scale, int(q_shared),
+                                       _stream()), "sb_attention_few_keys")
+    _count()
+    return out
+
+
+def mask_embed_keys(ds: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, image_embed: torch.Tensor) -> torch.Tensor:
+    """Per-prompt image stream of the m2m pass: bf16(image_embed[t] + bias + ds @ w^T); ds [B*T,16] bf16, w [256,16] fp32."""
+    _chk_cuda(ds, w, bias, image_embed)
+    assert ds.dtype == _BF16 and ds.is_contiguous() and ds.shape[1] == 16 and w.dtype == _F32 and w.shape == (256, 16)
+    assert image_embed.dtype == _F32 and image_embed.is_contiguous() and image_embed.shape[1] == 256
+    T = image_embed.shape[0]
+    assert ds.shape[0] % T == 0
+    keys = torch.empty((ds.shape[0], 256), dtype=_BF16, device=ds.device)
+    L = _lib.load()
+    _lib.check(L.sb_mask_embed_keys(ds.data_ptr(), w.data_ptr(), bias.data_ptr(), image_embed.data_ptr(), T, ds.shape[0],
+                                    keys.data_ptr(), _stream()), "sb_mask_embed_keys")
+    _count()
+    return keys
+
+
 def window_attention(qkv: torch.Tensor, qkv_bias: Optional[torch.Tensor], batch: int, H: int, W: int,
                      heads: int, ws: int, pool: int = 1, scale: Optional[float] = None) -> torch.Tensor:
     """Hiera (windowed / global, optionally q-pooled) attention over a fused qkv [B*H*W, 3*C] buffer."""

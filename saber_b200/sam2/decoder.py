@@ -58,7 +58,7 @@ class MaskDecoder:
                      f32(sd[pe + "mask_downscaling.1.weight"]), f32(sd[pe + "mask_downscaling.1.bias"]),
                      f32(sd[pe + "mask_downscaling.3.weight"].reshape(-1)), f32(sd[pe + "mask_downscaling.3.bias"]),
                      f32(sd[pe + "mask_downscaling.4.weight"]), f32(sd[pe + "mask_downscaling.4.bias"])]
-        self.md6_w = w16(sd[pe + "mask_downscaling.6.weight"].reshape(256, 16))
+        self.md6_w = f32(sd[pe + "mask_downscaling.6.weight"].reshape(256, 16))
         self.md6_b = f32(sd[pe + "mask_downscaling.6.bias"])
         image_pe = _dense_pe(gauss)  # [4096, 256] fp32 on CPU
         self.image_pe = f32(image_pe)
@@ -83,8 +83,10 @@ class MaskDecoder:
             L["sa_o_w"], L["sa_o_b"] = w16(sa["outw"]), f32(sa["outb"])
             L["t2i_q_w"], L["t2i_q_b"] = w16(t2i["qw"]), f32(t2i["qb"])
             L["t2i_kv_w"] = w16(torch.cat([t2i["kw"], t2i["vw"]], 0))
-            L["t2i_kv_res"] = f32(torch.cat([image_pe @ t2i["kw"].t() + t2i["kb"],
-                                             t2i["vb"].expand(NT_IMG, -1)], dim=1))  # [4096, 256]
+            # k = (keys + pe) Wk^T + bk: the pe term (weights only) is added inside the attention kernel as a second MMA
+            # (scores = q k^T + q k_add^T), so the big K|V GEMM carries a plain bias and no broadcast residual
+            L["t2i_kv_b"] = f32(torch.cat([torch.zeros(128), t2i["vb"]]))
+            L["t2i_k_add"] = w16(image_pe @ t2i["kw"].t() + t2i["kb"])  # [4096, 128]
             L["t2i_o_w"], L["t2i_o_b"] = w16(t2i["outw"]), f32(t2i["outb"])
             L["i2t_q_w"] = w16(i2t["qw"])
             L["i2t_q_res"] = f32(image_pe @ i2t["qw"].t() + i2t["qb"])  # [4096, 128]
@@ -99,7 +101,8 @@ class MaskDecoder:
         fa = attn_w(md + "transformer.final_attn_token_to_image")
         self.fa_q_w, self.fa_q_b = w16(fa["qw"]), f32(fa["qb"])
         self.fa_kv_w = w16(torch.cat([fa["kw"], fa["vw"]], 0))
-        self.fa_kv_res = f32(torch.cat([image_pe @ fa["kw"].t() + fa["kb"], fa["vb"].expand(NT_IMG, -1)], dim=1))
+        self.fa_kv_b = f32(torch.cat([torch.zeros(128), fa["vb"]]))
+        self.fa_k_add = w16(image_pe @ fa["kw"].t() + fa["kb"])
         self.fa_o_w, self.fa_o_b = w16(fa["outw"]), f32(fa["outb"])
         self.nf_w, self.nf_b = f32(sd[md + "transformer.norm_final_attn.weight"]), f32(sd[md + "transformer.norm_final_attn.bias"])
         # transposed convs as GEMMs: out column = (dy*2+dx)*Cout + co
@@ -158,7 +161,7 @@ class MaskDecoder:
             assert ds.shape[0] == B * NT_IMG, (ds.shape, B)
             # per-prompt image stream (image_embed + dense mask embedding) kept in bf16: it is re-normalised by
             # norm4 right after the first block, and an fp32 copy would be 805 MB per 192 prompts
-            keys = ops.gemm(ds, self.md6_w, self.md6_b, residual=image_embed, res_mod=NT_IMG, out_dtype=_BF16)
+            keys = ops.mask_embed_keys(ds, self.md6_w, self.md6_b, image_embed)
             keys_f32 = keys
         kb = 1 if shared else B  # batch entries of the image stream
 
@@ -176,8 +179,8 @@ class MaskDecoder:
             queries = ops.layernorm(queries, L["n1w"], L["n1b"], 1e-5, _F32)
             # ---- tokens attend to image
             q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["t2i_q_w"], L["t2i_q_b"])
-            kv = ops.gemm(keys, L["t2i_kv_w"], None, residual=L["t2i_kv_res"], res_mod=NT_IMG)
-            a = ops.attention(q, kv[:, 0:128], kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))
+            kv = ops.gemm(keys, L["t2i_kv_w"], L["t2i_kv_b"])
+            a = ops.attention_kadd(q, kv[:, 0:128], L["t2i_k_add"], kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))
             queries = ops.gemm(a, L["t2i_o_w"], L["t2i_o_b"], residual=queries, out_dtype=_F32)
             queries = ops.layernorm(queries, L["n2w"], L["n2b"], 1e-5, _F32)
             # ---- token MLP
@@ -187,8 +190,14 @@ class MaskDecoder:
             # ---- image attends to tokens
             kt = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["i2t_k_w"], L["i2t_k_b"])
             vt = ops.gemm(ops.add_cast(queries, None, _BF16), L["i2t_v_w"], L["i2t_v_b"])
-            qi = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
-            a = ops.attention(qi, kt, vt, B, 8, NT_IMG, Nt, q_shared=(kb == 1))  # [B*4096,128]
+            # q = keys @ Wq^T; its positional term (image_pe @ Wq^T + bq) is added inside the attention kernel, so the
+            # big GEMM has no residual stream to gather
+            if Nt <= 16:
+                qi = ops.gemm(keys, L["i2t_q_w"], None)
+                a = ops.attention_few_keys(qi, L["i2t_q_res"], kt, vt, B, NT_IMG, Nt, q_shared=(kb == 1))  # [B*4096,128]
+            else:  # many prompt points per object: generic flash kernel
+                qi = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
+                a = ops.attention(qi, kt, vt, B, 8, NT_IMG, Nt, q_shared=(kb == 1))
             # keys = norm4(keys + out_proj(attn)) fused in the GEMM epilogue (no fp32 round trip of the image stream)
             keys = ops.gemm_ln(a, L["i2t_o_w"], L["i2t_o_b"], keys_f32, L["n4w"], L["n4b"], 1e-5,
                                res_mod=(NT_IMG if kb == 1 else 0))
@@ -196,8 +205,8 @@ class MaskDecoder:
             kb = B
         # ---- final token -> image attention
         q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), self.fa_q_w, self.fa_q_b)
-        kv = ops.gemm(keys, self.fa_kv_w, None, residual=self.fa_kv_res, res_mod=NT_IMG)
-        a = ops.attention(q, kv[:, 0:128], kv[:, 128:256], B, 8, Nt, NT_IMG)
+        kv = ops.gemm(keys, self.fa_kv_w, self.fa_kv_b)
+        a = ops.attention_kadd(q, kv[:, 0:128], self.fa_k_add, kv[:, 128:256], B, 8, Nt, NT_IMG)
         queries = ops.gemm(a, self.fa_o_w, self.fa_o_b, residual=queries, out_dtype=_F32)
         hs = ops.layernorm(queries, self.nf_w, self.nf_b, 1e-5, _F32)  # [B*Nt,256]
         # ---- up-scaling + hyper-network masks

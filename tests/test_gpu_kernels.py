@@ -88,6 +88,68 @@ def test_attention(ops, B, heads, hd, nq, nk):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("nk,q_shared,nq", [(8, False, 4096), (9, True, 4096), (16, False, 1500), (1, False, 1024)])
+def test_attention_few_keys_streaming(ops, nk, q_shared, nq):
+    """image -> token attention of the mask decoder (few keys, 8 heads x 16): the streaming kernel, incl. a query
+    matrix shared by all prompts and a strided q view of a wider projection buffer."""
+    torch.manual_seed(3)
+    B = 3
+    qfull = torch.randn((1 if q_shared else B) * nq, 256, device="cuda").to(BF16)
+    q = qfull[:, 64:192]
+    k = torch.randn(B * nk, 128, device="cuda").to(BF16)
+    v = torch.randn(B * nk, 128, device="cuda").to(BF16)
+    out = ops.attention(q, k, v, B, 8, nq, nk, q_shared=q_shared)
+    qr = q.contiguous().repeat(B, 1) if q_shared else q.contiguous()
+    ref = _sdpa_ref(qr, k, v, B, 8, nq, nk)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+def test_attention_few_keys_with_query_term(ops):
+    torch.manual_seed(4)
+    B, nq, nk = 3, 4096, 8
+    q = torch.randn(B * nq, 128, device="cuda").to(BF16)
+    qa = torch.randn(nq, 128, device="cuda")
+    k = torch.randn(B * nk, 128, device="cuda").to(BF16)
+    v = torch.randn(B * nk, 128, device="cuda").to(BF16)
+    out = ops.attention_few_keys(q, qa, k, v, B, nq, nk)
+    qe = (q.float().view(B, nq, 128) + qa[None]).to(BF16).reshape(B * nq, 128)
+    ref = _sdpa_ref(qe, k, v, B, 8, nq, nk)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+    out1 = ops.attention_few_keys(q[:nq], qa, k, v, B, nq, nk, q_shared=True)
+    ref1 = _sdpa_ref(qe[:nq].repeat(B, 1), k, v, B, 8, nq, nk)
+    assert (out1.float() - ref1).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,heads,hd,nq,nk,shared", [(3, 8, 16, 8, 4096, False), (2, 8, 16, 7, 4096, True),
+                                                     (2, 2, 64, 100, 333, False), (1, 1, 256, 64, 200, False)])
+def test_attention_with_additive_key_term(ops, B, heads, hd, nq, nk, shared):
+    torch.manual_seed(6)
+    C = heads * hd
+    q = (torch.randn(B * nq, C, device="cuda") * 0.5).to(BF16)
+    k = torch.randn((1 if shared else B) * nk, C, device="cuda").to(BF16)
+    ka = torch.randn(nk, C, device="cuda").to(BF16)
+    v = torch.randn((1 if shared else B) * nk, C, device="cuda").to(BF16)
+    out = ops.attention_kadd(q, k, ka, v, B, heads, nq, nk, kv_shared=shared)
+    kr = k.float().view(-1, nk, C) + ka.float()[None]
+    kr = (kr.expand(B, -1, -1) if shared else kr).reshape(B * nk, C)
+    vr = (v.view(1, nk, C).expand(B, -1, -1).reshape(B * nk, C) if shared else v)
+    ref = _sdpa_ref(q, kr, vr, B, heads, nq, nk)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+def test_mask_embed_keys(ops):
+    torch.manual_seed(5)
+    B, T = 3, 4096
+    ds = torch.randn(B * T, 16, device="cuda").to(BF16)
+    w = torch.randn(256, 16, device="cuda") * 0.3
+    b = torch.randn(256, device="cuda")
+    ie = torch.randn(T, 256, device="cuda")
+    out = ops.mask_embed_keys(ds, w, b, ie)
+    ref = (ds.float() @ w.t() + b).view(B, T, 256) + ie[None]
+    assert (out.float().view(B, T, 256) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    assert ((out.float().view(B, T, 256) - ref).norm() / ref.norm()).item() < 4e-3
+
+
 def _window_ref(qkv, bias, B, H, W, heads, hd, ws, pool):
     """Hiera MultiScaleAttention on an already-projected qkv (padding tokens carry the bias), fp32."""
     C = heads * hd
