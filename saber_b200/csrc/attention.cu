@@ -382,7 +382,8 @@ flash_attn_kernel(const AttnParams p) {
 // prompt's K / V held in shared memory as fp32. One thread per (query row, head); HBM-bound.
 // ------------------------------------------------------------------------------------------------
 constexpr int FK_MAX_KEYS = 16;
-constexpr int FK_ROWS = 32;  // query rows per block iteration (256 threads = 32 rows x 8 heads)
+constexpr int FK_R = 2;            // query rows per thread: every K / V shared-memory load is reused FK_R times
+constexpr int FK_ROWS = 32 * FK_R;  // query rows per block iteration (256 threads = 32 row groups x 8 heads)
 
 __global__ void __launch_bounds__(256)
 fewkeys_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld, long long q_bstride,
@@ -391,8 +392,8 @@ fewkeys_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld, long lo
                     long long v_ld, __nv_bfloat16* __restrict__ o, long long o_ld, int nq, int nk, float scale_log2,
                     int rows_per_block) {
   constexpr int C = 128;
-  // per key: 8 heads x (16 values + 4 pad floats). The 8 lanes of a quarter-warp read the 8 heads of one row with
-  // LDS.128; a head pitch of 20 floats spreads them over all 32 banks (16 would be a 4-way conflict).
+  // per key: 8 heads x (16 values + 4 pad floats). The 8 lanes of a quarter-warp read the 8 heads with LDS.128; a head
+  // pitch of 20 floats spreads them over all 32 banks (16 would be a 4-way conflict).
   constexpr int HP = 20, KP = 8 * HP;
   __shared__ __align__(16) float sK[FK_MAX_KEYS * KP];
   __shared__ __align__(16) float sV[FK_MAX_KEYS * KP];
@@ -407,75 +408,106 @@ fewkeys_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld, long lo
   const int r_begin = blockIdx.x * rows_per_block;
   const int r_end = min(nq, r_begin + rows_per_block);
   for (int r0 = r_begin; r0 < r_end; r0 += FK_ROWS) {
-    const int r = r0 + rsub;
-    if (r >= r_end) continue;
-    const __nv_bfloat16* qp = q + (static_cast<long long>(b) * q_bstride + r) * q_ld + head * 16;
-    const uint4 qa = *reinterpret_cast<const uint4*>(qp);
-    const uint4 qb = *reinterpret_cast<const uint4*>(qp + 8);
-    float qf[16];
-    qf[0] = sb::bf16_lo(qa.x); qf[1] = sb::bf16_hi(qa.x); qf[2] = sb::bf16_lo(qa.y); qf[3] = sb::bf16_hi(qa.y);
-    qf[4] = sb::bf16_lo(qa.z); qf[5] = sb::bf16_hi(qa.z); qf[6] = sb::bf16_lo(qa.w); qf[7] = sb::bf16_hi(qa.w);
-    qf[8] = sb::bf16_lo(qb.x); qf[9] = sb::bf16_hi(qb.x); qf[10] = sb::bf16_lo(qb.y); qf[11] = sb::bf16_hi(qb.y);
-    qf[12] = sb::bf16_lo(qb.z); qf[13] = sb::bf16_hi(qb.z); qf[14] = sb::bf16_lo(qb.w); qf[15] = sb::bf16_hi(qb.w);
-    if (q_add != nullptr) {  // positional term of the query projection (shared by all prompts, L2-resident)
-      const float4* ap = reinterpret_cast<const float4*>(q_add + static_cast<long long>(r) * C + head * 16);
+    // this thread's rows: r0 + rsub + 32 * u (a warp still touches 4 consecutive rows x 256 B per load instruction)
+    float qf[FK_R][16];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float4 a4 = __ldg(ap + t);
-        // the GEMM this replaces rounded (acc + residual) to bf16 once; keep that rounding point
-        qf[4 * t + 0] = __bfloat162float(__float2bfloat16(qf[4 * t + 0] + a4.x));
-        qf[4 * t + 1] = __bfloat162float(__float2bfloat16(qf[4 * t + 1] + a4.y));
-        qf[4 * t + 2] = __bfloat162float(__float2bfloat16(qf[4 * t + 2] + a4.z));
-        qf[4 * t + 3] = __bfloat162float(__float2bfloat16(qf[4 * t + 3] + a4.w));
+    for (int u = 0; u < FK_R; ++u) {
+      const int r = min(r0 + rsub + 32 * u, r_end - 1);
+      const __nv_bfloat16* qp = q + (static_cast<long long>(b) * q_bstride + r) * q_ld + head * 16;
+      const uint4 qa = *reinterpret_cast<const uint4*>(qp);
+      const uint4 qb = *reinterpret_cast<const uint4*>(qp + 8);
+      const uint32_t w8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        qf[u][2 * e] = sb::bf16_lo(w8[e]);
+        qf[u][2 * e + 1] = sb::bf16_hi(w8[e]);
+      }
+      if (q_add != nullptr) {  // positional term of the query projection (shared by all prompts, L2-resident)
+        const float4* ap = reinterpret_cast<const float4*>(q_add + static_cast<long long>(r) * C + head * 16);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 a4 = __ldg(ap + t);
+          // the GEMM this replaces rounded (acc + residual) to bf16 once; keep that rounding point
+          qf[u][4 * t + 0] = __bfloat162float(__float2bfloat16(qf[u][4 * t + 0] + a4.x));
+          qf[u][4 * t + 1] = __bfloat162float(__float2bfloat16(qf[u][4 * t + 1] + a4.y));
+          qf[u][4 * t + 2] = __bfloat162float(__float2bfloat16(qf[u][4 * t + 2] + a4.z));
+          qf[u][4 * t + 3] = __bfloat162float(__float2bfloat16(qf[u][4 * t + 3] + a4.w));
+        }
       }
     }
-    float sc[FK_MAX_KEYS];
-    float mx = -INFINITY;
+    float sc[FK_R][FK_MAX_KEYS];
+    float mx[FK_R];
+#pragma unroll
+    for (int u = 0; u < FK_R; ++u) mx[u] = -INFINITY;
 #pragma unroll
     for (int j = 0; j < FK_MAX_KEYS; ++j) {
       if (j < nk) {
         const float4* kp = reinterpret_cast<const float4*>(sK + j * KP + head * HP);
-        float acc = 0.f;
+        float acc[FK_R];
+#pragma unroll
+        for (int u = 0; u < FK_R; ++u) acc[u] = 0.f;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float4 kk = kp[t];
-          acc = fmaf(qf[4 * t + 0], kk.x, acc);
-          acc = fmaf(qf[4 * t + 1], kk.y, acc);
-          acc = fmaf(qf[4 * t + 2], kk.z, acc);
-          acc = fmaf(qf[4 * t + 3], kk.w, acc);
+#pragma unroll
+          for (int u = 0; u < FK_R; ++u) {
+            acc[u] = fmaf(qf[u][4 * t + 0], kk.x, acc[u]);
+            acc[u] = fmaf(qf[u][4 * t + 1], kk.y, acc[u]);
+            acc[u] = fmaf(qf[u][4 * t + 2], kk.z, acc[u]);
+            acc[u] = fmaf(qf[u][4 * t + 3], kk.w, acc[u]);
+          }
         }
-        sc[j] = acc * scale_log2;
-        mx = fmaxf(mx, sc[j]);
+#pragma unroll
+        for (int u = 0; u < FK_R; ++u) {
+          sc[u][j] = acc[u] * scale_log2;
+          mx[u] = fmaxf(mx[u], sc[u][j]);
+        }
       }
     }
-    float l = 0.f;
-    float out[16];
+    float l[FK_R];
+    float out[FK_R][16];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) out[d] = 0.f;
+    for (int u = 0; u < FK_R; ++u) {
+      l[u] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) out[u][d] = 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < FK_MAX_KEYS; ++j) {
       if (j < nk) {
-        const float pj = exp2f(sc[j] - mx);  // ex2.approx
-        l += pj;
+        float pj[FK_R];
+#pragma unroll
+        for (int u = 0; u < FK_R; ++u) {
+          pj[u] = exp2f(sc[u][j] - mx[u]);
+          l[u] += pj[u];
+        }
         const float4* vp = reinterpret_cast<const float4*>(sV + j * KP + head * HP);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float4 vv = vp[t];
-          out[4 * t + 0] = fmaf(pj, vv.x, out[4 * t + 0]);
-          out[4 * t + 1] = fmaf(pj, vv.y, out[4 * t + 1]);
-          out[4 * t + 2] = fmaf(pj, vv.z, out[4 * t + 2]);
-          out[4 * t + 3] = fmaf(pj, vv.w, out[4 * t + 3]);
+#pragma unroll
+          for (int u = 0; u < FK_R; ++u) {
+            out[u][4 * t + 0] = fmaf(pj[u], vv.x, out[u][4 * t + 0]);
+            out[u][4 * t + 1] = fmaf(pj[u], vv.y, out[u][4 * t + 1]);
+            out[u][4 * t + 2] = fmaf(pj[u], vv.z, out[u][4 * t + 2]);
+            out[u][4 * t + 3] = fmaf(pj[u], vv.w, out[u][4 * t + 3]);
+          }
         }
       }
     }
-    const float inv = __fdividef(1.f, l);
-    __nv_bfloat16* op = o + (static_cast<long long>(b) * nq + r) * o_ld + head * 16;
-    *reinterpret_cast<uint4*>(op) =
-        make_uint4(sb::pack_bf16x2(out[0] * inv, out[1] * inv), sb::pack_bf16x2(out[2] * inv, out[3] * inv),
-                   sb::pack_bf16x2(out[4] * inv, out[5] * inv), sb::pack_bf16x2(out[6] * inv, out[7] * inv));
-    *reinterpret_cast<uint4*>(op + 8) =
-        make_uint4(sb::pack_bf16x2(out[8] * inv, out[9] * inv), sb::pack_bf16x2(out[10] * inv, out[11] * inv),
-                   sb::pack_bf16x2(out[12] * inv, out[13] * inv), sb::pack_bf16x2(out[14] * inv, out[15] * inv));
+#pragma unroll
+    for (int u = 0; u < FK_R; ++u) {
+      const int r = r0 + rsub + 32 * u;
+      if (r >= r_end) continue;
+      const float inv = __fdividef(1.f, l[u]);
+      __nv_bfloat16* op = o + (static_cast<long long>(b) * nq + r) * o_ld + head * 16;
+      *reinterpret_cast<uint4*>(op) = make_uint4(
+          sb::pack_bf16x2(out[u][0] * inv, out[u][1] * inv), sb::pack_bf16x2(out[u][2] * inv, out[u][3] * inv),
+          sb::pack_bf16x2(out[u][4] * inv, out[u][5] * inv), sb::pack_bf16x2(out[u][6] * inv, out[u][7] * inv));
+      *reinterpret_cast<uint4*>(op + 8) = make_uint4(
+          sb::pack_bf16x2(out[u][8] * inv, out[u][9] * inv), sb::pack_bf16x2(out[u][10] * inv, out[u][11] * inv),
+          sb::pack_bf16x2(out[u][12] * inv, out[u][13] * inv), sb::pack_bf16x2(out[u][14] * inv, out[u][15] * inv));
+    }
   }
 }
 
