@@ -310,12 +310,13 @@ def run_b200(args):
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one representative launch (ncu --set full, profiles/)
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
-            traffic = {"dram_bytes": tj["dram_bytes_per_launch"], "algorithmic_bytes": tj["algorithmic_bytes_per_launch"],
-                       "launch": tj["launch"], "source": tj["source"]}
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_detail = {"algorithmic_bytes": tj["algorithmic_bytes_per_launch"], "launch": tj["launch"],
+                              "source": tj["source"]}
         except Exception:
-            pass
+            traffic_detail = None
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": r["tflops"], "peak": peak,
-                    "unit": "TFLOP/s", "frac": r["tflops"] / peak, "traffic": traffic,
+                    "unit": "TFLOP/s", "frac": r["tflops"] / peak, "traffic": traffic, "traffic_detail": traffic_detail,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                     "launches": r["launches"], "gemm_ms_per_step": r["ms"], "flops_per_step": r["flops"],
                     "share_of_step": r["ms"] / (ms_max / args.steps),

@@ -194,6 +194,28 @@ int sb_gauss1d_mirror(const float* in, int Z, int H, int W, int axis, const doub
 int sb_gaussian_z(const float* in, int Z, long long plane, const float* w, int ks, float* out, void* stream); /* REF filters/gaussian.py:17-74 */
 int sb_mean_z(const float* in, long long plane, int z0, int z1, float* out, void* stream); /* REF utils/preprocessing.py:39-66 */
 
+/* ---- expert classifier (REF saber/classifier/models/{predictor,SAM2}.py, classifier/datasets/RandMaskCrop.py) ------- */
+int sb_mean_std(const float* in, long long n, float* ms, double* ws, void* stream);   /* monai NormalizeIntensity stats */
+int sb_standardize(const float* in, long long n, const float* ms, float* out, void* stream);
+int sb_mask_bbox(const unsigned char* masks, int N, int H, int W, int* bbox, void* stream); /* (ymin,ymax,xmin,xmax) | -1 */
+/* crop_and_resize_adaptive: crop geom[n] = (top,left,h,w) -> bilinear (image) / nearest (mask) resize to SxS + mask area */
+int sb_crop_resize(const float* img, const unsigned char* masks, const int* geom, int N, int H, int W, int S,
+                   float* out_img, unsigned char* out_mask, int* area, void* stream);
+/* SAM2Classifier.apply_mask_to_features: [feat*m | feat*(1-m)] with m nearest-resized to the GxG embedding grid */
+int sb_mask_features(const float* feat, const unsigned char* mask, int B, int G, int S, int C, void* out, void* stream);
+int sb_prelu(const void* in, int in_f32, long long n, float slope, void* out, void* stream);
+int sb_im2col_3x3s1(const void* in, int B, int H, int W, int C, void* cols, void* stream);
+int sb_mean_tokens(const void* in, int B, int T, int C, float* out, void* stream);     /* adaptive_avg_pool2d(1,1) */
+int sb_softmax_rows(const float* in, int B, int C, float* out, void* stream);
+
+/* ---- label-volume filters next to the path: fast_3d_gaussian_smoothing (REF saber/filters/masks.py:230-309, -------
+ * gaussian.py:76-138) and ball morphology (REF saber/analysis/refine_membranes.py:100-117,274-333) */
+int sb_label_equals(const void* vol, int elem_bytes, long long n, unsigned int label, float* out,
+                    unsigned long long* count, void* stream);
+int sb_corr1d_zero(const float* in, int Z, int Y, int X, int axis, const float* w, int ks, float* out, void* stream);
+int sb_threshold_label(const float* sm, long long n, float thr, int label, unsigned char* result, void* stream);
+int sb_morph_ball(const unsigned char* in, int Z, int Y, int X, int r, int op, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

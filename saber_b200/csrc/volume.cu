@@ -164,6 +164,79 @@ mean_z_kernel(const float* __restrict__ in, long long plane, int z0, int z1, flo
   }
 }
 
+
+// ---- REF saber/filters/masks.py:230-309 + gaussian.py:76-138 (fast_3d_gaussian_smoothing, R14) and
+// ---- REF saber/analysis/refine_membranes.py:100-117,274-333 (ball erosion / dilation / opening, R17) ----------------
+
+// out[i] = (vol[i] == label) ? 1 : 0 (fp32); *count += number of matches
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_equals_kernel(const T* __restrict__ vol, long long n, unsigned int label, float* __restrict__ out,
+                    unsigned long long* __restrict__ count) {
+  unsigned int c = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool m = static_cast<unsigned int>(vol[i]) == label;
+    out[i] = m ? 1.f : 0.f;
+    c += m;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, static_cast<unsigned long long>(c));
+}
+
+// 1-D correlation with zero padding along `axis` (0 = z, 1 = y, 2 = x) of a [Z, Y, X] fp32 volume
+__global__ void __launch_bounds__(256)
+corr1d_zero_kernel(const float* __restrict__ in, int Z, int Y, int X, int axis, const float* __restrict__ w, int ks,
+                   float* __restrict__ out) {
+  const int r = ks / 2;
+  const long long n = static_cast<long long>(Z) * Y * X;
+  const long long stride = axis == 0 ? static_cast<long long>(Y) * X : (axis == 1 ? X : 1);
+  const int len = axis == 0 ? Z : (axis == 1 ? Y : X);
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(t % X), y = static_cast<int>((t / X) % Y), z = static_cast<int>(t / (static_cast<long long>(X) * Y));
+    const int p = axis == 0 ? z : (axis == 1 ? y : x);
+    float acc = 0.f;
+    for (int k = 0; k < ks; ++k) {
+      const int q = p + k - r;
+      if (q >= 0 && q < len) acc = fmaf(w[k], in[t + static_cast<long long>(k - r) * stride], acc);
+    }
+    out[t] = acc;
+  }
+}
+
+// result[i] = label where smoothed[i] > thr (later labels overwrite earlier ones); result is uint8
+__global__ void __launch_bounds__(256)
+threshold_label_kernel(const float* __restrict__ sm, long long n, float thr, unsigned char label,
+                       unsigned char* __restrict__ result) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    if (sm[i] > thr) result[i] = label;
+}
+
+// Binary erosion (op 0: every ball voxel set; outside the volume counts as 0) / dilation (op 1: any ball voxel set) with
+// the radius-r ball {dz^2 + dy^2 + dx^2 <= r^2}: the exact outcome of the reference's conv3d >= sum / > 0 tests.
+__global__ void __launch_bounds__(256)
+morph_ball_kernel(const unsigned char* __restrict__ in, int Z, int Y, int X, int r, int op, unsigned char* __restrict__ out) {
+  const long long n = static_cast<long long>(Z) * Y * X;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(t % X), y = static_cast<int>((t / X) % Y), z = static_cast<int>(t / (static_cast<long long>(X) * Y));
+    bool res = (op == 0);
+    for (int dz = -r; dz <= r && res == (op == 0); ++dz)
+      for (int dy = -r; dy <= r && res == (op == 0); ++dy)
+        for (int dx = -r; dx <= r; ++dx) {
+          if (dz * dz + dy * dy + dx * dx > r * r) continue;
+          const int zz = z + dz, yy = y + dy, xx = x + dx;
+          const bool inb = zz >= 0 && zz < Z && yy >= 0 && yy < Y && xx >= 0 && xx < X;
+          const bool v = inb && in[(static_cast<long long>(zz) * Y + yy) * X + xx] != 0;
+          if (op == 0 && !v) { res = false; break; }
+          if (op == 1 && v) { res = true; break; }
+        }
+    out[t] = res ? 1 : 0;
+  }
+}
+
 }  // namespace
 
 // mm[0] = min, mm[1] = max of n floats; partials: 2 * 1024 float workspace. No host synchronisation.
@@ -221,6 +294,46 @@ extern "C" int sb_mean_z(const float* in, long long plane, int z0, int z1, float
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(plane > 0 && z1 > z0 && z0 >= 0, "sb_mean_z: bad arguments");
   mean_z_kernel<<<grid_for(plane), 256, 0, stream>>>(in, plane, z0, z1, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// out = (vol == label) as fp32; count (device u64, zeroed by the caller) += matches. elem_bytes in {1, 2, 4}.
+extern "C" int sb_label_equals(const void* vol, int elem_bytes, long long n, unsigned int label, float* out,
+                               unsigned long long* count, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0 && vol && out && count, "sb_label_equals: bad arguments");
+  const int g = grid_for(n);
+  if (elem_bytes == 1) label_equals_kernel<unsigned char><<<g, 256, 0, stream>>>(static_cast<const unsigned char*>(vol), n, label, out, count);
+  else if (elem_bytes == 2) label_equals_kernel<unsigned short><<<g, 256, 0, stream>>>(static_cast<const unsigned short*>(vol), n, label, out, count);
+  else if (elem_bytes == 4) label_equals_kernel<unsigned int><<<g, 256, 0, stream>>>(static_cast<const unsigned int*>(vol), n, label, out, count);
+  else { sb_set_error("sb_label_equals: elem_bytes %d", elem_bytes); return SB_ERR_ARG; }
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_corr1d_zero(const float* in, int Z, int Y, int X, int axis, const float* w, int ks, float* out,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && Y > 0 && X > 0 && axis >= 0 && axis <= 2 && ks > 0 && (ks & 1) && w, "sb_corr1d_zero: bad arguments");
+  corr1d_zero_kernel<<<grid_for(static_cast<long long>(Z) * Y * X), 256, 0, stream>>>(in, Z, Y, X, axis, w, ks, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_threshold_label(const float* sm, long long n, float thr, int label, unsigned char* result, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(n > 0 && sm && result, "sb_threshold_label: bad arguments");
+  threshold_label_kernel<<<grid_for(n), 256, 0, stream>>>(sm, n, thr, static_cast<unsigned char>(label), result);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// op: 0 erosion, 1 dilation; in / out uint8 {0,1} [Z, Y, X]
+extern "C" int sb_morph_ball(const unsigned char* in, int Z, int Y, int X, int r, int op, unsigned char* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && Y > 0 && X > 0 && r >= 0 && (op == 0 || op == 1) && in && out, "sb_morph_ball: bad arguments");
+  morph_ball_kernel<<<grid_for(static_cast<long long>(Z) * Y * X), 256, 0, stream>>>(in, Z, Y, X, r, op, out);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

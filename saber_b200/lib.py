@@ -90,6 +90,19 @@ SIGNATURES = {
     "sb_gauss1d_mirror": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "sb_gaussian_z": [c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p, c_void_p],
     "sb_mean_z": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "sb_mean_std": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
+    "sb_standardize": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
+    "sb_mask_bbox": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_crop_resize": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_mask_features": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_prelu": [c_void_p, c_int, c_ll, c_float, c_void_p, c_void_p],
+    "sb_im2col_3x3s1": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_mean_tokens": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_softmax_rows": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "sb_label_equals": [c_void_p, c_int, c_ll, C.c_uint, c_void_p, c_void_p, c_void_p],
+    "sb_corr1d_zero": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "sb_threshold_label": [c_void_p, c_ll, c_float, c_int, c_void_p, c_void_p],
+    "sb_morph_ball": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
 }
 
 

@@ -920,3 +920,148 @@ def mean_z(vol: torch.Tensor, z0: int, z1: int) -> torch.Tensor:
     _lib.check(L.sb_mean_z(vol.data_ptr(), vol.shape[1] * vol.shape[2], z0, z1, out.data_ptr(), _stream()), "sb_mean_z")
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# expert classifier kernels (csrc/classifier.cu)
+# ---------------------------------------------------------------------------------------------
+def standardize(x: torch.Tensor) -> torch.Tensor:
+    """monai NormalizeIntensity(): (x - mean) / std (population std; no division when std == 0)."""
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.is_contiguous()
+    ms = torch.empty((2,), dtype=_F32, device=x.device)
+    ws = torch.empty((2048,), dtype=torch.float64, device=x.device)
+    out = torch.empty_like(x)
+    L = _lib.load()
+    _lib.check(L.sb_mean_std(x.data_ptr(), x.numel(), ms.data_ptr(), ws.data_ptr(), _stream()), "sb_mean_std")
+    _lib.check(L.sb_standardize(x.data_ptr(), x.numel(), ms.data_ptr(), out.data_ptr(), _stream()), "sb_standardize")
+    _count(3)
+    return out
+
+
+def mask_bbox(masks: torch.Tensor) -> torch.Tensor:
+    """masks uint8 [N,H,W] -> int32 [N,4] (y_min, y_max, x_min, x_max), -1 for empty masks."""
+    _chk_cuda(masks)
+    assert masks.dtype == _U8 and masks.is_contiguous() and masks.dim() == 3
+    N, H, W = masks.shape
+    out = torch.empty((N, 4), dtype=_I32, device=masks.device)
+    L = _lib.load()
+    _lib.check(L.sb_mask_bbox(masks.data_ptr(), N, H, W, out.data_ptr(), _stream()), "sb_mask_bbox")
+    _count()
+    return out
+
+
+def crop_resize(img: torch.Tensor, masks: torch.Tensor, geom: torch.Tensor, S: int):
+    """-> (images fp32 [N,S,S], masks uint8 [N,S,S], areas int32 [N]) for crops geom[n] = (top, left, h, w)."""
+    _chk_cuda(img, masks, geom)
+    assert img.dtype == _F32 and img.is_contiguous() and img.dim() == 2 and masks.dtype == _U8 and masks.is_contiguous()
+    assert geom.dtype == _I32 and geom.is_contiguous() and geom.shape == (masks.shape[0], 4)
+    N, H, W = masks.shape
+    oi = torch.empty((N, S, S), dtype=_F32, device=img.device)
+    om = torch.empty((N, S, S), dtype=_U8, device=img.device)
+    area = torch.zeros((N,), dtype=_I32, device=img.device)
+    L = _lib.load()
+    _lib.check(L.sb_crop_resize(img.data_ptr(), masks.data_ptr(), geom.data_ptr(), N, H, W, S, oi.data_ptr(),
+                                om.data_ptr(), area.data_ptr(), _stream()), "sb_crop_resize")
+    _count()
+    return oi, om, area
+
+
+def mask_features(feat: torch.Tensor, mask: torch.Tensor, B: int, G: int = 64) -> torch.Tensor:
+    """feat fp32 [B*G*G, C] token-major, mask uint8 [B,S,S] -> bf16 [B*G*G, 2C] = [feat*m | feat*(1-m)]."""
+    _chk_cuda(feat, mask)
+    assert feat.dtype == _F32 and feat.is_contiguous() and mask.dtype == _U8 and mask.is_contiguous()
+    Cc = feat.shape[1]
+    out = torch.empty((feat.shape[0], 2 * Cc), dtype=_BF16, device=feat.device)
+    L = _lib.load()
+    _lib.check(L.sb_mask_features(feat.data_ptr(), mask.data_ptr(), B, G, mask.shape[1], Cc, out.data_ptr(), _stream()),
+               "sb_mask_features")
+    _count()
+    return out
+
+
+def prelu(x: torch.Tensor, slope: float) -> torch.Tensor:
+    _chk_cuda(x)
+    assert x.is_contiguous() and x.dtype in (_BF16, _F32)
+    out = torch.empty(x.shape, dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_prelu(x.data_ptr(), int(x.dtype == _F32), x.numel(), float(slope), out.data_ptr(), _stream()), "sb_prelu")
+    _count()
+    return out
+
+
+def im2col_3x3s1(x: torch.Tensor) -> torch.Tensor:
+    """NHWC bf16 [B,H,W,C] -> [B*H*W, 9*C] patches of a 3x3 stride-1 pad-1 conv."""
+    _chk_cuda(x)
+    assert x.dtype == _BF16 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    cols = torch.empty((B * H * W, 9 * Cc), dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_im2col_3x3s1(x.data_ptr(), B, H, W, Cc, cols.data_ptr(), _stream()), "sb_im2col_3x3s1")
+    _count()
+    return cols
+
+
+def mean_tokens(x: torch.Tensor, B: int) -> torch.Tensor:
+    _chk_cuda(x)
+    assert x.dtype == _BF16 and x.is_contiguous() and x.shape[0] % B == 0
+    out = torch.empty((B, x.shape[1]), dtype=_F32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_mean_tokens(x.data_ptr(), B, x.shape[0] // B, x.shape[1], out.data_ptr(), _stream()), "sb_mean_tokens")
+    _count()
+    return out
+
+
+def softmax_rows(x: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.is_contiguous() and x.dim() == 2
+    out = torch.empty_like(x)
+    L = _lib.load()
+    _lib.check(L.sb_softmax_rows(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "sb_softmax_rows")
+    _count()
+    return out
+
+
+def label_equals(vol: torch.Tensor, label: int):
+    """-> ((vol == label) as fp32, device uint64-in-int64 [1] count of matches)."""
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.element_size() in (1, 2, 4)
+    out = torch.empty(vol.shape, dtype=_F32, device=vol.device)
+    count = torch.zeros((1,), dtype=torch.int64, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_label_equals(vol.data_ptr(), vol.element_size(), vol.numel(), int(label), out.data_ptr(),
+                                 count.data_ptr(), _stream()), "sb_label_equals")
+    _count()
+    return out, count
+
+
+def corr1d_zero(vol: torch.Tensor, weights: torch.Tensor, axis: int) -> torch.Tensor:
+    _chk_cuda(vol, weights)
+    assert vol.dtype == _F32 and vol.is_contiguous() and vol.dim() == 3 and weights.dtype == _F32 and weights.is_contiguous()
+    out = torch.empty_like(vol)
+    L = _lib.load()
+    _lib.check(L.sb_corr1d_zero(vol.data_ptr(), vol.shape[0], vol.shape[1], vol.shape[2], axis, weights.data_ptr(),
+                                weights.numel(), out.data_ptr(), _stream()), "sb_corr1d_zero")
+    _count()
+    return out
+
+
+def threshold_label_(sm: torch.Tensor, thr: float, label: int, result: torch.Tensor) -> None:
+    _chk_cuda(sm, result)
+    assert sm.dtype == _F32 and sm.is_contiguous() and result.dtype == _U8 and result.is_contiguous()
+    L = _lib.load()
+    _lib.check(L.sb_threshold_label(sm.data_ptr(), sm.numel(), thr, int(label) & 0xFF, result.data_ptr(), _stream()),
+               "sb_threshold_label")
+    _count()
+
+
+def morph_ball(x: torch.Tensor, radius: int, op: int) -> torch.Tensor:
+    """Binary erosion (op 0) / dilation (op 1) of a uint8 {0,1} [Z,Y,X] volume with a radius-r ball, zero padding."""
+    _chk_cuda(x)
+    assert x.dtype == _U8 and x.is_contiguous() and x.dim() == 3
+    out = torch.empty_like(x)
+    L = _lib.load()
+    _lib.check(L.sb_morph_ball(x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], int(radius), int(op), out.data_ptr(),
+                               _stream()), "sb_morph_ball")
+    _count()
+    return out

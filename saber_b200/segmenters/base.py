@@ -3,7 +3,7 @@
 Same constructor arguments, attributes and method names. ``segment_image`` returns the reference's list of
 mask dicts; ``segment_image_device`` is the resident variant (CUDA slice in, ordered packed masks out) that
 ``propagationSegmenter.slice_by_slice`` uses so that only the final label volume is copied to the host.
-The expert-classifier branch of ``_apply_classifier`` (REF :170-174) is a later §8 row.
+The expert-classifier branch of ``_apply_classifier`` (REF :170-174) calls ``saber_b200.filters.masks.apply_classifier``.
 """
 from __future__ import annotations
 
@@ -78,7 +78,10 @@ class saber2D:
             masks = utils.remove_duplicate_masks(masks, device=self.device)
         if self.classifier is None:
             return sorted(masks, key=lambda m: m["area"], reverse=False)
-        raise NotImplementedError("saber_b200: the expert-classifier filter is not built yet (SURVEY §8a R15/R16)")
+        from ..filters import masks as filters
+        gray = image[:, :, 0] if image.ndim == 3 else image
+        # REF :170-174 passes (target_class, batchsize) positionally: batchsize lands in `min_mask_area`
+        return filters.apply_classifier(gray, masks, self.classifier, self.target_class, self.batchsize)
 
     @torch.inference_mode()
     def segment_image_device(self, image: torch.Tensor):
