@@ -191,7 +191,16 @@ class SAM2Adapter(BaseAdapter):
         del vol
         images = planes[:, None].expand(-1, 3, -1, -1)
         state = self._create_empty_inference_state(images, S, S, offload_video_to_cpu, offload_state_to_cpu)
-        p.encode_frames(state)
+        from .. import dist as sbdist
+        world, rank = sbdist.world_rank()
+        if world == 1:
+            p.encode_frames(state)
+        else:  # Phase A: every rank encodes its z-slab once, then the cached features are exchanged
+            z0, z1 = sbdist.zslab_range(len(images), rank, world)
+            p.encode_frames(state, list(range(z0, z1)))
+            if 0 not in range(z0, z1):
+                state["cached_features"].pop(0, None)  # frame 0 was warmed above on every rank; slab owner is authoritative
+            sbdist.exchange_frame_features(state["cached_features"], len(images))
         return state
 
     def _create_empty_inference_state(self, images, video_height, video_width, offload_video_to_cpu=False,
@@ -241,10 +250,16 @@ class SAM2Adapter(BaseAdapter):
 
     @torch.inference_mode()
     def segment_volume_device(self, start_frame_idx: int, masks=None, vol_shape=None, max_frame_num_to_track=None,
-                              min_presence_score: float = 0.5, inference_state=None) -> torch.Tensor:
-        """REF :232-348 with the label volume kept on the device: returns CUDA int16 (uint16 payload) [Z,H,W]."""
+                              min_presence_score: float = 0.5, inference_state=None, group=None) -> torch.Tensor:
+        """REF :232-348 with the label volume kept on the device: returns CUDA int16 (uint16 payload) [Z,H,W].
+        Under torch.distributed (one process per GPU) the tracked objects are sharded over the ranks (object k ->
+        rank k % world); label volumes are merged with an element-wise max (= "higher object id wins") after each
+        pass and the hook log is merged into the single-process order, so every rank returns the same volume as a
+        single GPU would."""
+        from .. import dist as sbdist
         from .. import ops
         from ..filters import estimate_thickness
+        world, rank = sbdist.world_rank(group)
         state = inference_state or self.inference_state
         if state is None:
             raise RuntimeError("Call set_volume() before segment_volume().")
@@ -255,10 +270,15 @@ class SAM2Adapter(BaseAdapter):
         Z, H, W = vol_shape
         p = self._video()
         mask_list = self._normalize_masks(masks)
+        k = 0  # index among the non-empty seeds (the objects that are actually tracked)
+        n_local = 0
         for obj_id, mask in enumerate(mask_list, start=1):
             if float(mask.max()) == 0:
                 continue
-            self.add_new_mask(frame_idx=start_frame_idx, obj_id=obj_id, mask=mask, inference_state=state)
+            if k % world == rank:
+                self.add_new_mask(frame_idx=start_frame_idx, obj_id=obj_id, mask=mask, inference_state=state)
+                n_local += 1
+            k += 1
         self._current_frame = None
         captured: Dict[Any, list] = {}
 
@@ -274,19 +294,31 @@ class SAM2Adapter(BaseAdapter):
             ids = torch.tensor([int(o) for o in obj_ids], dtype=torch.int32, device=self.device)
             ops.stitch_objects_(mask_logits[:, 0].contiguous(), ids, vol_masks[frame_idx])
 
-        for frame_idx, obj_ids, mask_logits, _, _ in self.propagate_in_video(
-                start_frame_idx=start_frame_idx, max_frame_num_to_track=max_frame_num_to_track, reverse=False,
-                inference_state=state):
+        def _frames(reverse):
+            """Frame schedule of one pass; a rank without objects still walks it (its hook log stays empty)."""
+            if n_local > 0:
+                yield from self.propagate_in_video(start_frame_idx=start_frame_idx,
+                                                   max_frame_num_to_track=max_frame_num_to_track, reverse=reverse,
+                                                   inference_state=state)
+
+        for frame_idx, obj_ids, mask_logits, _, _ in _frames(False):
             self._current_frame = frame_idx
             _apply(frame_idx, obj_ids, mask_logits)
+        sbdist.allreduce_max_labels(vol_masks, group)
         nonempty = ops.slice_any(vol_masks).cpu().numpy()  # one D2H of Z bytes: which slices the forward pass filled
-        for frame_idx, obj_ids, mask_logits, _, _ in self.propagate_in_video(
-                start_frame_idx=start_frame_idx, max_frame_num_to_track=max_frame_num_to_track, reverse=True,
-                inference_state=state):
+        for frame_idx, obj_ids, mask_logits, _, _ in _frames(True):
             self._current_frame = frame_idx
             if not nonempty[frame_idx]:
                 _apply(frame_idx, obj_ids, mask_logits)
+        sbdist.allreduce_max_labels(vol_masks, group)
         handle.remove()
+        if world > 1:
+            import torch.distributed as tdist
+            logs = [None] * world
+            tdist.all_gather_object(logs, ({f: [float(v) for s_ in sc for v in s_.flatten()] for f, sc in captured.items()},
+                                           n_local), group=group)
+            merged = sbdist.merge_captured_scores([l[0] for l in logs], [l[1] for l in logs])
+            captured = {f: [np.asarray(v, dtype=np.float32)] for f, v in merged.items()}
         nMasks = len(mask_list)
         self.frame_scores = np.zeros([Z, nMasks])
         if nMasks > 0:

@@ -55,3 +55,85 @@ def slice_by_slice_sharded(label_fn, separate_fn, volume_slab: torch.Tensor, Z: 
     if full is None:
         return None
     return separate_fn(full)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# z-axis propagation across GPUs: Phase A shards the frame encodes by z-slab and exchanges the
+# cached features; Phase B shards the tracked OBJECTS (GPUPool rule k -> rank k % world: every chain is sequential in
+# z, objects are independent); Phase C merges label volumes with an element-wise max ("higher object id wins").
+# ---------------------------------------------------------------------------------------------------------------------
+def world_rank(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def allreduce_max_labels(labels: torch.Tensor, group=None) -> torch.Tensor:
+    """Element-wise max of a uint16-payload (int16 storage) label volume over ranks, in place. 16-bit integers are not
+    collective dtypes: the payload is widened to int32 per z-chunk (<= 256 MiB in flight)."""
+    world, _ = world_rank(group)
+    if world == 1:
+        return labels
+    flat = labels.view(-1)
+    chunk = 64 * 1024 * 1024
+    for s in range(0, flat.numel(), chunk):
+        part = flat[s:s + chunk]
+        wide = part.to(torch.int32) & 0xFFFF  # uint16 payload
+        dist.all_reduce(wide, op=dist.ReduceOp.MAX, group=group)
+        part.copy_(wide.to(torch.int16))  # values < 2^16 wrap back to the same 16 bits
+    return labels
+
+
+def exchange_frame_features(cached: dict, Z: int, group=None) -> None:
+    """Phase A exchange: every rank holds `cached[f] = {"feat","s1","s0"}` for the frames of its z-slab; after the call
+    every rank holds all Z frames (one broadcast per slab and feature level over NVLink)."""
+    world, rank = world_rank(group)
+    if world == 1:
+        return
+    some = next(iter(cached.values()))
+    dev = some["feat"].device
+    for r in range(world):
+        z0, z1 = zslab_range(Z, r, world)
+        if z1 == z0:
+            continue
+        for key, width, rows in (("feat", 256, 4096), ("s1", 64, 16384), ("s0", 32, 65536)):
+            if rank == r:
+                buf = torch.stack([cached[f][key] for f in range(z0, z1)]).contiguous()
+            else:
+                buf = torch.empty((z1 - z0, rows, width), dtype=torch.float32, device=dev)
+            dist.broadcast(buf, src=r, group=group)
+            if rank != r:
+                for j, f in enumerate(range(z0, z1)):
+                    cached.setdefault(f, {})[key] = buf[j]
+
+
+def merge_captured_scores(per_rank: List[dict], n_local: List[int]) -> dict:
+    """Rebuild the single-process hook log from per-rank logs. per_rank[r][fidx] is rank r's flat list of object-score
+    values filed under frame key `fidx` (one value per local object per decoder call group, in call order); n_local[r]
+    is rank r's number of tracked objects; global object k lives on rank k % world at local index k // world. Every
+    rank saw the same sequence of call groups, so group g of the merged log lists the objects in global order."""
+    world = len(per_rank)
+    keys = []
+    for d in per_rank:
+        for k in d:
+            if k not in keys:
+                keys.append(k)
+    total = sum(n_local)
+    merged = {}
+    for k in keys:
+        groups = None
+        for r in range(world):
+            if n_local[r] == 0:
+                continue
+            vals = per_rank[r].get(k, [])
+            assert len(vals) % n_local[r] == 0, "ranks disagree on the call-group structure"
+            g = len(vals) // n_local[r]
+            groups = g if groups is None else groups
+            assert groups == g, "ranks disagree on the number of call groups"
+        out = []
+        for g in range(groups or 0):
+            for obj in range(total):
+                r, li = obj % world, obj // world
+                out.append(per_rank[r][k][g * n_local[r] + li])
+        merged[k] = out
+    return merged
