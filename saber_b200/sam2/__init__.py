@@ -6,7 +6,7 @@
 import importlib
 import sys
 
-_SUBMODULES = ("build_sam", "automatic_mask_generator", "sam2_image_predictor")
+_SUBMODULES = ("build_sam", "automatic_mask_generator", "sam2_image_predictor", "sam2_video_predictor")
 
 
 def install_as_sam2(force: bool = False) -> None:

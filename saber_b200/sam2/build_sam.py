@@ -105,3 +105,10 @@ def build_sam2(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_ov
     if mode == "eval":
         model.eval()
     return model
+
+
+def build_sam2_video_predictor(*args, **kwargs):
+    """``sam2.build_sam.build_sam2_video_predictor`` (REF saber/adapters/sam2/predictor.py:4,24-26); implemented in
+    ``sam2_video_predictor.py`` (imported lazily: that module subclasses SAM2Model from this one)."""
+    from .sam2_video_predictor import build_sam2_video_predictor as _b
+    return _b(*args, **kwargs)
