@@ -97,6 +97,8 @@ flash_attn_kernel(const AttnParams p) {
   const bool has_kadd = p.k_add != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hd = p.hd;
+  const int chunks = hd >> 3;  // 16-byte chunks per row
   const int head = blockIdx.y;
   const int qtile = blockIdx.x % p.qtiles;
   const int bw = blockIdx.x / p.qtiles;
@@ -115,28 +117,36 @@ flash_attn_kernel(const AttnParams p) {
     nq = wq * wq;
     nk = p.ws * p.ws;
   }
-  const int hd = p.hd;
-  const int chunks = hd >> 3;  // 16-byte chunks per row
   const int col0 = head * hd;
 
-  // zero the whole staging area once (padded columns must stay 0 / finite)
-  for (int i = tid; i < (QROWS + (has_kadd ? 6 : 4) * KT) * PITCH / 16; i += NT)
-    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
+  // The loaders below write columns [0, hd) of every staged row (data, bias or zeros); only the pad columns
+  // [hd, HDP) — never written afterwards — are zeroed here so that they contribute exact zeros to the dot products.
+  {
+    constexpr int PADMAX = HDP / 8;
+    const int npad = PADMAX - chunks;
+    if (npad > 0) {
+      const int nrows = QROWS + (has_kadd ? 6 : 4) * KT;
+      for (int i = tid; i < nrows * npad; i += NT)
+        *reinterpret_cast<uint4*>(smem + (i / npad) * PITCH + (chunks + i % npad) * 16) = make_uint4(0, 0, 0, 0);
+    }
+  }
 
   // ---- load the Q tile (with optional 2x2 max pooling; padded tokens = bias) ----
+  // Rows are split over threads so that the (division-heavy) row addressing is evaluated once per row, not once per
+  // 16-byte chunk: TPR threads share a row and stride over its chunks.
   const int q0 = qtile * QROWS;
-  for (int idx = tid; idx < QROWS * chunks; idx += NT) {
-    const int r = idx / chunks, c = idx % chunks;
+  constexpr int TPRQ = NT >= QROWS ? NT / QROWS : 1;
+  const int win_y = p.mode ? win / p.nwx : 0, win_x = p.mode ? win % p.nwx : 0;
+  for (int r = tid / TPRQ; r < QROWS; r += NT / TPRQ) {
     const int qi = q0 + r;
     if (qi >= nq) continue;
+    const int qy = p.mode ? win_y * wq + qi / wq : 0, qx = p.mode ? win_x * wq + qi % wq : 0;  // pooled padded grid coords
+    const __nv_bfloat16* qrow0 = p.q + (static_cast<long long>(b) * p.q_bstride + qi) * p.q_ld + col0;
+   for (int c = tid % TPRQ; c < chunks; c += TPRQ) {
     uint4 val;
     if (p.mode == 0) {
-      val = *reinterpret_cast<const uint4*>(p.q + (static_cast<long long>(b) * p.q_bstride + qi) * p.q_ld +
-                                            col0 + c * 8);
+      val = *reinterpret_cast<const uint4*>(qrow0 + c * 8);
     } else {
-      const int wy = win / p.nwx, wx = win % p.nwx;
-      const int qy = wy * wq + qi / wq, qx = wx * wq + qi % wq;  // pooled padded grid coords
       __nv_bfloat162 acc[4];
       bool first = true;
       for (int dy = 0; dy < p.pool; ++dy)
@@ -166,16 +176,18 @@ flash_attn_kernel(const AttnParams p) {
       val = *reinterpret_cast<uint4*>(acc);
     }
     *reinterpret_cast<uint4*>(sQ + r * PITCH + c * 16) = val;
+   }
   }
 
   // ---- K/V tile loader ----
   auto load_kv = [&](int t, int stage) {
     uint8_t* dK = sK + stage * KT * PITCH;
     uint8_t* dV = sV + stage * KT * PITCH;
-    for (int idx = tid; idx < KT * chunks; idx += NT) {
-      const int r = idx / chunks, c = idx % chunks;
+    constexpr int TPRK = NT >= KT ? NT / KT : 1;
+    for (int r = tid / TPRK; r < KT; r += NT / TPRK) {
       const int j = t * KT + r;
-      long long row = (j < nk) ? key_row(p, b, win, j) : -2;
+      const long long row = (j < nk) ? key_row(p, b, win, j) : -2;
+     for (int c = tid % TPRK; c < chunks; c += TPRK) {
       if (row >= 0) {
         cp_async16(dK + r * PITCH + c * 16, p.k + row * p.k_ld + col0 + c * 8);
         cp_async16(dV + r * PITCH + c * 16, p.v + row * p.v_ld + col0 + c * 8);
@@ -202,6 +214,7 @@ flash_attn_kernel(const AttnParams p) {
         *reinterpret_cast<uint4*>(dK + r * PITCH + c * 16) = kk;
         *reinterpret_cast<uint4*>(dV + r * PITCH + c * 16) = vv;
       }
+     }
     }
   };
 
@@ -511,9 +524,19 @@ fewkeys_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld, long lo
   }
 }
 
+template <int HDP, int NWARPS, int KT>
+int launch_attn_kt(const AttnParams& p, long long nblocks_x, cudaStream_t stream);
+
 template <int HDP, int NWARPS>
 int launch_attn(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
-  constexpr int KT = HDP > 128 ? 32 : 64;
+  // tiny key sets (Hiera 4x4 windows: 16 keys): a 16-key tile quarters the staging area, so 4x more CTAs fit per SM
+  const int nk_eff = p.mode == 0 ? p.nk : p.ws * p.ws;
+  if (NWARPS == 1 && HDP <= 128 && nk_eff <= 16 && p.k_add == nullptr) return launch_attn_kt<HDP, NWARPS, 16>(p, nblocks_x, stream);
+  return launch_attn_kt<HDP, NWARPS, (HDP > 128 ? 32 : 64)>(p, nblocks_x, stream);
+}
+
+template <int HDP, int NWARPS, int KT>
+int launch_attn_kt(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
   constexpr int PITCH = HDP * 2 + 16;
   constexpr int SMEM_MAX_ = (16 * NWARPS + 6 * KT) * PITCH;
   const int SMEM = (16 * NWARPS + (p.k_add ? 6 : 4) * KT) * PITCH;

@@ -63,7 +63,9 @@ def test_layernorm(ops, M, C, in_f32, act):
     ref = F.layer_norm(xi.float(), (C,), g, b, 1e-6)
     if act:
         ref = F.gelu(ref)
-    assert (out - ref).abs().max().item() < 1e-4
+    # GELU runs on the MUFU.TANH unit (common.cuh gelu_erf): |error| <= 4e-4 + 2.5e-4 |x|
+    tol = 1e-4 if not act else 4e-4 + 2.5e-4 * ref.abs().max().item() + 1e-4
+    assert (out - ref).abs().max().item() < tol
 
 
 def _sdpa_ref(q, k, v, B, heads, nq, nk):

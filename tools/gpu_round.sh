@@ -14,6 +14,8 @@ full) timeout 1200 ncu --set full --clock-control none --import-source on -k reg
 gprobe) timeout 300 python tools/gemm_probe.py > gpurun_out/${TAG}_gemm_probe.log 2>&1; cat gpurun_out/${TAG}_gemm_probe.log;;
 gncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 2 -o gpurun_out/${TAG}_gemm1 python tools/gemm_probe.py 0 > gpurun_out/${TAG}_gncu.log 2>&1; echo "gncu rc=$?"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 2 -o gpurun_out/${TAG}_gemm2 python tools/gemm_probe.py 11 >> gpurun_out/${TAG}_gncu.log 2>&1;;
 dprobe) timeout 600 python tools/decoder_probe.py > gpurun_out/${TAG}_decoder_probe.log 2>&1; cat gpurun_out/${TAG}_decoder_probe.log; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_dec_launches.csv python tools/decoder_probe.py --once > gpurun_out/${TAG}_dprobe_ncu.log 2>&1; echo "dprobe ncu rc=$?";;
+eprobe) timeout 600 python tools/encoder_probe.py > gpurun_out/${TAG}_encoder_probe.log 2>&1; cat gpurun_out/${TAG}_encoder_probe.log; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_enc_launches.csv python tools/encoder_probe.py --once > gpurun_out/${TAG}_eprobe_ncu.log 2>&1; echo "eprobe ncu rc=$?";;
+pprobe) timeout 900 python tools/propagation_probe.py 32 1 8 > gpurun_out/${TAG}_propagation_probe.log 2>&1; cat gpurun_out/${TAG}_propagation_probe.log;;
 diag) timeout 900 python tools/kernel_diag.py > gpurun_out/${TAG}_kernel_diag.log 2>&1; tail -40 gpurun_out/${TAG}_kernel_diag.log;;
 esac
 done
