@@ -141,53 +141,81 @@ mask_downscale_kernel(const float* __restrict__ in, int B, int S, int cpp, float
 
 // keys[b*T + t, n] = bf16(image_embed[t, n] + bias[n] + sum_c ds[b*T + t, c] * w[n, c])   (n < 256, c < 16):
 // mask_downscaling[6] (1x1 conv 16 -> 256) plus the dense-prompt add of the mask decoder (src = image_embeddings +
-// dense_prompt_embeddings), i.e. the per-prompt image stream of the m2m pass, written once. A K = 16 contraction is
-// not tensor-core work: one warp per token, 8 channels per lane with their 8 x 16 weights in registers; the kernel
-// is bound by the 512 B it stores per token.
+// dense_prompt_embeddings), i.e. the per-prompt image stream of the m2m pass, written once. The K = 16 contraction is
+// exactly one mma.sync.m16n8k16 step per 16 tokens x 8 channels (a CUDA-core version needs 128 FMA instructions per
+// token and is instruction-bound at ~6x the store time): the 16 x 256 weights live in registers as B fragments, the
+// accumulators are initialised with image_embed + bias (fp32, loaded once per token tile and reused for `PPW`
+// prompts), and the bf16 result is staged through a per-warp shared-memory tile so that every global store
+// instruction writes one full 512-byte row. The kernel is bound by the 512 B it stores per token.
+constexpr int MEK_PPW = 8;     // prompts per warp (reuse of the image_embed tile held in registers)
+constexpr int MEK_PITCH = 528; // staged row pitch (bytes): odd multiple of 16
+
+__device__ __forceinline__ void mek_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[4]), "f"(c[5]), "f"(c[6]), "f"(c[7]));
+}
+
 __global__ void __launch_bounds__(128)
 mask_embed_keys_kernel(const __nv_bfloat16* __restrict__ ds, const float* __restrict__ w /*[256,16]*/,
                        const float* __restrict__ bias, const float* __restrict__ image_embed /*[T,256]*/, int T,
-                       long long ntok, __nv_bfloat16* __restrict__ keys) {
-  // two warps per token (4 channels per lane: 64 weight registers), two tokens per iteration with all loads issued
-  // before the math, so enough bytes are in flight per SM to cover the latency of the streaming store / L2 loads
-  const int lane = threadIdx.x & 31;
-  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int c0 = static_cast<int>(gw & 1) * 128 + lane * 4;
-  float wr[4][16];
+                       int nprompts, __nv_bfloat16* __restrict__ keys) {
+  __shared__ __align__(16) uint8_t stage[4][16 * MEK_PITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  const int tile = blockIdx.x * 4 + warp;  // 16-token tile of the image grid
+  const int tok0 = tile * 16;
+  if (tok0 >= T) return;
+  // The k index is permuted identically on A and B (MMA k = 2*q4+e <-> dim 4*q4+e, MMA k = 8+2*q4+e <-> dim 4*q4+2+e),
+  // so the A fragment of a token row is one 8-byte load; the B fragments of a channel half stay in registers.
+  uint8_t* st = stage[warp];
+  const int b_begin = blockIdx.y * MEK_PPW;
+  const int b_end = min(nprompts, b_begin + MEK_PPW);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {  // channels [128*half, 128*half + 128): keeps init + accumulators at 64 + 64 regs
+    uint32_t wb[16][2];
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
-#pragma unroll
-    for (int c = 0; c < 16; ++c) wr[e][c] = w[(c0 + e) * 16 + c];
-  const float4 br = *reinterpret_cast<const float4*>(bias + c0);
-  // 32-bit token arithmetic (ntok < 2^31 is checked by the launcher): a 64-bit modulo per token costs more
-  // instructions than the 64 FMAs of the contraction
-  const unsigned npairs = (gridDim.x * blockDim.x) >> 6;  // warp pairs in the grid
-  const unsigned n = static_cast<unsigned>(ntok), uT = static_cast<unsigned>(T);
-  for (unsigned t0 = static_cast<unsigned>(gw >> 1) * 2; t0 < n; t0 += npairs * 2) {
-    uint4 d[2][2];
-    float4 ie[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned tok = t0 + u < n ? t0 + u : t0;
-      d[u][0] = *reinterpret_cast<const uint4*>(ds + static_cast<size_t>(tok) * 16);
-      d[u][1] = *reinterpret_cast<const uint4*>(ds + static_cast<size_t>(tok) * 16 + 8);
-      ie[u] = __ldg(reinterpret_cast<const float4*>(image_embed + static_cast<size_t>(tok % uT) * 256 + c0));
+    for (int n = 0; n < 16; ++n) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (half * 128 + n * 8 + g) * 16 + q4 * 4));
+      wb[n][0] = sb::pack_bf16x2(w4.x, w4.y);
+      wb[n][1] = sb::pack_bf16x2(w4.z, w4.w);
     }
+    float init[16][4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (t0 + u >= n) break;
-      float dv[16];
-      dv[0] = sb::bf16_lo(d[u][0].x); dv[1] = sb::bf16_hi(d[u][0].x); dv[2] = sb::bf16_lo(d[u][0].y); dv[3] = sb::bf16_hi(d[u][0].y);
-      dv[4] = sb::bf16_lo(d[u][0].z); dv[5] = sb::bf16_hi(d[u][0].z); dv[6] = sb::bf16_lo(d[u][0].w); dv[7] = sb::bf16_hi(d[u][0].w);
-      dv[8] = sb::bf16_lo(d[u][1].x); dv[9] = sb::bf16_hi(d[u][1].x); dv[10] = sb::bf16_lo(d[u][1].y); dv[11] = sb::bf16_hi(d[u][1].y);
-      dv[12] = sb::bf16_lo(d[u][1].z); dv[13] = sb::bf16_hi(d[u][1].z); dv[14] = sb::bf16_lo(d[u][1].w); dv[15] = sb::bf16_hi(d[u][1].w);
-      float acc[4] = {ie[u].x + br.x, ie[u].y + br.y, ie[u].z + br.z, ie[u].w + br.w};
+    for (int n = 0; n < 16; ++n) {
+      const int c = half * 128 + n * 8 + 2 * q4;
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c));
+      const float2 e0 = __ldg(reinterpret_cast<const float2*>(image_embed + static_cast<size_t>(tok0 + g) * 256 + c));
+      const float2 e1 = __ldg(reinterpret_cast<const float2*>(image_embed + static_cast<size_t>(tok0 + g + 8) * 256 + c));
+      init[n][0] = e0.x + bb.x;
+      init[n][1] = e0.y + bb.y;
+      init[n][2] = e1.x + bb.x;
+      init[n][3] = e1.y + bb.y;
+    }
+#pragma unroll 1
+    for (int b = b_begin; b < b_end; ++b) {
+      const size_t row0 = static_cast<size_t>(b) * T + tok0;
+      const uint2 alo = *reinterpret_cast<const uint2*>(ds + (row0 + g) * 16 + q4 * 4);
+      const uint2 ahi = *reinterpret_cast<const uint2*>(ds + (row0 + g + 8) * 16 + q4 * 4);
+      const uint32_t a[4] = {alo.x, ahi.x, alo.y, ahi.y};
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
+      for (int n = 0; n < 16; ++n) {
+        float c[8] = {0.f, 0.f, 0.f, 0.f, init[n][0], init[n][1], init[n][2], init[n][3]};
+        mek_mma(c, a, wb[n][0], wb[n][1]);
+        const int col = n * 8 + 2 * q4;
+        *reinterpret_cast<uint32_t*>(st + g * MEK_PITCH + col * 2) = sb::pack_bf16x2(c[0], c[1]);
+        *reinterpret_cast<uint32_t*>(st + (g + 8) * MEK_PITCH + col * 2) = sb::pack_bf16x2(c[2], c[3]);
+      }
+      __syncwarp();
+      // 16 rows x 256 B (this half): two rows per warp instruction, 16 B per lane
+      uint8_t* dst = reinterpret_cast<uint8_t*>(keys + row0 * 256 + half * 128);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = fmaf(dv[c], wr[e][c], acc[e]);
-      *reinterpret_cast<uint2*>(keys + static_cast<size_t>(t0 + u) * 256 + c0) =
-          make_uint2(sb::pack_bf16x2(acc[0], acc[1]), sb::pack_bf16x2(acc[2], acc[3]));
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 2 + (lane >> 4);
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * 512 + (lane & 15) * 16) =
+            *reinterpret_cast<const uint4*>(st + r * MEK_PITCH + (lane & 15) * 16);
+      }
+      __syncwarp();
     }
   }
 }
@@ -269,19 +297,39 @@ upscale2_mask_kernel(const __nv_bfloat16* __restrict__ g2, const float* __restri
 // dynamic_multimask_via_stability (single-mask output): per prompt, stability of mask token 0 =
 // count(logit > delta) / count(logit > -delta) (1 when the union is empty); if >= thresh keep token 0
 // else the best-IoU token among 1..3 (first max). Writes the chosen token index and IoU.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 select_mask_kernel(const float* __restrict__ masks /*[B,4,HW]*/, const float* __restrict__ ious /*[B,4]*/,
                    int HW, float delta, float thresh, int* __restrict__ sel_idx,
                    float* __restrict__ sel_iou) {
   const int b = blockIdx.x;
   const float* m0 = masks + static_cast<long long>(b) * 4 * HW;
   int ci = 0, cu = 0;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float v = m0[i];
+  // one plane (256 KB at 256^2) per block: 16-byte loads, four in flight per thread (the counts are integers, so the
+  // summation order is free)
+  const int n4 = ((reinterpret_cast<uintptr_t>(m0) & 15) == 0) ? (HW >> 2) : 0;
+  const float4* m4 = reinterpret_cast<const float4*>(m0);
+  int i = threadIdx.x;
+  for (; i + 3 * static_cast<int>(blockDim.x) < n4; i += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(m4 + i + u * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ci += (v[u].x > delta) + (v[u].y > delta) + (v[u].z > delta) + (v[u].w > delta);
+      cu += (v[u].x > -delta) + (v[u].y > -delta) + (v[u].z > -delta) + (v[u].w > -delta);
+    }
+  }
+  for (; i < n4; i += blockDim.x) {
+    const float4 v = __ldg(m4 + i);
+    ci += (v.x > delta) + (v.y > delta) + (v.z > delta) + (v.w > delta);
+    cu += (v.x > -delta) + (v.y > -delta) + (v.z > -delta) + (v.w > -delta);
+  }
+  for (int j = n4 * 4 + threadIdx.x; j < HW; j += blockDim.x) {
+    const float v = m0[j];
     ci += v > delta;
     cu += v > -delta;
   }
-  __shared__ int si[8], su[8];
+  __shared__ int si[32], su[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ci += __shfl_xor_sync(0xffffffffu, ci, o);
@@ -294,7 +342,7 @@ select_mask_kernel(const float* __restrict__ masks /*[B,4,HW]*/, const float* __
   __syncthreads();
   if (threadIdx.x == 0) {
     int ti = 0, tu = 0;
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) {
       ti += si[k];
       tu += su[k];
     }
@@ -353,10 +401,11 @@ extern "C" int sb_mask_embed_keys(const void* ds, const float* w, const float* b
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(ds && w && bias && image_embed && keys && T > 0 && ntok > 0 && ntok < (1ll << 31),
              "sb_mask_embed_keys: bad arguments");
-  long long blocks = (ntok + 3) / 4;  // 4 warps = 2 warp pairs = 4 tokens per block iteration
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  mask_embed_keys_kernel<<<static_cast<int>(blocks), 128, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(ds), w, bias, image_embed, T, ntok, static_cast<__nv_bfloat16*>(keys));
+  SB_REQUIRE((T % 16) == 0 && (ntok % T) == 0, "sb_mask_embed_keys: T must be a multiple of 16 and ntok a multiple of T");
+  const int nprompts = static_cast<int>(ntok / T);
+  dim3 grid((T / 16 + 3) / 4, (nprompts + MEK_PPW - 1) / MEK_PPW);
+  mask_embed_keys_kernel<<<grid, 128, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(ds), w, bias, image_embed, T, nprompts, static_cast<__nv_bfloat16*>(keys));
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
@@ -390,7 +439,7 @@ extern "C" int sb_select_mask(const float* masks, const float* ious, int B, int 
                               float thresh, int* sel_idx, float* sel_iou, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(B > 0 && HW > 0, "sb_select_mask: bad sizes");
-  select_mask_kernel<<<B, 256, 0, stream>>>(masks, ious, HW, delta, thresh, sel_idx, sel_iou);
+  select_mask_kernel<<<B, 1024, 0, stream>>>(masks, ious, HW, delta, thresh, sel_idx, sel_iou);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

@@ -1,0 +1,428 @@
+// saber_b200 — fused "image attends to tokens" block of the SAM2 mask decoder's two-way transformer.
+//
+// Upstream (sam2/modeling/sam/transformer.py TwoWayAttentionBlock.forward, step 4):
+//     q = keys + key_pe ; k = queries + query_pe ; v = queries
+//     attn_out = cross_attn_image_to_token(q, k, v)          # 8 heads x 16, 4096 image queries, <= 8 token keys
+//     keys = norm4(keys + attn_out)
+// Unfused this is three passes over the per-prompt image stream [B, 4096, 256] (Q projection GEMM, few-keys attention,
+// out-projection GEMM + LayerNorm: 5 x 2 MB of HBM traffic per prompt). Because a prompt has at most 8 tokens, both
+// projections fold into per-prompt weights:
+//     scores[i, (h,t)] = keys_i . (Wq_h^T kt_{t,h}) + qres_{i,h} . kt_{t,h}        qres = image_pe Wq^T + bq (weights only)
+//     keys_new_i       = LN(keys_i + bo + sum_{h,t} p[i,(h,t)] (Wo_h vt_{t,h}))
+// so the whole block is   S = X W1  ->  per-head softmax over 8 tokens  ->  O = P W2  ->  + residual, LayerNorm
+// with W1 [256 x 64], W2 [64 x 256] per prompt: one read and one write of the image stream (2 x 2 MB per prompt).
+// A 16-dim head is exactly one k16 MMA step and 8 tokens exactly one n8 tile, so the block-diagonal positional term is
+// one MMA per head, and the softmax of a head lives inside one accumulator tile (quad shuffles only).
+//
+// Warps are autonomous: each owns 16-row tiles of the stream with a private cp.async double buffer, computes both
+// GEMMs on mma.sync.m16n8k16 (bf16 in, fp32 accumulate), normalises in registers, writes the result over its own
+// staged tile and streams it out with 16-byte coalesced stores. The per-prompt operands are staged once per CTA.
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb::smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int I2T_C = 256;    // image stream width
+constexpr int I2T_QD = 128;   // attention width (8 heads x 16)
+constexpr int I2T_TOK = 8;    // token slots per head (padded with masked slots)
+constexpr int I2T_NC = 64;    // (head, token) columns
+
+// ------------------------------------------------------------------------------------------------
+// Per-prompt folded operands. One block per prompt, 256 threads.
+//   kts [B, 8, 128]  = scale*log2(e) * kt                     (zero rows for t >= nt)
+//   w1t [B, 64, 256] : row (h*8+t), col c = scale*log2(e) * sum_d Wq[h*16+d, c] kt[t, h*16+d]      (nullable)
+//   w2t [B, 256, 64] : row c, col (h*8+t) = sum_d Wo[c, h*16+d] vt[t, h*16+d]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __restrict__ vt, long long vt_ld,
+                const bf16* __restrict__ wq /* [128,256] */, const bf16* __restrict__ wo /* [256,128] */,
+                bf16* __restrict__ w1t, bf16* __restrict__ w2t, bf16* __restrict__ kts, int nt, float scale_log2) {
+  __shared__ float sk[I2T_TOK][I2T_QD];
+  __shared__ float sv[I2T_TOK][I2T_QD];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < I2T_TOK * I2T_QD; i += 256) {
+    const int t = i >> 7, c = i & 127;
+    float kv = 0.f, vv = 0.f;
+    if (t < nt) {
+      kv = __bfloat162float(kt[(static_cast<long long>(b) * nt + t) * kt_ld + c]) * scale_log2;
+      vv = __bfloat162float(vt[(static_cast<long long>(b) * nt + t) * vt_ld + c]);
+    }
+    sk[t][c] = kv;
+    sv[t][c] = vv;
+    kts[(static_cast<long long>(b) * I2T_TOK + t) * I2T_QD + c] = __float2bfloat16(kv);
+  }
+  __syncthreads();
+  const int c = tid;
+  if (w1t != nullptr) {
+#pragma unroll 1
+    for (int h = 0; h < 8; ++h) {
+      float acc[I2T_TOK];
+#pragma unroll
+      for (int t = 0; t < I2T_TOK; ++t) acc[t] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float w = __bfloat162float(wq[(h * 16 + d) * I2T_C + c]);
+#pragma unroll
+        for (int t = 0; t < I2T_TOK; ++t) acc[t] = fmaf(w, sk[t][h * 16 + d], acc[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < I2T_TOK; ++t)
+        w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * I2T_C + c] = __float2bfloat16(acc[t]);
+    }
+  }
+  {
+    const bf16* worow = wo + c * I2T_QD;
+    bf16* dst = w2t + (static_cast<long long>(b) * I2T_C + c) * I2T_NC;
+#pragma unroll 1
+    for (int h = 0; h < 8; ++h) {
+      float acc[I2T_TOK];
+#pragma unroll
+      for (int t = 0; t < I2T_TOK; ++t) acc[t] = 0.f;
+      const uint4 wa = *reinterpret_cast<const uint4*>(worow + h * 16);
+      const uint4 wb = *reinterpret_cast<const uint4*>(worow + h * 16 + 8);
+      const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float w0 = sb::bf16_lo(w8[e]), w1 = sb::bf16_hi(w8[e]);
+#pragma unroll
+        for (int t = 0; t < I2T_TOK; ++t) {
+          acc[t] = fmaf(w0, sv[t][h * 16 + 2 * e], acc[t]);
+          acc[t] = fmaf(w1, sv[t][h * 16 + 2 * e + 1], acc[t]);
+        }
+      }
+      *reinterpret_cast<uint4*>(dst + h * 8) =
+          make_uint4(sb::pack_bf16x2(acc[0], acc[1]), sb::pack_bf16x2(acc[2], acc[3]), sb::pack_bf16x2(acc[4], acc[5]),
+                     sb::pack_bf16x2(acc[6], acc[7]));
+    }
+  }
+}
+
+struct I2TParams {
+  const bf16* x;           // image stream [B*nq (or nq when shared), 256]
+  long long x_bstride;     // rows between prompts (0 = one stream shared by every prompt)
+  const bf16* qp;          // [nq, 128] shared by all prompts: qres (fold mode) or the full query projection (SHARED_Q)
+  const bf16* w1t;         // [B, 64, 256] (fold mode only)
+  const bf16* w2t;         // [B, 256, 64]
+  const bf16* kts;         // [B, 8, 128]
+  const float* bo;         // [256] out-projection bias
+  const float* gamma;      // [256]
+  const float* beta;       // [256]
+  float eps;
+  bf16* out;               // [B*nq, 256]
+  int nt, nq, rows_per_cta;
+};
+
+constexpr int I2T_XP = I2T_C * 2 + 16;     // staged row pitch of the image stream / W1^T (bytes): odd multiple of 16
+constexpr int I2T_B2P = I2T_NC * 2 + 16;   // W2^T row pitch
+constexpr int I2T_KTP = I2T_QD * 2 + 32;   // token-key row pitch (8-byte fragment loads, see below)
+constexpr int I2T_WARPS = 8;
+constexpr int I2T_SMEM_X = I2T_WARPS * 2 * 16 * I2T_XP;
+constexpr int I2T_SMEM_B2 = I2T_C * I2T_B2P;
+constexpr int I2T_SMEM_KT = I2T_TOK * I2T_KTP;
+constexpr int I2T_SMEM_VEC = 3 * I2T_C * 4;
+constexpr int I2T_SMEM_B1 = I2T_NC * I2T_XP;
+constexpr int I2T_SMEM_SHARED = I2T_SMEM_X + I2T_SMEM_B2 + I2T_SMEM_KT + I2T_SMEM_VEC;
+constexpr int I2T_SMEM_FOLD = I2T_SMEM_SHARED + I2T_SMEM_B1;
+
+template <bool SHARED_Q>
+__global__ void __launch_bounds__(I2T_WARPS * 32, 1)
+i2t_block_kernel(const I2TParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sX = smem;
+  uint8_t* sB2 = sX + I2T_SMEM_X;
+  uint8_t* sKT = sB2 + I2T_SMEM_B2;
+  float* sVec = reinterpret_cast<float*>(sKT + I2T_SMEM_KT);
+  uint8_t* sB1 = reinterpret_cast<uint8_t*>(sVec) + I2T_SMEM_VEC;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int b = blockIdx.y;
+  const int row_base = blockIdx.x * p.rows_per_cta;
+
+  // ---- per-prompt operands (one cp.async group) ----
+  {
+    const uint8_t* w2 = reinterpret_cast<const uint8_t*>(p.w2t + static_cast<long long>(b) * I2T_C * I2T_NC);
+    for (int i = tid; i < I2T_C * 8; i += I2T_WARPS * 32) cp_async16(sB2 + (i >> 3) * I2T_B2P + (i & 7) * 16, w2 + i * 16);
+    const uint8_t* kt = reinterpret_cast<const uint8_t*>(p.kts + static_cast<long long>(b) * I2T_TOK * I2T_QD);
+    for (int i = tid; i < I2T_TOK * 16; i += I2T_WARPS * 32) cp_async16(sKT + (i >> 4) * I2T_KTP + (i & 15) * 16, kt + i * 16);
+    if (!SHARED_Q) {
+      const uint8_t* w1 = reinterpret_cast<const uint8_t*>(p.w1t + static_cast<long long>(b) * I2T_NC * I2T_C);
+      for (int i = tid; i < I2T_NC * 32; i += I2T_WARPS * 32) cp_async16(sB1 + (i >> 5) * I2T_XP + (i & 31) * 16, w1 + i * 16);
+    }
+    sVec[tid] = p.bo[tid];
+    sVec[I2T_C + tid] = p.gamma[tid];
+    sVec[2 * I2T_C + tid] = p.beta[tid];
+    cp_async_commit();
+  }
+
+  const int ntiles = p.rows_per_cta / (16 * I2T_WARPS);
+  uint8_t* sXw = sX + warp * (2 * 16 * I2T_XP);
+  const bf16* xb = p.x + static_cast<long long>(b) * p.x_bstride * I2T_C;
+  auto load_tile = [&](int i, int buf) {
+    const int r0 = row_base + (i * I2T_WARPS + warp) * 16;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + static_cast<long long>(r0) * I2T_C);
+    uint8_t* dst = sXw + buf * 16 * I2T_XP;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) cp_async16(dst + it * I2T_XP + lane * 16, src + it * (I2T_C * 2) + lane * 16);
+  };
+  load_tile(0, 0);
+  cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();  // the per-prompt operands are visible to every warp; from here on warps never meet again
+
+  const uint32_t b1_addr = sb::smem_u32(sB1) + ((lane & 7) + ((lane >> 4) << 3)) * I2T_XP + ((lane >> 3) & 1) * 16;
+  const uint32_t b2_addr = sb::smem_u32(sB2) + ((lane & 7) + ((lane >> 4) << 3)) * I2T_B2P + ((lane >> 3) & 1) * 16;
+  const int nt = p.nt;
+
+#pragma unroll 1
+  for (int i = 0; i < ntiles; ++i) {
+    const int buf = i & 1;
+    __syncwarp();  // every lane has finished streaming the previous tile out of the other buffer
+    if (i + 1 < ntiles) load_tile(i + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    uint8_t* xt = sXw + buf * 16 * I2T_XP;
+    const uint32_t xt_s = sb::smem_u32(xt);
+    const int r0 = row_base + (i * I2T_WARPS + warp) * 16;  // first image token of this tile
+
+    // ---- S = X W1 (+ positional / shared-query term): 16 rows x 64 (head, token) columns ----
+    float s[8][4];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) s[h][0] = s[h][1] = s[h][2] = s[h][3] = 0.f;
+    {
+      // one MMA per head: A = the 16 query dims of head h (straight from the shared, L2-resident [nq,128] matrix),
+      // B = the 8 token keys of head h. The k index is permuted identically on both sides (MMA k = 2*q4+e <-> dim
+      // 4*q4+e, MMA k = 8+2*q4+e <-> dim 4*q4+2+e) so that each operand is one 8-byte load per thread.
+      const bf16* q0 = p.qp + static_cast<long long>(r0 + g) * I2T_QD + q4 * 4;
+      const bf16* q1 = q0 + 8 * I2T_QD;
+      const uint8_t* kp = sKT + g * I2T_KTP + q4 * 8;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const uint2 alo = __ldg(reinterpret_cast<const uint2*>(q0 + h * 16));
+        const uint2 ahi = __ldg(reinterpret_cast<const uint2*>(q1 + h * 16));
+        const uint2 bk = *reinterpret_cast<const uint2*>(kp + h * 32);
+        const uint32_t a[4] = {alo.x, ahi.x, alo.y, ahi.y};
+        mma_bf16_16816(s[h], a, bk.x, bk.y);
+      }
+    }
+    if (!SHARED_Q) {
+      const uint32_t a_addr = xt_s + (lane & 15) * I2T_XP + (lane >> 4) * 16;
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a_addr + ks * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(b1_addr + np * 16 * I2T_XP + ks * 32, b0, b1, b2, b3);
+          mma_bf16_16816(s[2 * np], a, b0, b1);
+          mma_bf16_16816(s[2 * np + 1], a, b2, b3);
+        }
+      }
+    }
+
+    // ---- per-head softmax over the 8 token slots (one accumulator tile per head; the quad holds a row) ----
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (2 * q4 >= nt) s[h][0] = s[h][2] = -INFINITY;
+      if (2 * q4 + 1 >= nt) s[h][1] = s[h][3] = -INFINITY;
+      float m0 = fmaxf(s[h][0], s[h][1]), m1 = fmaxf(s[h][2], s[h][3]);
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      s[h][0] = exp2f(s[h][0] - m0);
+      s[h][1] = exp2f(s[h][1] - m0);
+      s[h][2] = exp2f(s[h][2] - m1);
+      s[h][3] = exp2f(s[h][3] - m1);
+      float l0 = s[h][0] + s[h][1], l1 = s[h][2] + s[h][3];
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = __fdividef(1.f, l0), i1 = __fdividef(1.f, l1);
+      s[h][0] *= i0;
+      s[h][1] *= i0;
+      s[h][2] *= i1;
+      s[h][3] *= i1;
+    }
+    // accumulator tiles (2j, 2j+1) are exactly the A fragment of k16 step j of the second GEMM
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pa[j][0] = sb::pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      pa[j][1] = sb::pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      pa[j][2] = sb::pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[j][3] = sb::pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+    }
+
+    // ---- O = P W2: 16 rows x 256 ----
+    float o[32][4];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int np = 0; np < 16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(b2_addr + np * 16 * I2T_B2P + j * 32, b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * np], pa[j], b0, b1);
+        mma_bf16_16816(o[2 * np + 1], pa[j], b2, b3);
+      }
+    }
+
+    // ---- y = keys + bo + O ; LayerNorm over the 256 channels (two-pass, fp32, in registers) ----
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const int c = n * 8 + 2 * q4;
+      const float2 bo2 = *reinterpret_cast<const float2*>(sVec + c);
+      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(xt + g * I2T_XP + c * 2);
+      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(xt + (g + 8) * I2T_XP + c * 2);
+      o[n][0] += bo2.x + sb::bf16_lo(x0);
+      o[n][1] += bo2.y + sb::bf16_hi(x0);
+      o[n][2] += bo2.x + sb::bf16_lo(x1);
+      o[n][3] += bo2.y + sb::bf16_hi(x1);
+      sum0 += o[n][0] + o[n][1];
+      sum1 += o[n][2] + o[n][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float mean0 = sum0 * (1.f / I2T_C), mean1 = sum1 * (1.f / I2T_C);
+    float var0 = 0.f, var1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float d0 = o[n][0] - mean0, d1 = o[n][1] - mean0, d2 = o[n][2] - mean1, d3 = o[n][3] - mean1;
+      var0 = fmaf(d0, d0, fmaf(d1, d1, var0));
+      var1 = fmaf(d2, d2, fmaf(d3, d3, var1));
+    }
+    var0 += __shfl_xor_sync(0xffffffffu, var0, 1);
+    var1 += __shfl_xor_sync(0xffffffffu, var1, 1);
+    var0 += __shfl_xor_sync(0xffffffffu, var0, 2);
+    var1 += __shfl_xor_sync(0xffffffffu, var1, 2);
+    const float rstd0 = rsqrtf(var0 * (1.f / I2T_C) + p.eps), rstd1 = rsqrtf(var1 * (1.f / I2T_C) + p.eps);
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const int c = n * 8 + 2 * q4;
+      const float2 ga = *reinterpret_cast<const float2*>(sVec + I2T_C + c);
+      const float2 be = *reinterpret_cast<const float2*>(sVec + 2 * I2T_C + c);
+      *reinterpret_cast<uint32_t*>(xt + g * I2T_XP + c * 2) =
+          sb::pack_bf16x2(fmaf((o[n][0] - mean0) * rstd0, ga.x, be.x), fmaf((o[n][1] - mean0) * rstd0, ga.y, be.y));
+      *reinterpret_cast<uint32_t*>(xt + (g + 8) * I2T_XP + c * 2) =
+          sb::pack_bf16x2(fmaf((o[n][2] - mean1) * rstd1, ga.x, be.x), fmaf((o[n][3] - mean1) * rstd1, ga.y, be.y));
+    }
+    __syncwarp();
+    // ---- stream the normalised tile out: one 512-byte row per warp instruction ----
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out + (static_cast<long long>(b) * p.nq + r0) * I2T_C);
+#pragma unroll
+    for (int it = 0; it < 16; ++it)
+      *reinterpret_cast<uint4*>(dst + it * (I2T_C * 2) + lane * 16) = *reinterpret_cast<const uint4*>(xt + it * I2T_XP + lane * 16);
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace
+
+// Per-prompt folded operands of sb_i2t_block (see the header of this file). kt / vt [B*nt, 128] bf16 (the projected token
+// keys / values of cross_attn_image_to_token), wq [128,256] / wo [256,128] bf16 (its q_proj / out_proj weights).
+// w1t may be null (shared-query mode needs only kts and w2t).
+extern "C" int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld, const void* wq, const void* wo,
+                           void* w1t, void* w2t, void* kts, int batch, int nt, float scale, void* stream) {
+  SB_REQUIRE(batch > 0 && nt >= 1 && nt <= I2T_TOK, "sb_i2t_fold: nt must be in 1..%d (got %d)", I2T_TOK, nt);
+  SB_REQUIRE(kt && vt && wq && wo && w2t && kts, "sb_i2t_fold: null operand");
+  SB_REQUIRE(((reinterpret_cast<uintptr_t>(wo) | reinterpret_cast<uintptr_t>(w2t)) & 15) == 0, "sb_i2t_fold: wo / w2t must be 16-byte aligned");
+  i2t_fold_kernel<<<batch, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(kt), kt_ld, static_cast<const bf16*>(vt), vt_ld, static_cast<const bf16*>(wq),
+      static_cast<const bf16*>(wo), static_cast<bf16*>(w1t), static_cast<bf16*>(w2t), static_cast<bf16*>(kts), nt,
+      scale * 1.4426950408889634f);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// keys_new = LayerNorm(keys + out_proj(softmax((keys Wq^T + qp) kt^T) vt)) for every prompt, one pass over the stream.
+// x [batch*nq, 256] bf16 (or [nq, 256] when x_shared), qp [nq, 128] bf16: the positional term of the query projection
+// (w1t != null), or the complete query projection of a stream shared by all prompts (w1t == null: layer 0 of the first
+// AMG pass). out [batch*nq, 256] bf16 (may alias x when x is per-prompt). nq must be a multiple of 256.
+extern "C" int sb_i2t_block(const void* x, int x_shared, const void* qp, const void* w1t, const void* w2t, const void* kts,
+                            const float* bo, const float* gamma, const float* beta, float eps, void* out, int batch,
+                            int nq, int nt, void* stream) {
+  SB_REQUIRE(batch > 0 && nq > 0 && (nq % 256) == 0, "sb_i2t_block: nq must be a positive multiple of 256 (got %d)", nq);
+  SB_REQUIRE(nt >= 1 && nt <= I2T_TOK, "sb_i2t_block: nt must be in 1..%d (got %d)", I2T_TOK, nt);
+  SB_REQUIRE(x && qp && w2t && kts && bo && gamma && beta && out, "sb_i2t_block: null operand");
+  SB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(qp) | reinterpret_cast<uintptr_t>(w1t) |
+               reinterpret_cast<uintptr_t>(w2t) | reinterpret_cast<uintptr_t>(kts) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "sb_i2t_block: operands must be 16-byte aligned");
+  SB_REQUIRE(!(x_shared && x == out), "sb_i2t_block: a shared stream cannot be updated in place");
+  // rows per CTA: the per-prompt operands (73 KB) are staged once per CTA, so prefer long CTAs, but keep the grid a
+  // good fit for the 148 SMs (one CTA per SM): pick the candidate with the fewest SM-waves x rows.
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int best_rows = 256;
+  long long best_cost = -1;
+  for (int rows = 1024; rows >= 256; rows >>= 1) {
+    if (nq % rows) continue;
+    const long long ctas = static_cast<long long>(batch) * (nq / rows);
+    const long long waves = (ctas + sms - 1) / sms;
+    const long long cost = waves * (rows + 96);  // +96 rows ~ the operand staging latency of a CTA
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_rows = rows;
+    }
+  }
+  I2TParams p;
+  p.x = static_cast<const bf16*>(x);
+  p.x_bstride = x_shared ? 0 : nq;
+  p.qp = static_cast<const bf16*>(qp);
+  p.w1t = static_cast<const bf16*>(w1t);
+  p.w2t = static_cast<const bf16*>(w2t);
+  p.kts = static_cast<const bf16*>(kts);
+  p.bo = bo;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.eps = eps;
+  p.out = static_cast<bf16*>(out);
+  p.nt = nt;
+  p.nq = nq;
+  p.rows_per_cta = best_rows;
+  dim3 grid(nq / best_rows, batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2T_SMEM_FOLD));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2T_SMEM_SHARED));
+    attr_done = true;
+  }
+  if (w1t != nullptr)
+    i2t_block_kernel<false><<<grid, I2T_WARPS * 32, I2T_SMEM_FOLD, st>>>(p);
+  else
+    i2t_block_kernel<true><<<grid, I2T_WARPS * 32, I2T_SMEM_SHARED, st>>>(p);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

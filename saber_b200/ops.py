@@ -282,6 +282,50 @@ def attention_few_keys(q: torch.Tensor, q_add: Optional[torch.Tensor], k: torch.
     return out
 
 
+def i2t_fold(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch.Tensor, batch: int, nt: int,
+             with_w1: bool = True, scale: float = 0.25):
+    """Per-prompt folded operands of ``i2t_block`` (TwoWayAttentionBlock step 4 with <= 8 tokens per prompt):
+    kt / vt [batch*nt, 128] bf16 (row views allowed), wq [128,256] / wo [256,128] bf16 -> (w1t [B,64,256] or None,
+    w2t [B,256,64], kts [B,8,128]) bf16."""
+    _chk_cuda(kt, vt, wq, wo)
+    assert kt.dtype == _BF16 and vt.dtype == _BF16 and wq.dtype == _BF16 and wo.dtype == _BF16
+    assert kt.shape == (batch * nt, 128) and vt.shape == kt.shape and kt.stride(1) == 1 and vt.stride(1) == 1
+    assert wq.shape == (128, 256) and wq.is_contiguous() and wo.shape == (256, 128) and wo.is_contiguous()
+    dev = kt.device
+    w1t = torch.empty((batch, 64, 256), dtype=_BF16, device=dev) if with_w1 else None
+    w2t = torch.empty((batch, 256, 64), dtype=_BF16, device=dev)
+    kts = torch.empty((batch, 8, 128), dtype=_BF16, device=dev)
+    L = _lib.load()
+    _lib.check(L.sb_i2t_fold(kt.data_ptr(), kt.stride(0), vt.data_ptr(), vt.stride(0), wq.data_ptr(), wo.data_ptr(),
+                             _ptr(w1t), w2t.data_ptr(), kts.data_ptr(), batch, nt, scale, _stream()), "sb_i2t_fold")
+    _count()
+    return w1t, w2t, kts
+
+
+def i2t_block(x: torch.Tensor, qp: torch.Tensor, w1t: Optional[torch.Tensor], w2t: torch.Tensor, kts: torch.Tensor,
+              bo: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, batch: int, nq: int, nt: int,
+              x_shared: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """keys_new = LN(keys + out_proj(attn(keys -> tokens))) in one pass over the image stream; see csrc/decoder_fused.cu.
+    x [batch*nq (nq when x_shared), 256] bf16, qp [nq,128] bf16; ``out`` may be ``x`` itself for a per-prompt stream."""
+    _chk_cuda(x, qp, w1t, w2t, kts, bo, gamma, beta)
+    assert x.dtype == _BF16 and x.is_contiguous() and x.shape == ((1 if x_shared else batch) * nq, 256)
+    assert qp.dtype == _BF16 and qp.is_contiguous() and qp.shape == (nq, 128)
+    assert w1t is None or (w1t.dtype == _BF16 and w1t.is_contiguous() and w1t.shape == (batch, 64, 256))
+    assert w2t.dtype == _BF16 and w2t.is_contiguous() and w2t.shape == (batch, 256, 64)
+    assert kts.dtype == _BF16 and kts.is_contiguous() and kts.shape == (batch, 8, 128)
+    for v in (bo, gamma, beta):
+        assert v.dtype == _F32 and v.is_contiguous() and v.numel() == 256
+    if out is None:
+        out = torch.empty((batch * nq, 256), dtype=_BF16, device=x.device)
+    assert out.dtype == _BF16 and out.is_contiguous() and out.shape == (batch * nq, 256)
+    L = _lib.load()
+    _lib.check(L.sb_i2t_block(x.data_ptr(), int(x_shared), qp.data_ptr(), _ptr(w1t), w2t.data_ptr(), kts.data_ptr(),
+                              bo.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), batch, nq, nt,
+                              _stream()), "sb_i2t_block")
+    _count()
+    return out
+
+
 def mask_embed_keys(ds: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, image_embed: torch.Tensor) -> torch.Tensor:
     """Per-prompt image stream of the m2m pass: bf16(image_embed[t] + bias + ds @ w^T); ds [B*T,16] bf16, w [256,16] fp32."""
     _chk_cuda(ds, w, bias, image_embed)

@@ -136,6 +136,7 @@ class SAM2AutomaticMaskGenerator:
         # test hook: when a list, every post-processing call appends (crop, base, n, cpp, planes, ious4, sel) host copies
         self.capture: Optional[list] = None
         self.use_cuda_graph = True
+        self.graph_lanes = 2  # independent prompt batches in flight (one CUDA graph instance + stream each)
         self.phase_ms: Optional[Dict[str, float]] = None  # set to {} to accumulate encode / decode+post / total ms
         self._graphs: Dict[Tuple[int, int], Any] = {}
         self._plans: Dict[Tuple[int, int], _ImagePlan] = {}
@@ -227,21 +228,37 @@ class SAM2AutomaticMaskGenerator:
             s0 = tok["s0"][k * 65536:(k + 1) * 65536]
             s1 = tok["s1"][k * 16384:(k + 1) * 16384]
             graph = self._batch_graph(plan, ws) if (self.use_cuda_graph and self.capture is None) else None
+            main = torch.cuda.current_stream()
             if graph is not None:
                 graph["emb"].copy_(emb)
                 graph["s0"].copy_(s0)
                 graph["s1"].copy_(s1)
+                for lane in graph["lanes"]:
+                    lane["stream"].wait_stream(main)
+            nb = 0
             for p0 in range(0, crop.n_points, ppb):
                 pb = min(ppb, crop.n_points - p0)
                 base = crop.base + p0 * plan.cpp
                 if graph is not None and pb == ppb:
-                    graph["coords"].copy_(crop.in_points[p0:p0 + pb])
-                    graph["geom"].copy_(crop.geom_dev[p0 // ppb])
-                    graph["g"].replay()
-                    ops.launch_count += graph["launches"]
+                    # prompt batches are independent (disjoint slot ranges): replay them round-robin on the lanes'
+                    # streams so that the latency-bound token-side launches of one batch overlap the bandwidth-bound
+                    # image-stream kernels of another
+                    lane = graph["lanes"][nb % len(graph["lanes"])]
+                    nb += 1
+                    with torch.cuda.stream(lane["stream"]):
+                        lane["coords"].copy_(crop.in_points[p0:p0 + pb])
+                        lane["geom"].copy_(crop.geom_dev[p0 // ppb])
+                        lane["g"].replay()
+                    ops.launch_count += lane["launches"]
                 else:
+                    if graph is not None:
+                        for lane in graph["lanes"]:
+                            main.wait_stream(lane["stream"])
                     self._process_batch(k, crop.in_points[p0:p0 + pb], crop.labels[p0:p0 + pb], emb, s0, s1, plan, ws,
                                         crop.box, base, None)
+            if graph is not None:
+                for lane in graph["lanes"]:
+                    main.wait_stream(lane["stream"])
             n_crop = crop.n_points * plan.cpp
             ops.compact_keep(ws["keep"], crop.base, n_crop, ws["cand"], n_cand)
             ops.nms_dev(ws["bbox"], ws["iou"], ws["cand"], n_cand, n_crop, self.box_nms_thresh, ws["order"],
@@ -307,29 +324,33 @@ class SAM2AutomaticMaskGenerator:
             self._graphs[key] = None  # m2m split into several post calls with different bases: keep it eager
             return None
         st = dict(emb=torch.zeros((4096, 256), dtype=_F32, device=dev), s0=torch.zeros((65536, 32), dtype=_F32, device=dev),
-                  s1=torch.zeros((16384, 64), dtype=_F32, device=dev), coords=torch.zeros((ppb, 1, 2), dtype=_F32, device=dev),
-                  labels=torch.ones((ppb, 1), dtype=_I32, device=dev), geom=torch.zeros((8,), dtype=_I32, device=dev))
+                  s1=torch.zeros((16384, 64), dtype=_F32, device=dev), lanes=[])
         crop0 = plan.crops[0]
-        st["geom"].copy_(crop0.geom_dev[0])
-        st["coords"].copy_(crop0.in_points[:ppb])
+        for _ in range(max(1, int(self.graph_lanes))):
+            lane = dict(coords=torch.zeros((ppb, 1, 2), dtype=_F32, device=dev),
+                        labels=torch.ones((ppb, 1), dtype=_I32, device=dev), geom=torch.zeros((8,), dtype=_I32, device=dev),
+                        stream=torch.cuda.Stream(device=dev))
+            lane["geom"].copy_(crop0.geom_dev[0])
+            lane["coords"].copy_(crop0.in_points[:ppb])
 
-        def body():
-            self._process_batch(0, st["coords"], st["labels"], st["emb"], st["s0"], st["s1"], plan, ws, crop0.box, 0,
-                                st["geom"])
+            def body(lane=lane):
+                self._process_batch(0, lane["coords"], lane["labels"], st["emb"], st["s0"], st["s1"], plan, ws, crop0.box,
+                                    0, lane["geom"])
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            body()  # warm-up: sets function attributes, loads modules
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        n0 = ops.launch_count
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            body()
-        st["launches"] = ops.launch_count - n0
-        ops.launch_count = n0
-        st["g"] = g
+            side = lane["stream"]
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()  # warm-up: sets function attributes, loads modules
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = ops.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            lane["launches"] = ops.launch_count - n0
+            ops.launch_count = n0
+            lane["g"] = g
+            st["lanes"].append(lane)
         self._graphs[key] = st
         return st
 

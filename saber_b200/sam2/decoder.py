@@ -90,6 +90,7 @@ class MaskDecoder:
             L["t2i_o_w"], L["t2i_o_b"] = w16(t2i["outw"]), f32(t2i["outb"])
             L["i2t_q_w"] = w16(i2t["qw"])
             L["i2t_q_res"] = f32(image_pe @ i2t["qw"].t() + i2t["qb"])  # [4096, 128]
+            L["i2t_q_res16"] = w16(image_pe @ i2t["qw"].t() + i2t["qb"])
             L["i2t_k_w"], L["i2t_k_b"] = w16(i2t["kw"]), f32(i2t["kb"])
             L["i2t_v_w"], L["i2t_v_b"] = w16(i2t["vw"]), f32(i2t["vb"])
             L["i2t_o_w"], L["i2t_o_b"] = w16(i2t["outw"]), f32(i2t["outb"])
@@ -192,6 +193,20 @@ class MaskDecoder:
             vt = ops.gemm(ops.add_cast(queries, None, _BF16), L["i2t_v_w"], L["i2t_v_b"])
             # q = keys @ Wq^T; its positional term (image_pe @ Wq^T + bq) is added inside the attention kernel, so the
             # big GEMM has no residual stream to gather
+            if Nt <= 8:
+                # <= 8 tokens per prompt: q projection, attention, out projection, residual and norm4 in ONE pass over
+                # the image stream, with the projections folded into per-prompt operands (csrc/decoder_fused.cu)
+                if kb == 1:  # one stream shared by all prompts: its query projection is computed once
+                    qp = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
+                    w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt, with_w1=False)
+                else:
+                    qp = L["i2t_q_res16"]
+                    w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt)
+                keys = ops.i2t_block(keys, qp, w1t, w2t, kts, L["i2t_o_b"], L["n4w"], L["n4b"], 1e-5, B, NT_IMG, Nt,
+                                     x_shared=(kb == 1), out=(None if kb == 1 else keys))  # a per-prompt stream is private to this
+                # call (built above from the image embedding): updated in place
+                keys_f32, kb = keys, B
+                continue
             if Nt <= 16:
                 qi = ops.gemm(keys, L["i2t_q_w"], None)
                 a = ops.attention_few_keys(qi, L["i2t_q_res"], kt, vt, B, NT_IMG, Nt, q_shared=(kb == 1))  # [B*4096,128]

@@ -122,6 +122,43 @@ def test_attention_few_keys_with_query_term(ops):
     assert (out1.float() - ref1).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("nt,shared", [(8, False), (7, False), (8, True), (3, True), (1, False)])
+def test_i2t_block_fused(ops, nt, shared):
+    """Fused TwoWayAttentionBlock step 4 (q projection + image->token attention + out projection + residual + norm4 in
+    one pass over the image stream, projections folded per prompt) vs the unfused fp32 torch expression."""
+    torch.manual_seed(11)
+    B, nq = 3, 4096
+    x = torch.randn((1 if shared else B) * nq, 256, device="cuda").to(BF16)
+    wq = (torch.randn(128, 256, device="cuda") / 16).to(BF16)
+    wo = (torch.randn(256, 128, device="cuda") / 11).to(BF16)
+    qres = torch.randn(nq, 128, device="cuda")
+    kt = torch.randn(B * nt, 128, device="cuda").to(BF16)
+    vt = torch.randn(B * nt, 128, device="cuda").to(BF16)
+    bo, gamma, beta = (torch.randn(256, device="cuda") * 0.3, torch.rand(256, device="cuda") + 0.5,
+                       torch.randn(256, device="cuda") * 0.2)
+    xf = x.float().view(-1, nq, 256).expand(B, nq, 256)
+    q = (xf @ wq.float().t() + qres[None]).view(B, nq, 8, 16).transpose(1, 2)
+    k = kt.float().view(B, nt, 8, 16).transpose(1, 2)
+    v = vt.float().view(B, nt, 8, 16).transpose(1, 2)
+    a = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, nq, 128)
+    ref = torch.nn.functional.layer_norm(xf + a @ wo.float().t() + bo, (256,), gamma, beta, 1e-5).reshape(B * nq, 256)
+    if shared:
+        qp = (x.float() @ wq.float().t() + qres).to(BF16)
+        w1t, w2t, kts = ops.i2t_fold(kt, vt, wq, wo, B, nt, with_w1=False)
+        assert w1t is None
+    else:
+        qp = qres.to(BF16)
+        w1t, w2t, kts = ops.i2t_fold(kt, vt, wq, wo, B, nt)
+    out = ops.i2t_block(x, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, x_shared=shared)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-2, err  # outputs are O(1) LayerNorm values stored in bf16; folded weights are rounded to bf16 once
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2
+    if not shared:  # in-place update of a per-prompt stream
+        x2 = x.clone()
+        out2 = ops.i2t_block(x2, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, out=x2)
+        assert out2.data_ptr() == x2.data_ptr() and torch.equal(out2, out)
+
+
 @pytest.mark.parametrize("B,heads,hd,nq,nk,shared", [(3, 8, 16, 8, 4096, False), (2, 8, 16, 7, 4096, True),
                                                      (2, 2, 64, 100, 333, False), (1, 1, 256, 64, 200, False)])
 def test_attention_with_additive_key_term(ops, B, heads, hd, nq, nk, shared):
