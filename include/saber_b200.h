@@ -79,6 +79,16 @@ int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld
 int sb_i2t_block(const void* x, int x_shared, const void* qp, const void* w1t, const void* w2t, const void* kts,
                  const float* bo, const float* gamma, const float* beta, float eps, void* out, int batch, int nq, int nt,
                  void* stream);
+/* Mask-decoder "tokens attend to image" (TwoWayAttentionBlock step 2, final_attn_token_to_image) for prompts with <= 8
+ * tokens, computed straight on the image stream x [batch*nk (nk when x_shared), 256] bf16 without materialising K / V:
+ * the k / v projections (wk, wv [128,256] bf16, bv [128] fp32; kadd [nk,128] bf16 = image_pe Wk^T + bk) fold onto the
+ * token side. q [batch*nt,128] bf16 are the projected token queries; out [batch*nt,128] bf16 is the attention output
+ * before out_proj. Caller-owned workspaces: qf [batch,64,256] bf16, qs [batch,8,128] bf16,
+ * opart [batch,ns,64,256] fp32, ml [batch,ns,2,64] fp32 with ns = sb_t2i_fold_splits(batch, nk). */
+int sb_t2i_fold_splits(int batch, int nk);
+int sb_t2i_fold_attention(const void* q, long long q_ld, const void* x, int x_shared, const void* kadd, const void* wk,
+                          const void* wv, const float* bv, void* qf, void* qs, float* opart, float* ml, void* out,
+                          long long out_ld, int batch, int nt, int nk, float scale, void* stream);
 /* Hiera MultiScaleAttention over a fused qkv buffer [B*H*W, 3*heads*hd]: window partition (with upstream's zero
  * padding of ragged windows), optional 2x2 max-pool of q, SDPA, window unpartition — hieradet.py
  * MultiScaleBlock.forward / MultiScaleAttention.forward. ws >= max(H,W) = global attention. */

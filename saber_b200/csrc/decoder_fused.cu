@@ -36,6 +36,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -66,7 +71,7 @@ i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __rest
     float kv = 0.f, vv = 0.f;
     if (t < nt) {
       kv = __bfloat162float(kt[(static_cast<long long>(b) * nt + t) * kt_ld + c]) * scale_log2;
-      vv = __bfloat162float(vt[(static_cast<long long>(b) * nt + t) * vt_ld + c]);
+      if (vt != nullptr) vv = __bfloat162float(vt[(static_cast<long long>(b) * nt + t) * vt_ld + c]);
     }
     sk[t][c] = kv;
     sv[t][c] = vv;
@@ -91,7 +96,7 @@ i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __rest
         w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * I2T_C + c] = __float2bfloat16(acc[t]);
     }
   }
-  {
+  if (w2t != nullptr) {
     const bf16* worow = wo + c * I2T_QD;
     bf16* dst = w2t + (static_cast<long long>(b) * I2T_C + c) * I2T_NC;
 #pragma unroll 1
@@ -345,6 +350,267 @@ i2t_block_kernel(const I2TParams p) {
   cp_async_wait<0>();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// "Tokens attend to image" (TwoWayAttentionBlock step 2 and final_attn_token_to_image) without the K|V projection of
+// the image stream. With <= 8 tokens per prompt the projections fold onto the token side:
+//     score[(h,t), j] = (Wk_h^T q_{t,h}) . x_j + q_{t,h} . kadd_{j,h}          kadd = image_pe Wk^T + bk (weights only)
+//     out[t, h]       = Wv_h (sum_j p[(h,t), j] x_j) + bv_h                    (sum_j p = 1)
+// i.e. flash attention with 64 query rows of width 256 whose keys AND values are the raw image stream x [4096, 256]:
+// the stream is read once (2 MB per prompt) instead of being projected (read 2 MB, write 2 MB) and read again.
+// CTA = (prompt, key split): 4 warps x 16 query rows (= 2 heads x 8 tokens), 32-key tiles in a 3-stage cp.async ring,
+// online softmax with lazy rescaling (the running maximum only moves when a row exceeds it by 2^8), unnormalised
+// partial results per split; t2i_unfold_kernel merges the splits and applies Wv / bv.
+// ------------------------------------------------------------------------------------------------
+constexpr int T2I_KT = 32;                          // keys per tile
+constexpr int T2I_STAGES = 3;
+constexpr int T2I_XP = I2T_C * 2 + 16;              // 528
+constexpr int T2I_KAP = I2T_QD * 2 + 16;            // 272
+constexpr int T2I_STAGE_BYTES = T2I_KT * (T2I_XP + T2I_KAP);
+constexpr int T2I_SMEM = I2T_NC * T2I_XP + T2I_STAGES * T2I_STAGE_BYTES;
+
+struct T2IParams {
+  const bf16* x;        // [B*nk (nk when shared), 256]
+  long long x_bstride;  // rows between prompts (0 = shared)
+  const bf16* kadd;     // [nk, 128]
+  const bf16* qf;       // [B, 64, 256] folded queries (scale * log2 e included)
+  const bf16* qs;       // [B, 8, 128] scaled queries
+  float* opart;         // [B, ns, 64, 256]
+  float* ml;            // [B, ns, 2, 64] (running max (log2 domain), row sum)
+  int nk, ns;
+};
+
+__global__ void __launch_bounds__(128, 2)
+t2i_fold_attn_kernel(const T2IParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sT = smem + I2T_NC * T2I_XP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+  const int b = blockIdx.y, split = blockIdx.x;
+  const int keys_per_split = p.nk / p.ns;
+  const int key0 = split * keys_per_split;
+  const int ntiles = keys_per_split / T2I_KT;
+  const bf16* xb = p.x + (static_cast<long long>(b) * p.x_bstride + key0) * I2T_C;
+  const bf16* kab = p.kadd + static_cast<long long>(key0) * I2T_QD;
+
+  auto load_tile = [&](int t) {
+    uint8_t* dx = sT + (t % T2I_STAGES) * T2I_STAGE_BYTES;
+    uint8_t* dk = dx + T2I_KT * T2I_XP;
+    const uint8_t* srcx = reinterpret_cast<const uint8_t*>(xb + static_cast<long long>(t) * T2I_KT * I2T_C);
+    const uint8_t* srck = reinterpret_cast<const uint8_t*>(kab + static_cast<long long>(t) * T2I_KT * I2T_QD);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = tid + i * 128;  // 32 rows x 32 chunks
+      cp_async16(dx + (c >> 5) * T2I_XP + (c & 31) * 16, srcx + c * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + i * 128;  // 32 rows x 16 chunks
+      cp_async16(dk + (c >> 4) * T2I_KAP + (c & 15) * 16, srck + c * 16);
+    }
+  };
+  {
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(p.qf + static_cast<long long>(b) * I2T_NC * I2T_C);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = tid + i * 128;  // 64 rows x 32 chunks
+      cp_async16(sQ + (c >> 5) * T2I_XP + (c & 31) * 16, q + c * 16);
+    }
+  }
+  load_tile(0);
+  cp_async_commit();
+  if (ntiles > 1) load_tile(1);
+  cp_async_commit();
+
+  // positional-term A fragments: this warp's rows 0-7 are head 2*warp, rows 8-15 head 2*warp+1 (token = g)
+  const int hA = 2 * warp, hB = 2 * warp + 1;
+  const bf16* qsr = p.qs + (static_cast<long long>(b) * I2T_TOK + g) * I2T_QD;
+  uint32_t aA[4], aB[4];
+  aA[0] = *reinterpret_cast<const uint32_t*>(qsr + hA * 16 + 2 * q4);
+  aA[2] = *reinterpret_cast<const uint32_t*>(qsr + hA * 16 + 8 + 2 * q4);
+  aA[1] = aA[3] = 0u;
+  aB[1] = *reinterpret_cast<const uint32_t*>(qsr + hB * 16 + 2 * q4);
+  aB[3] = *reinterpret_cast<const uint32_t*>(qsr + hB * 16 + 8 + 2 * q4);
+  aB[0] = aB[2] = 0u;
+
+  float o[32][4];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  const uint32_t q_addr = sb::smem_u32(sQ) + (warp * 16 + (lane & 15)) * T2I_XP + (lane >> 4) * 16;
+  const uint32_t kb_off = ((lane & 7) + ((lane >> 4) << 3)) * T2I_XP + ((lane >> 3) & 1) * 16;     // QK B operand
+  const uint32_t ka_off = ((lane & 7) + ((lane >> 4) << 3)) * T2I_KAP + ((lane >> 3) & 1) * 16;    // kadd B operand
+  const uint32_t vb_off = ((lane & 7) + (((lane >> 3) & 1) << 3)) * T2I_XP + (lane >> 4) * 16;     // PV B operand (.trans)
+
+#pragma unroll 1
+  for (int t = 0; t < ntiles; ++t) {
+    cp_async_wait<1>();
+    __syncthreads();  // tile t visible to all warps; every warp is done with tile t-1 (whose stage is refilled next)
+    if (t + 2 < ntiles) load_tile(t + 2);
+    cp_async_commit();
+    const uint32_t xs = sb::smem_u32(sT + (t % T2I_STAGES) * T2I_STAGE_BYTES);
+    const uint32_t ks = xs + T2I_KT * T2I_XP;
+
+    float s[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    // positional term: one k16 step per head of this warp
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(ks + np * 16 * T2I_KAP + ka_off + hA * 32, b0, b1, b2, b3);
+      mma_bf16_16816(s[2 * np], aA, b0, b1);
+      mma_bf16_16816(s[2 * np + 1], aA, b2, b3);
+      ldsm_x4(ks + np * 16 * T2I_KAP + ka_off + hB * 32, b0, b1, b2, b3);
+      mma_bf16_16816(s[2 * np], aB, b0, b1);
+      mma_bf16_16816(s[2 * np + 1], aB, b2, b3);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      uint32_t a[4];
+      ldsm_x4(q_addr + kk * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(xs + np * 16 * T2I_XP + kb_off + kk * 32, b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * np], a, b0, b1);
+        mma_bf16_16816(s[2 * np + 1], a, b2, b3);
+      }
+    }
+    // ---- online softmax (log2 domain; scores arrive pre-scaled) with lazy rescaling ----
+    float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+    float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+    mx0 = fmaxf(mx0, fmaxf(fmaxf(s[2][0], s[2][1]), fmaxf(s[3][0], s[3][1])));
+    mx1 = fmaxf(mx1, fmaxf(fmaxf(s[2][2], s[2][3]), fmaxf(s[3][2], s[3][3])));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    if (__any_sync(0xffffffffu, (mx0 > m0 + 8.f) || (mx1 > m1 + 8.f))) {
+      const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
+      const float al0 = exp2f(m0 - n0), al1 = exp2f(m1 - n1);  // m = -inf on the first tile -> 0
+      m0 = n0;
+      m1 = n1;
+      l0 *= al0;
+      l1 *= al1;
+#pragma unroll
+      for (int n = 0; n < 32; ++n) {
+        o[n][0] *= al0;
+        o[n][1] *= al0;
+        o[n][2] *= al1;
+        o[n][3] *= al1;
+      }
+    }
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      s[n][0] = exp2f(s[n][0] - m0);
+      s[n][1] = exp2f(s[n][1] - m0);
+      s[n][2] = exp2f(s[n][2] - m1);
+      s[n][3] = exp2f(s[n][3] - m1);
+      l0 += s[n][0] + s[n][1];
+      l1 += s[n][2] + s[n][3];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      pa[kk][0] = sb::pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[kk][1] = sb::pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[kk][2] = sb::pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[kk][3] = sb::pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    }
+    // ---- O += P X (the key tile is also the value tile) ----
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_trans(xs + kk * 16 * T2I_XP + vb_off + np * 32, b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * np], pa[kk], b0, b1);
+        mma_bf16_16816(o[2 * np + 1], pa[kk], b2, b3);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const long long pb = static_cast<long long>(b) * p.ns + split;
+  float* op = p.opart + pb * I2T_NC * I2T_C;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int n = 0; n < 32; ++n) {
+    const int c = n * 8 + 2 * q4;
+    *reinterpret_cast<float2*>(op + r0 * I2T_C + c) = make_float2(o[n][0], o[n][1]);
+    *reinterpret_cast<float2*>(op + r1 * I2T_C + c) = make_float2(o[n][2], o[n][3]);
+  }
+  if (q4 == 0) {
+    float* ml = p.ml + pb * 2 * I2T_NC;
+    ml[r0] = m0;
+    ml[r1] = m1;
+    ml[I2T_NC + r0] = l0;
+    ml[I2T_NC + r1] = l1;
+  }
+}
+
+// Merge the key splits and apply the value projection: a[b*nt + t, h*16+d] = bv[h*16+d] + sum_c Wv[h*16+d, c] O[(h,t), c]
+// with O = sum_s 2^(m_s - m) O_s / sum_s 2^(m_s - m) l_s. One block per prompt, 256 threads.
+__global__ void __launch_bounds__(256)
+t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml, int ns, const bf16* __restrict__ wv /*[128,256]*/,
+                  const float* __restrict__ bv, bf16* __restrict__ out, long long out_ld, int nt) {
+  __shared__ float so[I2T_TOK][I2T_C + 4];
+  __shared__ float sw[I2T_NC][8];  // per (row, split) weight 2^(m_s - m) / L
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < I2T_NC) {
+    float m = -INFINITY;
+    for (int s = 0; s < ns; ++s) m = fmaxf(m, ml[(static_cast<long long>(b) * ns + s) * 2 * I2T_NC + tid]);
+    float L = 0.f;
+    for (int s = 0; s < ns; ++s) {
+      const float* q = ml + (static_cast<long long>(b) * ns + s) * 2 * I2T_NC;
+      const float wgt = exp2f(q[tid] - m);
+      sw[tid][s] = wgt;
+      L += wgt * q[I2T_NC + tid];
+    }
+    const float inv = 1.f / L;
+    for (int s = 0; s < ns; ++s) sw[tid][s] *= inv;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int h = 0; h < 8; ++h) {
+    // merged rows of head h: 8 tokens x 256 channels (thread = channel)
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t) {
+      float acc = 0.f;
+      for (int s = 0; s < ns; ++s)
+        acc = fmaf(sw[h * 8 + t][s], opart[((static_cast<long long>(b) * ns + s) * I2T_NC + h * 8 + t) * I2T_C + tid], acc);
+      so[t][tid] = acc;
+    }
+    __syncthreads();
+    // 8 tokens x 16 dims = 128 outputs, two threads (channel halves) each
+    const int half = tid & 1, d = (tid >> 1) & 15, t = tid >> 5;
+    const bf16* wrow = wv + (h * 16 + d) * I2T_C + half * 128;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c8 = 0; c8 < 16; ++c8) {
+      const uint4 w8 = *reinterpret_cast<const uint4*>(wrow + c8 * 8);
+      const float* ov = &so[t][half * 128 + c8 * 8];
+      acc = fmaf(sb::bf16_lo(w8.x), ov[0], acc);
+      acc = fmaf(sb::bf16_hi(w8.x), ov[1], acc);
+      acc = fmaf(sb::bf16_lo(w8.y), ov[2], acc);
+      acc = fmaf(sb::bf16_hi(w8.y), ov[3], acc);
+      acc = fmaf(sb::bf16_lo(w8.z), ov[4], acc);
+      acc = fmaf(sb::bf16_hi(w8.z), ov[5], acc);
+      acc = fmaf(sb::bf16_lo(w8.w), ov[6], acc);
+      acc = fmaf(sb::bf16_hi(w8.w), ov[7], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0 && t < nt)
+      out[(static_cast<long long>(b) * nt + t) * out_ld + h * 16 + d] = __float2bfloat16(acc + bv[h * 16 + d]);
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 // Per-prompt folded operands of sb_i2t_block (see the header of this file). kt / vt [B*nt, 128] bf16 (the projected token
@@ -353,7 +619,7 @@ i2t_block_kernel(const I2TParams p) {
 extern "C" int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld, const void* wq, const void* wo,
                            void* w1t, void* w2t, void* kts, int batch, int nt, float scale, void* stream) {
   SB_REQUIRE(batch > 0 && nt >= 1 && nt <= I2T_TOK, "sb_i2t_fold: nt must be in 1..%d (got %d)", I2T_TOK, nt);
-  SB_REQUIRE(kt && vt && wq && wo && w2t && kts, "sb_i2t_fold: null operand");
+  SB_REQUIRE(kt && wq && kts && (w1t || w2t) && (!w2t || (vt && wo)), "sb_i2t_fold: null operand");
   SB_REQUIRE(((reinterpret_cast<uintptr_t>(wo) | reinterpret_cast<uintptr_t>(w2t)) & 15) == 0, "sb_i2t_fold: wo / w2t must be 16-byte aligned");
   i2t_fold_kernel<<<batch, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(kt), kt_ld, static_cast<const bf16*>(vt), vt_ld, static_cast<const bf16*>(wq),
@@ -423,6 +689,57 @@ extern "C" int sb_i2t_block(const void* x, int x_shared, const void* qp, const v
     i2t_block_kernel<false><<<grid, I2T_WARPS * 32, I2T_SMEM_FOLD, st>>>(p);
   else
     i2t_block_kernel<true><<<grid, I2T_WARPS * 32, I2T_SMEM_SHARED, st>>>(p);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// Token -> image attention of the mask decoder straight on the image stream (see t2i_fold_attn_kernel).
+// q [batch*nt, 128] bf16 (projected token queries incl. bias), x [batch*nk (nk when x_shared), 256] bf16, kadd [nk,128]
+// bf16 (= image_pe Wk^T + bk), wk / wv [128,256] bf16 (the k_proj / v_proj weights), bv [128] fp32.
+// Workspaces (caller-owned): qf [batch,64,256] bf16, qs [batch,8,128] bf16, opart [batch,ns,64,256] fp32,
+// ml [batch,ns,2,64] fp32 with ns = sb_t2i_fold_splits(batch, nk). out [batch*nt, 128] bf16 = the attention output
+// before out_proj. nt <= 8, nk a multiple of 256.
+extern "C" int sb_t2i_fold_splits(int batch, int nk) {
+  int ns = batch >= 96 ? 4 : 8;
+  while (ns > 1 && (nk % (ns * T2I_KT)) != 0) ns >>= 1;
+  return ns;
+}
+
+extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* x, int x_shared, const void* kadd,
+                                     const void* wk, const void* wv, const float* bv, void* qf, void* qs, float* opart,
+                                     float* ml, void* out, long long out_ld, int batch, int nt, int nk, float scale,
+                                     void* stream) {
+  SB_REQUIRE(batch > 0 && nt >= 1 && nt <= I2T_TOK, "sb_t2i_fold_attention: nt must be in 1..%d (got %d)", I2T_TOK, nt);
+  SB_REQUIRE(nk > 0 && (nk % 256) == 0, "sb_t2i_fold_attention: nk must be a positive multiple of 256 (got %d)", nk);
+  SB_REQUIRE(q && x && kadd && wk && wv && bv && qf && qs && opart && ml && out, "sb_t2i_fold_attention: null operand");
+  SB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(kadd) | reinterpret_cast<uintptr_t>(qf) |
+               reinterpret_cast<uintptr_t>(qs) | reinterpret_cast<uintptr_t>(wv) | reinterpret_cast<uintptr_t>(opart)) & 15) == 0,
+             "sb_t2i_fold_attention: operands must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ns = sb_t2i_fold_splits(batch, nk);
+  // folded queries: the same fold as the image->token block (W1^T rows = Wk_h^T q_{t,h}, scaled; kts = scaled q)
+  i2t_fold_kernel<<<batch, 256, 0, st>>>(static_cast<const bf16*>(q), q_ld, nullptr, 0, static_cast<const bf16*>(wk), nullptr,
+                                         static_cast<bf16*>(qf), nullptr, static_cast<bf16*>(qs), nt,
+                                         scale * 1.4426950408889634f);
+  SB_CHECK_LAUNCH();
+  static bool attr_done = false;
+  if (!attr_done) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(t2i_fold_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2I_SMEM));
+    attr_done = true;
+  }
+  T2IParams p;
+  p.x = static_cast<const bf16*>(x);
+  p.x_bstride = x_shared ? 0 : nk;
+  p.kadd = static_cast<const bf16*>(kadd);
+  p.qf = static_cast<const bf16*>(qf);
+  p.qs = static_cast<const bf16*>(qs);
+  p.opart = opart;
+  p.ml = ml;
+  p.nk = nk;
+  p.ns = ns;
+  t2i_fold_attn_kernel<<<dim3(ns, batch), 128, T2I_SMEM, st>>>(p);
+  SB_CHECK_LAUNCH();
+  t2i_unfold_kernel<<<batch, 256, 0, st>>>(opart, ml, ns, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

@@ -86,6 +86,7 @@ class MaskDecoder:
             # k = (keys + pe) Wk^T + bk: the pe term (weights only) is added inside the attention kernel as a second MMA
             # (scores = q k^T + q k_add^T), so the big K|V GEMM carries a plain bias and no broadcast residual
             L["t2i_kv_b"] = f32(torch.cat([torch.zeros(128), t2i["vb"]]))
+            L["t2i_v_b"] = f32(t2i["vb"])
             L["t2i_k_add"] = w16(image_pe @ t2i["kw"].t() + t2i["kb"])  # [4096, 128]
             L["t2i_o_w"], L["t2i_o_b"] = w16(t2i["outw"]), f32(t2i["outb"])
             L["i2t_q_w"] = w16(i2t["qw"])
@@ -103,6 +104,7 @@ class MaskDecoder:
         self.fa_q_w, self.fa_q_b = w16(fa["qw"]), f32(fa["qb"])
         self.fa_kv_w = w16(torch.cat([fa["kw"], fa["vw"]], 0))
         self.fa_kv_b = f32(torch.cat([torch.zeros(128), fa["vb"]]))
+        self.fa_v_b = f32(fa["vb"])
         self.fa_k_add = w16(image_pe @ fa["kw"].t() + fa["kb"])
         self.fa_o_w, self.fa_o_b = w16(fa["outw"]), f32(fa["outb"])
         self.nf_w, self.nf_b = f32(sd[md + "transformer.norm_final_attn.weight"]), f32(sd[md + "transformer.norm_final_attn.bias"])
@@ -180,8 +182,13 @@ class MaskDecoder:
             queries = ops.layernorm(queries, L["n1w"], L["n1b"], 1e-5, _F32)
             # ---- tokens attend to image
             q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["t2i_q_w"], L["t2i_q_b"])
-            kv = ops.gemm(keys, L["t2i_kv_w"], L["t2i_kv_b"])
-            a = ops.attention_kadd(q, kv[:, 0:128], L["t2i_k_add"], kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))
+            if Nt <= 8:  # k / v projections folded onto the tokens: the image stream is read once, K|V never exist
+                a = ops.t2i_fold_attention(q, keys, L["t2i_k_add"], L["t2i_kv_w"][0:128], L["t2i_kv_w"][128:256],
+                                           L["t2i_v_b"], B, Nt, NT_IMG, x_shared=(kb == 1))
+            else:
+                kv = ops.gemm(keys, L["t2i_kv_w"], L["t2i_kv_b"])
+                a = ops.attention_kadd(q, kv[:, 0:128], L["t2i_k_add"], kv[:, 128:256], B, 8, Nt, NT_IMG,
+                                       kv_shared=(kb == 1))
             queries = ops.gemm(a, L["t2i_o_w"], L["t2i_o_b"], residual=queries, out_dtype=_F32)
             queries = ops.layernorm(queries, L["n2w"], L["n2b"], 1e-5, _F32)
             # ---- token MLP
@@ -220,8 +227,12 @@ class MaskDecoder:
             kb = B
         # ---- final token -> image attention
         q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), self.fa_q_w, self.fa_q_b)
-        kv = ops.gemm(keys, self.fa_kv_w, self.fa_kv_b)
-        a = ops.attention_kadd(q, kv[:, 0:128], self.fa_k_add, kv[:, 128:256], B, 8, Nt, NT_IMG)
+        if Nt <= 8:
+            a = ops.t2i_fold_attention(q, keys, self.fa_k_add, self.fa_kv_w[0:128], self.fa_kv_w[128:256], self.fa_v_b, B,
+                                       Nt, NT_IMG, x_shared=(kb == 1))
+        else:
+            kv = ops.gemm(keys, self.fa_kv_w, self.fa_kv_b)
+            a = ops.attention_kadd(q, kv[:, 0:128], self.fa_k_add, kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))
         queries = ops.gemm(a, self.fa_o_w, self.fa_o_b, residual=queries, out_dtype=_F32)
         hs = ops.layernorm(queries, self.nf_w, self.nf_b, 1e-5, _F32)  # [B*Nt,256]
         # ---- up-scaling + hyper-network masks

@@ -122,6 +122,29 @@ def test_attention_few_keys_with_query_term(ops):
     assert (out1.float() - ref1).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("B,nt,shared", [(3, 8, False), (2, 7, True), (100, 8, False), (1, 1, False)])
+def test_t2i_fold_attention(ops, B, nt, shared):
+    """Token -> image attention with the k / v projections folded onto the tokens (image stream read once) vs the
+    unfused fp32 expression softmax(q ((x Wk^T) + kadd)^T / 4) (x Wv^T + bv)."""
+    torch.manual_seed(12)
+    nk = 4096
+    x = torch.randn((1 if shared else B) * nk, 256, device="cuda").to(BF16)
+    wk = (torch.randn(128, 256, device="cuda") / 16).to(BF16)
+    wv = (torch.randn(128, 256, device="cuda") / 16).to(BF16)
+    bv = torch.randn(128, device="cuda") * 0.2
+    kadd = torch.randn(nk, 128, device="cuda").to(BF16)
+    q = (torch.randn(B * nt, 128, device="cuda") * 1.5).to(BF16)
+    out = ops.t2i_fold_attention(q, x, kadd, wk, wv, bv, B, nt, nk, x_shared=shared)
+    xf = x.float().view(-1, nk, 256).expand(B, nk, 256)
+    k = (xf @ wk.float().t() + kadd.float()[None]).view(B, nk, 8, 16).transpose(1, 2)
+    v = (xf @ wv.float().t() + bv).view(B, nk, 8, 16).transpose(1, 2)
+    qq = q.float().view(B, nt, 8, 16).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(qq, k, v).transpose(1, 2).reshape(B * nt, 128)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1.5e-2
+
+
 @pytest.mark.parametrize("nt,shared", [(8, False), (7, False), (8, True), (3, True), (1, False)])
 def test_i2t_block_fused(ops, nt, shared):
     """Fused TwoWayAttentionBlock step 4 (q projection + image->token attention + out projection + residual + norm4 in
