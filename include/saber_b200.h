@@ -70,12 +70,17 @@ int sb_attention_few_keys(const void* q, long long q_ld, const float* q_add, con
 /* Fused TwoWayAttentionBlock step 4 (sam2/modeling/sam/transformer.py: `keys = norm4(keys + cross_attn_image_to_token(
  * q=keys+key_pe, k=queries+query_pe, v=queries))`) for prompts with <= 8 tokens. sb_i2t_fold folds the q / out
  * projections into per-prompt operands (kts [B,8,128], w1t [B,64,256] (nullable), w2t [B,256,64], all bf16) from the
- * projected token keys / values kt, vt [B*nt,128] bf16; sb_i2t_block then makes one pass over the image stream
+ * projected token keys / values kt, vt [B*nt,128] bf16 (bo != NULL folds the out-projection bias into w2t: only for
+ * sb_i2t_block_tc); sb_i2t_block then makes one pass over the image stream
  * x [B*nq,256] bf16 (or [nq,256] when x_shared): scores, per-head softmax, out projection, residual, LayerNorm.
  * qp [nq,128] bf16 is shared by all prompts: the positional term image_pe Wq^T + bq (w1t != NULL) or the whole query
  * projection of a shared stream (w1t == NULL). out [B*nq,256] bf16 may alias a per-prompt x. */
-int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld, const void* wq, const void* wo, void* w1t,
-                void* w2t, void* kts, int batch, int nt, float scale, void* stream);
+int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld, const void* wq, const void* wo,
+                const float* bo, void* w1t, void* w2t, void* kts, int batch, int nt, float scale, void* stream);
+/* sb_i2t_block for a per-prompt stream on tcgen05 / TMEM / TMA (128-row tiles, both GEMMs as UMMA, softmax + LayerNorm in
+ * the epilogue warps); w2t must carry the folded out-projection bias (sb_i2t_fold with bo != NULL). */
+int sb_i2t_block_tc(const void* x, const void* qres, const void* w1t, const void* w2t, const void* kts, const float* gamma,
+                    const float* beta, float eps, void* out, int batch, int nq, int nt, void* stream);
 int sb_i2t_block(const void* x, int x_shared, const void* qp, const void* w1t, const void* w2t, const void* kts,
                  const float* bo, const float* gamma, const float* beta, float eps, void* out, int batch, int nq, int nt,
                  void* stream);

@@ -62,58 +62,66 @@ constexpr int I2T_NC = 64;    // (head, token) columns
 __global__ void __launch_bounds__(256)
 i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __restrict__ vt, long long vt_ld,
                 const bf16* __restrict__ wq /* [128,256] */, const bf16* __restrict__ wo /* [256,128] */,
-                bf16* __restrict__ w1t, bf16* __restrict__ w2t, bf16* __restrict__ kts, int nt, float scale_log2) {
+                bf16* __restrict__ w1t, bf16* __restrict__ w2t, bf16* __restrict__ kts, int nt, float scale_log2,
+                const float* __restrict__ bo /* nullable: out-projection bias folded into w2t (bo / 8 per column) */) {
+  // blockIdx.y == 0: kts + w1t (from kt); blockIdx.y == 1: w2t (from vt). The two halves are independent.
   __shared__ float sk[I2T_TOK][I2T_QD];
-  __shared__ float sv[I2T_TOK][I2T_QD];
   const int b = blockIdx.x, tid = threadIdx.x;
+  const bool second = blockIdx.y == 1;
+  if (second ? (w2t == nullptr) : false) return;
+  const bf16* src = second ? vt : kt;
+  const long long src_ld = second ? vt_ld : kt_ld;
+  const float mul = second ? 1.f : scale_log2;
   for (int i = tid; i < I2T_TOK * I2T_QD; i += 256) {
     const int t = i >> 7, c = i & 127;
-    float kv = 0.f, vv = 0.f;
-    if (t < nt) {
-      kv = __bfloat162float(kt[(static_cast<long long>(b) * nt + t) * kt_ld + c]) * scale_log2;
-      if (vt != nullptr) vv = __bfloat162float(vt[(static_cast<long long>(b) * nt + t) * vt_ld + c]);
-    }
-    sk[t][c] = kv;
-    sv[t][c] = vv;
-    kts[(static_cast<long long>(b) * I2T_TOK + t) * I2T_QD + c] = __float2bfloat16(kv);
+    const float v = t < nt ? __bfloat162float(src[(static_cast<long long>(b) * nt + t) * src_ld + c]) * mul : 0.f;
+    sk[t][c] = v;
+    if (!second) kts[(static_cast<long long>(b) * I2T_TOK + t) * I2T_QD + c] = __float2bfloat16(v);
   }
   __syncthreads();
   const int c = tid;
-  if (w1t != nullptr) {
-#pragma unroll 1
+  if (!second) {
+    if (w1t == nullptr) return;
+    // column c of Wq for all 128 rows: 128 independent coalesced loads in flight
+    float wcol[128];
+#pragma unroll
+    for (int r = 0; r < 128; ++r) wcol[r] = __bfloat162float(wq[r * I2T_C + c]);
+#pragma unroll
     for (int h = 0; h < 8; ++h) {
       float acc[I2T_TOK];
 #pragma unroll
       for (int t = 0; t < I2T_TOK; ++t) acc[t] = 0.f;
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
-        const float w = __bfloat162float(wq[(h * 16 + d) * I2T_C + c]);
 #pragma unroll
-        for (int t = 0; t < I2T_TOK; ++t) acc[t] = fmaf(w, sk[t][h * 16 + d], acc[t]);
+        for (int t = 0; t < I2T_TOK; ++t) acc[t] = fmaf(wcol[h * 16 + d], sk[t][h * 16 + d], acc[t]);
       }
 #pragma unroll
       for (int t = 0; t < I2T_TOK; ++t)
         w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * I2T_C + c] = __float2bfloat16(acc[t]);
     }
-  }
-  if (w2t != nullptr) {
+  } else {
     const bf16* worow = wo + c * I2T_QD;
     bf16* dst = w2t + (static_cast<long long>(b) * I2T_C + c) * I2T_NC;
-#pragma unroll 1
+    // every head's softmax row sums to 1, so bo[c] / 8 added to all 64 (head, token) columns contributes exactly bo[c]
+    const float bfold = bo != nullptr ? bo[c] * 0.125f : 0.f;
+    uint4 wr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wr[i] = *reinterpret_cast<const uint4*>(worow + i * 8);
+#pragma unroll
     for (int h = 0; h < 8; ++h) {
       float acc[I2T_TOK];
 #pragma unroll
-      for (int t = 0; t < I2T_TOK; ++t) acc[t] = 0.f;
-      const uint4 wa = *reinterpret_cast<const uint4*>(worow + h * 16);
-      const uint4 wb = *reinterpret_cast<const uint4*>(worow + h * 16 + 8);
-      const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      for (int t = 0; t < I2T_TOK; ++t) acc[t] = bfold;
+      const uint32_t w8[8] = {wr[2 * h].x, wr[2 * h].y, wr[2 * h].z, wr[2 * h].w,
+                              wr[2 * h + 1].x, wr[2 * h + 1].y, wr[2 * h + 1].z, wr[2 * h + 1].w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float w0 = sb::bf16_lo(w8[e]), w1 = sb::bf16_hi(w8[e]);
 #pragma unroll
         for (int t = 0; t < I2T_TOK; ++t) {
-          acc[t] = fmaf(w0, sv[t][h * 16 + 2 * e], acc[t]);
-          acc[t] = fmaf(w1, sv[t][h * 16 + 2 * e + 1], acc[t]);
+          acc[t] = fmaf(w0, sk[t][h * 16 + 2 * e], acc[t]);
+          acc[t] = fmaf(w1, sk[t][h * 16 + 2 * e + 1], acc[t]);
         }
       }
       *reinterpret_cast<uint4*>(dst + h * 8) =
@@ -555,76 +563,83 @@ t2i_fold_attn_kernel(const T2IParams p) {
 }
 
 // Merge the key splits and apply the value projection: a[b*nt + t, h*16+d] = bv[h*16+d] + sum_c Wv[h*16+d, c] O[(h,t), c]
-// with O = sum_s 2^(m_s - m) O_s / sum_s 2^(m_s - m) l_s. One block per prompt, 256 threads.
+// with O = sum_s 2^(m_s - m) O_s / sum_s 2^(m_s - m) l_s. One block per (head, prompt), 256 threads.
 __global__ void __launch_bounds__(256)
 t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml, int ns, const bf16* __restrict__ wv /*[128,256]*/,
                   const float* __restrict__ bv, bf16* __restrict__ out, long long out_ld, int nt) {
   __shared__ float so[I2T_TOK][I2T_C + 4];
-  __shared__ float sw[I2T_NC][8];  // per (row, split) weight 2^(m_s - m) / L
-  const int b = blockIdx.x, tid = threadIdx.x;
-  if (tid < I2T_NC) {
+  __shared__ float sw[I2T_TOK][8];  // per (token row, split) weight 2^(m_s - m) / L
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  if (tid < I2T_TOK) {
+    const int row = h * 8 + tid;
     float m = -INFINITY;
-    for (int s = 0; s < ns; ++s) m = fmaxf(m, ml[(static_cast<long long>(b) * ns + s) * 2 * I2T_NC + tid]);
+    for (int s = 0; s < ns; ++s) m = fmaxf(m, ml[(static_cast<long long>(b) * ns + s) * 2 * I2T_NC + row]);
     float L = 0.f;
     for (int s = 0; s < ns; ++s) {
       const float* q = ml + (static_cast<long long>(b) * ns + s) * 2 * I2T_NC;
-      const float wgt = exp2f(q[tid] - m);
+      const float wgt = exp2f(q[row] - m);
       sw[tid][s] = wgt;
-      L += wgt * q[I2T_NC + tid];
+      L += wgt * q[I2T_NC + row];
     }
     const float inv = 1.f / L;
     for (int s = 0; s < ns; ++s) sw[tid][s] *= inv;
   }
-  __syncthreads();
-#pragma unroll 1
-  for (int h = 0; h < 8; ++h) {
-    // merged rows of head h: 8 tokens x 256 channels (thread = channel)
+  // merged rows of head h: 8 tokens x 256 channels (thread = channel); all partial loads issued before the weights
+  // are needed
+  float part[I2T_TOK];
 #pragma unroll
-    for (int t = 0; t < I2T_TOK; ++t) {
-      float acc = 0.f;
-      for (int s = 0; s < ns; ++s)
-        acc = fmaf(sw[h * 8 + t][s], opart[((static_cast<long long>(b) * ns + s) * I2T_NC + h * 8 + t) * I2T_C + tid], acc);
-      so[t][tid] = acc;
-    }
-    __syncthreads();
-    // 8 tokens x 16 dims = 128 outputs, two threads (channel halves) each
-    const int half = tid & 1, d = (tid >> 1) & 15, t = tid >> 5;
-    const bf16* wrow = wv + (h * 16 + d) * I2T_C + half * 128;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int c8 = 0; c8 < 16; ++c8) {
-      const uint4 w8 = *reinterpret_cast<const uint4*>(wrow + c8 * 8);
-      const float* ov = &so[t][half * 128 + c8 * 8];
-      acc = fmaf(sb::bf16_lo(w8.x), ov[0], acc);
-      acc = fmaf(sb::bf16_hi(w8.x), ov[1], acc);
-      acc = fmaf(sb::bf16_lo(w8.y), ov[2], acc);
-      acc = fmaf(sb::bf16_hi(w8.y), ov[3], acc);
-      acc = fmaf(sb::bf16_lo(w8.z), ov[4], acc);
-      acc = fmaf(sb::bf16_hi(w8.z), ov[5], acc);
-      acc = fmaf(sb::bf16_lo(w8.w), ov[6], acc);
-      acc = fmaf(sb::bf16_hi(w8.w), ov[7], acc);
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (half == 0 && t < nt)
-      out[(static_cast<long long>(b) * nt + t) * out_ld + h * 16 + d] = __float2bfloat16(acc + bv[h * 16 + d]);
-    __syncthreads();
+  for (int t = 0; t < I2T_TOK; ++t) part[t] = 0.f;
+  const float* ob = opart + (static_cast<long long>(b) * ns * I2T_NC + h * 8) * I2T_C + tid;
+  __syncthreads();
+  for (int s = 0; s < ns; ++s) {
+    float v[I2T_TOK];
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t) v[t] = __ldg(ob + (static_cast<long long>(s) * I2T_NC + t) * I2T_C);
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t) part[t] = fmaf(sw[t][s], v[t], part[t]);
   }
+#pragma unroll
+  for (int t = 0; t < I2T_TOK; ++t) so[t][tid] = part[t];
+  __syncthreads();
+  // 8 tokens x 16 dims = 128 outputs, two threads (channel halves) each
+  const int half = tid & 1, d = (tid >> 1) & 15, t = tid >> 5;
+  const bf16* wrow = wv + (h * 16 + d) * I2T_C + half * 128;
+  uint4 w8[16];
+#pragma unroll
+  for (int c8 = 0; c8 < 16; ++c8) w8[c8] = __ldg(reinterpret_cast<const uint4*>(wrow + c8 * 8));
+  float acc = 0.f;
+#pragma unroll
+  for (int c8 = 0; c8 < 16; ++c8) {
+    const float* ov = &so[t][half * 128 + c8 * 8];
+    acc = fmaf(sb::bf16_lo(w8[c8].x), ov[0], acc);
+    acc = fmaf(sb::bf16_hi(w8[c8].x), ov[1], acc);
+    acc = fmaf(sb::bf16_lo(w8[c8].y), ov[2], acc);
+    acc = fmaf(sb::bf16_hi(w8[c8].y), ov[3], acc);
+    acc = fmaf(sb::bf16_lo(w8[c8].z), ov[4], acc);
+    acc = fmaf(sb::bf16_hi(w8[c8].z), ov[5], acc);
+    acc = fmaf(sb::bf16_lo(w8[c8].w), ov[6], acc);
+    acc = fmaf(sb::bf16_hi(w8[c8].w), ov[7], acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (half == 0 && t < nt)
+    out[(static_cast<long long>(b) * nt + t) * out_ld + h * 16 + d] = __float2bfloat16(acc + bv[h * 16 + d]);
 }
 
 }  // namespace
 
 // Per-prompt folded operands of sb_i2t_block (see the header of this file). kt / vt [B*nt, 128] bf16 (the projected token
 // keys / values of cross_attn_image_to_token), wq [128,256] / wo [256,128] bf16 (its q_proj / out_proj weights).
-// w1t may be null (shared-query mode needs only kts and w2t).
+// w1t may be null (shared-query mode needs only kts and w2t). bo (nullable, [256] fp32): the out-projection bias is folded
+// into w2t (the tcgen05 block kernel then adds no bias); with bo == NULL w2t is the plain fold (sb_i2t_block adds bo).
 extern "C" int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld, const void* wq, const void* wo,
-                           void* w1t, void* w2t, void* kts, int batch, int nt, float scale, void* stream) {
+                           const float* bo, void* w1t, void* w2t, void* kts, int batch, int nt, float scale, void* stream) {
   SB_REQUIRE(batch > 0 && nt >= 1 && nt <= I2T_TOK, "sb_i2t_fold: nt must be in 1..%d (got %d)", I2T_TOK, nt);
   SB_REQUIRE(kt && wq && kts && (w1t || w2t) && (!w2t || (vt && wo)), "sb_i2t_fold: null operand");
   SB_REQUIRE(((reinterpret_cast<uintptr_t>(wo) | reinterpret_cast<uintptr_t>(w2t)) & 15) == 0, "sb_i2t_fold: wo / w2t must be 16-byte aligned");
-  i2t_fold_kernel<<<batch, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  i2t_fold_kernel<<<dim3(batch, w2t ? 2 : 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(kt), kt_ld, static_cast<const bf16*>(vt), vt_ld, static_cast<const bf16*>(wq),
       static_cast<const bf16*>(wo), static_cast<bf16*>(w1t), static_cast<bf16*>(w2t), static_cast<bf16*>(kts), nt,
-      scale * 1.4426950408889634f);
+      scale * 1.4426950408889634f, bo);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
@@ -718,9 +733,9 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ns = sb_t2i_fold_splits(batch, nk);
   // folded queries: the same fold as the image->token block (W1^T rows = Wk_h^T q_{t,h}, scaled; kts = scaled q)
-  i2t_fold_kernel<<<batch, 256, 0, st>>>(static_cast<const bf16*>(q), q_ld, nullptr, 0, static_cast<const bf16*>(wk), nullptr,
+  i2t_fold_kernel<<<dim3(batch, 1), 256, 0, st>>>(static_cast<const bf16*>(q), q_ld, nullptr, 0, static_cast<const bf16*>(wk), nullptr,
                                          static_cast<bf16*>(qf), nullptr, static_cast<bf16*>(qs), nt,
-                                         scale * 1.4426950408889634f);
+                                         scale * 1.4426950408889634f, nullptr);
   SB_CHECK_LAUNCH();
   static bool attr_done = false;
   if (!attr_done) {
@@ -739,7 +754,7 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
   p.ns = ns;
   t2i_fold_attn_kernel<<<dim3(ns, batch), 128, T2I_SMEM, st>>>(p);
   SB_CHECK_LAUNCH();
-  t2i_unfold_kernel<<<batch, 256, 0, st>>>(opart, ml, ns, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
+  t2i_unfold_kernel<<<dim3(8, batch), 256, 0, st>>>(opart, ml, ns, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

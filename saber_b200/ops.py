@@ -283,7 +283,7 @@ def attention_few_keys(q: torch.Tensor, q_add: Optional[torch.Tensor], k: torch.
 
 
 def i2t_fold(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch.Tensor, batch: int, nt: int,
-             with_w1: bool = True, scale: float = 0.25):
+             with_w1: bool = True, scale: float = 0.25, bo: Optional[torch.Tensor] = None):
     """Per-prompt folded operands of ``i2t_block`` (TwoWayAttentionBlock step 4 with <= 8 tokens per prompt):
     kt / vt [batch*nt, 128] bf16 (row views allowed), wq [128,256] / wo [256,128] bf16 -> (w1t [B,64,256] or None,
     w2t [B,256,64], kts [B,8,128]) bf16."""
@@ -296,8 +296,10 @@ def i2t_fold(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch.Ten
     w2t = torch.empty((batch, 256, 64), dtype=_BF16, device=dev)
     kts = torch.empty((batch, 8, 128), dtype=_BF16, device=dev)
     L = _lib.load()
+    assert bo is None or (bo.dtype == _F32 and bo.is_contiguous() and bo.numel() == 256 and bo.is_cuda)
     _lib.check(L.sb_i2t_fold(kt.data_ptr(), kt.stride(0), vt.data_ptr(), vt.stride(0), wq.data_ptr(), wo.data_ptr(),
-                             _ptr(w1t), w2t.data_ptr(), kts.data_ptr(), batch, nt, scale, _stream()), "sb_i2t_fold")
+                             _ptr(bo), _ptr(w1t), w2t.data_ptr(), kts.data_ptr(), batch, nt, scale, _stream()),
+               "sb_i2t_fold")
     _count()
     return w1t, w2t, kts
 
@@ -322,6 +324,30 @@ def i2t_block(x: torch.Tensor, qp: torch.Tensor, w1t: Optional[torch.Tensor], w2
     _lib.check(L.sb_i2t_block(x.data_ptr(), int(x_shared), qp.data_ptr(), _ptr(w1t), w2t.data_ptr(), kts.data_ptr(),
                               bo.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), batch, nq, nt,
                               _stream()), "sb_i2t_block")
+    _count()
+    return out
+
+
+def i2t_block_tc(x: torch.Tensor, qres: torch.Tensor, w1t: torch.Tensor, w2t: torch.Tensor, kts: torch.Tensor,
+                 gamma: torch.Tensor, beta: torch.Tensor, eps: float, batch: int, nq: int, nt: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``i2t_block`` of a per-prompt stream on tcgen05 / TMEM / TMA (csrc/decoder_i2t_tc.cu); ``w2t`` must come from
+    ``i2t_fold(..., bo=out_proj_bias)``."""
+    _chk_cuda(x, qres, w1t, w2t, kts, gamma, beta)
+    assert x.dtype == _BF16 and x.is_contiguous() and x.shape == (batch * nq, 256)
+    assert qres.dtype == _BF16 and qres.is_contiguous() and qres.shape == (nq, 128)
+    assert w1t.dtype == _BF16 and w1t.is_contiguous() and w1t.shape == (batch, 64, 256)
+    assert w2t.dtype == _BF16 and w2t.is_contiguous() and w2t.shape == (batch, 256, 64)
+    assert kts.dtype == _BF16 and kts.is_contiguous() and kts.shape == (batch, 8, 128)
+    for v in (gamma, beta):
+        assert v.dtype == _F32 and v.is_contiguous() and v.numel() == 256
+    if out is None:
+        out = torch.empty((batch * nq, 256), dtype=_BF16, device=x.device)
+    assert out.dtype == _BF16 and out.is_contiguous() and out.shape == (batch * nq, 256)
+    L = _lib.load()
+    _lib.check(L.sb_i2t_block_tc(x.data_ptr(), qres.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), kts.data_ptr(),
+                                 gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), batch, nq, nt, _stream()),
+               "sb_i2t_block_tc")
     _count()
     return out
 

@@ -12,6 +12,7 @@ Restates sam2/modeling/sam/{prompt_encoder,mask_decoder,transformer}.py (SURVEY 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -40,6 +41,7 @@ class MaskDecoder:
         md, pe = "sam_mask_decoder.", "sam_prompt_encoder."
         self.dynamic_multimask_via_stability = dynamic_multimask_via_stability
         self.stab_delta, self.stab_thresh = 0.05, 0.98
+        self.i2t_tensor_core = os.environ.get("SB_I2T_TC", "1") != "0"  # tcgen05 image->token block (0: mma.sync kernel)
 
         def w16(t):
             return t.to(dev, _BF16).contiguous()
@@ -206,6 +208,12 @@ class MaskDecoder:
                 if kb == 1:  # one stream shared by all prompts: its query projection is computed once
                     qp = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
                     w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt, with_w1=False)
+                elif self.i2t_tensor_core:  # per-prompt stream: both GEMMs on tcgen05 (csrc/decoder_i2t_tc.cu)
+                    w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt, bo=L["i2t_o_b"])
+                    keys = ops.i2t_block_tc(keys, L["i2t_q_res16"], w1t, w2t, kts, L["n4w"], L["n4b"], 1e-5, B, NT_IMG, Nt,
+                                            out=keys)
+                    keys_f32 = keys
+                    continue
                 else:
                     qp = L["i2t_q_res16"]
                     w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt)

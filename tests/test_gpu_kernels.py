@@ -145,8 +145,9 @@ def test_t2i_fold_attention(ops, B, nt, shared):
     assert ((out.float() - ref).norm() / ref.norm()).item() < 1.5e-2
 
 
-@pytest.mark.parametrize("nt,shared", [(8, False), (7, False), (8, True), (3, True), (1, False)])
-def test_i2t_block_fused(ops, nt, shared):
+@pytest.mark.parametrize("nt,shared,tc", [(8, False, False), (7, False, False), (8, True, False), (3, True, False),
+                                          (1, False, False), (8, False, True), (5, False, True), (1, False, True)])
+def test_i2t_block_fused(ops, nt, shared, tc):
     """Fused TwoWayAttentionBlock step 4 (q projection + image->token attention + out projection + residual + norm4 in
     one pass over the image stream, projections folded per prompt) vs the unfused fp32 torch expression."""
     torch.manual_seed(11)
@@ -171,14 +172,20 @@ def test_i2t_block_fused(ops, nt, shared):
         assert w1t is None
     else:
         qp = qres.to(BF16)
-        w1t, w2t, kts = ops.i2t_fold(kt, vt, wq, wo, B, nt)
-    out = ops.i2t_block(x, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, x_shared=shared)
+        w1t, w2t, kts = ops.i2t_fold(kt, vt, wq, wo, B, nt, bo=(bo if tc else None))
+    if tc:
+        out = ops.i2t_block_tc(x, qp, w1t, w2t, kts, gamma, beta, 1e-5, B, nq, nt)
+    else:
+        out = ops.i2t_block(x, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, x_shared=shared)
     err = (out.float() - ref).abs().max().item()
     assert err < 6e-2, err  # outputs are O(1) LayerNorm values stored in bf16; folded weights are rounded to bf16 once
     assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2
     if not shared:  # in-place update of a per-prompt stream
         x2 = x.clone()
-        out2 = ops.i2t_block(x2, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, out=x2)
+        if tc:
+            out2 = ops.i2t_block_tc(x2, qp, w1t, w2t, kts, gamma, beta, 1e-5, B, nq, nt, out=x2)
+        else:
+            out2 = ops.i2t_block(x2, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, out=x2)
         assert out2.data_ptr() == x2.data_ptr() and torch.equal(out2, out)
 
 
