@@ -234,6 +234,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// 2^x on the MUFU unit without exp2f()'s denormal-range fix-up (3 extra instructions per call): inputs here are
+// softmax exponents <= 0 (or -inf -> 0); results below 2^-126 flush to zero, which is what a softmax wants.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

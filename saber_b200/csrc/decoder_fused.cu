@@ -64,70 +64,63 @@ i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __rest
                 const bf16* __restrict__ wq /* [128,256] */, const bf16* __restrict__ wo /* [256,128] */,
                 bf16* __restrict__ w1t, bf16* __restrict__ w2t, bf16* __restrict__ kts, int nt, float scale_log2,
                 const float* __restrict__ bo /* nullable: out-projection bias folded into w2t (bo / 8 per column) */) {
-  // blockIdx.y == 0: kts + w1t (from kt); blockIdx.y == 1: w2t (from vt). The two halves are independent.
-  __shared__ float sk[I2T_TOK][I2T_QD];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const bool second = blockIdx.y == 1;
-  if (second ? (w2t == nullptr) : false) return;
-  const bf16* src = second ? vt : kt;
-  const long long src_ld = second ? vt_ld : kt_ld;
-  const float mul = second ? 1.f : scale_log2;
-  for (int i = tid; i < I2T_TOK * I2T_QD; i += 256) {
-    const int t = i >> 7, c = i & 127;
-    const float v = t < nt ? __bfloat162float(src[(static_cast<long long>(b) * nt + t) * src_ld + c]) * mul : 0.f;
-    sk[t][c] = v;
-    if (!second) kts[(static_cast<long long>(b) * I2T_TOK + t) * I2T_QD + c] = __float2bfloat16(v);
-  }
-  __syncthreads();
+  // One block per (head, prompt, operand): blockIdx.z == 0 -> kts + w1t (from kt), 1 -> w2t (from vt). Each thread owns
+  // one of the 256 channels and needs 16 weights: a single round of independent loads (the kernel is pure latency).
+  __shared__ float sk[I2T_TOK][16];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const bool second = blockIdx.z == 1;
   const int c = tid;
   if (!second) {
-    if (w1t == nullptr) return;
-    // column c of Wq for all 128 rows: 128 independent coalesced loads in flight
-    float wcol[128];
+    float w[16];
+    if (w1t != nullptr) {
 #pragma unroll
-    for (int r = 0; r < 128; ++r) wcol[r] = __bfloat162float(wq[r * I2T_C + c]);
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      float acc[I2T_TOK];
-#pragma unroll
-      for (int t = 0; t < I2T_TOK; ++t) acc[t] = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-#pragma unroll
-        for (int t = 0; t < I2T_TOK; ++t) acc[t] = fmaf(wcol[h * 16 + d], sk[t][h * 16 + d], acc[t]);
-      }
-#pragma unroll
-      for (int t = 0; t < I2T_TOK; ++t)
-        w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * I2T_C + c] = __float2bfloat16(acc[t]);
+      for (int d = 0; d < 16; ++d) w[d] = __bfloat162float(wq[(h * 16 + d) * I2T_C + c]);
     }
+    if (tid < I2T_TOK * 16) {
+      const int t = tid >> 4, d = tid & 15;
+      const float v = t < nt ? __bfloat162float(kt[(static_cast<long long>(b) * nt + t) * kt_ld + h * 16 + d]) * scale_log2 : 0.f;
+      sk[t][d] = v;
+      kts[(static_cast<long long>(b) * I2T_TOK + t) * I2T_QD + h * 16 + d] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    if (w1t == nullptr) return;
+    float acc[I2T_TOK];
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t) acc[t] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+#pragma unroll
+      for (int t = 0; t < I2T_TOK; ++t) acc[t] = fmaf(w[d], sk[t][d], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t)
+      w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * I2T_C + c] = __float2bfloat16(acc[t]);
   } else {
-    const bf16* worow = wo + c * I2T_QD;
-    bf16* dst = w2t + (static_cast<long long>(b) * I2T_C + c) * I2T_NC;
+    const uint4 wa = *reinterpret_cast<const uint4*>(wo + c * I2T_QD + h * 16);
+    const uint4 wb = *reinterpret_cast<const uint4*>(wo + c * I2T_QD + h * 16 + 8);
     // every head's softmax row sums to 1, so bo[c] / 8 added to all 64 (head, token) columns contributes exactly bo[c]
     const float bfold = bo != nullptr ? bo[c] * 0.125f : 0.f;
-    uint4 wr[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) wr[i] = *reinterpret_cast<const uint4*>(worow + i * 8);
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      float acc[I2T_TOK];
-#pragma unroll
-      for (int t = 0; t < I2T_TOK; ++t) acc[t] = bfold;
-      const uint32_t w8[8] = {wr[2 * h].x, wr[2 * h].y, wr[2 * h].z, wr[2 * h].w,
-                              wr[2 * h + 1].x, wr[2 * h + 1].y, wr[2 * h + 1].z, wr[2 * h + 1].w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float w0 = sb::bf16_lo(w8[e]), w1 = sb::bf16_hi(w8[e]);
-#pragma unroll
-        for (int t = 0; t < I2T_TOK; ++t) {
-          acc[t] = fmaf(w0, sk[t][h * 16 + 2 * e], acc[t]);
-          acc[t] = fmaf(w1, sk[t][h * 16 + 2 * e + 1], acc[t]);
-        }
-      }
-      *reinterpret_cast<uint4*>(dst + h * 8) =
-          make_uint4(sb::pack_bf16x2(acc[0], acc[1]), sb::pack_bf16x2(acc[2], acc[3]), sb::pack_bf16x2(acc[4], acc[5]),
-                     sb::pack_bf16x2(acc[6], acc[7]));
+    if (tid < I2T_TOK * 16) {
+      const int t = tid >> 4, d = tid & 15;
+      sk[t][d] = t < nt ? __bfloat162float(vt[(static_cast<long long>(b) * nt + t) * vt_ld + h * 16 + d]) : 0.f;
     }
+    __syncthreads();
+    float acc[I2T_TOK];
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t) acc[t] = bfold;
+    const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float w0 = sb::bf16_lo(w8[e]), w1 = sb::bf16_hi(w8[e]);
+#pragma unroll
+      for (int t = 0; t < I2T_TOK; ++t) {
+        acc[t] = fmaf(w0, sk[t][2 * e], acc[t]);
+        acc[t] = fmaf(w1, sk[t][2 * e + 1], acc[t]);
+      }
+    }
+    *reinterpret_cast<uint4*>(w2t + (static_cast<long long>(b) * I2T_C + c) * I2T_NC + h * 8) =
+        make_uint4(sb::pack_bf16x2(acc[0], acc[1]), sb::pack_bf16x2(acc[2], acc[3]), sb::pack_bf16x2(acc[4], acc[5]),
+                   sb::pack_bf16x2(acc[6], acc[7]));
   }
 }
 
@@ -266,10 +259,10 @@ i2t_block_kernel(const I2TParams p) {
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      s[h][0] = exp2f(s[h][0] - m0);
-      s[h][1] = exp2f(s[h][1] - m0);
-      s[h][2] = exp2f(s[h][2] - m1);
-      s[h][3] = exp2f(s[h][3] - m1);
+      s[h][0] = sb::fast_exp2(s[h][0] - m0);
+      s[h][1] = sb::fast_exp2(s[h][1] - m0);
+      s[h][2] = sb::fast_exp2(s[h][2] - m1);
+      s[h][3] = sb::fast_exp2(s[h][3] - m1);
       float l0 = s[h][0] + s[h][1], l1 = s[h][2] + s[h][3];
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -497,7 +490,7 @@ t2i_fold_attn_kernel(const T2IParams p) {
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     if (__any_sync(0xffffffffu, (mx0 > m0 + 8.f) || (mx1 > m1 + 8.f))) {
       const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
-      const float al0 = exp2f(m0 - n0), al1 = exp2f(m1 - n1);  // m = -inf on the first tile -> 0
+      const float al0 = sb::fast_exp2(m0 - n0), al1 = sb::fast_exp2(m1 - n1);  // m = -inf on the first tile -> 0
       m0 = n0;
       m1 = n1;
       l0 *= al0;
@@ -513,10 +506,10 @@ t2i_fold_attn_kernel(const T2IParams p) {
     uint32_t pa[2][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      s[n][0] = exp2f(s[n][0] - m0);
-      s[n][1] = exp2f(s[n][1] - m0);
-      s[n][2] = exp2f(s[n][2] - m1);
-      s[n][3] = exp2f(s[n][3] - m1);
+      s[n][0] = sb::fast_exp2(s[n][0] - m0);
+      s[n][1] = sb::fast_exp2(s[n][1] - m0);
+      s[n][2] = sb::fast_exp2(s[n][2] - m1);
+      s[n][3] = sb::fast_exp2(s[n][3] - m1);
       l0 += s[n][0] + s[n][1];
       l1 += s[n][2] + s[n][3];
     }
@@ -564,49 +557,57 @@ t2i_fold_attn_kernel(const T2IParams p) {
 
 // Merge the key splits and apply the value projection: a[b*nt + t, h*16+d] = bv[h*16+d] + sum_c Wv[h*16+d, c] O[(h,t), c]
 // with O = sum_s 2^(m_s - m) O_s / sum_s 2^(m_s - m) l_s. One block per (head, prompt), 256 threads.
+template <int NS>
 __global__ void __launch_bounds__(256)
-t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml, int ns, const bf16* __restrict__ wv /*[128,256]*/,
+t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml, const bf16* __restrict__ wv /*[128,256]*/,
                   const float* __restrict__ bv, bf16* __restrict__ out, long long out_ld, int nt) {
   __shared__ float so[I2T_TOK][I2T_C + 4];
-  __shared__ float sw[I2T_TOK][8];  // per (token row, split) weight 2^(m_s - m) / L
+  __shared__ float sw[I2T_TOK][NS];  // per (token row, split) weight 2^(m_s - m) / L
+  constexpr int ns = NS;
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  // all partial rows of head h (8 tokens x NS splits, thread = channel): one round of independent loads
+  float v[NS][I2T_TOK];
+  const float* ob = opart + (static_cast<long long>(b) * ns * I2T_NC + h * 8) * I2T_C + tid;
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int t = 0; t < I2T_TOK; ++t) v[s][t] = __ldg(ob + (static_cast<long long>(s) * I2T_NC + t) * I2T_C);
   if (tid < I2T_TOK) {
     const int row = h * 8 + tid;
+    float mm[NS], ll[NS];
     float m = -INFINITY;
-    for (int s = 0; s < ns; ++s) m = fmaxf(m, ml[(static_cast<long long>(b) * ns + s) * 2 * I2T_NC + row]);
-    float L = 0.f;
-    for (int s = 0; s < ns; ++s) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
       const float* q = ml + (static_cast<long long>(b) * ns + s) * 2 * I2T_NC;
-      const float wgt = exp2f(q[row] - m);
-      sw[tid][s] = wgt;
-      L += wgt * q[I2T_NC + row];
+      mm[s] = q[row];
+      ll[s] = q[I2T_NC + row];
+      m = fmaxf(m, mm[s]);
+    }
+    float L = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      mm[s] = sb::fast_exp2(mm[s] - m);
+      L = fmaf(mm[s], ll[s], L);
     }
     const float inv = 1.f / L;
-    for (int s = 0; s < ns; ++s) sw[tid][s] *= inv;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) sw[tid][s] = mm[s] * inv;
   }
-  // merged rows of head h: 8 tokens x 256 channels (thread = channel); all partial loads issued before the weights
-  // are needed
-  float part[I2T_TOK];
-#pragma unroll
-  for (int t = 0; t < I2T_TOK; ++t) part[t] = 0.f;
-  const float* ob = opart + (static_cast<long long>(b) * ns * I2T_NC + h * 8) * I2T_C + tid;
   __syncthreads();
-  for (int s = 0; s < ns; ++s) {
-    float v[I2T_TOK];
 #pragma unroll
-    for (int t = 0; t < I2T_TOK; ++t) v[t] = __ldg(ob + (static_cast<long long>(s) * I2T_NC + t) * I2T_C);
+  for (int t = 0; t < I2T_TOK; ++t) {
+    float acc = 0.f;
 #pragma unroll
-    for (int t = 0; t < I2T_TOK; ++t) part[t] = fmaf(sw[t][s], v[t], part[t]);
+    for (int s = 0; s < NS; ++s) acc = fmaf(sw[t][s], v[s][t], acc);
+    so[t][tid] = acc;
   }
-#pragma unroll
-  for (int t = 0; t < I2T_TOK; ++t) so[t][tid] = part[t];
-  __syncthreads();
   // 8 tokens x 16 dims = 128 outputs, two threads (channel halves) each
   const int half = tid & 1, d = (tid >> 1) & 15, t = tid >> 5;
   const bf16* wrow = wv + (h * 16 + d) * I2T_C + half * 128;
   uint4 w8[16];
 #pragma unroll
   for (int c8 = 0; c8 < 16; ++c8) w8[c8] = __ldg(reinterpret_cast<const uint4*>(wrow + c8 * 8));
+  __syncthreads();
   float acc = 0.f;
 #pragma unroll
   for (int c8 = 0; c8 < 16; ++c8) {
@@ -636,7 +637,7 @@ extern "C" int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long
   SB_REQUIRE(batch > 0 && nt >= 1 && nt <= I2T_TOK, "sb_i2t_fold: nt must be in 1..%d (got %d)", I2T_TOK, nt);
   SB_REQUIRE(kt && wq && kts && (w1t || w2t) && (!w2t || (vt && wo)), "sb_i2t_fold: null operand");
   SB_REQUIRE(((reinterpret_cast<uintptr_t>(wo) | reinterpret_cast<uintptr_t>(w2t)) & 15) == 0, "sb_i2t_fold: wo / w2t must be 16-byte aligned");
-  i2t_fold_kernel<<<dim3(batch, w2t ? 2 : 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  i2t_fold_kernel<<<dim3(8, batch, w2t ? 2 : 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(kt), kt_ld, static_cast<const bf16*>(vt), vt_ld, static_cast<const bf16*>(wq),
       static_cast<const bf16*>(wo), static_cast<bf16*>(w1t), static_cast<bf16*>(w2t), static_cast<bf16*>(kts), nt,
       scale * 1.4426950408889634f, bo);
@@ -733,7 +734,7 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ns = sb_t2i_fold_splits(batch, nk);
   // folded queries: the same fold as the image->token block (W1^T rows = Wk_h^T q_{t,h}, scaled; kts = scaled q)
-  i2t_fold_kernel<<<dim3(batch, 1), 256, 0, st>>>(static_cast<const bf16*>(q), q_ld, nullptr, 0, static_cast<const bf16*>(wk), nullptr,
+  i2t_fold_kernel<<<dim3(8, batch, 1), 256, 0, st>>>(static_cast<const bf16*>(q), q_ld, nullptr, 0, static_cast<const bf16*>(wk), nullptr,
                                          static_cast<bf16*>(qf), nullptr, static_cast<bf16*>(qs), nt,
                                          scale * 1.4426950408889634f, nullptr);
   SB_CHECK_LAUNCH();
@@ -754,7 +755,14 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
   p.ns = ns;
   t2i_fold_attn_kernel<<<dim3(ns, batch), 128, T2I_SMEM, st>>>(p);
   SB_CHECK_LAUNCH();
-  t2i_unfold_kernel<<<dim3(8, batch), 256, 0, st>>>(opart, ml, ns, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
+  if (ns == 8)
+    t2i_unfold_kernel<8><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
+  else if (ns == 4)
+    t2i_unfold_kernel<4><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
+  else if (ns == 2)
+    t2i_unfold_kernel<2><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
+  else
+    t2i_unfold_kernel<1><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

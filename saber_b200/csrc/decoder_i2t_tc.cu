@@ -67,6 +67,34 @@ __device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
 __device__ __forceinline__ uint32_t swz64(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
+// Blackwell packed fp32 pairs (one issue slot for two lanes of math): the LayerNorm passes are issue-bound
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
 __device__ __forceinline__ void pair_barrier(int q) {  // the two warps (column halves) that share 32 rows
   asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory");
 }
@@ -190,6 +218,13 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int nt = p.nt;
     const bf16* ktsb = p.kts + static_cast<long long>(b) * 8 * 128;
     float mean = 0.f, rstd = 0.f;
+    // token-key B fragments of this warp's 4 heads: constant for the whole CTA
+    uint2 bk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bk[j] = __ldg(reinterpret_cast<const uint2*>(ktsb + g * 128 + (hf * 4 + j) * 16 + q4 * 4));
+    // this lane's row of the positional-term matrix (128 B = heads 4*hf..4*hf+3): prefetched into L1 one stage ahead
+    const bf16* qpf = p.qres + static_cast<long long>(row_base + q * 32 + lane) * 128 + hf * 64;
+    prefetch_l1(qpf);
 
     auto s_stage = [&](int m) {
       const int buf = m & 1;
@@ -202,14 +237,13 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int head = hf * 4 + hp * 2 + hh;
-          const uint2 bk = __ldg(reinterpret_cast<const uint2*>(ktsb + g * 128 + head * 16 + q4 * 4));
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             const uint2 alo = __ldg(reinterpret_cast<const uint2*>(qrow + (mt * 16 + g) * 128 + head * 16));
             const uint2 ahi = __ldg(reinterpret_cast<const uint2*>(qrow + (mt * 16 + g + 8) * 128 + head * 16));
             const uint32_t a[4] = {alo.x, ahi.x, alo.y, ahi.y};
             float c[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_bf16_16816(c, a, bk.x, bk.y);
+            mma_bf16_16816(c, a, bk[hp * 2 + hh].x, bk[hp * 2 + hh].y);
             // rows mt*16+g / +8, columns hh*8 + 2*q4 (+1) of the 32 x 16 fp32 staging tile
             const int col = hh * 8 + 2 * q4;
             sts64(stg + swz64(mt * 16 + g, col >> 2) + (col & 3) * 4, c[0], c[1]);
@@ -248,7 +282,7 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         float l = 0.f;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          s[t] = exp2f(s[t] - mx);
+          s[t] = sb::fast_exp2(s[t] - mx);
           l += s[t];
         }
         const float inv = __fdividef(1.f, l);
@@ -269,10 +303,11 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const int buf = n & 1;
       const uint32_t to = tmem_base + tlane + static_cast<uint32_t>(buf * 256 + hf * 128);
       // ---------------- LN1(n): y = O + residual, row statistics, y parked back in TMEM ----------------
+      if (n + 1 < T) prefetch_l1(qpf + static_cast<long long>(n + 1) * 128 * 128);
       sb::mbar_wait(&o_full[buf], static_cast<uint32_t>((n >> 1) & 1));
       sb::tc_fence_after();
       sb::mbar_wait(&x_full[buf], static_cast<uint32_t>((n >> 1) & 1));  // (already complete) TMA writes -> this thread
-      float sum = 0.f, sumsq = 0.f;
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -289,19 +324,19 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const uint32_t w4[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            y[8 * j + 2 * e] = __uint_as_float(v[8 * j + 2 * e]) + sb::bf16_lo(w4[e]);
-            y[8 * j + 2 * e + 1] = __uint_as_float(v[8 * j + 2 * e + 1]) + sb::bf16_hi(w4[e]);
+            const float2 yy = add2(make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])),
+                                   make_float2(sb::bf16_lo(w4[e]), sb::bf16_hi(w4[e])));
+            y[8 * j + 2 * e] = yy.x;
+            y[8 * j + 2 * e + 1] = yy.y;
+            sum2 = add2(sum2, yy);
+            sq2 = fma2(yy, yy, sq2);
           }
-        }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          sum += y[e];
-          sumsq = fmaf(y[e], y[e], sumsq);
         }
         sb::tmem_st_32x16(to + c * 32, reinterpret_cast<const uint32_t*>(y));
         sb::tmem_st_32x16(to + c * 32 + 16, reinterpret_cast<const uint32_t*>(y) + 16);
       }
       sb::tmem_st_wait();
+      float sum = sum2.x + sum2.y, sumsq = sq2.x + sq2.y;
       __syncwarp();
       if (lane == 0) sb::mbar_arrive(&x_empty[buf]);  // residual consumed (the first MMA of this tile retired long ago)
       // statistics of the other column half (partner warp, same rows) through the staging tiles
@@ -332,16 +367,17 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const float* ga = sVec + hf * 128 + c * 32;
         const float* be = sVec + 256 + hf * 128 + c * 32;
         uint32_t o16[16];
+        const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean, -mean);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 g4 = *reinterpret_cast<const float4*>(ga + 4 * j);
           const float4 b4 = *reinterpret_cast<const float4*>(be + 4 * j);
-          const float f0 = fmaf((__uint_as_float(v[4 * j + 0]) - mean) * rstd, g4.x, b4.x);
-          const float f1 = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g4.y, b4.y);
-          const float f2 = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g4.z, b4.z);
-          const float f3 = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g4.w, b4.w);
-          o16[2 * j] = sb::pack_bf16x2(f0, f1);
-          o16[2 * j + 1] = sb::pack_bf16x2(f2, f3);
+          const float2 d0 = add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), nm2);
+          const float2 d1 = add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), nm2);
+          const float2 f01 = fma2(d0, mul2(rs2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
+          const float2 f23 = fma2(d1, mul2(rs2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
+          o16[2 * j] = sb::pack_bf16x2(f01.x, f01.y);
+          o16[2 * j + 1] = sb::pack_bf16x2(f23.x, f23.y);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
