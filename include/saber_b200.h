@@ -91,6 +91,13 @@ int sb_i2t_block(const void* x, int x_shared, const void* qp, const void* w1t, c
  * before out_proj. Caller-owned workspaces: qf [batch,64,256] bf16, qs [batch,8,128] bf16,
  * opart [batch,ns,64,256] fp32, ml [batch,ns,2,64] fp32 with ns = sb_t2i_fold_splits(batch, nk). */
 int sb_t2i_fold_splits(int batch, int nk);
+/* The same attention on tcgen05 / TMEM / TMA (csrc/decoder_t2i_tc.cu): QK^T and PV as M = 64 UMMAs, the TMA-staged key
+ * tile is the K-major B operand of QK^T and the MN-major B operand of PV. Workspaces as above except
+ * qf [batch,64,384] bf16 and ns = sb_t2i_tc_splits(batch, nk). */
+int sb_t2i_tc_splits(int batch, int nk);
+int sb_t2i_fold_attention_tc(const void* q, long long q_ld, const void* x, int x_shared, const void* kadd, const void* wk,
+                             const void* wv, const float* bv, void* qf, void* qs, float* opart, float* ml, void* out,
+                             long long out_ld, int batch, int nt, int nk, float scale, void* stream);
 int sb_t2i_fold_attention(const void* q, long long q_ld, const void* x, int x_shared, const void* kadd, const void* wk,
                           const void* wv, const float* bv, void* qf, void* qs, float* opart, float* ml, void* out,
                           long long out_ld, int batch, int nt, int nk, float scale, void* stream);

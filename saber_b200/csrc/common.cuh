@@ -234,6 +234,45 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: one issue slot for two lanes of fp32 math). The epilogues of
+// the decoder GEMMs and the fused attention blocks are issue-bound on a handful of warps per SM. --------------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+// gelu_erf on a pair: 6 packed instructions + 2 MUFU.TANH for two elements (7 + 1 per element in the scalar form)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 z = mul2(x, splat2(0.70710678118654752440f));
+  const float2 p = fma2(mul2(z, z), splat2(0.0997927f), splat2(1.12967583f));
+  const float2 a = mul2(z, p);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
+  const float2 hx = mul2(x, splat2(0.5f));
+  return fma2(hx, t, hx);
+}
+
 // 2^x on the MUFU unit without exp2f()'s denormal-range fix-up (3 extra instructions per call): inputs here are
 // softmax exponents <= 0 (or -inf -> 0); results below 2^-126 flush to zero, which is what a softmax wants.
 __device__ __forceinline__ float fast_exp2(float x) {

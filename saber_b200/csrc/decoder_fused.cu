@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(256)
 i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __restrict__ vt, long long vt_ld,
                 const bf16* __restrict__ wq /* [128,256] */, const bf16* __restrict__ wo /* [256,128] */,
                 bf16* __restrict__ w1t, bf16* __restrict__ w2t, bf16* __restrict__ kts, int nt, float scale_log2,
-                const float* __restrict__ bo /* nullable: out-projection bias folded into w2t (bo / 8 per column) */) {
+                const float* __restrict__ bo /* nullable: out-projection bias folded into w2t (bo / 8 per column) */,
+                int w1_ld /* row pitch of w1t (elements) */, int blockdiag /* w1t rows continue with the block-diagonal
+                scaled keys in columns [256, 384): row (h,t) holds kts[t, h*16..h*16+15] at 256 + h*16 */) {
   // One block per (head, prompt, operand): blockIdx.z == 0 -> kts + w1t (from kt), 1 -> w2t (from vt). Each thread owns
   // one of the 256 channels and needs 16 weights: a single round of independent loads (the kernel is pure latency).
   __shared__ float sk[I2T_TOK][16];
@@ -94,7 +96,14 @@ i2t_fold_kernel(const bf16* __restrict__ kt, long long kt_ld, const bf16* __rest
     }
 #pragma unroll
     for (int t = 0; t < I2T_TOK; ++t)
-      w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * I2T_C + c] = __float2bfloat16(acc[t]);
+      w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * w1_ld + c] = __float2bfloat16(acc[t]);
+    if (blockdiag) {
+      for (int i = tid; i < I2T_TOK * I2T_QD; i += 256) {
+        const int t = i >> 7, col = i & 127;
+        w1t[(static_cast<long long>(b) * I2T_NC + h * 8 + t) * w1_ld + I2T_C + col] =
+            __float2bfloat16((col >> 4) == h ? sk[t][col & 15] : 0.f);
+      }
+    }
   } else {
     const uint4 wa = *reinterpret_cast<const uint4*>(wo + c * I2T_QD + h * 16);
     const uint4 wb = *reinterpret_cast<const uint4*>(wo + c * I2T_QD + h * 16 + 8);
@@ -628,6 +637,40 @@ t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml,
 
 }  // namespace
 
+// ---- internal launchers shared with decoder_t2i_tc.cu ----------------------------------------------------------------
+int sb_internal_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld, const void* wq, const void* wo,
+                         const float* bo, void* w1t, int w1_ld, int blockdiag, void* w2t, void* kts, int batch, int nt,
+                         float scale, cudaStream_t stream) {
+  i2t_fold_kernel<<<dim3(8, batch, w2t ? 2 : 1), 256, 0, stream>>>(
+      static_cast<const bf16*>(kt), kt_ld, static_cast<const bf16*>(vt), vt_ld, static_cast<const bf16*>(wq),
+      static_cast<const bf16*>(wo), static_cast<bf16*>(w1t), static_cast<bf16*>(w2t), static_cast<bf16*>(kts), nt,
+      scale * 1.4426950408889634f, bo, w1_ld, blockdiag);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+int sb_internal_t2i_unfold(const float* opart, const float* ml, int ns, const void* wv, const float* bv, void* out,
+                           long long out_ld, int batch, int nt, cudaStream_t st) {
+  const bf16* w = static_cast<const bf16*>(wv);
+  bf16* o = static_cast<bf16*>(out);
+  if (ns == 16)
+    t2i_unfold_kernel<16><<<dim3(8, batch), 256, 0, st>>>(opart, ml, w, bv, o, out_ld, nt);
+  else if (ns == 8)
+    t2i_unfold_kernel<8><<<dim3(8, batch), 256, 0, st>>>(opart, ml, w, bv, o, out_ld, nt);
+  else if (ns == 4)
+    t2i_unfold_kernel<4><<<dim3(8, batch), 256, 0, st>>>(opart, ml, w, bv, o, out_ld, nt);
+  else if (ns == 2)
+    t2i_unfold_kernel<2><<<dim3(8, batch), 256, 0, st>>>(opart, ml, w, bv, o, out_ld, nt);
+  else if (ns == 1)
+    t2i_unfold_kernel<1><<<dim3(8, batch), 256, 0, st>>>(opart, ml, w, bv, o, out_ld, nt);
+  else {
+    sb_set_error("t2i unfold: unsupported split count %d", ns);
+    return SB_ERR_ARG;
+  }
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
 // Per-prompt folded operands of sb_i2t_block (see the header of this file). kt / vt [B*nt, 128] bf16 (the projected token
 // keys / values of cross_attn_image_to_token), wq [128,256] / wo [256,128] bf16 (its q_proj / out_proj weights).
 // w1t may be null (shared-query mode needs only kts and w2t). bo (nullable, [256] fp32): the out-projection bias is folded
@@ -637,12 +680,8 @@ extern "C" int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long
   SB_REQUIRE(batch > 0 && nt >= 1 && nt <= I2T_TOK, "sb_i2t_fold: nt must be in 1..%d (got %d)", I2T_TOK, nt);
   SB_REQUIRE(kt && wq && kts && (w1t || w2t) && (!w2t || (vt && wo)), "sb_i2t_fold: null operand");
   SB_REQUIRE(((reinterpret_cast<uintptr_t>(wo) | reinterpret_cast<uintptr_t>(w2t)) & 15) == 0, "sb_i2t_fold: wo / w2t must be 16-byte aligned");
-  i2t_fold_kernel<<<dim3(8, batch, w2t ? 2 : 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(kt), kt_ld, static_cast<const bf16*>(vt), vt_ld, static_cast<const bf16*>(wq),
-      static_cast<const bf16*>(wo), static_cast<bf16*>(w1t), static_cast<bf16*>(w2t), static_cast<bf16*>(kts), nt,
-      scale * 1.4426950408889634f, bo);
-  SB_CHECK_LAUNCH();
-  return SB_OK;
+  return sb_internal_i2t_fold(kt, kt_ld, vt, vt_ld, wq, wo, bo, w1t, I2T_C, 0, w2t, kts, batch, nt, scale,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 // keys_new = LayerNorm(keys + out_proj(softmax((keys Wq^T + qp) kt^T) vt)) for every prompt, one pass over the stream.
@@ -734,10 +773,10 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ns = sb_t2i_fold_splits(batch, nk);
   // folded queries: the same fold as the image->token block (W1^T rows = Wk_h^T q_{t,h}, scaled; kts = scaled q)
-  i2t_fold_kernel<<<dim3(8, batch, 1), 256, 0, st>>>(static_cast<const bf16*>(q), q_ld, nullptr, 0, static_cast<const bf16*>(wk), nullptr,
-                                         static_cast<bf16*>(qf), nullptr, static_cast<bf16*>(qs), nt,
-                                         scale * 1.4426950408889634f, nullptr);
-  SB_CHECK_LAUNCH();
+  {
+    const int rc = sb_internal_i2t_fold(q, q_ld, nullptr, 0, wk, nullptr, nullptr, qf, I2T_C, 0, nullptr, qs, batch, nt, scale, st);
+    if (rc != SB_OK) return rc;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(t2i_fold_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2I_SMEM));
@@ -755,14 +794,5 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
   p.ns = ns;
   t2i_fold_attn_kernel<<<dim3(ns, batch), 128, T2I_SMEM, st>>>(p);
   SB_CHECK_LAUNCH();
-  if (ns == 8)
-    t2i_unfold_kernel<8><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
-  else if (ns == 4)
-    t2i_unfold_kernel<4><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
-  else if (ns == 2)
-    t2i_unfold_kernel<2><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
-  else
-    t2i_unfold_kernel<1><<<dim3(8, batch), 256, 0, st>>>(opart, ml, static_cast<const bf16*>(wv), bv, static_cast<bf16*>(out), out_ld, nt);
-  SB_CHECK_LAUNCH();
-  return SB_OK;
+  return sb_internal_t2i_unfold(opart, ml, ns, wv, bv, out, out_ld, batch, nt, st);
 }

@@ -67,31 +67,6 @@ __device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
 __device__ __forceinline__ uint32_t swz64(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
-// Blackwell packed fp32 pairs (one issue slot for two lanes of math): the LayerNorm passes are issue-bound
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
 __device__ __forceinline__ void prefetch_l1(const void* ptr) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 }
@@ -324,12 +299,12 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const uint32_t w4[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 yy = add2(make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])),
+            const float2 yy = sb::add2(make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])),
                                    make_float2(sb::bf16_lo(w4[e]), sb::bf16_hi(w4[e])));
             y[8 * j + 2 * e] = yy.x;
             y[8 * j + 2 * e + 1] = yy.y;
-            sum2 = add2(sum2, yy);
-            sq2 = fma2(yy, yy, sq2);
+            sum2 = sb::add2(sum2, yy);
+            sq2 = sb::fma2(yy, yy, sq2);
           }
         }
         sb::tmem_st_32x16(to + c * 32, reinterpret_cast<const uint32_t*>(y));
@@ -372,10 +347,10 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int j = 0; j < 8; ++j) {
           const float4 g4 = *reinterpret_cast<const float4*>(ga + 4 * j);
           const float4 b4 = *reinterpret_cast<const float4*>(be + 4 * j);
-          const float2 d0 = add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), nm2);
-          const float2 d1 = add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), nm2);
-          const float2 f01 = fma2(d0, mul2(rs2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
-          const float2 f23 = fma2(d1, mul2(rs2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
+          const float2 d0 = sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), nm2);
+          const float2 d1 = sb::add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), nm2);
+          const float2 f01 = sb::fma2(d0, sb::mul2(rs2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
+          const float2 f23 = sb::fma2(d1, sb::mul2(rs2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
           o16[2 * j] = sb::pack_bf16x2(f01.x, f01.y);
           o16[2 * j + 1] = sb::pack_bf16x2(f23.x, f23.y);
         }

@@ -257,25 +257,34 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
         if (c0 + CH < p.N && (g * 2 + h + 1) < 2 * NG)  // next chunk of this tile row
           sb::tmem_ld_32x16(taddr + static_cast<uint32_t>((g * 2 + h + 1) * CH), v[(h + 1) & 1]);
         float f[CH];
+        const float2 al2 = sb::splat2(p.alpha);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b = *reinterpret_cast<const float4*>(es.vec + (c0 - n_idx) + 4 * j);  // staged bias (LDS broadcast)
-          if (!LN) {  // act(alpha * acc + bias)
-            f[4 * j + 0] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 0]), p.alpha, b.x));
-            f[4 * j + 1] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 1]), p.alpha, b.y));
-            f[4 * j + 2] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 2]), p.alpha, b.z));
-            f[4 * j + 3] = apply_act<ACT>(fmaf(__uint_as_float(v[h][4 * j + 3]), p.alpha, b.w));
+          const float2 v01 = make_float2(__uint_as_float(v[h][4 * j + 0]), __uint_as_float(v[h][4 * j + 1]));
+          const float2 v23 = make_float2(__uint_as_float(v[h][4 * j + 2]), __uint_as_float(v[h][4 * j + 3]));
+          float2 r01, r23;
+          if (!LN) {  // act(alpha * acc + bias); packed fp32 pairs (GELU: 6 packed + 2 MUFU per pair)
+            r01 = sb::fma2(v01, al2, make_float2(b.x, b.y));
+            r23 = sb::fma2(v23, al2, make_float2(b.z, b.w));
+            if (ACT == 1) {
+              r01 = sb::gelu_erf2(r01);
+              r23 = sb::gelu_erf2(r23);
+            } else if (ACT != 0) {
+              r01 = make_float2(apply_act<ACT>(r01.x), apply_act<ACT>(r01.y));
+              r23 = make_float2(apply_act<ACT>(r23.x), apply_act<ACT>(r23.y));
+            }
           } else if (pass == 0) {
-            f[4 * j + 0] = __uint_as_float(v[h][4 * j + 0]) + b.x;
-            f[4 * j + 1] = __uint_as_float(v[h][4 * j + 1]) + b.y;
-            f[4 * j + 2] = __uint_as_float(v[h][4 * j + 2]) + b.z;
-            f[4 * j + 3] = __uint_as_float(v[h][4 * j + 3]) + b.w;
+            r01 = sb::add2(v01, make_float2(b.x, b.y));
+            r23 = sb::add2(v23, make_float2(b.z, b.w));
           } else {
-            f[4 * j + 0] = __uint_as_float(v[h][4 * j + 0]);
-            f[4 * j + 1] = __uint_as_float(v[h][4 * j + 1]);
-            f[4 * j + 2] = __uint_as_float(v[h][4 * j + 2]);
-            f[4 * j + 3] = __uint_as_float(v[h][4 * j + 3]);
+            r01 = v01;
+            r23 = v23;
           }
+          f[4 * j + 0] = r01.x;
+          f[4 * j + 1] = r01.y;
+          f[4 * j + 2] = r23.x;
+          f[4 * j + 3] = r23.y;
         }
         if (use_res) {
           if (p.res_f32)
@@ -285,11 +294,15 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
         }
         if (LN) {
           if (pass == 0) {
+            float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              sum += f[j];
-              sumsq += f[j] * f[j];
+            for (int j = 0; j < CH / 2; ++j) {
+              const float2 ff = make_float2(f[2 * j], f[2 * j + 1]);
+              s2 = sb::add2(s2, ff);
+              q2 = sb::fma2(ff, ff, q2);
             }
+            sum += s2.x + s2.y;
+            sumsq += q2.x + q2.y;
             sb::tmem_st_32x16(taddr + static_cast<uint32_t>((g * 2 + h) * CH), reinterpret_cast<const uint32_t*>(f));
             continue;
           }
@@ -297,10 +310,15 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
           for (int j = 0; j < 4; ++j) {
             const float4 ga = *reinterpret_cast<const float4*>(es.vec + 256 + c0 + 4 * j);
             const float4 be = *reinterpret_cast<const float4*>(es.vec + 512 + c0 + 4 * j);
-            f[4 * j + 0] = (f[4 * j + 0] - mean) * rstd * ga.x + be.x;
-            f[4 * j + 1] = (f[4 * j + 1] - mean) * rstd * ga.y + be.y;
-            f[4 * j + 2] = (f[4 * j + 2] - mean) * rstd * ga.z + be.z;
-            f[4 * j + 3] = (f[4 * j + 3] - mean) * rstd * ga.w + be.w;
+            const float2 nm2 = sb::splat2(-mean), rs2 = sb::splat2(rstd);
+            const float2 o01 = sb::fma2(sb::add2(make_float2(f[4 * j + 0], f[4 * j + 1]), nm2),
+                                        sb::mul2(rs2, make_float2(ga.x, ga.y)), make_float2(be.x, be.y));
+            const float2 o23 = sb::fma2(sb::add2(make_float2(f[4 * j + 2], f[4 * j + 3]), nm2),
+                                        sb::mul2(rs2, make_float2(ga.z, ga.w)), make_float2(be.z, be.w));
+            f[4 * j + 0] = o01.x;
+            f[4 * j + 1] = o01.y;
+            f[4 * j + 2] = o23.x;
+            f[4 * j + 3] = o23.y;
           }
         }
         stage_out(es.out_stg, lane, h, p.out_f32, f);
@@ -379,7 +397,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
     const int skip_off16 = row_ok ? static_cast<int>((b * p.skip_bstride + pix * 64) / 4) : -1;
     const int out_off16 = row_ok ? static_cast<int>(((b * (2 * p.gh) + oy) * (2 * p.gw) + ox) * 8) : -1;
     float f[64];
-    float sum = 0.f;
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       gather_async<128>(es.res_stg[0], skip, skip_off16 < 0 ? -1 : skip_off16 + h * 8, 128, lane);
@@ -394,30 +412,42 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
         const uint4 sk = lds128(es.res_stg[0] + swz<128>(lane, j));
         const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 64 + h * 32 + 4 * j);
         const int e = h * 32 + 4 * j;
-        f[e + 0] = __uint_as_float(v[4 * j + 0]) + bb.x + __uint_as_float(sk.x);
-        f[e + 1] = __uint_as_float(v[4 * j + 1]) + bb.y + __uint_as_float(sk.y);
-        f[e + 2] = __uint_as_float(v[4 * j + 2]) + bb.z + __uint_as_float(sk.z);
-        f[e + 3] = __uint_as_float(v[4 * j + 3]) + bb.w + __uint_as_float(sk.w);
-        sum += f[e + 0] + f[e + 1] + f[e + 2] + f[e + 3];
+        const float2 f01 = sb::add2(
+            sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), make_float2(bb.x, bb.y)),
+            make_float2(__uint_as_float(sk.x), __uint_as_float(sk.y)));
+        const float2 f23 = sb::add2(
+            sb::add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(bb.z, bb.w)),
+            make_float2(__uint_as_float(sk.z), __uint_as_float(sk.w)));
+        f[e + 0] = f01.x;
+        f[e + 1] = f01.y;
+        f[e + 2] = f23.x;
+        f[e + 3] = f23.y;
+        sum2 = sb::add2(sum2, sb::add2(f01, f23));
       }
       __syncwarp();
     }
-    const float mean = sum * (1.f / 64.f);
-    float vs = 0.f;
+    const float mean = (sum2.x + sum2.y) * (1.f / 64.f);
+    const float2 nmean = sb::splat2(-mean);
+    float2 vs2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      const float dd = f[j] - mean;
-      vs += dd * dd;
+    for (int j = 0; j < 32; ++j) {
+      const float2 dd = sb::add2(make_float2(f[2 * j], f[2 * j + 1]), nmean);
+      vs2 = sb::fma2(dd, dd, vs2);
     }
-    const float rstd = rsqrtf(vs * (1.f / 64.f) + p.eps);
+    const float rstd = rsqrtf((vs2.x + vs2.y) * (1.f / 64.f) + p.eps);
+    const float2 rs2 = sb::splat2(rstd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float g[8];
+      float2 g[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        g[e] = sb::gelu_erf((f[8 * j + e] - mean) * rstd * es.vec[256 + 8 * j + e] + es.vec[512 + 8 * j + e]);
-      sts128(es.out_stg + swz<128>(lane, j), make_uint4(sb::pack_bf16x2(g[0], g[1]), sb::pack_bf16x2(g[2], g[3]),
-                                                         sb::pack_bf16x2(g[4], g[5]), sb::pack_bf16x2(g[6], g[7])));
+      for (int e = 0; e < 4; ++e) {
+        const float2 ga = *reinterpret_cast<const float2*>(es.vec + 256 + 8 * j + 2 * e);
+        const float2 be = *reinterpret_cast<const float2*>(es.vec + 512 + 8 * j + 2 * e);
+        const float2 dd = sb::add2(make_float2(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]), nmean);
+        g[e] = sb::gelu_erf2(sb::fma2(dd, sb::mul2(rs2, ga), be));
+      }
+      sts128(es.out_stg + swz<128>(lane, j), make_uint4(sb::pack_bf16x2(g[0].x, g[0].y), sb::pack_bf16x2(g[1].x, g[1].y),
+                                                         sb::pack_bf16x2(g[2].x, g[2].y), sb::pack_bf16x2(g[3].x, g[3].y)));
     }
     __syncwarp();
     scatter_store<128>(es.out_stg, reinterpret_cast<uint8_t*>(p.out), out_off16, 128, lane);
@@ -457,20 +487,25 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
     __syncwarp();
     if (d + 1 < 4) gather_async<128>(es.res_stg[(d + 1) & 1], skip, skip_off(d + 1), 128, lane);
     sb::tmem_ld_wait();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // packed fp32 pairs throughout: the epilogue is issue-bound (128 GELUs + 512 MACs per row on 8 warps per SM)
+    float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 32 + 4 * j);
-      const float g0 = sb::gelu_erf(__uint_as_float(v[4 * j + 0]) + bb.x + __uint_as_float(sk[j].x));
-      const float g1 = sb::gelu_erf(__uint_as_float(v[4 * j + 1]) + bb.y + __uint_as_float(sk[j].y));
-      const float g2 = sb::gelu_erf(__uint_as_float(v[4 * j + 2]) + bb.z + __uint_as_float(sk[j].z));
-      const float g3 = sb::gelu_erf(__uint_as_float(v[4 * j + 3]) + bb.w + __uint_as_float(sk[j].w));
+      const float2 g01 = sb::gelu_erf2(sb::add2(
+          sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), make_float2(bb.x, bb.y)),
+          make_float2(__uint_as_float(sk[j].x), __uint_as_float(sk[j].y))));
+      const float2 g23 = sb::gelu_erf2(sb::add2(
+          sb::add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(bb.z, bb.w)),
+          make_float2(__uint_as_float(sk[j].z), __uint_as_float(sk[j].w))));
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const float4 h = hy[m * 8 + j];  // warp-uniform shared-memory address: broadcast
-        acc[m] += g0 * h.x + g1 * h.y + g2 * h.z + g3 * h.w;
+        acc2[m] = sb::fma2(g01, make_float2(h.x, h.y), acc2[m]);
+        acc2[m] = sb::fma2(g23, make_float2(h.z, h.w), acc2[m]);
       }
     }
+    const float acc[4] = {acc2[0].x + acc2[0].y, acc2[1].x + acc2[1].y, acc2[2].x + acc2[2].y, acc2[3].x + acc2[3].y};
     if (row_ok) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) masks[((b * 4 + m) * H2 + oy) * W2 + ox] = acc[m];

@@ -354,7 +354,7 @@ def i2t_block_tc(x: torch.Tensor, qres: torch.Tensor, w1t: torch.Tensor, w2t: to
 
 def t2i_fold_attention(q: torch.Tensor, x: torch.Tensor, kadd: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor,
                        bv: torch.Tensor, batch: int, nt: int, nk: int, x_shared: bool = False,
-                       scale: float = 0.25) -> torch.Tensor:
+                       scale: float = 0.25, tc: bool = False) -> torch.Tensor:
     """Mask-decoder token -> image attention on the raw image stream (k / v projections folded onto the <= 8 tokens of a
     prompt; csrc/decoder_fused.cu). q [batch*nt,128] bf16, x [batch*nk (nk when shared),256] bf16, kadd [nk,128] bf16,
     wk / wv [128,256] bf16 (row views of a stacked weight allowed), bv [128] fp32 -> [batch*nt,128] bf16."""
@@ -366,14 +366,15 @@ def t2i_fold_attention(q: torch.Tensor, x: torch.Tensor, kadd: torch.Tensor, wk:
         assert w_.dtype == _BF16 and w_.shape == (128, 256) and w_.is_contiguous()
     assert bv.dtype == _F32 and bv.is_contiguous() and bv.numel() == 128
     L = _lib.load()
-    ns = L.sb_t2i_fold_splits(batch, nk)
+    ns = (L.sb_t2i_tc_splits if tc else L.sb_t2i_fold_splits)(batch, nk)
     dev = q.device
-    qf = torch.empty((batch, 64, 256), dtype=_BF16, device=dev)
+    qf = torch.empty((batch, 64, 384 if tc else 256), dtype=_BF16, device=dev)
     qs = torch.empty((batch, 8, 128), dtype=_BF16, device=dev)
     opart = torch.empty((batch, ns, 64, 256), dtype=_F32, device=dev)
     ml = torch.empty((batch, ns, 2, 64), dtype=_F32, device=dev)
     out = torch.empty((batch * nt, 128), dtype=_BF16, device=dev)
-    _lib.check(L.sb_t2i_fold_attention(q.data_ptr(), q.stride(0), x.data_ptr(), int(x_shared), kadd.data_ptr(),
+    fn = L.sb_t2i_fold_attention_tc if tc else L.sb_t2i_fold_attention  # tc: both GEMMs on tcgen05 (decoder_t2i_tc.cu)
+    _lib.check(fn(q.data_ptr(), q.stride(0), x.data_ptr(), int(x_shared), kadd.data_ptr(),
                                        wk.data_ptr(), wv.data_ptr(), bv.data_ptr(), qf.data_ptr(), qs.data_ptr(),
                                        opart.data_ptr(), ml.data_ptr(), out.data_ptr(), out.stride(0), batch, nt, nk, scale,
                                        _stream()), "sb_t2i_fold_attention")

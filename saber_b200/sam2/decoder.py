@@ -41,6 +41,7 @@ class MaskDecoder:
         md, pe = "sam_mask_decoder.", "sam_prompt_encoder."
         self.dynamic_multimask_via_stability = dynamic_multimask_via_stability
         self.stab_delta, self.stab_thresh = 0.05, 0.98
+        self.t2i_tensor_core = os.environ.get("SB_T2I_TC", "1") != "0"  # tcgen05 token->image attention (0: mma.sync)
         self.i2t_tensor_core = os.environ.get("SB_I2T_TC", "1") != "0"  # tcgen05 image->token block (0: mma.sync kernel)
 
         def w16(t):
@@ -186,7 +187,7 @@ class MaskDecoder:
             q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["t2i_q_w"], L["t2i_q_b"])
             if Nt <= 8:  # k / v projections folded onto the tokens: the image stream is read once, K|V never exist
                 a = ops.t2i_fold_attention(q, keys, L["t2i_k_add"], L["t2i_kv_w"][0:128], L["t2i_kv_w"][128:256],
-                                           L["t2i_v_b"], B, Nt, NT_IMG, x_shared=(kb == 1))
+                                           L["t2i_v_b"], B, Nt, NT_IMG, x_shared=(kb == 1), tc=self.t2i_tensor_core)
             else:
                 kv = ops.gemm(keys, L["t2i_kv_w"], L["t2i_kv_b"])
                 a = ops.attention_kadd(q, kv[:, 0:128], L["t2i_k_add"], kv[:, 128:256], B, 8, Nt, NT_IMG,
@@ -237,7 +238,7 @@ class MaskDecoder:
         q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), self.fa_q_w, self.fa_q_b)
         if Nt <= 8:
             a = ops.t2i_fold_attention(q, keys, self.fa_k_add, self.fa_kv_w[0:128], self.fa_kv_w[128:256], self.fa_v_b, B,
-                                       Nt, NT_IMG, x_shared=(kb == 1))
+                                       Nt, NT_IMG, x_shared=(kb == 1), tc=self.t2i_tensor_core)
         else:
             kv = ops.gemm(keys, self.fa_kv_w, self.fa_kv_b)
             a = ops.attention_kadd(q, kv[:, 0:128], self.fa_k_add, kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))

@@ -122,8 +122,9 @@ def test_attention_few_keys_with_query_term(ops):
     assert (out1.float() - ref1).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("B,nt,shared", [(3, 8, False), (2, 7, True), (100, 8, False), (1, 1, False)])
-def test_t2i_fold_attention(ops, B, nt, shared):
+def test_t2i_fold_attention(ops, B, nt, shared, tc):
     """Token -> image attention with the k / v projections folded onto the tokens (image stream read once) vs the
     unfused fp32 expression softmax(q ((x Wk^T) + kadd)^T / 4) (x Wv^T + bv)."""
     torch.manual_seed(12)
@@ -134,7 +135,7 @@ def test_t2i_fold_attention(ops, B, nt, shared):
     bv = torch.randn(128, device="cuda") * 0.2
     kadd = torch.randn(nk, 128, device="cuda").to(BF16)
     q = (torch.randn(B * nt, 128, device="cuda") * 1.5).to(BF16)
-    out = ops.t2i_fold_attention(q, x, kadd, wk, wv, bv, B, nt, nk, x_shared=shared)
+    out = ops.t2i_fold_attention(q, x, kadd, wk, wv, bv, B, nt, nk, x_shared=shared, tc=tc)
     xf = x.float().view(-1, nk, 256).expand(B, nk, 256)
     k = (xf @ wk.float().t() + kadd.float()[None]).view(B, nk, 8, 16).transpose(1, 2)
     v = (xf @ wv.float().t() + bv).view(B, nk, 8, 16).transpose(1, 2)
