@@ -142,8 +142,8 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-converged, one elected lane per tcgen05 instruction) =====================
+    {
       constexpr uint32_t idesc1 = sb::umma_idesc_bf16(128, 64);
       constexpr uint32_t idesc2 = sb::umma_idesc_bf16(128, 256);
       const uint32_t sbase = sb::smem_u32(smem);
@@ -159,10 +159,12 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const uint64_t db = sb::umma_desc_k_sw128(sbase + TC_OFF_W1 + kb * 8192);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc1,
-                          static_cast<uint32_t>((kb | k) != 0));
+            if (sb::elect_one())
+              sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc1,
+                            static_cast<uint32_t>((kb | k) != 0));
         }
-        sb::umma_commit(&s_full[buf]);
+        if (sb::elect_one()) sb::umma_commit(&s_full[buf]);
+        __syncwarp();
       };
       sb::mbar_wait(w_full, 0);
       issue_mma1(0);
@@ -174,9 +176,11 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const uint32_t d = tmem_base + static_cast<uint32_t>((n & 1) * 256);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          sb::umma_bf16(d, dp + static_cast<uint64_t>(2 * k), dw2 + static_cast<uint64_t>(2 * k), idesc2,
-                        static_cast<uint32_t>(k != 0));
-        sb::umma_commit(&o_full[n & 1]);
+          if (sb::elect_one())
+            sb::umma_bf16(d, dp + static_cast<uint64_t>(2 * k), dw2 + static_cast<uint64_t>(2 * k), idesc2,
+                          static_cast<uint32_t>(k != 0));
+        if (sb::elect_one()) sb::umma_commit(&o_full[n & 1]);
+        __syncwarp();
         if (n + 1 < T) issue_mma1(n + 1);
       }
     }

@@ -11,8 +11,8 @@
 //   * QK^T: A = Q'' (K-major, resident), B = the TMA-staged key tile [64 keys x (256 + 128)] (K-major), D = S in TMEM
 //   * PV  : A = P (bf16, written by the softmax warps as a K-major 128B-swizzled tile), B = the SAME key tile read as
 //           an MN-major operand (N = 256 channels contiguous, K = keys), D = O in TMEM (fp32, 64 x 256)
-// With M = 64 the accumulator rows live in lanes 0-15 of each TMEM lane quadrant, so each of the 4 softmax warps owns
-// 16 rows, one thread per row: the online softmax needs no cross-thread reduction. Rescaling of O is lazy (only when
+// With M = 64 the accumulator rows live in lanes 0-15 of each TMEM lane quadrant: two softmax warps per quadrant, thread =
+// (row, key half), exchange only the row maximum through shared memory. Rescaling of O is lazy (only when
 // a row maximum grows by more than 2^8). CTA = (key split, prompt); unnormalised partials per split are merged and
 // projected by t2i_unfold_kernel.
 #include "common.cuh"
@@ -23,14 +23,15 @@ using bf16 = __nv_bfloat16;
 
 constexpr int TT_KT = 64;                               // keys per tile
 constexpr int TT_STAGES = 3;
-constexpr int TT_THREADS = 256;                         // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 softmax
+constexpr int TT_THREADS = 384;                         // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 softmax
 constexpr int TT_KBLK = TT_KT * 128;                    // one K-block of a key tile: [64 keys x 128 B] = 8 KB
 constexpr int TT_OFF_Q = 0;                             // 6 K-blocks x [64 rows x 128 B]
 constexpr int TT_STAGE_BYTES = 6 * TT_KBLK;             // x: 4 K-blocks, kadd: 2 K-blocks
 constexpr int TT_OFF_ST = 6 * 8192;
 constexpr int TT_OFF_P = TT_OFF_ST + TT_STAGES * TT_STAGE_BYTES;   // 2 x [64 rows x 128 B]
 constexpr int TT_OFF_BAR = TT_OFF_P + 2 * 8192;
-constexpr int TT_SMEM = TT_OFF_BAR + 256;
+constexpr int TT_OFF_XCH = TT_OFF_BAR + 256;            // row-max / row-sum exchange between the two column halves
+constexpr int TT_SMEM = TT_OFF_XCH + 2048;
 
 struct T2ITCParams {
   float* opart;   // [B, ns, 64, 256] unnormalised partial outputs
@@ -49,6 +50,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+__device__ __forceinline__ void pair_barrier(int q) {  // the two warps (key halves) that share a TMEM lane quadrant
+  asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -87,7 +91,7 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       sb::mbar_init(&s_full[i], 1);
-      sb::mbar_init(&p_full[i], 4);
+      sb::mbar_init(&p_full[i], 8);
       sb::mbar_init(&pv_done[i], 1);
     }
     sb::fence_barrier_init();
@@ -120,7 +124,10 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this role converged and one elected lane issues each tcgen05 instruction: inside a divergent
+    // `if (lane == 0)` the compiler wraps every UMMA in an ELECT / BRA.U.ANY loop (~13 instructions and several R2UR
+    // round trips per UMMA), which made the M = 64 UMMAs of this kernel issue-bound (the MMA thread never waited).
+    {
       constexpr uint32_t idesc_qk = sb::umma_idesc_bf16(64, 64);
       constexpr uint32_t idesc_pv = sb::umma_idesc_bf16(64, 256) | (1u << 16);  // B operand MN-major
       const uint32_t sbase = sb::smem_u32(smem);
@@ -135,10 +142,12 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const uint64_t db = sb::umma_desc_k_sw128(sbase + TT_OFF_ST + s * TT_STAGE_BYTES + kb * TT_KBLK);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc_qk,
-                          static_cast<uint32_t>((kb | k) != 0));
+            if (sb::elect_one())
+              sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc_qk,
+                            static_cast<uint32_t>((kb | k) != 0));
         }
-        sb::umma_commit(&s_full[t & 1]);
+        if (sb::elect_one()) sb::umma_commit(&s_full[t & 1]);
+        __syncwarp();
       };
       sb::mbar_wait(q_full, 0);
       issue_qk(0);
@@ -153,37 +162,51 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int k = 0; k < 4; ++k) {
           // 16 keys per step: two 8-key swizzle atoms (1024 B each) of every 64-channel K-block of the x tile
           const uint64_t db = umma_desc_mn_sw128(sbase + TT_OFF_ST + s * TT_STAGE_BYTES + k * 2048, TT_KBLK, 1024);
-          sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db, idesc_pv, static_cast<uint32_t>((t | k) != 0));
+          if (sb::elect_one())
+            sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db, idesc_pv, static_cast<uint32_t>((t | k) != 0));
         }
-        sb::umma_commit(&pv_done[t & 1]);
-        sb::umma_commit(&st_empty[s]);
+        if (sb::elect_one()) {
+          sb::umma_commit(&pv_done[t & 1]);
+          sb::umma_commit(&st_empty[s]);
+        }
+        __syncwarp();
         if (t + 2 < T) issue_qk(t + 2);
       }
     }
   } else if (warp >= 4) {
-    // ===================== online softmax: warp q owns rows 16q..16q+15 (its TMEM lanes 0..15) =====================
+    // ===================== online softmax =====================
+    // With M = 64 the rows 16q..16q+15 live in lanes 0..15 of TMEM lane quadrant q. Two warps share a quadrant and
+    // split the 64 keys of a tile (and the 256 columns of O): thread = (row, key half). The row maximum is exchanged
+    // through shared memory, so both halves keep identical running maxima.
     const int q = warp & 3;
+    const int hf = (warp - 4) >> 2;
     const bool active = lane < 16;
     const int r = q * 16 + (lane & 15);
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sbase = sb::smem_u32(smem);
+    float* xch = reinterpret_cast<float*>(smem + TT_OFF_XCH);  // [2 parities][2 halves][64 rows] maxima, then [2][64] sums
     float m = -INFINITY, l = 0.f;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       sb::mbar_wait(&s_full[t & 1], static_cast<uint32_t>((t >> 1) & 1));
       sb::tc_fence_after();
-      uint32_t v[64];
-      const uint32_t ta = tmem_base + tlane + static_cast<uint32_t>((t & 1) * 64);
+      uint32_t v[32];
+      const uint32_t ta = tmem_base + tlane + static_cast<uint32_t>((t & 1) * 64 + hf * 32);
       sb::tmem_ld_32x16(ta, v);
       sb::tmem_ld_32x16(ta + 16, v + 16);
-      sb::tmem_ld_32x16(ta + 32, v + 32);
-      sb::tmem_ld_32x16(ta + 48, v + 48);
       sb::tmem_ld_wait();
-      float mx = __uint_as_float(v[0]);
+      float mx4[4];
 #pragma unroll
-      for (int j = 1; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int j = 0; j < 4; ++j) mx4[j] = __uint_as_float(v[j]);
+#pragma unroll
+      for (int j = 4; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (active) xch[((t & 1) * 2 + hf) * 64 + r] = mx;
+      pair_barrier(q);
+      mx = fmaxf(mx, xch[((t & 1) * 2 + (hf ^ 1)) * 64 + r]);
       if (__any_sync(0xffffffffu, active && (mx > m + 8.f))) {
-        // lazy rescale of O (rare): every previous PV has to be complete before O is touched
+        // lazy rescale of O (rare): every previous PV has to be complete before O is touched; each half rescales its
+        // 128 columns
         const float mn = fmaxf(m, mx);
         const float alpha = sb::fast_exp2(m - mn);  // m = -inf on the first tile -> 0 (O holds nothing yet)
         m = mn;
@@ -191,9 +214,9 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (t > 0) {
           sb::mbar_wait(&pv_done[(t - 1) & 1], static_cast<uint32_t>(((t - 1) >> 1) & 1));
           sb::tc_fence_after();
-          const uint32_t to = tmem_base + tlane + 128u;
+          const uint32_t to = tmem_base + tlane + 128u + static_cast<uint32_t>(hf * 128);
 #pragma unroll 1
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < 8; ++c) {
             uint32_t o[16];
             sb::tmem_ld_32x16(to + c * 16, o);
             sb::tmem_ld_wait();
@@ -207,31 +230,39 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // P(t) overwrites the buffer the PV of tile t-2 read
       if (t >= 2) sb::mbar_wait(&pv_done[t & 1], static_cast<uint32_t>(((t >> 1) - 1) & 1));
       const uint32_t prow = sbase + TT_OFF_P + (t & 1) * 8192 + r * 128;
+      const float2 nm2 = sb::splat2(-m);
+      float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float e[8];
+      for (int c = 0; c < 4; ++c) {
+        float2 e[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          e[j] = sb::fast_exp2(__uint_as_float(v[c * 8 + j]) - m);
-          l += e[j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 d = sb::add2(make_float2(__uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1])), nm2);
+          e[j] = make_float2(sb::fast_exp2(d.x), sb::fast_exp2(d.y));
+          l2[j & 1] = sb::add2(l2[j & 1], e[j]);
         }
         if (active)
-          sts128(prow + ((c ^ (r & 7)) << 4), make_uint4(sb::pack_bf16x2(e[0], e[1]), sb::pack_bf16x2(e[2], e[3]),
-                                                         sb::pack_bf16x2(e[4], e[5]), sb::pack_bf16x2(e[6], e[7])));
+          sts128(prow + (((hf * 4 + c) ^ (r & 7)) << 4),
+                 make_uint4(sb::pack_bf16x2(e[0].x, e[0].y), sb::pack_bf16x2(e[1].x, e[1].y),
+                            sb::pack_bf16x2(e[2].x, e[2].y), sb::pack_bf16x2(e[3].x, e[3].y)));
       }
+      l += (l2[0].x + l2[0].y) + (l2[1].x + l2[1].y);
       sb::tc_fence_before();
       sb::fence_proxy_async();
       __syncwarp();
       if (lane == 0) sb::mbar_arrive(&p_full[t & 1]);
     }
-    // ---- partial result of this split: unnormalised O, running max and row sum
+    // ---- partial result of this split: unnormalised O (this half's 128 columns), running max and row sum
+    if (active) xch[256 + hf * 64 + r] = l;
+    pair_barrier(q);
+    l += xch[256 + (hf ^ 1) * 64 + r];
     sb::mbar_wait(&pv_done[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
     sb::tc_fence_after();
     const long long pb = static_cast<long long>(b) * p.ns + split;
-    float* orow = p.opart + (pb * 64 + r) * 256;
-    const uint32_t to = tmem_base + tlane + 128u;
+    float* orow = p.opart + (pb * 64 + r) * 256 + hf * 128;
+    const uint32_t to = tmem_base + tlane + 128u + static_cast<uint32_t>(hf * 128);
 #pragma unroll 1
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < 8; ++c) {
       uint32_t o[16];
       sb::tmem_ld_32x16(to + c * 16, o);
       sb::tmem_ld_wait();
@@ -241,7 +272,7 @@ t2i_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           *reinterpret_cast<uint4*>(orow + c * 16 + 4 * j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       }
     }
-    if (active) {
+    if (active && hf == 0) {
       float* ml = p.ml + pb * 128;
       ml[r] = m;
       ml[64 + r] = l;

@@ -587,7 +587,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // warp-converged; one elected lane issues each tcgen05 instruction (inside a divergent `if (lane == 0)` every UMMA is
+    // wrapped in an ELECT / BRA.U.ANY loop: ~13 instructions per UMMA, which bounds the BN = 64 / 128 tiles)
+    {
       constexpr uint32_t idesc = sb::umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -605,16 +607,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const int ksteps = (kb == num_kb - 1) ? last_ksteps : (BK / 16);
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in 16-B units
-            sb::umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                          static_cast<uint32_t>((kb | k) != 0));
+            if (sb::elect_one())
+              sb::umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                            static_cast<uint32_t>((kb | k) != 0));
           }
-          sb::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (sb::elect_one()) sb::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        sb::umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+        if (sb::elect_one()) sb::umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -16,7 +16,7 @@ gncu) timeout 600 ncu --set full --clock-control none --import-source on -k rege
 dprobe) timeout 600 python tools/decoder_probe.py > gpurun_out/${TAG}_decoder_probe.log 2>&1; cat gpurun_out/${TAG}_decoder_probe.log; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_dec_launches.csv python tools/decoder_probe.py --once > gpurun_out/${TAG}_dprobe_ncu.log 2>&1; echo "dprobe ncu rc=$?";;
 eprobe) timeout 600 python tools/encoder_probe.py > gpurun_out/${TAG}_encoder_probe.log 2>&1; cat gpurun_out/${TAG}_encoder_probe.log; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_enc_launches.csv python tools/encoder_probe.py --once > gpurun_out/${TAG}_eprobe_ncu.log 2>&1; echo "eprobe ncu rc=$?";;
 pprobe) timeout 900 python tools/propagation_probe.py 32 1 8 > gpurun_out/${TAG}_propagation_probe.log 2>&1; cat gpurun_out/${TAG}_propagation_probe.log;;
-dfull) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"i2t_tc|t2i_fold_attn" -s 6 -c 4 -o gpurun_out/${TAG}_dec_fused python tools/decoder_probe.py --once > gpurun_out/${TAG}_dfull.log 2>&1; echo "dfull rc=$?";;
+dfull) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"i2t_tc|t2i_tc" -s 5 -c 3 -o gpurun_out/${TAG}_dec_fused python tools/decoder_probe.py --once > gpurun_out/${TAG}_dfull.log 2>&1; echo "dfull rc=$?";;
 efull) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"flash_attn" -s 14 -c 2 -o gpurun_out/${TAG}_enc_attn python tools/encoder_probe.py --once > gpurun_out/${TAG}_efull.log 2>&1; echo "efull rc=$?";;
 diag) timeout 900 python tools/kernel_diag.py > gpurun_out/${TAG}_kernel_diag.log 2>&1; tail -40 gpurun_out/${TAG}_kernel_diag.log;;
 esac
