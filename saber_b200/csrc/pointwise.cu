@@ -48,6 +48,64 @@ layernorm_kernel(const void* __restrict__ in, long long ld_in, void* __restrict_
   }
 }
 
+// Fast path for fp32 rows of up to 1536 channels (every Hiera LayerNorm): one 16-byte load per lane and 128 channels,
+// the row stays in registers for the two-pass statistics and the normalisation (the generic kernel walks the row three
+// times with 4-byte accesses: 2.6 TB/s on the [32768, 576] streams of stage 3), 8- / 16-byte stores.
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256)
+layernorm_rows_f32_kernel(const float* __restrict__ in, long long ld_in, void* __restrict__ out, long long ld_out,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, int M, int C, float eps,
+                          int act) {
+  constexpr int MAXV = 12;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 2;  // float4 per row
+  const float inv_c = 1.f / static_cast<float>(C);
+  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < M;
+       row += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const float4* src = reinterpret_cast<const float4*>(in + row * ld_in);
+    float4 v[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c4 = lane + 32 * i;
+      v[i] = c4 < nv ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = sb::warp_sum(sum) * inv_c;
+    float vs = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + 32 * i < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        vs += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(sb::warp_sum(vs) * inv_c + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+        float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+        if (act == 1) {
+          y0 = sb::gelu_erf(y0);
+          y1 = sb::gelu_erf(y1);
+          y2 = sb::gelu_erf(y2);
+          y3 = sb::gelu_erf(y3);
+        }
+        if (OUT_F32)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * ld_out + 4 * c4) = make_float4(y0, y1, y2, y3);
+        else
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * ld_out + 4 * c4) =
+              make_uint2(sb::pack_bf16x2(y0, y1), sb::pack_bf16x2(y2, y3));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // im2col for Conv2d(k=7, stride=4, pad=3): img [B, Cin, S, S] fp32 -> cols [B*(S/4)^2, Kp] bf16,
 // column index = c*49 + ky*7 + kx, zero beyond Cin*49 (Kp is the padded pitch).
@@ -193,6 +251,19 @@ extern "C" int sb_layernorm(const void* in, long long ld_in, int in_f32, void* o
   long long blocks = (static_cast<long long>(M) + warps - 1) / warps;
   if (blocks > 148 * 8) blocks = 148 * 8;
   const int g = static_cast<int>(blocks);
+  const bool fast = in_f32 && (C % 4) == 0 && C <= 1536 && (ld_in % 4) == 0 && (ld_out % 4) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (fast) {
+    if (out_f32)
+      layernorm_rows_f32_kernel<true><<<g, 256, 0, stream>>>(static_cast<const float*>(in), ld_in, out, ld_out, gamma,
+                                                            beta, M, C, eps, act);
+    else
+      layernorm_rows_f32_kernel<false><<<g, 256, 0, stream>>>(static_cast<const float*>(in), ld_in, out, ld_out, gamma,
+                                                             beta, M, C, eps, act);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+  }
   if (in_f32 && out_f32)
     layernorm_kernel<true, true><<<g, 256, 0, stream>>>(in, ld_in, out, ld_out, gamma, beta, M, C, eps, act);
   else if (in_f32)

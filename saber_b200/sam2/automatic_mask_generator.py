@@ -16,6 +16,7 @@ fetches the survivor count.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from itertools import product
 from typing import Any, Dict, List, Optional, Tuple
@@ -136,7 +137,8 @@ class SAM2AutomaticMaskGenerator:
         # test hook: when a list, every post-processing call appends (crop, base, n, cpp, planes, ious4, sel) host copies
         self.capture: Optional[list] = None
         self.use_cuda_graph = True
-        self.graph_lanes = 2  # independent prompt batches in flight (one CUDA graph instance + stream each)
+        # independent prompt batches in flight (one CUDA graph instance + stream each)
+        self.graph_lanes = int(os.environ.get("SB_GRAPH_LANES", "4"))
         self.phase_ms: Optional[Dict[str, float]] = None  # set to {} to accumulate encode / decode+post / total ms
         self._graphs: Dict[Tuple[int, int], Any] = {}
         self._plans: Dict[Tuple[int, int], _ImagePlan] = {}

@@ -10,6 +10,7 @@ mean/std, ``no_mem_embed`` is added to the lowest-resolution feature.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -51,7 +52,7 @@ class SAM2ImagePredictor:
         self.mask_threshold = mask_threshold
         self.resolution = sam_model.image_size
         self._bb_feat_sizes = [(256, 256), (128, 128), (64, 64)]
-        self.max_encode_batch = 8
+        self.max_encode_batch = int(os.environ.get("SB_ENCODE_BATCH", "24"))  # crops per encoder pass (all 21 AMG crops at once)
         self.reset_predictor()
 
     @property

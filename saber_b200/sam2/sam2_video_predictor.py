@@ -16,6 +16,7 @@ Restates sam2/sam2_video_predictor.py + sam2/modeling/sam2_base.py (SURVEY §8a 
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -73,7 +74,7 @@ class SAM2VideoPredictor(SAM2Model):
         self.mem_enc: Optional[MemoryEncoder] = None
         self.sam_mask_decoder: Optional[_DecoderModule] = None
         self._const_cache: Dict[Any, Any] = {}
-        self.max_encode_batch = 8
+        self.max_encode_batch = int(os.environ.get("SB_ENCODE_BATCH", "8"))  # crops / frames per encoder pass
         super().__init__(cfg, state_dict, device=device, dynamic_multimask_via_stability=dynamic_multimask_via_stability,
                          num_maskmem=num_maskmem)
 
