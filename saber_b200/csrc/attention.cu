@@ -310,7 +310,7 @@ flash_attn_kernel(const AttnParams p) {
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float c0 = exp2f((m0 - mn0) * p.scale_log2), c1 = exp2f((m1 - mn1) * p.scale_log2);
+    const float c0 = sb::fast_exp2((m0 - mn0) * p.scale_log2), c1 = sb::fast_exp2((m1 - mn1) * p.scale_log2);
     m0 = mn0;
     m1 = mn1;
     const float ms0 = mn0 * p.scale_log2, ms1 = mn1 * p.scale_log2;
@@ -318,10 +318,10 @@ flash_attn_kernel(const AttnParams p) {
     uint32_t pf[KT / 16][4];
 #pragma unroll
     for (int i = 0; i < KT / 8; ++i) {
-      const float p0 = exp2f(s[i][0] * p.scale_log2 - ms0);
-      const float p1 = exp2f(s[i][1] * p.scale_log2 - ms0);
-      const float p2 = exp2f(s[i][2] * p.scale_log2 - ms1);
-      const float p3 = exp2f(s[i][3] * p.scale_log2 - ms1);
+      const float p0 = sb::fast_exp2(s[i][0] * p.scale_log2 - ms0);
+      const float p1 = sb::fast_exp2(s[i][1] * p.scale_log2 - ms0);
+      const float p2 = sb::fast_exp2(s[i][2] * p.scale_log2 - ms1);
+      const float p3 = sb::fast_exp2(s[i][3] * p.scale_log2 - ms1);
       rs0 += p0 + p1;
       rs1 += p2 + p3;
       pf[i >> 1][(i & 1) * 2 + 0] = sb::pack_bf16x2(p0, p1);
@@ -491,7 +491,7 @@ fewkeys_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld, long lo
         float pj[FK_R];
 #pragma unroll
         for (int u = 0; u < FK_R; ++u) {
-          pj[u] = exp2f(sc[u][j] - mx[u]);
+          pj[u] = sb::fast_exp2(sc[u][j] - mx[u]);
           l[u] += pj[u];
         }
         const float4* vp = reinterpret_cast<const float4*>(sV + j * KP + head * HP);
