@@ -322,6 +322,18 @@ def run_b200(args):
                     "share_of_step": r["ms"] / (ms_max / args.steps),
                     "how": "1 extra instrumented step after the timed region, launched eagerly (no CUDA graph) so every tcgen05 GEMM launch of the step (encoder + both decoder passes: std / LN / up-scaling epilogues) is bracketed by CUDA events on the launch stream; achieved = sum(2MNK) / sum(duration)"}
 
+        # north_star's encoder figure: algorithmic Hiera FLOPs of the slice's crops (incl. window padding)
+        # over the device-timed encode phase
+        enc_gf = {"tiny": 292.0, "small": 360.0, "base_plus": 647.0, "base+": 647.0, "large": 1823.0}.get(args.cfg)
+        if enc_gf and phases and phases.get("encode"):
+            n_crops = sum(len(pl.crops) for pl in gen._plans.values()) // max(1, len(gen._plans))
+            enc_tf = enc_gf * 1e9 * n_crops / (phases["encode"] * 1e-3) / 1e12
+            roofline["encoder"] = {"crops_per_slice": n_crops, "gflop_per_crop": enc_gf, "ms_per_slice": phases["encode"],
+                                   "achieved": enc_tf, "unit": "TFLOP/s", "frac": enc_tf / peak,
+                                   "note": "all encoder kernels (GEMMs on tcgen05, attention on mma.sync, LayerNorm, pooling)"}
+        roofline["not_counted"] = ("i2t_tc_kernel / t2i_tc_kernel (fused mask-decoder attention blocks on tcgen05) are not "
+                                   "GEMM launches: HBM-bound, 4 MB resp. 2 MB of image stream per prompt; see DESIGN.md section 3")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, desc, cores = cpu_reference_sample(args.cfg, args.thresholds, n_points=16)
@@ -335,7 +347,9 @@ def run_b200(args):
                            "voxels_per_s": value * SHAPE[1] * SHAPE[2], "masks_kept_per_slice": kept / max(1, S * args.steps),
                            "l2": "256 MiB flush write between timed steps; per-step activations (>10 GB) exceed L2",
                            "weights": "random-init (seed 0) of the named architecture",
-                           "phase_ms_per_slice": phases},
+                           "phase_ms_per_slice": phases,
+                           "graph_lanes": int(os.environ.get("SB_GRAPH_LANES", "4")),
+                           "encode_batch": int(os.environ.get("SB_ENCODE_BATCH", "24"))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

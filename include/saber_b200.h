@@ -79,8 +79,8 @@ int sb_i2t_fold(const void* kt, long long kt_ld, const void* vt, long long vt_ld
                 const float* bo, void* w1t, void* w2t, void* kts, int batch, int nt, float scale, void* stream);
 /* sb_i2t_block for a per-prompt stream on tcgen05 / TMEM / TMA (128-row tiles, both GEMMs as UMMA, softmax + LayerNorm in
  * the epilogue warps); w2t must carry the folded out-projection bias (sb_i2t_fold with bo != NULL). */
-int sb_i2t_block_tc(const void* x, const void* qres, const void* w1t, const void* w2t, const void* kts, const float* gamma,
-                    const float* beta, float eps, void* out, int batch, int nq, int nt, void* stream);
+int sb_i2t_block_tc(const void* x, int x_shared, const void* qres, const void* w1t, const void* w2t, const void* kts,
+                    const float* gamma, const float* beta, float eps, void* out, int batch, int nq, int nt, void* stream);
 int sb_i2t_block(const void* x, int x_shared, const void* qp, const void* w1t, const void* w2t, const void* kts,
                  const float* bo, const float* gamma, const float* beta, float eps, void* out, int batch, int nq, int nt,
                  void* stream);

@@ -44,6 +44,7 @@ struct I2TTCParams {
   float eps;
   bf16* out;          // [B*nq, 256]
   int nt, nq, tiles;  // tokens per prompt, image tokens per prompt, 128-row tiles per CTA
+  int x_bstride;      // rows between the prompts' streams in x (0: one stream shared by all prompts)
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
@@ -132,7 +133,7 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       sb::mbar_arrive_expect_tx(w_full, 65536);
       for (int kb = 0; kb < 4; ++kb) sb::tma_load_2d(smem + TC_OFF_W1 + kb * 8192, &tmW1, w_full, kb * 64, b * 64);
       sb::tma_load_2d(smem + TC_OFF_W2, &tmW2, w_full, 0, b * 256);
-      const int xrow0 = b * p.nq + row_base;
+      const int xrow0 = b * p.x_bstride + row_base;
       for (int n = 0; n < T; ++n) {
         const int buf = n & 1;
         if (n >= 2) sb::mbar_wait(&x_empty[buf], static_cast<uint32_t>(((n >> 1) - 1) & 1));
@@ -386,12 +387,12 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
 }  // namespace
 
-// tcgen05 version of sb_i2t_block for a per-prompt image stream (fold mode): x [batch*nq, 256] bf16, qres [nq,128] bf16,
+// tcgen05 version of sb_i2t_block (fold mode): x [batch*nq, 256] bf16 (or [nq, 256] shared by all prompts), qres [nq,128] bf16,
 // w1t [batch,64,256], w2t [batch,256,64] (out-projection bias folded in: sb_i2t_fold with bo != NULL), kts [batch,8,128].
 // out [batch*nq, 256] bf16 may alias x. nq must be a multiple of 256.
-extern "C" int sb_i2t_block_tc(const void* x, const void* qres, const void* w1t, const void* w2t, const void* kts,
-                               const float* gamma, const float* beta, float eps, void* out, int batch, int nq, int nt,
-                               void* stream) {
+extern "C" int sb_i2t_block_tc(const void* x, int x_shared, const void* qres, const void* w1t, const void* w2t,
+                               const void* kts, const float* gamma, const float* beta, float eps, void* out, int batch,
+                               int nq, int nt, void* stream) {
   SB_REQUIRE(batch > 0 && nq > 0 && (nq % 256) == 0, "sb_i2t_block_tc: nq must be a positive multiple of 256 (got %d)", nq);
   SB_REQUIRE(nt >= 1 && nt <= 8, "sb_i2t_block_tc: nt must be in 1..8 (got %d)", nt);
   SB_REQUIRE(x && qres && w1t && w2t && kts && gamma && beta && out, "sb_i2t_block_tc: null operand");
@@ -399,7 +400,8 @@ extern "C" int sb_i2t_block_tc(const void* x, const void* qres, const void* w1t,
                reinterpret_cast<uintptr_t>(w2t) | reinterpret_cast<uintptr_t>(kts) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
              "sb_i2t_block_tc: operands must be 16-byte aligned");
   CUtensorMap tmX, tmW1, tmW2;
-  int rc = sb_make_tmap_2d_bf16(&tmX, x, static_cast<uint64_t>(batch) * nq, 256, 256, 128, 64);
+  SB_REQUIRE(!(x_shared && x == out), "sb_i2t_block_tc: a shared stream cannot be updated in place");
+  int rc = sb_make_tmap_2d_bf16(&tmX, x, static_cast<uint64_t>(x_shared ? 1 : batch) * nq, 256, 256, 128, 64);
   if (rc != SB_OK) return rc;
   rc = sb_make_tmap_2d_bf16(&tmW1, w1t, static_cast<uint64_t>(batch) * 64, 256, 256, 64, 64);
   if (rc != SB_OK) return rc;
@@ -433,6 +435,7 @@ extern "C" int sb_i2t_block_tc(const void* x, const void* qres, const void* w1t,
   p.nt = nt;
   p.nq = nq;
   p.tiles = best_rows / 128;
+  p.x_bstride = x_shared ? 0 : nq;
   static bool attr_done = false;
   if (!attr_done) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));

@@ -35,8 +35,8 @@ SIGNATURES = {
                               c_int, c_float, c_int, c_void_p],
     "sb_i2t_fold": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                     c_float, c_void_p],
-    "sb_i2t_block_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int,
-                        c_int, c_void_p],
+    "sb_i2t_block_tc": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                        c_int, c_int, c_void_p],
     "sb_i2t_block": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                      c_void_p, c_int, c_int, c_int, c_void_p],
     "sb_t2i_fold_splits": [c_int, c_int],

@@ -330,11 +330,11 @@ def i2t_block(x: torch.Tensor, qp: torch.Tensor, w1t: Optional[torch.Tensor], w2
 
 def i2t_block_tc(x: torch.Tensor, qres: torch.Tensor, w1t: torch.Tensor, w2t: torch.Tensor, kts: torch.Tensor,
                  gamma: torch.Tensor, beta: torch.Tensor, eps: float, batch: int, nq: int, nt: int,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, x_shared: bool = False) -> torch.Tensor:
     """``i2t_block`` of a per-prompt stream on tcgen05 / TMEM / TMA (csrc/decoder_i2t_tc.cu); ``w2t`` must come from
     ``i2t_fold(..., bo=out_proj_bias)``."""
     _chk_cuda(x, qres, w1t, w2t, kts, gamma, beta)
-    assert x.dtype == _BF16 and x.is_contiguous() and x.shape == (batch * nq, 256)
+    assert x.dtype == _BF16 and x.is_contiguous() and x.shape == ((1 if x_shared else batch) * nq, 256)
     assert qres.dtype == _BF16 and qres.is_contiguous() and qres.shape == (nq, 128)
     assert w1t.dtype == _BF16 and w1t.is_contiguous() and w1t.shape == (batch, 64, 256)
     assert w2t.dtype == _BF16 and w2t.is_contiguous() and w2t.shape == (batch, 256, 64)
@@ -345,7 +345,7 @@ def i2t_block_tc(x: torch.Tensor, qres: torch.Tensor, w1t: torch.Tensor, w2t: to
         out = torch.empty((batch * nq, 256), dtype=_BF16, device=x.device)
     assert out.dtype == _BF16 and out.is_contiguous() and out.shape == (batch * nq, 256)
     L = _lib.load()
-    _lib.check(L.sb_i2t_block_tc(x.data_ptr(), qres.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), kts.data_ptr(),
+    _lib.check(L.sb_i2t_block_tc(x.data_ptr(), int(x_shared), qres.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), kts.data_ptr(),
                                  gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), batch, nq, nt, _stream()),
                "sb_i2t_block_tc")
     _count()

@@ -206,15 +206,16 @@ class MaskDecoder:
             if Nt <= 8:
                 # <= 8 tokens per prompt: q projection, attention, out projection, residual and norm4 in ONE pass over
                 # the image stream, with the projections folded into per-prompt operands (csrc/decoder_fused.cu)
+                if self.i2t_tensor_core:  # both GEMMs on tcgen05 (csrc/decoder_i2t_tc.cu); a stream shared by all
+                    # prompts (layer 0 of the first pass) is read through the same tensor map by every prompt
+                    w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt, bo=L["i2t_o_b"])
+                    keys = ops.i2t_block_tc(keys, L["i2t_q_res16"], w1t, w2t, kts, L["n4w"], L["n4b"], 1e-5, B, NT_IMG, Nt,
+                                            out=(None if kb == 1 else keys), x_shared=(kb == 1))
+                    keys_f32, kb = keys, B
+                    continue
                 if kb == 1:  # one stream shared by all prompts: its query projection is computed once
                     qp = ops.gemm(keys, L["i2t_q_w"], None, residual=L["i2t_q_res"], res_mod=NT_IMG)
                     w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt, with_w1=False)
-                elif self.i2t_tensor_core:  # per-prompt stream: both GEMMs on tcgen05 (csrc/decoder_i2t_tc.cu)
-                    w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt, bo=L["i2t_o_b"])
-                    keys = ops.i2t_block_tc(keys, L["i2t_q_res16"], w1t, w2t, kts, L["n4w"], L["n4b"], 1e-5, B, NT_IMG, Nt,
-                                            out=keys)
-                    keys_f32 = keys
-                    continue
                 else:
                     qp = L["i2t_q_res16"]
                     w1t, w2t, kts = ops.i2t_fold(kt, vt, L["i2t_q_w"], L["i2t_o_w"], B, Nt)

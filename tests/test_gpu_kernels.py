@@ -147,7 +147,8 @@ def test_t2i_fold_attention(ops, B, nt, shared, tc):
 
 
 @pytest.mark.parametrize("nt,shared,tc", [(8, False, False), (7, False, False), (8, True, False), (3, True, False),
-                                          (1, False, False), (8, False, True), (5, False, True), (1, False, True)])
+                                          (1, False, False), (8, False, True), (5, False, True), (1, False, True),
+                                          (8, True, True)])
 def test_i2t_block_fused(ops, nt, shared, tc):
     """Fused TwoWayAttentionBlock step 4 (q projection + image->token attention + out projection + residual + norm4 in
     one pass over the image stream, projections folded per prompt) vs the unfused fp32 torch expression."""
@@ -167,7 +168,7 @@ def test_i2t_block_fused(ops, nt, shared, tc):
     v = vt.float().view(B, nt, 8, 16).transpose(1, 2)
     a = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, nq, 128)
     ref = torch.nn.functional.layer_norm(xf + a @ wo.float().t() + bo, (256,), gamma, beta, 1e-5).reshape(B * nq, 256)
-    if shared:
+    if shared and not tc:
         qp = (x.float() @ wq.float().t() + qres).to(BF16)
         w1t, w2t, kts = ops.i2t_fold(kt, vt, wq, wo, B, nt, with_w1=False)
         assert w1t is None
@@ -175,7 +176,7 @@ def test_i2t_block_fused(ops, nt, shared, tc):
         qp = qres.to(BF16)
         w1t, w2t, kts = ops.i2t_fold(kt, vt, wq, wo, B, nt, bo=(bo if tc else None))
     if tc:
-        out = ops.i2t_block_tc(x, qp, w1t, w2t, kts, gamma, beta, 1e-5, B, nq, nt)
+        out = ops.i2t_block_tc(x, qp, w1t, w2t, kts, gamma, beta, 1e-5, B, nq, nt, x_shared=shared)
     else:
         out = ops.i2t_block(x, qp, w1t, w2t, kts, bo, gamma, beta, 1e-5, B, nq, nt, x_shared=shared)
     err = (out.float() - ref).abs().max().item()
