@@ -10,6 +10,11 @@
 //
 // v1 math runs on mma.sync.m16n8k16 (bf16 in, fp32 accumulate); softmax statistics are fp32.
 #include "common.cuh"
+#include <stdlib.h>
+
+int sb_internal_attention_d256_tc(const void* q, long long q_ld, const void* k, long long k_ld, const void* v,
+                                  long long v_ld, void* o, long long o_ld, int batch, int nq, int nk, float scale,
+                                  int q_shared, int kv_shared, cudaStream_t stream);
 
 namespace {
 
@@ -615,6 +620,19 @@ extern "C" int sb_attention(const void* q, long long q_ld, const void* k, long l
         p.q, q_ld, p.q_bstride, nullptr, p.k, k_ld, p.v, v_ld, p.o, o_ld, nq, nk, p.scale_log2, rows_per_block);
     SB_CHECK_LAUNCH();
     return SB_OK;
+  }
+  // single head x 256 (SAM2 memory attention): tcgen05 / TMA flash kernel (attention_tc.cu); SB_ATTN_TC=0 keeps mma.sync
+  if (heads == 1 && hd == 256 && (nq % 128) == 0 && nk >= 64) {
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* e = getenv("SB_ATTN_TC");
+      use_tc = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_tc) {
+      const int rc = sb_internal_attention_d256_tc(q, q_ld, k, k_ld, v, v_ld, o, o_ld, batch, nq, nk, scale, q_shared,
+                                                   kv_shared, reinterpret_cast<cudaStream_t>(stream));
+      if (rc != SB_ERR_UNSUPPORTED) return rc;
+    }
   }
   return run_attn(p, batch, nq, 1, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -78,7 +78,10 @@ def _sdpa_ref(q, k, v, B, heads, nq, nk):
 
 
 @pytest.mark.parametrize("B,heads,hd,nq,nk", [(2, 8, 72, 4096, 4096), (3, 8, 16, 7, 4096), (3, 8, 16, 4096, 7),
-                                              (3, 8, 32, 8, 8), (2, 1, 64, 100, 333), (1, 1, 128, 64, 200)])
+                                              (3, 8, 32, 8, 8), (2, 1, 64, 100, 333), (1, 1, 128, 64, 200),
+                                              # single head x 256 (memory attention): tcgen05 kernel, ragged key counts
+                                              (2, 1, 256, 4096, 4096), (3, 1, 256, 256, 8196), (2, 1, 256, 128, 70),
+                                              (1, 1, 256, 384, 64)])
 def test_attention(ops, B, heads, hd, nq, nk):
     torch.manual_seed(2)
     C = heads * hd
