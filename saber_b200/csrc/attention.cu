@@ -545,11 +545,11 @@ int launch_attn_kt(const AttnParams& p, long long nblocks_x, cudaStream_t stream
   constexpr int PITCH = HDP * 2 + 16;
   constexpr int SMEM_MAX_ = (16 * NWARPS + 6 * KT) * PITCH;
   const int SMEM = (16 * NWARPS + (p.k_add ? 6 : 4) * KT) * PITCH;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HDP, NWARPS, KT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_ > 227 * 1024 ? 227 * 1024 : SMEM_MAX_));
-    attr_done = true;
+    attr_once.mark();
   }
   SB_REQUIRE(SMEM <= 227 * 1024, "sb_attention: k_add does not fit in shared memory at head_dim %d", p.hd);
   dim3 grid(static_cast<unsigned>(nblocks_x), static_cast<unsigned>(p.heads), 1);

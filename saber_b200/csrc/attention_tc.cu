@@ -314,10 +314,10 @@ int sb_internal_attention_d256_tc(const void* q, long long q_ld, const void* k, 
   if (rc != SB_OK) return rc;
   rc = sb_make_tmap_2d_bf16(&tmV, v, static_cast<uint64_t>(kv_shared ? 1 : batch) * nk, 256, static_cast<uint64_t>(v_ld), AT_KT, 64);
   if (rc != SB_OK) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_d256_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_done = true;
+    attr_once.mark();
   }
   AttnTCParams p;
   p.out = static_cast<bf16*>(o);

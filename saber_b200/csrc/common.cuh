@@ -39,6 +39,23 @@ void sb_set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
+// cudaFuncSetAttribute is per device (context): SABER's GPUPool drives several GPUs from the threads of one process
+// (REF saber/utils/parallelization.py:155), so the "attribute already set" caches are kept per device, not per process.
+#include <atomic>
+struct SbPerDeviceOnce {
+  std::atomic<unsigned long long> done{0};  // bit d: set on device d (d < 64)
+  bool need() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return ((done.load(std::memory_order_acquire) >> (d & 63)) & 1ull) == 0ull;
+  }
+  void mark() {
+    int d = 0;
+    cudaGetDevice(&d);
+    done.fetch_or(1ull << (d & 63), std::memory_order_release);
+  }
+};
+
 // Host: encode a 2-D bf16 row-major tensor map (rows x cols, row pitch ld elements), 128B swizzle.
 // box = (box_cols elements [inner], box_rows). Returns SB_OK or error.
 int sb_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,

@@ -734,11 +734,11 @@ extern "C" int sb_i2t_block(const void* x, int x_shared, const void* qp, const v
   p.rows_per_cta = best_rows;
   dim3 grid(nq / best_rows, batch);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2T_SMEM_FOLD));
     SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2T_SMEM_SHARED));
-    attr_done = true;
+    attr_once.mark();
   }
   if (w1t != nullptr)
     i2t_block_kernel<false><<<grid, I2T_WARPS * 32, I2T_SMEM_FOLD, st>>>(p);
@@ -777,10 +777,10 @@ extern "C" int sb_t2i_fold_attention(const void* q, long long q_ld, const void* 
     const int rc = sb_internal_i2t_fold(q, q_ld, nullptr, 0, wk, nullptr, nullptr, qf, I2T_C, 0, nullptr, qs, batch, nt, scale, st);
     if (rc != SB_OK) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(t2i_fold_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2I_SMEM));
-    attr_done = true;
+    attr_once.mark();
   }
   T2IParams p;
   p.x = static_cast<const bf16*>(x);

@@ -436,10 +436,10 @@ extern "C" int sb_i2t_block_tc(const void* x, int x_shared, const void* qres, co
   p.nq = nq;
   p.tiles = best_rows / 128;
   p.x_bstride = x_shared ? 0 : nq;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_done = true;
+    attr_once.mark();
   }
   i2t_tc_kernel<<<dim3(nq / best_rows, batch), TC_THREADS, TC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW1, tmW2, p);
   SB_CHECK_LAUNCH();

@@ -327,10 +327,10 @@ extern "C" int sb_t2i_fold_attention_tc(const void* q, long long q_ld, const voi
   if (rc != SB_OK) return rc;
   rc = sb_make_tmap_2d_bf16(&tmKA, kadd, static_cast<uint64_t>(nk), 128, 128, TT_KT, 64);
   if (rc != SB_OK) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(t2i_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
-    attr_done = true;
+    attr_once.mark();
   }
   T2ITCParams p;
   p.opart = opart;

@@ -699,11 +699,11 @@ template <int BN, int EPI, int ACT = 0>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                 cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, ACT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    attr_done = true;
+    attr_once.mark();
   }
   // staged (coalesced) epilogue needs 16-byte-aligned pitches and N % 16 == 0
   int staged = 1;

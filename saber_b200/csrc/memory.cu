@@ -585,11 +585,11 @@ int launch_conv(const void* in, int B, int Hi, int Wi, const float* w, const flo
                 cudaStream_t stream) {
   const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
   const int smem = (9 * CIN * COUT + 3 * COUT) * static_cast<int>(sizeof(float));
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
+  static SbPerDeviceOnce attr_once;
+  if (smem > 48 * 1024 && attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(conv3x3s2_ln_gelu_kernel<CIN, COUT, IN_BF16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_once.mark();
   }
   conv3x3s2_ln_gelu_kernel<CIN, COUT, IN_BF16>
       <<<grid_for(static_cast<long long>(B) * Ho * Wo, 128, 148 * 32), 128, smem, stream>>>(
@@ -650,10 +650,10 @@ extern "C" int sb_dwconv7_ln(const float* in, int B, int H, int W, int C, const 
   SB_REQUIRE(B > 0 && H > 0 && W > 0 && C == 256, "sb_dwconv7_ln: C must be 256 (got %d)", C);
   const long long total = static_cast<long long>(B) * H * ((W + 3) / 4);  // one warp per 4-pixel group
   const int smem = 49 * 256 * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static SbPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_once.mark();
   }
   long long blocks = (total + 7) / 8;
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -700,10 +700,10 @@ extern "C" int sb_fill_holes(const float* in, float* out, int B, int S, int max_
   SB_REQUIRE(B > 0 && S > 0 && max_area > 0 && ws, "sb_fill_holes: bad arguments");
   if ((S % 32) == 0 && S * S <= 65536) {
     const int smem = S * S * 2 + (S * S / 32) * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static SbPerDeviceOnce attr_once;
+    if (attr_once.need()) {
       SB_CHECK_CUDA(cudaFuncSetAttribute(fill_holes_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2 + 8192));
-      attr_done = true;
+      attr_once.mark();
     }
     fill_holes_smem_kernel<<<B, 1024, smem, stream>>>(in, out, S, max_area, ws);
   } else {
