@@ -88,7 +88,7 @@ __device__ __forceinline__ long long key_row(const AttnParams& p, int b, int win
 // KT = keys per tile. HDP > 128 (memory attention: one head of 256) keeps the Q fragments in shared memory instead of
 // registers (the fp32 output accumulator alone is 128 registers per thread) and uses 32-key tiles.
 template <int HDP, int NWARPS, int KT>
-__global__ void __launch_bounds__(NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS * 32, NWARPS == 8 ? 2 : 1)
 flash_attn_kernel(const AttnParams p) {
   constexpr bool Q_IN_REGS = HDP <= 128;
   constexpr int PITCH = HDP * 2 + 16;  // bytes; odd multiple of 16 -> conflict-free ldmatrix
@@ -576,11 +576,20 @@ int run_attn(AttnParams& p, int batch, int nq_per_window, int nwin, cudaStream_t
   SB_REQUIRE((p.hd % 8) == 0, "sb_attention: head_dim must be a multiple of 8 (got %d)", p.hd);
   SB_REQUIRE((p.q_ld % 8) == 0 && (p.k_ld % 8) == 0 && (p.v_ld % 8) == 0 && (p.o_ld % 2) == 0,
              "sb_attention: row pitches must be multiples of 8 elements");
-  const int nwarps = nq_per_window <= 16 ? 1 : 4;
+  // 128-query CTAs (8 warps) for Hiera's 256-token windows and global blocks: the K / V tiles (and the loaders' per-row
+  // addressing) are shared by twice as many queries as with 64-query CTAs
+  static int wide = -1;
+  if (wide < 0) {
+    const char* e = getenv("SB_ATTN_WIDE");
+    wide = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool use8 = wide && p.mode == 1 && p.hd > 64 && p.hd <= 80 && nq_per_window > 16 && (nq_per_window % 128) == 0;
+  const int nwarps = nq_per_window <= 16 ? 1 : (use8 ? 8 : 4);  // (256-query CTAs measured slower: 38.3 vs 37.7 ms / batch)
   p.qtiles = (nq_per_window + 16 * nwarps - 1) / (16 * nwarps);
   const long long nbx = static_cast<long long>(batch) * nwin * p.qtiles;
   SB_REQUIRE(nbx > 0 && nbx < (1ll << 31), "sb_attention: grid too large");
   if (nwarps == 1) return dispatch_hd<1>(p, nbx, stream);
+  if (nwarps == 8) return launch_attn<80, 8>(p, nbx, stream);
   return dispatch_hd<4>(p, nbx, stream);
 }
 
