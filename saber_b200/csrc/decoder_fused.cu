@@ -574,11 +574,13 @@ t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml,
   __shared__ float sw[I2T_TOK][NS];  // per (token row, split) weight 2^(m_s - m) / L
   constexpr int ns = NS;
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  // all partial rows of head h (8 tokens x NS splits, thread = channel): one round of independent loads
-  float v[NS][I2T_TOK];
+  // partial rows of head h (8 tokens x NS splits, thread = channel), in groups of <= 4 splits (32 independent loads in
+  // flight; the first group is issued before the split weights are known)
+  constexpr int G = NS < 4 ? NS : 4;
+  float v[G][I2T_TOK];
   const float* ob = opart + (static_cast<long long>(b) * ns * I2T_NC + h * 8) * I2T_C + tid;
 #pragma unroll
-  for (int s = 0; s < NS; ++s)
+  for (int s = 0; s < G; ++s)
 #pragma unroll
     for (int t = 0; t < I2T_TOK; ++t) v[s][t] = __ldg(ob + (static_cast<long long>(s) * I2T_NC + t) * I2T_C);
   if (tid < I2T_TOK) {
@@ -603,32 +605,48 @@ t2i_unfold_kernel(const float* __restrict__ opart, const float* __restrict__ ml,
     for (int s = 0; s < NS; ++s) sw[tid][s] = mm[s] * inv;
   }
   __syncthreads();
+  float part[I2T_TOK];
 #pragma unroll
-  for (int t = 0; t < I2T_TOK; ++t) {
-    float acc = 0.f;
+  for (int t = 0; t < I2T_TOK; ++t) part[t] = 0.f;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc = fmaf(sw[t][s], v[s][t], acc);
-    so[t][tid] = acc;
+  for (int g0 = 0; g0 < NS; g0 += G) {
+    if (g0 > 0) {
+#pragma unroll
+      for (int s = 0; s < G; ++s)
+#pragma unroll
+        for (int t = 0; t < I2T_TOK; ++t) v[s][t] = __ldg(ob + (static_cast<long long>(g0 + s) * I2T_NC + t) * I2T_C);
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s)
+#pragma unroll
+      for (int t = 0; t < I2T_TOK; ++t) part[t] = fmaf(sw[t][g0 + s], v[s][t], part[t]);
   }
+#pragma unroll
+  for (int t = 0; t < I2T_TOK; ++t) so[t][tid] = part[t];
   // 8 tokens x 16 dims = 128 outputs, two threads (channel halves) each
   const int half = tid & 1, d = (tid >> 1) & 15, t = tid >> 5;
   const bf16* wrow = wv + (h * 16 + d) * I2T_C + half * 128;
-  uint4 w8[16];
-#pragma unroll
-  for (int c8 = 0; c8 < 16; ++c8) w8[c8] = __ldg(reinterpret_cast<const uint4*>(wrow + c8 * 8));
   __syncthreads();
+  // the 64 KB weight matrix is shared by every block (L1 / L2 hits): loaded four 16-byte pieces at a time so that the
+  // kernel stays at ~48 registers (holding all 16 pieces next to the NS x 8 partial rows capped it at 2 blocks per SM)
   float acc = 0.f;
 #pragma unroll
-  for (int c8 = 0; c8 < 16; ++c8) {
-    const float* ov = &so[t][half * 128 + c8 * 8];
-    acc = fmaf(sb::bf16_lo(w8[c8].x), ov[0], acc);
-    acc = fmaf(sb::bf16_hi(w8[c8].x), ov[1], acc);
-    acc = fmaf(sb::bf16_lo(w8[c8].y), ov[2], acc);
-    acc = fmaf(sb::bf16_hi(w8[c8].y), ov[3], acc);
-    acc = fmaf(sb::bf16_lo(w8[c8].z), ov[4], acc);
-    acc = fmaf(sb::bf16_hi(w8[c8].z), ov[5], acc);
-    acc = fmaf(sb::bf16_lo(w8[c8].w), ov[6], acc);
-    acc = fmaf(sb::bf16_hi(w8[c8].w), ov[7], acc);
+  for (int c32 = 0; c32 < 4; ++c32) {
+    uint4 w8[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w8[j] = __ldg(reinterpret_cast<const uint4*>(wrow + (c32 * 4 + j) * 8));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* ov = &so[t][half * 128 + (c32 * 4 + j) * 8];
+      acc = fmaf(sb::bf16_lo(w8[j].x), ov[0], acc);
+      acc = fmaf(sb::bf16_hi(w8[j].x), ov[1], acc);
+      acc = fmaf(sb::bf16_lo(w8[j].y), ov[2], acc);
+      acc = fmaf(sb::bf16_hi(w8[j].y), ov[3], acc);
+      acc = fmaf(sb::bf16_lo(w8[j].z), ov[4], acc);
+      acc = fmaf(sb::bf16_hi(w8[j].z), ov[5], acc);
+      acc = fmaf(sb::bf16_lo(w8[j].w), ov[6], acc);
+      acc = fmaf(sb::bf16_hi(w8[j].w), ov[7], acc);
+    }
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   if (half == 0 && t < nt)
