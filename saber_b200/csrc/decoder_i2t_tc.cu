@@ -21,14 +21,12 @@
 // so that the second MMA of tile n runs under LN2(n-1), the first MMA of tile n+1 under LN1(n), and the X tile n+2
 // streams in under S(n+1) / LN2(n) / LN1(n+1).
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace {
 
 using bf16 = __nv_bfloat16;
 
 constexpr int TC_THREADS = 384;
-constexpr int TC4_THREADS = 640;  // 16 epilogue warps
 constexpr int TC_XBUF = 65536;                       // one X tile: 4 K-blocks x [128 rows x 128 B]
 constexpr int TC_OFF_W1 = 2 * TC_XBUF;               // 4 K-blocks x [64 rows x 128 B]
 constexpr int TC_OFF_W2 = TC_OFF_W1 + 32768;         // [256 rows x 128 B]
@@ -75,9 +73,6 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) {
 }
 __device__ __forceinline__ void pair_barrier(int q) {  // the two warps (column halves) that share 32 rows
   asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory");
-}
-__device__ __forceinline__ void quad_barrier(int q) {  // the four warps (column quarters) that share 32 rows
-  asm volatile("bar.sync %0, 128;" ::"r"(q + 2) : "memory");
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -390,303 +385,6 @@ i2t_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
-__global__ void __launch_bounds__(TC4_THREADS, 1)
-i2t_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-              const __grid_constant__ CUtensorMap tmW2, const I2TTCParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
-  uint64_t* w_full = bars;            // 1
-  uint64_t* x_full = bars + 1;        // 2
-  uint64_t* x_empty = bars + 3;       // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* p_full = bars + 7;        // 1
-  uint64_t* o_full = bars + 8;        // 2
-  uint64_t* o_empty = bars + 10;      // 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-  float* sVec = reinterpret_cast<float*>(smem + TC_OFF_VEC);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int row_base = blockIdx.x * p.tiles * 128;  // first image token of this CTA
-  const int T = p.tiles;
-
-  if ((sb::smem_u32(smem) & 1023u) != 0u) __trap();  // SW128 operand tiles need 1024-byte alignment
-  if (warp == 0 && lane == 0) {
-    sb::tma_prefetch_desc(&tmX);
-    sb::tma_prefetch_desc(&tmW1);
-    sb::tma_prefetch_desc(&tmW2);
-  }
-  if (warp == 1 && lane == 0) {
-    sb::mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      sb::mbar_init(&x_full[i], 1);
-      sb::mbar_init(&x_empty[i], 16);
-      sb::mbar_init(&s_full[i], 1);
-      sb::mbar_init(&o_full[i], 1);
-      sb::mbar_init(&o_empty[i], 16);
-    }
-    sb::mbar_init(p_full, 16);
-    sb::fence_barrier_init();
-  }
-  if (warp == 2) {
-    sb::tmem_alloc(tmem_ptr, 512);
-    sb::tmem_relinquish();
-  }
-  if (warp >= 4 && threadIdx.x < 128 + 256) {
-    const int te = threadIdx.x - 128;
-    sVec[te] = p.gamma[te];
-    sVec[256 + te] = p.beta[te];
-  }
-  sb::tc_fence_before();
-  __syncthreads();
-  sb::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      sb::mbar_arrive_expect_tx(w_full, 65536);
-      for (int kb = 0; kb < 4; ++kb) sb::tma_load_2d(smem + TC_OFF_W1 + kb * 8192, &tmW1, w_full, kb * 64, b * 64);
-      sb::tma_load_2d(smem + TC_OFF_W2, &tmW2, w_full, 0, b * 256);
-      const int xrow0 = b * p.x_bstride + row_base;
-      for (int n = 0; n < T; ++n) {
-        const int buf = n & 1;
-        if (n >= 2) sb::mbar_wait(&x_empty[buf], static_cast<uint32_t>(((n >> 1) - 1) & 1));
-        sb::mbar_arrive_expect_tx(&x_full[buf], TC_XBUF);
-        for (int kb = 0; kb < 4; ++kb)
-          sb::tma_load_2d(smem + buf * TC_XBUF + kb * 16384, &tmX, &x_full[buf], kb * 64, xrow0 + n * 128);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-converged, one elected lane per tcgen05 instruction) =====================
-    {
-      constexpr uint32_t idesc1 = sb::umma_idesc_bf16(128, 64);
-      constexpr uint32_t idesc2 = sb::umma_idesc_bf16(128, 256);
-      const uint32_t sbase = sb::smem_u32(smem);
-      auto issue_mma1 = [&](int m) {
-        const int buf = m & 1;
-        sb::mbar_wait(&x_full[buf], static_cast<uint32_t>((m >> 1) & 1));
-        if (m >= 2) sb::mbar_wait(&o_empty[buf], static_cast<uint32_t>(((m >> 1) - 1) & 1));
-        sb::tc_fence_after();
-        const uint32_t d = tmem_base + static_cast<uint32_t>(buf * 256);
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = sb::umma_desc_k_sw128(sbase + buf * TC_XBUF + kb * 16384);
-          const uint64_t db = sb::umma_desc_k_sw128(sbase + TC_OFF_W1 + kb * 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (sb::elect_one())
-              sb::umma_bf16(d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc1,
-                            static_cast<uint32_t>((kb | k) != 0));
-        }
-        if (sb::elect_one()) sb::umma_commit(&s_full[buf]);
-        __syncwarp();
-      };
-      sb::mbar_wait(w_full, 0);
-      issue_mma1(0);
-      const uint64_t dp = sb::umma_desc_k_sw128(sbase + TC_OFF_P);
-      const uint64_t dw2 = sb::umma_desc_k_sw128(sbase + TC_OFF_W2);
-      for (int n = 0; n < T; ++n) {
-        sb::mbar_wait(p_full, static_cast<uint32_t>(n & 1));
-        sb::tc_fence_after();
-        const uint32_t d = tmem_base + static_cast<uint32_t>((n & 1) * 256);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (sb::elect_one())
-            sb::umma_bf16(d, dp + static_cast<uint64_t>(2 * k), dw2 + static_cast<uint64_t>(2 * k), idesc2,
-                          static_cast<uint32_t>(k != 0));
-        if (sb::elect_one()) sb::umma_commit(&o_full[n & 1]);
-        __syncwarp();
-        if (n + 1 < T) issue_mma1(n + 1);
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue: thread = (row r of the tile, column quarter cq): 16 warps =====================
-    // Same pipeline as i2t_tc_kernel with half the work per thread: the 8-warp epilogue is issue-bound (2 warps per
-    // scheduler, 34 % issue utilisation); four warps per scheduler hide the TMEM / shared-memory / MUFU latencies.
-    const int q = warp & 3;            // TMEM lane quadrant of this warp
-    const int cq = (warp - 4) >> 2;    // column quarter: heads 2*cq, 2*cq+1 of S, channels 64*cq.. of O
-    const int r = q * 32 + lane;
-    const int g = lane >> 2, q4 = lane & 3;
-    const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sbase = sb::smem_u32(smem);
-    const uint32_t stg = sbase + TC_OFF_STG + (warp - 4) * 1024;  // 1 KB per warp
-    const int nt = p.nt;
-    const bf16* ktsb = p.kts + static_cast<long long>(b) * 8 * 128;
-    float mean = 0.f, rstd = 0.f;
-    uint2 bk[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) bk[j] = __ldg(reinterpret_cast<const uint2*>(ktsb + g * 128 + (cq * 2 + j) * 16 + q4 * 4));
-    const bf16* qpf = p.qres + static_cast<long long>(row_base + q * 32 + lane) * 128 + cq * 32;
-    prefetch_l1(qpf);
-
-    auto s_stage = [&](int m) {
-      const int buf = m & 1;
-      float pe[16];
-      const bf16* qrow = p.qres + static_cast<long long>(row_base + m * 128 + q * 32) * 128 + q4 * 4;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int head = cq * 2 + hh;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint2 alo = __ldg(reinterpret_cast<const uint2*>(qrow + (mt * 16 + g) * 128 + head * 16));
-          const uint2 ahi = __ldg(reinterpret_cast<const uint2*>(qrow + (mt * 16 + g + 8) * 128 + head * 16));
-          const uint32_t a[4] = {alo.x, ahi.x, alo.y, ahi.y};
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(c, a, bk[hh].x, bk[hh].y);
-          sts64(stg + (mt * 16 + g) * 32 + q4 * 8, c[0], c[1]);       // 32 rows x 8 tokens fp32
-          sts64(stg + (mt * 16 + g + 8) * 32 + q4 * 8, c[2], c[3]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint4 v = lds128(stg + lane * 32 + j * 16);
-          pe[hh * 8 + 4 * j + 0] = __uint_as_float(v.x);
-          pe[hh * 8 + 4 * j + 1] = __uint_as_float(v.y);
-          pe[hh * 8 + 4 * j + 2] = __uint_as_float(v.z);
-          pe[hh * 8 + 4 * j + 3] = __uint_as_float(v.w);
-        }
-        __syncwarp();
-      }
-      sb::mbar_wait(&s_full[buf], static_cast<uint32_t>((m >> 1) & 1));
-      sb::tc_fence_after();
-      uint32_t v[16];
-      sb::tmem_ld_32x16(tmem_base + tlane + static_cast<uint32_t>(buf * 256 + cq * 16), v);
-      sb::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float s[8];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          s[t] = t < nt ? __uint_as_float(v[j * 8 + t]) + pe[j * 8 + t] : -INFINITY;
-          mx = fmaxf(mx, s[t]);
-        }
-        float l = 0.f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          s[t] = sb::fast_exp2(s[t] - mx);
-          l += s[t];
-        }
-        const float inv = __fdividef(1.f, l);
-        const int chunk = cq * 2 + j;
-        sts128(sbase + TC_OFF_P + r * 128 + ((chunk ^ (r & 7)) << 4),
-               make_uint4(sb::pack_bf16x2(s[0] * inv, s[1] * inv), sb::pack_bf16x2(s[2] * inv, s[3] * inv),
-                          sb::pack_bf16x2(s[4] * inv, s[5] * inv), sb::pack_bf16x2(s[6] * inv, s[7] * inv)));
-      }
-      sb::tc_fence_before();
-      sb::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) sb::mbar_arrive(p_full);
-    };
-
-    s_stage(0);
-#pragma unroll 1
-    for (int n = 0; n < T; ++n) {
-      const int buf = n & 1;
-      const uint32_t to = tmem_base + tlane + static_cast<uint32_t>(buf * 256 + cq * 64);
-      // ---------------- LN1(n) ----------------
-      if (n + 1 < T) prefetch_l1(qpf + static_cast<long long>(n + 1) * 128 * 128);
-      sb::mbar_wait(&o_full[buf], static_cast<uint32_t>((n >> 1) & 1));
-      sb::tc_fence_after();
-      sb::mbar_wait(&x_full[buf], static_cast<uint32_t>((n >> 1) & 1));
-      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
-      const uint32_t xrow = sbase + buf * TC_XBUF + cq * 16384 + r * 128;  // channels 64*cq.. = K-block cq of the X tile
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[16];
-        sb::tmem_ld_32x16(to + c * 16, v);
-        uint4 res[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) res[j] = lds128(xrow + (((c * 2 + j) ^ (r & 7)) << 4));
-        sb::tmem_ld_wait();
-        float y[16];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t w4[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 yy = sb::add2(make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])),
-                                       make_float2(sb::bf16_lo(w4[e]), sb::bf16_hi(w4[e])));
-            y[8 * j + 2 * e] = yy.x;
-            y[8 * j + 2 * e + 1] = yy.y;
-            sum2 = sb::add2(sum2, yy);
-            sq2 = sb::fma2(yy, yy, sq2);
-          }
-        }
-        sb::tmem_st_32x16(to + c * 16, reinterpret_cast<const uint32_t*>(y));
-      }
-      sb::tmem_st_wait();
-      float sum = sum2.x + sum2.y, sumsq = sq2.x + sq2.y;
-      __syncwarp();
-      if (lane == 0) sb::mbar_arrive(&x_empty[buf]);
-      // statistics of the other three column quarters (same rows) through the staging tiles
-      sts64(stg + lane * 8, sum, sumsq);
-      quad_barrier(q);
-#pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        float ps, pq;
-        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];"
-                     : "=f"(ps), "=f"(pq)
-                     : "r"(sbase + TC_OFF_STG + ((((cq + k) & 3) * 4 + q) * 1024) + lane * 8));
-        sum += ps;
-        sumsq += pq;
-      }
-      quad_barrier(q);
-      mean = sum * (1.f / 256.f);
-      rstd = rsqrtf(fmaxf(sumsq * (1.f / 256.f) - mean * mean, 0.f) + p.eps);
-
-      // ---------------- S(n+1) ----------------
-      if (n + 1 < T) s_stage(n + 1);
-
-      // ---------------- LN2(n) ----------------
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out + (static_cast<long long>(b) * p.nq + row_base + n * 128 + q * 32) * 256 +
-                                                 cq * 64);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[16];
-        sb::tmem_ld_32x16(to + c * 16, v);
-        sb::tmem_ld_wait();
-        const float* ga = sVec + cq * 64 + c * 16;
-        const float* be = sVec + 256 + cq * 64 + c * 16;
-        uint32_t o8[8];
-        const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean, -mean);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 g4 = *reinterpret_cast<const float4*>(ga + 4 * j);
-          const float4 b4 = *reinterpret_cast<const float4*>(be + 4 * j);
-          const float2 d0 = sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), nm2);
-          const float2 d1 = sb::add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), nm2);
-          const float2 f01 = sb::fma2(d0, sb::mul2(rs2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
-          const float2 f23 = sb::fma2(d1, sb::mul2(rs2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
-          o8[2 * j] = sb::pack_bf16x2(f01.x, f01.y);
-          o8[2 * j + 1] = sb::pack_bf16x2(f23.x, f23.y);
-        }
-        sts128(stg + lane * 32, make_uint4(o8[0], o8[1], o8[2], o8[3]));
-        sts128(stg + lane * 32 + 16, make_uint4(o8[4], o8[5], o8[6], o8[7]));
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int id = t * 32 + lane;
-          const int row = id >> 1, ch = id & 1;
-          *reinterpret_cast<uint4*>(orow + static_cast<long long>(row) * 512 + c * 32 + ch * 16) = lds128(stg + row * 32 + ch * 16);
-        }
-        __syncwarp();
-      }
-      sb::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) sb::mbar_arrive(&o_empty[buf]);
-    }
-  }
-
-  sb::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    sb::tc_fence_after();
-    sb::tmem_dealloc(tmem_base, 512);
-  }
-}
-
 }  // namespace
 
 // tcgen05 version of sb_i2t_block (fold mode): x [batch*nq, 256] bf16 (or [nq, 256] shared by all prompts), qres [nq,128] bf16,
@@ -741,18 +439,9 @@ extern "C" int sb_i2t_block_tc(const void* x, int x_shared, const void* qres, co
   static SbPerDeviceOnce attr_once;
   if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(i2t_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     attr_once.mark();
   }
-  static int epi16 = -1;  // SB_I2T_EPI16=1: 16 epilogue warps (thread = row x column quarter)
-  if (epi16 < 0) {
-    const char* e = getenv("SB_I2T_EPI16");
-    epi16 = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (epi16)
-    i2t_tc4_kernel<<<dim3(nq / best_rows, batch), TC4_THREADS, TC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW1, tmW2, p);
-  else
-    i2t_tc_kernel<<<dim3(nq / best_rows, batch), TC_THREADS, TC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW1, tmW2, p);
+  i2t_tc_kernel<<<dim3(nq / best_rows, batch), TC_THREADS, TC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW1, tmW2, p);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
