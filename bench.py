@@ -178,7 +178,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "slices/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,8 +201,6 @@ def run_b200(args):
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner (and NCCL_DEBUG output) on stdout: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ops.require_b200()
 
@@ -353,13 +351,32 @@ def run_b200(args):
                            "graph_lanes": int(os.environ.get("SB_GRAPH_LANES", "4")),
                            "encode_batch": int(os.environ.get("SB_ENCODE_BATCH", "24"))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL's version banner, torchrun children) write to file
+    descriptor 1 directly, so keep a private duplicate of the real stdout for the JSON line and point fd 1 at stderr."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
