@@ -53,3 +53,18 @@ def test_product_fails_loudly_without_gpu():
     from saber_b200.adapters.base import cfgAMG
     with pytest.raises(RuntimeError):
         propagationSegmenter(amg_cfg=cfgAMG(sam2_cfg="tiny"))
+
+
+def test_key_split_heuristics_are_host_only_and_consistent():
+    """sb_t2i_*_splits are pure host arithmetic (callable without a GPU): the split count must divide the key count into
+    whole 64-key tiles (tcgen05 kernel) / 32-key tiles (mma.sync kernel) for every batch size the decoder uses."""
+    from saber_b200 import lib
+
+    L = lib.load()
+    for batch in (1, 8, 32, 64, 100, 192, 384):
+        for nk in (256, 1024, 4096):
+            ns = L.sb_t2i_tc_splits(batch, nk)
+            assert ns >= 1 and nk % (ns * 64) == 0, (batch, nk, ns)
+            ns2 = L.sb_t2i_fold_splits(batch, nk)
+            assert ns2 >= 1 and nk % (ns2 * 32) == 0, (batch, nk, ns2)
+            assert ns in (1, 2, 4, 8, 16) and ns2 in (1, 2, 4, 8)
