@@ -106,6 +106,11 @@ int sb_t2i_fold_attention(const void* q, long long q_ld, const void* x, int x_sh
  * MultiScaleBlock.forward / MultiScaleAttention.forward. ws >= max(H,W) = global attention. */
 int sb_window_attention(const void* qkv, const float* qkv_bias, void* o, int batch, int H, int W, int heads, int hd,
                         int ws, int pool, float scale, void* stream);
+/* The same op for hiera-L's head_dim 72 without q-pooling on tcgen05 / TMEM with TMA loads and a TMA tensor store
+ * (16 x 16 windows and the global blocks of stage 3; sb_window_attention routes here by default). Returns -3
+ * (unsupported) for other window shapes. */
+int sb_hiera_attention_tc(const void* qkv, void* out, int batch, int H, int W, int heads, int ws, float scale,
+                          void* stream);
 
 /* ---- token-major bandwidth kernels of the encoder / decoder ----------------------------------------- */
 int sb_layernorm(const void* in, long long ld_in, int in_f32, void* out, long long ld_out, int out_f32,

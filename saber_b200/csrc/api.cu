@@ -46,8 +46,7 @@ extern "C" int sb_require_sm100(void) {
   return SB_OK;
 }
 
-int sb_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                         uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+static int sb_resolve_encode() {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -58,6 +57,47 @@ int sb_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint
       return SB_ERR_DRIVER;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  return SB_OK;
+}
+
+int sb_make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  int rc = sb_resolve_encode();
+  if (rc != SB_OK) return rc;
+  if (rank < 1 || rank > 5) {
+    sb_set_error("sb_make_tmap_nd_bf16: bad rank %d", rank);
+    return SB_ERR_ARG;
+  }
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstride[i] = strides_bytes[i];
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                        gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sb_set_error("cuTensorMapEncodeTiled (rank %d, swizzle %d) failed (%d): base=%p dims=%llu,%llu,.. box=%u,%u,..",
+                 rank, swizzle_bytes, (int)r, base, (unsigned long long)dims[0],
+                 (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return SB_ERR_DRIVER;
+  }
+  return SB_OK;
+}
+
+int sb_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                         uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  {
+    int rc = sb_resolve_encode();
+    if (rc != SB_OK) return rc;
   }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld_elems * 2};

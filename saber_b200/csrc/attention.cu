@@ -12,8 +12,8 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-int sb_internal_window_attn_tc(const void* qkv, void* o, int batch, int H, int W, int heads, float scale,
-                               cudaStream_t stream);
+extern "C" int sb_hiera_attention_tc(const void* qkv, void* out, int batch, int H, int W, int heads, int ws, float scale,
+                                     void* stream);
 int sb_internal_attention_d256_tc(const void* q, long long q_ld, const void* k, long long k_ld, const void* v,
                                   long long v_ld, void* o, long long o_ld, int batch, int nq, int nk, float scale,
                                   int q_shared, int kv_shared, cudaStream_t stream);
@@ -708,15 +708,16 @@ extern "C" int sb_window_attention(const void* qkv, const float* qkv_bias, void*
   SB_REQUIRE(pool == 1 || pool == 2, "sb_window_attention: pool must be 1 or 2");
   SB_REQUIRE(ws > 0 && (ws % pool) == 0, "sb_window_attention: ws %% pool != 0");
   const int C = heads * hd;
-  // EXPERIMENTAL tcgen05 kernel for Hiera's 16 x 16 windows (window_attn_tc.cu): parity-green, opt-in until it is timed
-  if (ws == 16 && pool == 1 && hd == 72 && (H % 16) == 0 && (W % 16) == 0) {
-    static int win_tc = -1;
-    if (win_tc < 0) {
-      const char* e = getenv("SB_WINDOW_TC");
-      win_tc = (e && e[0] == '1') ? 1 : 0;
+  // hiera-L (head_dim 72), no q-pooling, 16 x 16 windows or global: tcgen05 / TMA kernel (hiera_attn_tc.cu);
+  // SB_HIERA_TC=0 keeps the mma.sync kernel for A/B timing
+  if (pool == 1 && hd == 72) {
+    static int hiera_tc = -1;
+    if (hiera_tc < 0) {
+      const char* e = getenv("SB_HIERA_TC");
+      hiera_tc = (e && e[0] == '0') ? 0 : 1;
     }
-    if (win_tc) {
-      const int rc = sb_internal_window_attn_tc(qkv, o, batch, H, W, heads, scale, reinterpret_cast<cudaStream_t>(stream));
+    if (hiera_tc) {
+      const int rc = sb_hiera_attention_tc(qkv, o, batch, H, W, heads, ws, scale, stream);
       if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
   }

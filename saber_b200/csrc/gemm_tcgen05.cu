@@ -58,7 +58,8 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two
+  static constexpr int ACC_STRIDE = BN == 192 ? 256 : BN;  // TMEM column distance between the two accumulator stages
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;         // 128 / 256 / 512: powers of two
 };
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int BAR_BYTES = 1024;           // barriers + tmem pointer, at the (1024-aligned) start of dynamic smem
@@ -598,7 +599,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         sb::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         sb::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE);
         for (int kb = 0; kb < num_kb; ++kb) {
           sb::mbar_wait(&full_bar[stage], phase);
           sb::tc_fence_after();
@@ -667,7 +668,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       set_barrier(set);
       sb::mbar_wait(&tfull_bar[set], acc_phase);
       sb::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(set * BN);
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(set * C::ACC_STRIDE);
       if (EPI == EPI_STD) {
         if (staged)
           epilogue_rows<BN, false, ACT>(p, es, tmem_acc, m_idx, n_idx, q, lane);
@@ -796,8 +797,9 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
     } else {
       const long long m_tiles = (M + BM - 1) / BM;
       long long best = -1;
-      const int cands[3] = {256, 128, 64};
-      for (int i = 0; i < 3; ++i) {
+      // 192 divides Hiera-L's 576 / 1152 / 1728-wide projections exactly (256 wastes a quarter of the last tile)
+      const int cands[4] = {256, 192, 128, 64};
+      for (int i = 0; i < 4; ++i) {
         const int c = cands[i];
         const long long tiles = m_tiles * ((N + c - 1) / c);
         const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
@@ -809,7 +811,7 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
       }
     }
   }
-  SB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "sb_gemm_bf16: bad tile N %d", bn);
+  SB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "sb_gemm_bf16: bad tile N %d", bn);
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, M, N, K, bn, &tmA, &tmB);
   if (rc != SB_OK) return rc;
@@ -821,6 +823,7 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
     default: return launch_gemm<BN_, EPI_STD, 0>(tmA, tmB, p, g_num_sms, stream);  \
   }
   if (bn == 256) { SB_DISPATCH_ACT(256) }
+  if (bn == 192) { SB_DISPATCH_ACT(192) }
   if (bn == 128) { SB_DISPATCH_ACT(128) }
   SB_DISPATCH_ACT(64)
 #undef SB_DISPATCH_ACT

@@ -419,6 +419,21 @@ def window_attention(qkv: torch.Tensor, qkv_bias: Optional[torch.Tensor], batch:
     return out
 
 
+def hiera_attention_tc(qkv: torch.Tensor, batch: int, H: int, W: int, heads: int, ws: int,
+                       scale: Optional[float] = None) -> torch.Tensor:
+    """The tcgen05 Hiera attention (head_dim 72, no q-pooling) called directly; raises for unsupported windows."""
+    _chk_cuda(qkv)
+    assert qkv.dtype == _BF16 and qkv.is_contiguous() and qkv.shape == (batch * H * W, 3 * heads * 72)
+    if scale is None:
+        scale = 1.0 / math.sqrt(72)
+    out = torch.empty((batch * H * W, heads * 72), dtype=_BF16, device=qkv.device)
+    L = _lib.load()
+    _lib.check(L.sb_hiera_attention_tc(qkv.data_ptr(), out.data_ptr(), batch, H, W, heads, ws, scale, _stream()),
+               "sb_hiera_attention_tc")
+    _count()
+    return out
+
+
 def im2col_k7s4(img: torch.Tensor, kp: int) -> torch.Tensor:
     """[B,Cin,S,S] fp32 -> [B*(S/4)^2, kp] bf16 patches for the 7x7 stride-4 pad-3 patch embedding."""
     _chk_cuda(img)
