@@ -111,6 +111,9 @@ int sb_window_attention(const void* qkv, const float* qkv_bias, void* o, int bat
  * (unsupported) for other window shapes. */
 int sb_hiera_attention_tc(const void* qkv, void* out, int batch, int H, int W, int heads, int ws, float scale,
                           void* stream);
+/* Instrumented build (tools/attn_probe.py): prof [num_sms][16] int64 per-CTA clock sums per pipeline role. */
+int sb_hiera_attention_tc_prof(const void* qkv, void* out, int batch, int H, int W, int heads, int ws, float scale,
+                               long long* prof, void* stream);
 
 /* ---- token-major bandwidth kernels of the encoder / decoder ----------------------------------------- */
 int sb_layernorm(const void* in, long long ld_in, int in_f32, void* out, long long ld_out, int out_f32,

@@ -109,6 +109,146 @@ class SAM2VideoPredictor(SAM2Base):
         _, video_res = self._get_orig_video_res_output(state, cons["pred_masks_video_res"])
         return frame_idx, state["obj_ids"], video_res
 
+    @torch.inference_mode()
+    def add_new_points_or_box(self, inference_state, frame_idx, obj_id, points=None, labels=None, clear_old_points=True,
+                              normalize_coords=True, box=None):
+        """sam2_video_predictor.SAM2VideoPredictor.add_new_points_or_box (forwarded by REF saber/adapters/sam2/
+        predictor.py:171-180): a box is two extra points with labels 2, 3 placed before the clicks; coordinates are
+        normalised by the video size and scaled to the model input; a previous prediction on the frame becomes the
+        dense mask prompt (clamped to +-32)."""
+        state = inference_state
+        obj_idx = self._obj_id_to_idx(state, obj_id)
+        point_inputs_per_frame = state["point_inputs_per_obj"][obj_idx]
+        mask_inputs_per_frame = state["mask_inputs_per_obj"][obj_idx]
+        if (points is not None) != (labels is not None):
+            raise ValueError("points and labels must be provided together")
+        if points is None and box is None:
+            raise ValueError("at least one of points or box must be provided as input")
+        if points is None:
+            points = torch.zeros(0, 2, dtype=torch.float32)
+        elif not isinstance(points, torch.Tensor):
+            points = torch.tensor(points, dtype=torch.float32)
+        if labels is None:
+            labels = torch.zeros(0, dtype=torch.int32)
+        elif not isinstance(labels, torch.Tensor):
+            labels = torch.tensor(labels, dtype=torch.int32)
+        if points.dim() == 2:
+            points = points.unsqueeze(0)
+        if labels.dim() == 1:
+            labels = labels.unsqueeze(0)
+        if box is not None:
+            if not clear_old_points:
+                raise ValueError("cannot add box without clearing old points, since box prompt must be provided before "
+                                 "any point prompt (please use clear_old_points=True instead)")
+            if not isinstance(box, torch.Tensor):
+                box = torch.tensor(box, dtype=torch.float32, device=points.device)
+            box_coords = box.reshape(1, 2, 2)
+            box_labels = torch.tensor([2, 3], dtype=torch.int32, device=labels.device).reshape(1, 2)
+            points = torch.cat([box_coords, points], dim=1)
+            labels = torch.cat([box_labels, labels], dim=1)
+        if normalize_coords:
+            points = points / torch.tensor([state["video_width"], state["video_height"]]).to(points.device)
+        points = points * self.image_size
+        points = points.to(state["device"])
+        labels = labels.to(state["device"])
+        old = None if clear_old_points else point_inputs_per_frame.get(frame_idx, None)
+        if old is None:
+            point_inputs = {"point_coords": points, "point_labels": labels}
+        else:
+            point_inputs = {"point_coords": torch.cat([old["point_coords"], points], dim=1),
+                            "point_labels": torch.cat([old["point_labels"], labels], dim=1)}
+        point_inputs_per_frame[frame_idx] = point_inputs
+        mask_inputs_per_frame.pop(frame_idx, None)
+        tracked = state["frames_tracked_per_obj"][obj_idx]
+        is_init_cond_frame = frame_idx not in tracked
+        reverse = False if is_init_cond_frame else tracked[frame_idx]["reverse"]
+        obj_out = state["output_dict_per_obj"][obj_idx]
+        obj_tmp = state["temp_output_dict_per_obj"][obj_idx]
+        is_cond = is_init_cond_frame or self.add_all_frames_to_correct_as_cond
+        key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+        prev_sam_mask_logits = None
+        prev_out = obj_tmp[key].get(frame_idx)
+        if prev_out is None:
+            prev_out = obj_out["cond_frame_outputs"].get(frame_idx)
+            if prev_out is None:
+                prev_out = obj_out["non_cond_frame_outputs"].get(frame_idx)
+        if prev_out is not None and prev_out["pred_masks"] is not None:
+            prev_sam_mask_logits = torch.clamp(prev_out["pred_masks"].to(state["device"]), -32.0, 32.0)
+        current_out, _ = self._run_single_frame_inference(
+            state, obj_out, frame_idx, 1, is_init_cond_frame, point_inputs, None, reverse, run_mem_encoder=False,
+            prev_sam_mask_logits=prev_sam_mask_logits)
+        obj_tmp[key][frame_idx] = current_out
+        cons = self._consolidate_temp_output_across_obj(state, frame_idx, is_cond, consolidate_at_video_res=True)
+        _, video_res = self._get_orig_video_res_output(state, cons["pred_masks_video_res"])
+        return frame_idx, state["obj_ids"], video_res
+
+    @torch.inference_mode()
+    def clear_all_prompts_in_frame(self, inference_state, frame_idx, obj_id, need_output=True):
+        """Remove every input of one object on one frame; a conditioning output of that frame is downgraded to a
+        non-conditioning one (REF saber/adapters/sam2/predictor.py:358-361 forwards here)."""
+        state = inference_state
+        obj_idx = self._obj_id_to_idx(state, obj_id)
+        state["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        state["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        tmp = state["temp_output_dict_per_obj"]
+        tmp[obj_idx]["cond_frame_outputs"].pop(frame_idx, None)
+        tmp[obj_idx]["non_cond_frame_outputs"].pop(frame_idx, None)
+        obj_out = state["output_dict_per_obj"][obj_idx]
+        out = obj_out["cond_frame_outputs"].pop(frame_idx, None)
+        if out is not None:
+            obj_out["non_cond_frame_outputs"][frame_idx] = out
+            state["frames_tracked_per_obj"][obj_idx].pop(frame_idx, None)
+        if not need_output:
+            return None
+        is_cond = any(frame_idx in d["cond_frame_outputs"] for d in tmp.values())
+        cons = self._consolidate_temp_output_across_obj(state, frame_idx, is_cond, consolidate_at_video_res=True)
+        _, video_res = self._get_orig_video_res_output(state, cons["pred_masks_video_res"])
+        return frame_idx, state["obj_ids"], video_res
+
+    @torch.inference_mode()
+    def remove_object(self, inference_state, obj_id, strict=False, need_output=True):
+        """Drop one object from the state and re-index the per-object containers (REF :363-366 forwards here)."""
+        state = inference_state
+        old_idx = state["obj_id_to_idx"].get(obj_id, None)
+        updated_frames = []
+        if old_idx is None:
+            if not strict:
+                return state["obj_ids"], updated_frames
+            raise RuntimeError(f"Cannot remove object id {obj_id} as it doesn't exist. "
+                               f"All existing object ids: {state['obj_ids']}.")
+        if len(state["obj_id_to_idx"]) == 1:
+            self.reset_state(state)
+            return state["obj_ids"], updated_frames
+        input_frames = set(state["point_inputs_per_obj"][old_idx]) | set(state["mask_inputs_per_obj"][old_idx])
+        for frame_idx in input_frames:
+            self.clear_all_prompts_in_frame(state, frame_idx, obj_id, need_output=False)
+        old_obj_ids = state["obj_ids"]
+        old_inds = list(range(len(old_obj_ids)))
+        remain = [k for k in old_inds if k != old_idx]
+        new_obj_ids = [old_obj_ids[k] for k in remain]
+        new_inds = list(range(len(new_obj_ids)))
+        old_to_new = dict(zip(remain, new_inds))
+        state["obj_id_to_idx"] = dict(zip(new_obj_ids, new_inds))
+        state["obj_idx_to_id"] = dict(zip(new_inds, new_obj_ids))
+        state["obj_ids"] = new_obj_ids
+        for name in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj",
+                     "frames_tracked_per_obj"):
+            container = state[name]
+            kept = []
+            for k in old_inds:
+                v = container.pop(k)
+                if k in old_to_new:
+                    kept.append((old_to_new[k], v))
+            container.update(kept)
+        if need_output:
+            tmp = state["temp_output_dict_per_obj"]
+            for frame_idx in input_frames:
+                is_cond = any(frame_idx in d["cond_frame_outputs"] for d in tmp.values())
+                cons = self._consolidate_temp_output_across_obj(state, frame_idx, is_cond, consolidate_at_video_res=True)
+                _, video_res = self._get_orig_video_res_output(state, cons["pred_masks_video_res"])
+                updated_frames.append((frame_idx, video_res))
+        return state["obj_ids"], updated_frames
+
     def _consolidate_temp_output_across_obj(self, state, frame_idx, is_cond, consolidate_at_video_res=False):
         B = self._get_obj_num(state)
         key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"

@@ -4,7 +4,8 @@ B200 kernels — the surface REF saber/adapters/sam2/predictor.py binds:
   ``maskmem_tpos_enc`` (re-assigned, REF :31-32), ``num_maskmem`` (REF :33-34), ``image_size`` (:101), ``device``,
   ``sam_mask_decoder.register_forward_hook`` (hook reads ``output[3]``, REF :278,284),
   ``_get_image_feature(state, frame_idx=, batch_size=)`` (:114,152), ``add_new_mask`` (:164-169),
-  ``propagate_in_video`` -> ``(frame_idx, obj_ids, logits [N,1,Hv,Wv])`` (:196-202), ``reset_state``.
+  ``propagate_in_video`` -> ``(frame_idx, obj_ids, logits [N,1,Hv,Wv])`` (:196-202), ``reset_state``,
+  ``add_new_points_or_box`` (:171-180), ``clear_all_prompts_in_frame`` / ``remove_object`` (:358-366).
   The inference-state dict is the one SABER builds itself (REF :130-150).
 
 B200 design (SURVEY §7 "device-resident batched state machine"): all objects tracked in a frame run as ONE batch
@@ -207,19 +208,7 @@ class SAM2VideoPredictor(SAM2Model):
         key = "cond_frame_outputs" if is_init_cond_frame else "non_cond_frame_outputs"
         st["temp_output_dict_per_obj"][obj_idx][key][frame_idx] = self._use_mask_as_output(st, frame_idx, mi)
         # consolidated video-resolution scores of every object on this frame (upstream's return value)
-        B = self._get_obj_num(st)
-        vh, vw = st["video_height"], st["video_width"]
-        low = torch.full((B, 256, 256), NO_OBJ_SCORE, dtype=_F32, device=self.device)
-        for i in range(B):
-            out = st["temp_output_dict_per_obj"][i][key].get(frame_idx)
-            if out is None:
-                out = st["output_dict_per_obj"][i]["cond_frame_outputs"].get(frame_idx)
-            if out is None:
-                out = st["output_dict_per_obj"][i]["non_cond_frame_outputs"].get(frame_idx)
-            if out is not None:
-                low[i] = out["pred_masks"].view(256, 256)
-        video_res = ops.upsample_bilinear(low, vh, vw).view(B, 1, vh, vw)
-        return frame_idx, st["obj_ids"], video_res
+        return frame_idx, st["obj_ids"], self._consolidated_video_res(st, frame_idx, is_init_cond_frame)
 
     def _use_mask_as_output(self, st, frame_idx, mask_inputs: torch.Tensor) -> Dict[str, Any]:
         """SAM2Base._use_mask_as_output for one object: scores = mask*20-10, low-res = antialiased x1/4, pointer from a
@@ -309,10 +298,10 @@ class SAM2VideoPredictor(SAM2Model):
         sig = (tuple(tp for tp, _, _ in spatial), tuple(td for td, _, _ in ptrs))
         return sig, spatial, ptrs
 
-    def _track_group(self, st, frame_idx, objs: List[int], sig, plans, reverse) -> Dict[int, Dict[str, Any]]:
-        """One tracking step for a batch of objects that share the memory layout `sig`."""
+    def _conditioned_features(self, st, c, objs: List[int], sig, plans) -> torch.Tensor:
+        """Memory attention for a batch of objects that share the memory layout `sig` (SAM2Base._prepare_memory_
+        conditioned_features for a non-initial frame) -> [B*4096, 256] fp32."""
         B = len(objs)
-        c = self._frame(st, frame_idx)
         t_pos_list, t_diff_list = sig
         n_ptr_tok = 4 * len(t_diff_list)
         Nk = NT * len(t_pos_list) + n_ptr_tok
@@ -334,8 +323,13 @@ class SAM2VideoPredictor(SAM2Model):
                 parts.append(self._ptr_key_pos(tuple(t_diff_list), st["num_frames"]))
             self._const_cache[ck] = [torch.cat([p[l] for p in parts], 0).contiguous() for l in range(4)]
         pos_k = self._const_cache[ck]
-        pix = self.mem_attn.forward(c["feat"], memory.view(B * Nk, 64), pos_k, n_ptr_tok, B)  # [B*4096,256]
-        del memory
+        return self.mem_attn.forward(c["feat"], memory.view(B * Nk, 64), pos_k, n_ptr_tok, B)  # [B*4096,256]
+
+    def _track_group(self, st, frame_idx, objs: List[int], sig, plans, reverse) -> Dict[int, Dict[str, Any]]:
+        """One tracking step for a batch of objects that share the memory layout `sig`."""
+        B = len(objs)
+        c = self._frame(st, frame_idx)
+        pix = self._conditioned_features(st, c, objs, sig, plans)
         dec = self.decoder
         coords = torch.zeros((B, 1, 2), dtype=_F32, device=self.device)
         labels = torch.full((B, 1), -1, dtype=_I32, device=self.device)
@@ -402,15 +396,162 @@ class SAM2VideoPredictor(SAM2Model):
                   "output_dict_per_obj", "temp_output_dict_per_obj", "frames_tracked_per_obj"):
             s[k].clear()
 
-    def add_new_points_or_box(self, *a, **k):
-        raise NotImplementedError("saber_b200: point / box prompts of the video predictor are not on SABER's segmenter "
-                                  "path (REF saber/segmenters/* seed with masks only)")
+    # ---- point / box prompts, prompt removal, object removal (forwarded by REF saber/adapters/sam2/predictor.py:171-180,
+    # 358-366; restates sam2_video_predictor.SAM2VideoPredictor.{add_new_points_or_box, clear_all_prompts_in_frame,
+    # remove_object}) --------------------------------------------------------------------------------------------
+    def _consolidated_video_res(self, st, frame_idx, is_cond: bool) -> torch.Tensor:
+        """_consolidate_temp_output_across_obj(consolidate_at_video_res=True) + _get_orig_video_res_output."""
+        key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+        B = self._get_obj_num(st)
+        vh, vw = st["video_height"], st["video_width"]
+        low = torch.full((B, 256, 256), NO_OBJ_SCORE, dtype=_F32, device=self.device)
+        for i in range(B):
+            out = st["temp_output_dict_per_obj"][i][key].get(frame_idx)
+            if out is None:
+                out = st["output_dict_per_obj"][i]["cond_frame_outputs"].get(frame_idx)
+            if out is None:
+                out = st["output_dict_per_obj"][i]["non_cond_frame_outputs"].get(frame_idx)
+            if out is not None:
+                low[i] = out["pred_masks"].view(256, 256)
+        return ops.upsample_bilinear(low, vh, vw).view(B, 1, vh, vw)
 
-    def clear_all_prompts_in_frame(self, *a, **k):
-        raise NotImplementedError("saber_b200: clear_all_prompts_in_frame is not on SABER's segmenter path")
+    @torch.no_grad()
+    def add_new_points_or_box(self, inference_state, frame_idx, obj_id, points=None, labels=None, clear_old_points=True,
+                              normalize_coords=True, box=None):
+        self._require_gpu()
+        st = inference_state
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        point_inputs_per_frame = st["point_inputs_per_obj"][obj_idx]
+        if (points is not None) != (labels is not None):
+            raise ValueError("points and labels must be provided together")
+        if points is None and box is None:
+            raise ValueError("at least one of points or box must be provided as input")
+        pts = torch.zeros(0, 2, dtype=_F32) if points is None else torch.as_tensor(points, dtype=_F32).cpu()
+        lbl = torch.zeros(0, dtype=_I32) if labels is None else torch.as_tensor(labels, dtype=_I32).cpu()
+        if pts.dim() == 2:
+            pts = pts.unsqueeze(0)
+        if lbl.dim() == 1:
+            lbl = lbl.unsqueeze(0)
+        if box is not None:
+            if not clear_old_points:
+                raise ValueError("cannot add box without clearing old points, since box prompt must be provided before "
+                                 "any point prompt (please use clear_old_points=True instead)")
+            bc = torch.as_tensor(box, dtype=_F32).cpu().reshape(1, 2, 2)
+            pts = torch.cat([bc, pts], dim=1)
+            lbl = torch.cat([torch.tensor([[2, 3]], dtype=_I32), lbl], dim=1)
+        if normalize_coords:
+            pts = pts / torch.tensor([st["video_width"], st["video_height"]], dtype=_F32)
+        pts = pts * self.image_size
+        old = None if clear_old_points else point_inputs_per_frame.get(frame_idx)
+        if old is not None:
+            pts = torch.cat([old["point_coords"].cpu(), pts], dim=1)
+            lbl = torch.cat([old["point_labels"].cpu(), lbl], dim=1)
+        point_inputs = {"point_coords": pts.to(self.device).contiguous(), "point_labels": lbl.to(self.device).contiguous()}
+        point_inputs_per_frame[frame_idx] = point_inputs
+        st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        tracked = st["frames_tracked_per_obj"][obj_idx]
+        is_init_cond_frame = frame_idx not in tracked
+        reverse = False if is_init_cond_frame else tracked[frame_idx]["reverse"]
+        obj_out = st["output_dict_per_obj"][obj_idx]
+        obj_tmp = st["temp_output_dict_per_obj"][obj_idx]
+        is_cond = is_init_cond_frame  # add_all_frames_to_correct_as_cond = False
+        key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+        prev = obj_tmp[key].get(frame_idx)
+        if prev is None:
+            prev = obj_out["cond_frame_outputs"].get(frame_idx)
+            if prev is None:
+                prev = obj_out["non_cond_frame_outputs"].get(frame_idx)
+        prev_logits = prev["pred_masks"].view(1, 256, 256) if prev is not None and prev["pred_masks"] is not None else None
+        obj_tmp[key][frame_idx] = self._point_step(st, obj_out, frame_idx, is_init_cond_frame, point_inputs, reverse,
+                                                   prev_logits)
+        return frame_idx, st["obj_ids"], self._consolidated_video_res(st, frame_idx, is_cond)
 
-    def remove_object(self, *a, **k):
-        raise NotImplementedError("saber_b200: remove_object is not on SABER's segmenter path")
+    def _point_step(self, st, obj_out, frame_idx, is_init_cond_frame, point_inputs, reverse, prev_logits):
+        """SAM2Base.track_step for one object with point inputs (run_mem_encoder=False): the frame embedding is
+        `feat + no_mem_embed` on an initial conditioning frame, otherwise conditioned on the object's memory; the
+        previous prediction on the frame (clamped to +-32) is the dense mask prompt; multimask output for <= 1 point."""
+        c = self._frame(st, frame_idx)
+        if is_init_cond_frame:
+            pix = ops.add_cast(c["feat"], self.no_mem_embed_vec, _F32)
+        else:
+            plan = self._memory_plan(obj_out, frame_idx, st["num_frames"], reverse)
+            pix = self._conditioned_features(st, c, [0], plan[0], {0: plan})
+        npts = int(point_inputs["point_labels"].shape[1])
+        multimask = 0 <= npts <= 1  # multimask_min_pt_num = 0, multimask_max_pt_num = 1 (SAM2.1 configs)
+        dec = self.decoder
+        tokens = dec.prompt_tokens(point_inputs["point_coords"], point_inputs["point_labels"])
+        out = dec.forward(pix, c["s0"], c["s1"], tokens, prev_logits, multimask_output=multimask,
+                          mask_clamp=(32.0 if prev_logits is not None else 0.0))
+        obj = out["obj"].reshape(-1).contiguous()
+        if multimask:
+            self.sam_mask_decoder.fire(out["masks"][:, 1:4], out["ious"][:, 1:4], out["hs"][:, 3:6], out["obj"])
+        else:
+            self.sam_mask_decoder.fire(out["masks"][:, 0:1], out["ious"][:, 0:1], out["hs"][:, 2:3], out["obj"])
+        low, tok, _ = ops.track_select(out["masks"], out["ious"], obj, out["hs"].contiguous(), out.get("sel_idx"), multimask)
+        ptr = self._obj_ptr(tok, obj)
+        pred = ops.fill_holes(low, self.fill_hole_area) if self.fill_hole_area > 0 else low
+        return {"maskmem_features": None, "maskmem_pos_enc": None, "pred_masks": pred.view(1, 1, 256, 256),
+                "obj_ptr": ptr, "object_score_logits": obj.view(1, 1)}
+
+    @torch.no_grad()
+    def clear_all_prompts_in_frame(self, inference_state, frame_idx, obj_id, need_output=True):
+        st = inference_state
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        st["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        tmp = st["temp_output_dict_per_obj"]
+        tmp[obj_idx]["cond_frame_outputs"].pop(frame_idx, None)
+        tmp[obj_idx]["non_cond_frame_outputs"].pop(frame_idx, None)
+        obj_out = st["output_dict_per_obj"][obj_idx]
+        out = obj_out["cond_frame_outputs"].pop(frame_idx, None)
+        if out is not None:  # no inputs left on the frame: its output is downgraded to a non-conditioning one
+            obj_out["non_cond_frame_outputs"][frame_idx] = out
+            st["frames_tracked_per_obj"][obj_idx].pop(frame_idx, None)
+        if not need_output:
+            return None
+        is_cond = any(frame_idx in d["cond_frame_outputs"] for d in tmp.values())
+        return frame_idx, st["obj_ids"], self._consolidated_video_res(st, frame_idx, is_cond)
+
+    @torch.no_grad()
+    def remove_object(self, inference_state, obj_id, strict=False, need_output=True):
+        st = inference_state
+        old_idx = st["obj_id_to_idx"].get(obj_id, None)
+        updated_frames = []
+        if old_idx is None:
+            if not strict:
+                return st["obj_ids"], updated_frames
+            raise RuntimeError(f"Cannot remove object id {obj_id} as it doesn't exist. "
+                               f"All existing object ids: {st['obj_ids']}.")
+        if len(st["obj_id_to_idx"]) == 1:
+            self.reset_state(st)
+            return st["obj_ids"], updated_frames
+        input_frames = set(st["point_inputs_per_obj"][old_idx]) | set(st["mask_inputs_per_obj"][old_idx])
+        for frame_idx in input_frames:
+            self.clear_all_prompts_in_frame(st, frame_idx, obj_id, need_output=False)
+        old_obj_ids = st["obj_ids"]
+        old_inds = list(range(len(old_obj_ids)))
+        remain = [k for k in old_inds if k != old_idx]
+        new_obj_ids = [old_obj_ids[k] for k in remain]
+        new_inds = list(range(len(new_obj_ids)))
+        old_to_new = dict(zip(remain, new_inds))
+        st["obj_id_to_idx"] = dict(zip(new_obj_ids, new_inds))
+        st["obj_idx_to_id"] = dict(zip(new_inds, new_obj_ids))
+        st["obj_ids"] = new_obj_ids
+        for name in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj",
+                     "frames_tracked_per_obj"):
+            container = st[name]
+            kept = []
+            for k in old_inds:
+                v = container.pop(k)
+                if k in old_to_new:
+                    kept.append((old_to_new[k], v))
+            container.update(kept)
+        if need_output:
+            tmp = st["temp_output_dict_per_obj"]
+            for frame_idx in input_frames:
+                is_cond = any(frame_idx in d["cond_frame_outputs"] for d in tmp.values())
+                updated_frames.append((frame_idx, self._consolidated_video_res(st, frame_idx, is_cond)))
+        return st["obj_ids"], updated_frames
 
 
 def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_overrides_extra=None,
