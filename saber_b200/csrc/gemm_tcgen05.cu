@@ -19,14 +19,19 @@
 // drains stage s, so two tile epilogues (the bottleneck of the small-K, HBM-bound GEMMs of this model) run
 // concurrently and overlap the main loop of the following tiles. Inside an epilogue the TMEM load and the residual
 // loads of column chunk c+1 are issued before chunk c is processed.
+// The two up-scaling epilogues (UP1 / UP2: 128 resp. 32 GELUs + 128 MACs per accumulator row and d-group) are bound by
+// the issue rate of the epilogue warps (round 1: 34 % issue utilisation on 8 warps), so they run with SIXTEEN epilogue
+// warps (640 threads): every tile is drained by four sets at once, set q taking the q-th of the four d-groups of the
+// transposed convolution (64 resp. 32 accumulator columns), still double-buffered in TMEM against the main loop.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int CH = 16;  // epilogue column chunk
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 384;   // 8 epilogue warps; the EW = 16 variants run 640 threads
 
 enum { EPI_STD = 0, EPI_LN = 1, EPI_UP1 = 2, EPI_UP2 = 3 };
 
@@ -383,7 +388,7 @@ __device__ __forceinline__ void epilogue_scalar(const GemmParams& p, uint32_t tm
 
 // ---- UP1 epilogue: N = 4 groups x 64 channels; row m = (b, y, x) of the gh x gw token grid ---------------
 __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
-                                             int q, int lane) {
+                                             int q, int lane, int d_begin, int d_end) {
   const int row = m_idx + q * 32 + lane;
   const bool row_ok = row < p.M;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
@@ -391,7 +396,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
   const long long b = row / (p.gw * p.gh);
   const uint8_t* skip = reinterpret_cast<const uint8_t*>(p.skip);
 #pragma unroll 1
-  for (int d = 0; d < 4; ++d) {
+  for (int d = d_begin; d < d_end; ++d) {
     const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
     const long long pix = static_cast<long long>(oy) * (2 * p.gw) + ox;
     // skip row: 64 fp32 = 256 bytes = 16 x 16 B ; output row: 64 bf16 = 128 bytes = 8 x 16 B
@@ -458,7 +463,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
 
 // ---- UP2 epilogue: N = 4 groups x 32 channels -> 4 mask logits per output pixel --------------------------
 __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
-                                             int q, int lane) {
+                                             int q, int lane, int d_begin, int d_end) {
   const int row = m_idx + q * 32 + lane;
   const bool row_ok = row < p.M;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
@@ -473,32 +478,29 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
     const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
     return row_ok ? static_cast<int>((b * p.skip_bstride + (static_cast<long long>(oy) * W2 + ox) * 32) / 4) : -1;
   };
-  gather_async<128>(es.res_stg[0], skip, skip_off(0), 128, lane);
+  gather_async<128>(es.res_stg[d_begin & 1], skip, skip_off(d_begin), 128, lane);
 #pragma unroll 1
-  for (int d = 0; d < 4; ++d) {
+  for (int d = d_begin; d < d_end; ++d) {
     const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
     uint32_t v[32];
     sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 32), v);
     sb::tmem_ld_32x16(taddr + static_cast<uint32_t>(d * 32 + CH), v + CH);
     cp_async_wait_all();
     __syncwarp();
-    uint4 sk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sk[j] = lds128(es.res_stg[d & 1] + swz<128>(lane, j));
-    __syncwarp();
-    if (d + 1 < 4) gather_async<128>(es.res_stg[(d + 1) & 1], skip, skip_off(d + 1), 128, lane);
+    if (d + 1 < d_end) gather_async<128>(es.res_stg[(d + 1) & 1], skip, skip_off(d + 1), 128, lane);
     sb::tmem_ld_wait();
     // packed fp32 pairs throughout: the epilogue is issue-bound (128 GELUs + 512 MACs per row on 8 warps per SM)
     float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 32 + 4 * j);
+      const uint4 sk = lds128(es.res_stg[d & 1] + swz<128>(lane, j));  // skip tile of d (the tile of d + 1 is the other one)
       const float2 g01 = sb::gelu_erf2(sb::add2(
           sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), make_float2(bb.x, bb.y)),
-          make_float2(__uint_as_float(sk[j].x), __uint_as_float(sk[j].y))));
+          make_float2(__uint_as_float(sk.x), __uint_as_float(sk.y))));
       const float2 g23 = sb::gelu_erf2(sb::add2(
           sb::add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(bb.z, bb.w)),
-          make_float2(__uint_as_float(sk[j].z), __uint_as_float(sk[j].w))));
+          make_float2(__uint_as_float(sk.z), __uint_as_float(sk.w))));
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const float4 h = hy[m * 8 + j];  // warp-uniform shared-memory address: broadcast
@@ -514,10 +516,11 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
   }
 }
 
-template <int BN, int EPI, int ACT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int BN, int EPI, int ACT, int EW>
+__global__ void __launch_bounds__((4 + EW) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p, const int stages, const int res_bufs, const int staged) {
+  static_assert(EW == 8 || (EW == 16 && (EPI == EPI_UP1 || EPI == EPI_UP2)), "16 epilogue warps: up-scaling epilogues only");
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -553,7 +556,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       sb::mbar_init(&tfull_bar[i], 1);
-      sb::mbar_init(&tempty_bar[i], 4);  // one arrive per warp of the epilogue set that drains this stage
+      sb::mbar_init(&tempty_bar[i], EW == 16 ? 16 : 4);  // one arrive per warp that drains this stage
     }
     sb::fence_barrier_init();
   }
@@ -631,6 +634,50 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===================== epilogue: set s = (warp - 4) / 4 drains accumulator stage s =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int set = (warp - 4) >> 2;
+    if (EW == 16) {
+      // ---- four sets drain every tile together: set `set` takes d-group `set` of the transposed convolution
+      EpiSmem es;
+      {
+        // UP1: one 4 KB tile per warp (the output staging re-uses the skip staging: the skip values are in registers
+        // before the normalised row is written); UP2: two skip tiles (this tile's and, prefetched, the next tile's are
+        // not needed: one d-group per warp and tile -> a single tile)
+        uint8_t* mine = sEpi + (warp - 4) * STG_BYTES;
+        es.out_stg = sb::smem_u32(mine);
+        es.res_stg[0] = es.res_stg[1] = sb::smem_u32(mine);
+        es.nres = 1;
+      }
+      const int tid512 = (warp - 4) * 32 + lane;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t acc_phase = static_cast<uint32_t>((it >> 1) & 1);
+        const int m_idx = (tile / n_tiles) * BM;
+        float* vec = sVec + st * VEC_FLOATS;
+        es.vec = vec;
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp is done with the previous tiles' vectors
+        if (EPI == EPI_UP1) {
+          for (int c = tid512 * 4; c < 256; c += 2048) *reinterpret_cast<float4*>(vec + c) = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          if (tid512 < 16) *reinterpret_cast<float4*>(vec + 256 + tid512 * 4) = __ldg(reinterpret_cast<const float4*>(p.gamma + tid512 * 4));
+          else if (tid512 < 32) *reinterpret_cast<float4*>(vec + 512 + (tid512 - 16) * 4) = __ldg(reinterpret_cast<const float4*>(p.beta + (tid512 - 16) * 4));
+        } else {
+          if (tid512 < 32) *reinterpret_cast<float4*>(vec + tid512 * 4) = __ldg(reinterpret_cast<const float4*>(p.bias + tid512 * 4));
+          else if (tid512 < 64)
+            *reinterpret_cast<float4*>(vec + 256 + (tid512 - 32) * 4) =
+                __ldg(reinterpret_cast<const float4*>(p.hyper + static_cast<long long>(m_idx / (p.gh * p.gw)) * 128 + (tid512 - 32) * 4));
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        sb::mbar_wait(&tfull_bar[st], acc_phase);
+        sb::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(st * C::ACC_STRIDE);
+        if (EPI == EPI_UP1)
+          epilogue_up1(p, es, tmem_acc, m_idx, q, lane, set, set + 1);
+        else
+          epilogue_up2(p, es, tmem_acc, m_idx, q, lane, set, set + 1);
+        sb::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sb::mbar_arrive(&tempty_bar[st]);
+      }
+    } else {
     EpiSmem es;
     {
       uint8_t* mine = sEpi + (warp - 4) * (1 + res_bufs) * STG_BYTES;
@@ -677,14 +724,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       } else if (EPI == EPI_LN) {
         epilogue_rows<BN, true, 0>(p, es, tmem_acc, m_idx, 0, q, lane);
       } else if (EPI == EPI_UP1) {
-        epilogue_up1(p, es, tmem_acc, m_idx, q, lane);
+        epilogue_up1(p, es, tmem_acc, m_idx, q, lane, 0, 4);
       } else {
-        epilogue_up2(p, es, tmem_acc, m_idx, q, lane);
+        epilogue_up2(p, es, tmem_acc, m_idx, q, lane, 0, 4);
       }
       sb::tc_fence_before();
       __syncwarp();
       if (lane == 0) sb::mbar_arrive(&tempty_bar[set]);
       acc_phase ^= 1;
+    }
     }
   }
 
@@ -696,13 +744,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BN, int EPI, int ACT = 0>
+template <int BN, int EPI, int ACT = 0, int EW = 8>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                 cudaStream_t stream) {
   using C = Cfg<BN>;
   static SbPerDeviceOnce attr_once;
   if (attr_once.need()) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, ACT>,
+    SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, ACT, EW>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     attr_once.mark();
   }
@@ -716,26 +764,25 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
              (static_cast<long long>(p.M) * ob < (1ll << 35)) && (!p.res || static_cast<long long>(p.M) * rb < (1ll << 35));
   }
   const bool needs_res = (EPI == EPI_UP1 || EPI == EPI_UP2) || (p.res != nullptr);
-  int res_bufs = needs_res ? 2 : 0;
+  int res_bufs = EW == 16 ? 0 : (needs_res ? 2 : 0);  // 16 epilogue warps: one 4 KB staging tile per warp
   const int num_kb = (p.K + BK - 1) / BK;
   auto stages_for = [&](int rbufs) {
-    const int epi = NEPI_WARPS * (1 + rbufs) * STG_BYTES + VEC_BYTES;
+    const int epi = EW * (1 + rbufs) * STG_BYTES + VEC_BYTES;
     return (SMEM_MAX - 1024 - BAR_BYTES - epi) / C::STAGE_BYTES;
   };
   int stages = stages_for(res_bufs);
-  if (needs_res && stages < 3 && EPI != EPI_UP2) {  // BN = 256: trade the second residual buffer for a pipeline stage
+  if (EW == 8 && needs_res && stages < 3 && EPI != EPI_UP2) {  // BN = 256: trade the second residual buffer for a pipeline stage
     res_bufs = 1;
     stages = stages_for(res_bufs);
   }
   if (stages > C::MAX_STAGES) stages = C::MAX_STAGES;
   if (stages > num_kb + 2) stages = num_kb + 2 > 2 ? num_kb + 2 : 2;
-  const int smem_bytes =
-      1024 + BAR_BYTES + stages * C::STAGE_BYTES + VEC_BYTES + NEPI_WARPS * (1 + res_bufs) * STG_BYTES;
+  const int smem_bytes = 1024 + BAR_BYTES + stages * C::STAGE_BYTES + VEC_BYTES + EW * (1 + res_bufs) * STG_BYTES;
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI, ACT><<<grid, NTHREADS, smem_bytes, stream>>>(tmA, tmB, p, stages, res_bufs, staged);
+  gemm_bf16_tcgen05_kernel<BN, EPI, ACT, EW><<<grid, (4 + EW) * 32, smem_bytes, stream>>>(tmA, tmB, p, stages, res_bufs, staged);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
@@ -797,10 +844,13 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
     } else {
       const long long m_tiles = (M + BM - 1) / BM;
       long long best = -1;
-      // 192 divides Hiera-L's 576 / 1152 / 1728-wide projections exactly (256 wastes a quarter of the last tile)
+      // 192 divides Hiera-L's 576 / 1152-wide MLP outputs exactly (256 wastes a quarter of the last tile). Measured
+      // (profiles/r02d_encoder_probe.log vs r01zc): a win for the main-loop-bound K >= 1152 shapes (fc2: 605 -> 754
+      // TFLOP/s), a loss for the epilogue-bound K <= 576 ones (qkv: 935 -> 876), so it is only a candidate for large K.
       const int cands[4] = {256, 192, 128, 64};
       for (int i = 0; i < 4; ++i) {
         const int c = cands[i];
+        if (c == 192 && K < 1152) continue;
         const long long tiles = m_tiles * ((N + c - 1) / c);
         const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
         const long long cost = waves * (c + 24);  // +24: fixed per-tile overhead proxy
@@ -892,6 +942,12 @@ extern "C" int sb_gemm_upscale1(const void* A, long long lda, const void* W, lon
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, p.M, 256, 256, 256, &tmA, &tmB);
   if (rc != SB_OK) return rc;
+  static int wide = -1;  // SB_UP_WARPS=8 keeps the 8-warp epilogue for A/B timing
+  if (wide < 0) {
+    const char* e = getenv("SB_UP_WARPS");
+    wide = (e && atoi(e) == 8) ? 0 : 1;
+  }
+  if (wide) return launch_gemm<256, EPI_UP1, 0, 16>(tmA, tmB, p, g_num_sms, stream);
   return launch_gemm<256, EPI_UP1>(tmA, tmB, p, g_num_sms, stream);
 }
 
@@ -919,5 +975,11 @@ extern "C" int sb_gemm_upscale2(const void* A, long long lda, const void* W, lon
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, p.M, 128, 64, 128, &tmA, &tmB);
   if (rc != SB_OK) return rc;
+  static int wide = -1;
+  if (wide < 0) {
+    const char* e = getenv("SB_UP_WARPS");
+    wide = (e && atoi(e) == 8) ? 0 : 1;
+  }
+  if (wide) return launch_gemm<128, EPI_UP2, 0, 16>(tmA, tmB, p, g_num_sms, stream);
   return launch_gemm<128, EPI_UP2>(tmA, tmB, p, g_num_sms, stream);
 }

@@ -99,5 +99,35 @@ class propagationSegmenter(saber3D):
             np.maximum(final_masks, masks3d, out=final_masks)
         return utils.separate_masks(final_masks, device=self.device)
 
+    @torch.inference_mode()
     def multiclass_segment(self, volume):
-        raise NotImplementedError("saber_b200: multiclass_segment needs the expert classifier (SURVEY §8a R15/R16)")
+        """REF :121-161, quirks included: the seed image is ``prepare``d here and again inside the adapter,
+        and ``segment_image_2d`` is called with a ``target_class`` keyword that ``SAM2Adapter.segment_image_2d`` does
+        not take (REF adapters/sam2/predictor.py:49-54) — with the SAM2 adapter the call raises TypeError exactly as
+        the reference does; adapters that accept the keyword run the loop below. Every voxel keeps the class of the
+        most confident propagated object."""
+        from ..utils import preprocessing
+        final_masks = np.zeros(volume.shape, dtype=np.uint16)
+        max_confidence = np.zeros(volume.shape, dtype=np.float32)
+        for ii in range(2, volume.shape[0], self.ini_depth):
+            im = preprocessing.prepare(volume[ii], to_rgb=True)
+            raw_masks = self.adapter.segment_image_2d(im, target_class=self.target_class)
+            raw_masks = [m for m in raw_masks if m["area"] >= self.min_mask_area]
+            if len(raw_masks) == 0:
+                continue
+            mask_arrays = np.array([m["segmentation"].astype(np.uint8) for m in raw_masks])
+            predictions = self.classifier.batch_predict(im[:, :, 0], mask_arrays, self.batchsize)
+            predicted_classes = np.argmax(predictions, axis=1)
+            valid = predicted_classes > 0
+            if not np.any(valid):
+                continue
+            mask_list = [raw_masks[i]["segmentation"] for i, ok in enumerate(valid) if ok]
+            masks3d = self.segment_3d(volume, mask_list, ann_frame_idx=ii)
+            for idx, (probs, class_id) in enumerate(zip(predictions[valid], predicted_classes[valid])):
+                region = masks3d == (idx + 1)
+                if np.any(region):
+                    confidence = probs[class_id]
+                    update = region & (confidence > max_confidence)
+                    final_masks[update] = class_id
+                    max_confidence[update] = confidence
+        return final_masks
