@@ -209,7 +209,8 @@ def run_b200(args):
     if args.thresholds == "open":
         amg_kw.update(pred_iou_thresh=0.3, stability_score_thresh=0.0)
     seg = propagationSegmenter(deviceID=local, cfg=SAM2AdapterConfig(cfg=sam_cfg, amg_cfg=cfgAMG(**amg_kw),
-                                                                    min_mask_area=100), min_mask_area=100)
+                                                                    min_mask_area=100, allow_random_init=True),
+                               min_mask_area=100)  # random-init weights of the named architecture (BASELINE: no checkpoints)
     if os.environ.get("SB_NO_GRAPH"):
         seg.adapter._amg().base_generator.use_cuda_graph = False
     S = args.slices_per_step

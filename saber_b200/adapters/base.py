@@ -49,7 +49,10 @@ class SAM2AdapterConfig(BaseModel):
     amg_cfg: Optional[Any] = None
     min_mask_area: int = 50
     classifier: Optional[Any] = None
-    seed: int = 0  # random-init seed used when no checkpoint file is given (no network here)
+    # not in the reference: without a checkpoint file the adapter raises unless random initialisation (seed `seed`) of the
+    # named architecture is requested explicitly (synthetic benchmarks / parity tests; saber_b200.pretrained_weights)
+    allow_random_init: bool = False
+    seed: int = 0
 
     @model_validator(mode="after")
     def _derive_from_classifier(self) -> "SAM2AdapterConfig":

@@ -94,11 +94,13 @@ class FilteredSAM2MaskGenerator:
 
 
 def build_amg(amg_params: Dict[str, Any], min_mask_area: int, device="cuda", checkpoint: Optional[str] = None,
-              seed: int = 0, model=None):
-    """REF saber/adapters/sam2/automask.py:49-86: build_sam2(apply_postprocessing=True) + AMG + area filter."""
+              seed: int = 0, model=None, allow_random_init: bool = False):
+    """REF saber/adapters/sam2/automask.py:49-86: build_sam2(apply_postprocessing=True) + AMG + area filter. The
+    checkpoint is resolved as the reference does (pretrained_weights.get_sam2_checkpoint); a missing file raises unless
+    random initialisation was allowed explicitly."""
     if model is None:
         model = build_sam2(_CFG_TO_ARCH[amg_params["sam2_cfg"]], checkpoint, device=device,
-                           apply_postprocessing=True, seed=seed)
+                           apply_postprocessing=True, seed=seed, allow_random_init=allow_random_init)
         model.eval()
     gen = SAM2AutomaticMaskGenerator(
         model=model, points_per_side=amg_params["npoints"], points_per_batch=amg_params["points_per_batch"],
@@ -131,7 +133,8 @@ class SAM2Adapter(BaseAdapter):
             else:
                 amg_dict = cfgAMG(sam2_cfg=self._config.cfg).dict()
             self._mask_generator = build_amg(amg_dict, self._config.min_mask_area, device=self.device,
-                                             checkpoint=self._config.checkpoint, seed=self._config.seed)
+                                             checkpoint=self._config.checkpoint, seed=self._config.seed,
+                                             allow_random_init=getattr(self._config, "allow_random_init", False))
         return self._mask_generator
 
     @torch.inference_mode()
@@ -158,7 +161,8 @@ class SAM2Adapter(BaseAdapter):
         if self.predictor is None:
             from ..sam2.sam2_video_predictor import build_sam2_video_predictor
             p = build_sam2_video_predictor(_CFG_TO_ARCH[self._config.cfg], self._config.checkpoint, device=self.device,
-                                           vos_optimized=False, seed=self._config.seed)
+                                           vos_optimized=False, seed=self._config.seed,
+                                           allow_random_init=getattr(self._config, "allow_random_init", False))
             maskmem = p.maskmem_tpos_enc[:self._config.num_maskmem]
             p.maskmem_tpos_enc = torch.nn.Parameter(maskmem, requires_grad=False)
             p.num_maskmem = self._config.num_maskmem

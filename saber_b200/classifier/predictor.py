@@ -38,7 +38,12 @@ class SAM2Classifier:
     (``projection.{0,1,2,4,5,6,9,10,11}.*``, ``classifier.{0,1,2,4}.*``)."""
 
     def __init__(self, num_classes: int, backbone_type: str = "large", hidden_dims: int = 256, fuse_features: bool = False,
-                 deviceID: int = 0, head_sd: Optional[Dict[str, torch.Tensor]] = None, sam_model=None, seed: int = 0):
+                 deviceID: int = 0, head_sd: Optional[Dict[str, torch.Tensor]] = None, sam_model=None, seed: int = 0,
+                 sam2_checkpoint: Optional[str] = None, allow_random_init: bool = False):
+        """The classifier checkpoint only carries ``projection.*`` / ``classifier.*``; the frozen backbone comes from
+        the pretrained SAM2.1 checkpoint (REF SAM2.py:27-51 resolves it with pretrained_weights.get_sam2_checkpoint):
+        ``sam2_checkpoint`` or the resolver of saber_b200.pretrained_weights; a missing file raises (a trained head on
+        a random backbone would classify noise) unless ``allow_random_init`` is set (synthetic parity tests)."""
         if fuse_features:
             raise NotImplementedError("fuse_features=True is commented out in the reference's forward (REF SAM2.py:154-159)")
         self.name = self.__class__.__name__
@@ -46,8 +51,8 @@ class SAM2Classifier:
         self.num_classes = num_classes
         self.device = torch.device(f"cuda:{deviceID}")
         if sam_model is None:
-            sam_model = build_sam2(_CFG_TO_ARCH.get(backbone_type, backbone_type), None, device=self.device,
-                                   apply_postprocessing=True, seed=seed)
+            sam_model = build_sam2(_CFG_TO_ARCH.get(backbone_type, backbone_type), sam2_checkpoint, device=self.device,
+                                   apply_postprocessing=True, seed=seed, allow_random_init=allow_random_init)
         self.backbone = SAM2ImagePredictor(sam_model)
         if head_sd is None:
             raise ValueError("saber_b200 SAM2Classifier needs the trained head weights (head_sd)")
@@ -115,9 +120,12 @@ class SAM2Classifier:
 
 class Predictor:
     def __init__(self, model_config=None, model_weights=None, min_area: int = 250, deviceID: int = 0, model=None,
-                 num_classes: Optional[int] = None):
+                 num_classes: Optional[int] = None, sam2_checkpoint: Optional[str] = None,
+                 allow_random_init: bool = False):
         """Reference signature ``Predictor(model_config.yaml, model_weights.pth, deviceID=)``; alternatively pass a built
-        ``model`` (and ``num_classes``) directly."""
+        ``model`` (and ``num_classes``) directly. As in the reference the backbone is ALWAYS hiera-large:
+        ``get_classifier_model('SAM2', ...)`` drops ``model_size`` (REF classifier/models/common.py:15-17, SAM2.py:27), so
+        the head was trained on large embeddings whatever ``amg_params.sam2_cfg`` says."""
         self.min_area = min_area
         self.device = torch.device(f"cuda:{deviceID}")
         if model is None:
@@ -126,8 +134,8 @@ class Predictor:
                 self.config = yaml.safe_load(f)
             ck = torch.load(model_weights, map_location="cpu", weights_only=True)
             sd = ck["model"] if isinstance(ck, dict) and "model" in ck else ck
-            model = SAM2Classifier(self.config["model"]["num_classes"], self.config["amg_params"]["sam2_cfg"],
-                                   deviceID=deviceID, head_sd=sd)
+            model = SAM2Classifier(self.config["model"]["num_classes"], "large", deviceID=deviceID, head_sd=sd,
+                                   sam2_checkpoint=sam2_checkpoint, allow_random_init=allow_random_init)
         else:
             self.config = {"model": {"num_classes": num_classes if num_classes is not None else model.num_classes}}
         self.model = model
@@ -197,7 +205,8 @@ class Predictor:
         return out
 
 
-def get_predictor(model_weights, model_config, deviceID: int = 0):
+def get_predictor(model_weights, model_config, deviceID: int = 0, sam2_checkpoint: Optional[str] = None,
+                  allow_random_init: bool = False):
     """REF saber/classifier/models/common.py:24-50."""
     if model_weights is None or model_config is None:
         return None
@@ -205,4 +214,5 @@ def get_predictor(model_weights, model_config, deviceID: int = 0):
         raise FileNotFoundError(f"Model weights file {model_weights} does not exist.")
     if not os.path.exists(model_config):
         raise FileNotFoundError(f"Model config file {model_config} does not exist.")
-    return Predictor(model_config, model_weights, deviceID=deviceID)
+    return Predictor(model_config, model_weights, deviceID=deviceID, sam2_checkpoint=sam2_checkpoint,
+                     allow_random_init=allow_random_init)

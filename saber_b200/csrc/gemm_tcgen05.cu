@@ -19,10 +19,10 @@
 // drains stage s, so two tile epilogues (the bottleneck of the small-K, HBM-bound GEMMs of this model) run
 // concurrently and overlap the main loop of the following tiles. Inside an epilogue the TMEM load and the residual
 // loads of column chunk c+1 are issued before chunk c is processed.
-// The two up-scaling epilogues (UP1 / UP2: 128 resp. 32 GELUs + 128 MACs per accumulator row and d-group) are bound by
-// the issue rate of the epilogue warps (round 1: 34 % issue utilisation on 8 warps), so they run with SIXTEEN epilogue
-// warps (640 threads): every tile is drained by four sets at once, set q taking the q-th of the four d-groups of the
-// transposed convolution (64 resp. 32 accumulator columns), still double-buffered in TMEM against the main loop.
+// An optional variant of the two up-scaling epilogues (UP1 / UP2) runs SIXTEEN epilogue warps (640 threads): every tile
+// is drained by four sets at once, set q taking the q-th of the four d-groups of the transposed convolution (64 resp.
+// 32 accumulator columns). It was built on the hypothesis that 8 warps cannot fill the issue slots; measured, it is 10 %
+// slower (same instruction count, more barriers), so it is opt-in (SB_UP_WARPS=16) and kept for A/B measurements.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -116,6 +116,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// staged per-column vectors: float index -> float4 / float2 (warp-uniform address: one broadcast wavefront)
+__device__ __forceinline__ float4 ldsf4(uint32_t base, int fidx) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + fidx * 4));
+  return v;
+}
+__device__ __forceinline__ float2 ldsf2(uint32_t base, int fidx) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(base + fidx * 4));
+  return v;
+}
 
 // Asynchronous cooperative gather of 32 rows x `valid` bytes (valid <= RB, multiple of 16) into a staging tile.
 // Lane r owns row r: its source is gbase + off16 * 16 bytes (off16 < 0 = row not loaded).
@@ -151,7 +162,9 @@ struct EpiSmem {
   uint32_t out_stg;     // shared-space address of this warp's output staging tile
   uint32_t res_stg[2];  // residual / skip staging tiles (res_stg[1] == res_stg[0] when single-buffered)
   int nres;             // number of distinct residual staging tiles (0, 1 or 2)
-  const float* vec;     // this set's staged vectors: [0,256) bias, [256,512) gamma / hyper, [512,768) beta
+  uint32_t vec;         // shared-space address of this set's staged vectors: [0,256) bias, [256,512) gamma / hyper,
+                        // [512,768) beta. Read with ld.shared (a generic-pointer dereference compiles to LD.E: the
+                        // generic-address path, reported by ncu as long-scoreboard stalls in every epilogue)
 };
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4 r, float* f) {
@@ -266,7 +279,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
         const float2 al2 = sb::splat2(p.alpha);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 b = *reinterpret_cast<const float4*>(es.vec + (c0 - n_idx) + 4 * j);  // staged bias (LDS broadcast)
+          const float4 b = ldsf4(es.vec, (c0 - n_idx) + 4 * j);  // staged bias (LDS broadcast)
           const float2 v01 = make_float2(__uint_as_float(v[h][4 * j + 0]), __uint_as_float(v[h][4 * j + 1]));
           const float2 v23 = make_float2(__uint_as_float(v[h][4 * j + 2]), __uint_as_float(v[h][4 * j + 3]));
           float2 r01, r23;
@@ -314,8 +327,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const EpiSmem
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 ga = *reinterpret_cast<const float4*>(es.vec + 256 + c0 + 4 * j);
-            const float4 be = *reinterpret_cast<const float4*>(es.vec + 512 + c0 + 4 * j);
+            const float4 ga = ldsf4(es.vec, 256 + c0 + 4 * j);
+            const float4 be = ldsf4(es.vec, 512 + c0 + 4 * j);
             const float2 nm2 = sb::splat2(-mean), rs2 = sb::splat2(rstd);
             const float2 o01 = sb::fma2(sb::add2(make_float2(f[4 * j + 0], f[4 * j + 1]), nm2),
                                         sb::mul2(rs2, make_float2(ga.x, ga.y)), make_float2(be.x, be.y));
@@ -416,7 +429,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint4 sk = lds128(es.res_stg[0] + swz<128>(lane, j));
-        const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 64 + h * 32 + 4 * j);
+        const float4 bb = ldsf4(es.vec, d * 64 + h * 32 + 4 * j);
         const int e = h * 32 + 4 * j;
         const float2 f01 = sb::add2(
             sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), make_float2(bb.x, bb.y)),
@@ -447,8 +460,8 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
       float2 g[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 ga = *reinterpret_cast<const float2*>(es.vec + 256 + 8 * j + 2 * e);
-        const float2 be = *reinterpret_cast<const float2*>(es.vec + 512 + 8 * j + 2 * e);
+        const float2 ga = ldsf2(es.vec, 256 + 8 * j + 2 * e);
+        const float2 be = ldsf2(es.vec, 512 + 8 * j + 2 * e);
         const float2 dd = sb::add2(make_float2(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]), nmean);
         g[e] = sb::gelu_erf2(sb::fma2(dd, sb::mul2(rs2, ga), be));
       }
@@ -463,7 +476,7 @@ __device__ __forceinline__ void epilogue_up1(const GemmParams& p, const EpiSmem&
 
 // ---- UP2 epilogue: N = 4 groups x 32 channels -> 4 mask logits per output pixel --------------------------
 __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem& es, uint32_t tmem_acc, int m_idx,
-                                             int q, int lane, int d_begin, int d_end) {
+                                             int q, int lane, int d_begin, int d_end, int hy_off = 256) {
   const int row = m_idx + q * 32 + lane;
   const bool row_ok = row < p.M;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
@@ -471,7 +484,7 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
   const long long b = row / (p.gw * p.gh);
   const int H2 = 2 * p.gh, W2 = 2 * p.gw;
   float* masks = reinterpret_cast<float*>(p.out);
-  const float4* hy = reinterpret_cast<const float4*>(es.vec + 256);  // this tile's prompt: staged hyper-network vectors
+  const uint32_t hy = es.vec + hy_off * 4;  // this tile's prompt: staged hyper-network vectors
   const uint8_t* skip = reinterpret_cast<const uint8_t*>(p.skip);
   // skip row of (d): 32 fp32 = 128 bytes
   auto skip_off = [&](int d) -> int {
@@ -493,7 +506,7 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
     float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 bb = *reinterpret_cast<const float4*>(es.vec + d * 32 + 4 * j);
+      const float4 bb = ldsf4(es.vec, d * 32 + 4 * j);
       const uint4 sk = lds128(es.res_stg[d & 1] + swz<128>(lane, j));  // skip tile of d (the tile of d + 1 is the other one)
       const float2 g01 = sb::gelu_erf2(sb::add2(
           sb::add2(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), make_float2(bb.x, bb.y)),
@@ -503,7 +516,7 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
           make_float2(__uint_as_float(sk.z), __uint_as_float(sk.w))));
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const float4 h = hy[m * 8 + j];  // warp-uniform shared-memory address: broadcast
+        const float4 h = ldsf4(hy, (m * 8 + j) * 4);  // warp-uniform shared-memory address: broadcast
         acc2[m] = sb::fma2(g01, make_float2(h.x, h.y), acc2[m]);
         acc2[m] = sb::fma2(g23, make_float2(h.z, h.w), acc2[m]);
       }
@@ -653,7 +666,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t acc_phase = static_cast<uint32_t>((it >> 1) & 1);
         const int m_idx = (tile / n_tiles) * BM;
         float* vec = sVec + st * VEC_FLOATS;
-        es.vec = vec;
+        es.vec = sb::smem_u32(vec);
         asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp is done with the previous tiles' vectors
         if (EPI == EPI_UP1) {
           for (int c = tid512 * 4; c < 256; c += 2048) *reinterpret_cast<float4*>(vec + c) = __ldg(reinterpret_cast<const float4*>(p.bias + c));
@@ -685,21 +698,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       es.res_stg[0] = sb::smem_u32(mine + (res_bufs > 0 ? STG_BYTES : 0));
       es.res_stg[1] = sb::smem_u32(mine + (res_bufs > 1 ? 2 * STG_BYTES : (res_bufs > 0 ? STG_BYTES : 0)));
       es.nres = res_bufs;
-      es.vec = sVec + set * VEC_FLOATS;
+      es.vec = sb::smem_u32(sVec + set * VEC_FLOATS);
     }
     float* myvec = sVec + set * VEC_FLOATS;
     const int tid128 = (warp & 3) * 32 + lane;
     uint32_t acc_phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != set) continue;
-      const int m_idx = (tile / n_tiles) * BM;
-      const int n_idx = (tile % n_tiles) * BN;
-      // stage this tile's per-column vectors once per set: every read in the epilogues is a shared-memory broadcast
-      // (per-chunk __ldg of bias / gamma / hyper was the epilogue's critical path: ~4x the main loop at K = 576)
-      set_barrier(set);  // the previous tile's readers are done
+    // Per-column vectors that do not change from tile to tile are staged ONCE: the two 128-thread barriers per tile
+    // that guarded the re-staging were 1.8 stalled warps per issued instruction in the up-scaling epilogues
+    // (profiles/r02f_upscale_ncu_summary.txt). UP2's per-prompt hyper-network vectors are staged per warp (512 B,
+    // one LDG.128 + STS.128 per lane, __syncwarp only).
+    const bool const_vec = EPI == EPI_UP1 || EPI == EPI_UP2 || EPI == EPI_LN || (EPI == EPI_STD && n_tiles == 1);
+    if (const_vec) {
       if (EPI == EPI_STD) {
-        stage_vec(myvec, p.bias ? p.bias + n_idx : nullptr, BN, ((p.N - n_idx) + 3) & ~3, tid128);
+        stage_vec(myvec, p.bias, BN, (p.N + 3) & ~3, tid128);
       } else if (EPI == EPI_LN) {
         stage_vec(myvec, p.bias, BN, p.N, tid128);
         stage_vec(myvec + 256, p.gamma, BN, p.N, tid128);
@@ -710,9 +722,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         stage_vec(myvec + 512, p.beta, 64, 64, tid128);
       } else {
         stage_vec(myvec, p.bias, 128, 128, tid128);
-        stage_vec(myvec + 256, p.hyper + static_cast<long long>(m_idx / (p.gh * p.gw)) * 128, 128, 128, tid128);
       }
       set_barrier(set);
+    }
+    const int hy_off = 256 + (warp & 3) * 128;  // UP2: this warp's private copy of the prompt's 4 x 32 hyper vector
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != set) continue;
+      const int m_idx = (tile / n_tiles) * BM;
+      const int n_idx = (tile % n_tiles) * BN;
+      if (!const_vec) {
+        // stage this tile's per-column vectors once per set: every read in the epilogues is a shared-memory broadcast
+        // (per-chunk __ldg of bias / gamma / hyper was the epilogue's critical path: ~4x the main loop at K = 576)
+        set_barrier(set);  // the previous tile's readers are done
+        stage_vec(myvec, p.bias ? p.bias + n_idx : nullptr, BN, ((p.N - n_idx) + 3) & ~3, tid128);
+        set_barrier(set);
+      } else if (EPI == EPI_UP2) {
+        __syncwarp();  // the previous tile's reads of this warp's hyper copy are done
+        *reinterpret_cast<float4*>(myvec + hy_off + lane * 4) =
+            __ldg(reinterpret_cast<const float4*>(p.hyper + static_cast<long long>(m_idx / (p.gh * p.gw)) * 128 + lane * 4));
+        __syncwarp();
+      }
       sb::mbar_wait(&tfull_bar[set], acc_phase);
       sb::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(set * C::ACC_STRIDE);
@@ -726,7 +755,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       } else if (EPI == EPI_UP1) {
         epilogue_up1(p, es, tmem_acc, m_idx, q, lane, 0, 4);
       } else {
-        epilogue_up2(p, es, tmem_acc, m_idx, q, lane, 0, 4);
+        epilogue_up2(p, es, tmem_acc, m_idx, q, lane, 0, 4, hy_off);
       }
       sb::tc_fence_before();
       __syncwarp();
@@ -942,10 +971,13 @@ extern "C" int sb_gemm_upscale1(const void* A, long long lda, const void* W, lon
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, p.M, 256, 256, 256, &tmA, &tmB);
   if (rc != SB_OK) return rc;
-  static int wide = -1;  // SB_UP_WARPS=8 keeps the 8-warp epilogue for A/B timing
+  // SB_UP_WARPS=16 selects the 16-warp epilogue. Measured (profiles/r02e_decoder_probe*.log): 336 vs 289 us for the
+  // 192-prompt batch — the epilogue is bound by the number of instructions the SM has to issue (ncu: issue slots),
+  // not by per-warp latency, so more warps only add barrier and staging overhead; 8 warps stay the default.
+  static int wide = -1;
   if (wide < 0) {
     const char* e = getenv("SB_UP_WARPS");
-    wide = (e && atoi(e) == 8) ? 0 : 1;
+    wide = (e && atoi(e) == 16) ? 1 : 0;
   }
   if (wide) return launch_gemm<256, EPI_UP1, 0, 16>(tmA, tmB, p, g_num_sms, stream);
   return launch_gemm<256, EPI_UP1>(tmA, tmB, p, g_num_sms, stream);
@@ -975,10 +1007,10 @@ extern "C" int sb_gemm_upscale2(const void* A, long long lda, const void* W, lon
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, p.M, 128, 64, 128, &tmA, &tmB);
   if (rc != SB_OK) return rc;
-  static int wide = -1;
+  static int wide = -1;  // see sb_gemm_upscale1: 592 vs 539 us per 192-prompt batch with 16 epilogue warps
   if (wide < 0) {
     const char* e = getenv("SB_UP_WARPS");
-    wide = (e && atoi(e) == 8) ? 0 : 1;
+    wide = (e && atoi(e) == 16) ? 1 : 0;
   }
   if (wide) return launch_gemm<128, EPI_UP2, 0, 16>(tmA, tmB, p, g_num_sms, stream);
   return launch_gemm<128, EPI_UP2>(tmA, tmB, p, g_num_sms, stream);

@@ -16,13 +16,17 @@ def make_gaussian_kernel(sigma):
     return gauss / gauss.sum()
 
 
-def gaussian_smoothing(input_tensor, sigma, dim=0, device="cuda"):
-    """numpy (Z,Y,X) in -> numpy out (the reference's contract); CUDA tensor in -> CUDA tensor out. dim must be 0:
-    the only call on the path is `gaussian_smoothing(vol, 5, dim=0)` (REF saber/segmenters/tomo.py:45)."""
-    if dim not in (0, -3):
-        raise NotImplementedError("saber_b200 gaussian_smoothing: only dim=0 (z) is on the path")
+def gaussian_smoothing(input_tensor, sigma, dim=-1, device="cuda"):
+    """REF saber/filters/gaussian.py:17-74: zero-padded 1-D Gaussian correlation along `dim` of a 3-D volume (default
+    -1 as in the reference; the path calls `gaussian_smoothing(vol, 5, dim=0)`, REF saber/segmenters/tomo.py:45).
+    numpy (Z,Y,X) in -> numpy out (the reference's contract); CUDA tensor in -> CUDA tensor out (the reference itself
+    fails on tensor input: `is_numpy` is unbound)."""
     is_numpy = isinstance(input_tensor, np.ndarray)
     x = (torch.from_numpy(np.ascontiguousarray(input_tensor)).float().to(device) if is_numpy
          else input_tensor.to(dtype=torch.float32).contiguous())
-    y = ops.gaussian_z(x, make_gaussian_kernel(sigma).to(x.device, torch.float32).contiguous())
+    if x.dim() != 3:
+        raise ValueError("gaussian_smoothing expects a 3-D volume")
+    axis = dim % 3
+    w = make_gaussian_kernel(sigma).to(x.device, torch.float32).contiguous()
+    y = ops.gaussian_z(x, w) if axis == 0 else ops.corr1d_zero(x, w, axis)
     return y.cpu().numpy() if is_numpy else y

@@ -131,10 +131,14 @@ def load() -> C.CDLL:
         if _LIB is not None:
             return _LIB
         path = lib_path()
-        if not path.exists():
-            from . import build as _build
-
+        from . import build as _build
+        # always consult the source digest: build() returns at once when the library matches csrc/ (a stale library
+        # after a pull would silently keep the old kernels); a box without nvcc uses the shipped library as is
+        try:
             _build.build()
+        except RuntimeError:
+            if not path.exists():
+                raise
         lib = C.CDLL(str(path))
         lib.sb_last_error.restype = C.c_char_p
         lib.sb_last_error.argtypes = []

@@ -57,6 +57,7 @@ class GemmProfiler:
 
 
 def _stream() -> int:
+    # the current stream of the calling thread's current device, which _chk_cuda has just made the operands' device
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -65,9 +66,23 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _chk_cuda(*ts):
+    """Every wrapper calls this first: all tensor operands must live on ONE CUDA device, and that device becomes the
+    calling thread's current device, so the kernel launch (C side: current device, stream from ``_stream()``) runs
+    where the data is. SABER's GPUPool drives several GPUs from the threads of one process (REF saber/utils/
+    parallelization.py:139-155); the current device is per-thread state, so pool threads do not disturb each other."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("saber_b200 ops need CUDA tensors: there is no CPU fallback")
+        idx = t.device.index
+        if dev is None:
+            dev = idx
+        elif idx != dev:
+            raise RuntimeError(f"saber_b200 ops: operands on different devices (cuda:{dev} and cuda:{idx})")
+    if dev is not None and dev != torch.cuda.current_device():
+        torch.cuda.set_device(dev)
 
 
 def _count(n=1):

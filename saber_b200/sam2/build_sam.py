@@ -1,9 +1,11 @@
 """Drop-in for ``sam2.build_sam`` (the seam SABER binds: REF saber/adapters/sam2/automask.py:55-62,
 REF saber/adapters/sam2/predictor.py:4,24-26, REF saber/classifier/models/SAM2.py:14,45).
 
-``build_sam2`` / ``build_sam2_video_predictor`` return objects backed by the B200 kernels. With no
-checkpoint file (no network in this environment) the named architecture is random-initialised
-deterministically (``seed``); a real upstream ``sam2.1_hiera_*.pt`` loads by name.
+``build_sam2`` / ``build_sam2_video_predictor`` return objects backed by the B200 kernels. A real upstream
+``sam2.1_hiera_*.pt`` loads by name (``ckpt_path``, or resolved by ``saber_b200.pretrained_weights`` as the reference
+resolves its own, REF saber/pretrained_weights.py:174-202). Without a checkpoint construction RAISES unless random
+initialisation of the named architecture (deterministic, ``seed``) is requested explicitly — ``state_dict=``,
+``allow_random_init=True`` or ``SABER_B200_ALLOW_RANDOM_INIT=1`` (synthetic benchmarks / parity tests).
 """
 from __future__ import annotations
 
@@ -88,19 +90,27 @@ class SAM2Model(nn.Module):
         return self.encoder.forward(img_batch)
 
 
-def _load_state_dict(cfg: str, ckpt_path: Optional[str], seed: int, num_maskmem: int = 7):
+def _load_state_dict(cfg: str, ckpt_path: Optional[str], seed: int, num_maskmem: int = 7,
+                     allow_random_init: bool = False):
+    from .. import pretrained_weights as pw
     if ckpt_path is None:
+        ckpt_path = pw.find_sam2_checkpoint(cfg)
+    if ckpt_path is None:
+        if not pw.random_init_allowed(allow_random_init):
+            raise FileNotFoundError("saber_b200: " + pw.missing_message(cfg))
         return arch.random_state_dict(cfg, seed=seed, num_maskmem=num_maskmem)
     ck = torch.load(ckpt_path, map_location="cpu", weights_only=True)
     return ck["model"] if "model" in ck else ck
 
 
 def build_sam2(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_overrides_extra=None,
-               apply_postprocessing=True, seed: int = 0, state_dict=None, **kwargs) -> SAM2Model:
+               apply_postprocessing=True, seed: int = 0, state_dict=None, allow_random_init: bool = False,
+               **kwargs) -> SAM2Model:
     """Same call shape as upstream ``sam2.build_sam.build_sam2``. ``apply_postprocessing`` switches on
     dynamic multimask via stability (delta 0.05, thresh 0.98) in the mask decoder, as upstream does."""
     cfg = arch.resolve(config_file)
-    sd = state_dict if state_dict is not None else _load_state_dict(cfg, ckpt_path, seed)
+    sd = state_dict if state_dict is not None else _load_state_dict(cfg, ckpt_path, seed,
+                                                                    allow_random_init=allow_random_init)
     model = SAM2Model(cfg, sd, device=device, dynamic_multimask_via_stability=bool(apply_postprocessing))
     if mode == "eval":
         model.eval()

@@ -556,12 +556,13 @@ class SAM2VideoPredictor(SAM2Model):
 
 def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_overrides_extra=None,
                                apply_postprocessing=True, vos_optimized=False, seed: int = 0, state_dict=None,
-                               **kwargs) -> SAM2VideoPredictor:
+                               allow_random_init: bool = False, **kwargs) -> SAM2VideoPredictor:
     """Same call shape as upstream ``sam2.build_sam.build_sam2_video_predictor`` (REF saber/adapters/sam2/
     predictor.py:24-26); applies upstream's overrides: binarize_mask_from_pts_for_mem_enc, fill_hole_area=8 and (with
     apply_postprocessing) dynamic multimask via stability."""
     cfg = arch.resolve(config_file)
-    sd = state_dict if state_dict is not None else _load_state_dict(cfg, ckpt_path, seed)
+    sd = state_dict if state_dict is not None else _load_state_dict(cfg, ckpt_path, seed,
+                                                                    allow_random_init=allow_random_init)
     model = SAM2VideoPredictor(cfg, sd, device=device, dynamic_multimask_via_stability=bool(apply_postprocessing),
                                fill_hole_area=8, binarize_mask_from_pts_for_mem_enc=True)
     if mode == "eval":

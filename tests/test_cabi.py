@@ -55,6 +55,31 @@ def test_product_fails_loudly_without_gpu():
         propagationSegmenter(amg_cfg=cfgAMG(sam2_cfg="tiny"))
 
 
+def test_missing_checkpoint_is_an_error_unless_random_init_is_explicit(monkeypatch, tmp_path):
+    """ADVICE r1: a segmenter must not silently run on random weights. Without a checkpoint file construction raises;
+    the explicit opt-ins (argument / env var / state_dict) reach the weight initialiser."""
+    import pytest
+    from saber_b200 import pretrained_weights as pw
+    from saber_b200.sam2 import build_sam
+    monkeypatch.delenv("SABER_B200_ALLOW_RANDOM_INIT", raising=False)
+    monkeypatch.setenv("SABER_B200_CHECKPOINT_DIR", str(tmp_path))
+    assert pw.find_sam2_checkpoint("tiny") is None and pw.get_sam2_checkpoint("base") == ("base_plus", None)
+    with pytest.raises(FileNotFoundError, match="allow_random_init"):
+        build_sam._load_state_dict("tiny", None, 0)
+    sd = build_sam._load_state_dict("tiny", None, 0, allow_random_init=True)
+    assert "image_encoder.trunk.patch_embed.proj.weight" in sd
+    monkeypatch.setenv("SABER_B200_ALLOW_RANDOM_INIT", "1")
+    assert pw.random_init_allowed() and build_sam._load_state_dict("tiny", None, 0).keys() == sd.keys()
+    # a checkpoint file under the directory is found by name (REF saber/pretrained_weights.py:183-188 file names)
+    import torch
+    torch.save({"model": {"x": torch.zeros(1)}}, tmp_path / "sam2.1_hiera_tiny.pt")
+    monkeypatch.delenv("SABER_B200_ALLOW_RANDOM_INIT")
+    assert pw.find_sam2_checkpoint("tiny") == str(tmp_path / "sam2.1_hiera_tiny.pt")
+    assert list(build_sam._load_state_dict("tiny", None, 0)) == ["x"]
+    with pytest.raises(ValueError):
+        pw.get_sam2_checkpoint("giant")
+
+
 def test_key_split_heuristics_are_host_only_and_consistent():
     """sb_t2i_*_splits are pure host arithmetic (callable without a GPU): the split count must divide the key count into
     whole 64-key tiles (tcgen05 kernel) / 32-key tiles (mma.sync kernel) for every batch size the decoder uses."""

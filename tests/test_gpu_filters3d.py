@@ -47,3 +47,18 @@ def test_gaussian_z_and_slab_matches_reference_golden(golden_dir):
     np.testing.assert_allclose(nv.cpu().numpy(), want, atol=1e-6, rtol=0)
     proj = ops.mean_z(nv, 10, 30)
     np.testing.assert_allclose(proj.cpu().numpy(), saber_ref.project_tomogram(want, 20, 10), atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("dim", [1, 2, -1])
+def test_gaussian_smoothing_other_axes_match_oracle(dim):
+    """REF saber/filters/gaussian.py:17-74 smooths along any axis (default -1); only dim 0 is on the path, the others
+    run the zero-padded correlation kernel along y / x. fp32, 1e-5 vs the oracle restatement of F.conv1d."""
+    from oracle import saber_ref
+    from saber_b200 import synth
+    from saber_b200.filters.gaussian import gaussian_smoothing
+    vol = synth.make_tomogram((20, 37, 45), seed=23, n_ellipsoids=4).numpy()
+    out = gaussian_smoothing(vol, 3, dim=dim, device="cuda:0")
+    assert isinstance(out, np.ndarray) and out.shape == vol.shape
+    np.testing.assert_allclose(out, saber_ref.gaussian_smoothing(vol, 3, dim=dim % 3), atol=1e-5, rtol=0)
+    t = gaussian_smoothing(torch.from_numpy(vol).cuda(), 3, dim=dim)
+    assert t.is_cuda and torch.equal(t.cpu(), torch.from_numpy(out))

@@ -115,3 +115,50 @@ def test_oracle_encoder_matches_hf_golden(golden_dir):
     s1 = vf[1][:, 0]
     np.testing.assert_allclose(emb[::16, ::4].numpy(), g["embed_sub"], rtol=0, atol=2e-5)
     np.testing.assert_allclose(s1[::64, ::4].numpy(), g["s1_sub"], rtol=0, atol=2e-5)
+
+
+@pytest.fixture(scope="module")
+def hf_tiny_oracle():
+    """HF-initialised (seed 0) tiny weights loaded into the oracle's SAM2Base (dynamic multimask as upstream's
+    apply_postprocessing builds it)."""
+    from transformers import Sam2Model
+    from oracle.hf_bridge import hf_image_config, hf_to_upstream
+    from oracle.sam2_ref.sam2_base import SAM2Base
+    from oracle.make_golden_hf import tie_shared_pe
+    torch.manual_seed(0)
+    hf = Sam2Model(hf_image_config("tiny")).eval()
+    tie_shared_pe(hf)
+    orc = SAM2Base("tiny", dynamic_multimask_via_stability=True).eval()
+    missing, unexpected = orc.load_state_dict(hf_to_upstream(hf.state_dict()), strict=False)
+    assert not unexpected, unexpected[:5]
+    return orc
+
+
+@pytest.mark.parametrize("tag,n_pts,use_mask,multi", [("p1_multi", 1, False, True), ("p1_single", 1, False, False),
+                                                     ("p2_multi", 2, False, True), ("p2_single", 2, False, False),
+                                                     ("mask_single", 1, True, False), ("mask_multi", 1, True, True)])
+def test_oracle_prompt_encoder_and_mask_decoder_match_hf_golden(golden_dir, hf_tiny_oracle, tag, n_pts, use_mask, multi):
+    """U2 / U3 pin: prompt encoder (points with labels 0-3 and the pad point, dense mask prompt, dense PE) and mask
+    decoder (two-way transformer, up-scaling with high-res skips, hyper-networks, IoU head, object-score head, multimask
+    selection incl. dynamic multimask via stability) of oracle.sam2_ref vs the independent HF implementation on the same
+    weights and inputs (oracle/make_golden_hf.py). fp32 on both sides: 1e-4 on logits of magnitude ~1e1."""
+    from oracle.make_golden_hf import decoder_inputs
+    g = np.load(os.path.join(golden_dir, "hf_decoder.npz"))
+    orc = hf_tiny_oracle
+    emb, s0, s1, p1, p2, (mask_in, mpts, mlab) = decoder_inputs(int(g["input_seed"]))
+    pts, lab = (mpts, mlab) if use_mask else (p1 if n_pts == 1 else p2)
+    P = pts.shape[0]
+    with torch.no_grad():
+        pe = orc.sam_prompt_encoder.get_dense_pe()
+        np.testing.assert_allclose(pe[0, ::8, ::4, ::4].numpy(), g["dense_pe_sub"], rtol=0, atol=1e-5)
+        sparse, dense = orc.sam_prompt_encoder(points=(pts, lab), boxes=None, masks=(mask_in if use_mask else None))
+        np.testing.assert_allclose(sparse.numpy(), g[f"{tag}_sparse"], rtol=0, atol=1e-5)
+        low, iou, tokens, obj = orc.sam_mask_decoder(
+            image_embeddings=emb.expand(P, -1, -1, -1), image_pe=pe, sparse_prompt_embeddings=sparse,
+            dense_prompt_embeddings=dense, multimask_output=multi, repeat_image=False,
+            high_res_features=[s0.expand(P, -1, -1, -1), s1.expand(P, -1, -1, -1)])
+    scale = float(g[f"{tag}_low_stats"][2])
+    np.testing.assert_allclose(low[:, :, ::4, ::4].numpy(), g[f"{tag}_low_sub"], rtol=0, atol=1e-4 * max(1.0, scale))
+    np.testing.assert_allclose(iou.numpy(), g[f"{tag}_iou"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(obj.numpy(), g[f"{tag}_obj"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(tokens.numpy(), g[f"{tag}_tokens"], rtol=0, atol=1e-4)

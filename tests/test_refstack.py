@@ -98,13 +98,8 @@ def _twin(cls, seed, monkeypatch, **kw):
     from saber_b200.segmenters import base as B
     fake = refstack.FakeAdapter(seed=seed)
     monkeypatch.setattr(B, "get_adapter", lambda cfg, device: fake)
-    seg = cls(deviceID=0, cfg=SAM2AdapterConfig(cfg="tiny", allow_random_init=True) if _has_flag() else SAM2AdapterConfig(cfg="tiny"), **kw)
+    seg = cls(deviceID=0, cfg=SAM2AdapterConfig(cfg="tiny", allow_random_init=True), **kw)
     return seg, fake
-
-
-def _has_flag():
-    from saber_b200.adapters.base import SAM2AdapterConfig
-    return "allow_random_init" in getattr(SAM2AdapterConfig, "model_fields", {})
 
 
 def _assert_calls_equal(got, want):

@@ -3,6 +3,7 @@ one 1024^2 crop, eager launches (no CUDA graph) so ncu / the GEMM profiler see e
   python tools/decoder_probe.py            # CUDA-event time of the batch + per-GEMM-shape table
   ncu --metrics gpu__time_duration.sum ... python tools/decoder_probe.py --once"""
 import os, sys
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from saber_b200 import ops, synth

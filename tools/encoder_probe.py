@@ -1,5 +1,6 @@
 """One Hiera-L encoder batch (8 x 1024^2 crops) eagerly, for ncu launch lists / CUDA-event timing (run under gpurun)."""
 import os, sys
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from saber_b200 import ops

@@ -3,6 +3,8 @@
 Each case runs in its own subprocess under a timeout so a dead-locked kernel cannot hang the box.
 Prints max-abs / relative error against a torch fp32 computation of the same op on the GPU.
 """
+import os
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 import subprocess, sys, os, json
 
 CASES = [

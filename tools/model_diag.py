@@ -4,6 +4,7 @@ The oracle runs in fp32 on the same GPU (TF32 off) purely as the checker.
 usage: python tools/model_diag.py [cfg=tiny] [what=enc,dec,m2m]
 """
 import os
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 import sys
 import time
 

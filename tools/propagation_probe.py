@@ -2,6 +2,7 @@
 of Z frames, N seed masks at the middle slice -> SAM2Adapter.set_volume + segment_volume. Run under gpurun:
   python tools/propagation_probe.py [Z] [N_obj]"""
 import os, sys, time
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch

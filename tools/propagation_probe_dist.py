@@ -6,6 +6,7 @@ merged with an element-wise max after the forward and after the backward pass. P
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
       tools/propagation_probe_dist.py [Z] [N_obj ...]"""
 import os, sys, time, zlib
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch

@@ -1,5 +1,6 @@
 """Stage-by-stage diagnostics of the z-propagation modules against the oracle (run under gpurun)."""
 import os, sys
+os.environ.setdefault("SABER_B200_ALLOW_RANDOM_INIT", "1")  # probes run on synthetic random-init weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle.sam2_ref.video_predictor import build_sam2_video_predictor as oracle_build
