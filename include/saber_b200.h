@@ -182,6 +182,10 @@ int sb_box_filter(const float* in, float* out, int H, int W, int axis, int size,
 /* REF saber/utils/preprocessing.py:15-18,36 contrast + clip + min-max; partials: 2048-float workspace */
 int sb_contrast_normalize(const float* img, const float* mean, const float* sq, float* out, long long n,
                           float cutoff, float* partials, void* stream);
+/* (H,W,3) inputs of prepare(): the reference's uniform_filter also runs along the channel axis (REF saber/utils/
+ * preprocessing.py:12-13 on a 3-D array) = a constant 3x3 mix; img [npix,3] -> out [3,npix] (of img or img^2), and back. */
+int sb_rgb_mix_planar(const float* img, const float* mix, int square, long long npix, float* out, void* stream);
+int sb_planar_to_hwc3(const float* planar, long long npix, float* out, void* stream);
 /* SAM2Transforms: crop -> Resize(S, bilinear, antialias) -> Normalize(mean, std). mean3/std3 are [host]. */
 int sb_resize_normalize(const float* img, int H, int W, int C, const int* crops, int ncrops, int S,
                         const float* mean3, const float* std3, float* out, void* stream);

@@ -139,9 +139,10 @@ class SAM2Adapter(BaseAdapter):
 
     @torch.inference_mode()
     def segment_image_2d(self, image: np.ndarray, text_prompt: str = None, threshold: float = None):
+        """REF :48-70: prepare (to RGB when the input is a grayscale slice; an (H,W,3) input keeps its channels) -> AMG."""
         out_rgb = True if image.ndim == 2 else False
-        if image.ndim != 2:
-            raise NotImplementedError("saber_b200: segment_image_2d takes a grayscale (H,W) slice")
+        if image.ndim not in (2, 3) or (image.ndim == 3 and image.shape[2] != 3):
+            raise ValueError("segment_image_2d expects an (H,W) slice or an (H,W,3) image")
         x = (image.to(self.device, torch.float32) if isinstance(image, torch.Tensor) else
              torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.device))
         x = prep.prepare(x, to_rgb=out_rgb)
@@ -193,6 +194,8 @@ class SAM2Adapter(BaseAdapter):
         S = p.image_size
         planes = ops.skimage_resize_stack(vol, S, 2.0, -1.0)  # load_grayscale_image_array: resize, then 2*x - 1
         del vol
+        if self._config.light_modality:  # REF adapters/preprocessing.py:66-68: rescale the frames to [0, 255]
+            planes = ops.minmax_affine(planes, ops.minmax(planes), 0.0, 255.0, 0.0)
         images = planes[:, None].expand(-1, 3, -1, -1)
         state = self._create_empty_inference_state(images, S, S, offload_video_to_cpu, offload_state_to_cpu)
         from .. import dist as sbdist

@@ -492,6 +492,7 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
     return row_ok ? static_cast<int>((b * p.skip_bstride + (static_cast<long long>(oy) * W2 + ox) * 32) / 4) : -1;
   };
   gather_async<128>(es.res_stg[d_begin & 1], skip, skip_off(d_begin), 128, lane);
+  float held[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int d = d_begin; d < d_end; ++d) {
     const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
@@ -522,7 +523,18 @@ __device__ __forceinline__ void epilogue_up2(const GemmParams& p, const EpiSmem&
       }
     }
     const float acc[4] = {acc2[0].x + acc2[0].y, acc2[1].x + acc2[1].y, acc2[2].x + acc2[2].y, acc2[3].x + acc2[3].y};
-    if (row_ok) {
+    // d = 2 dy + dx: the two dx of an output row are adjacent pixels -> one 8-byte store per mask (a warp then writes 256
+    // contiguous bytes per instruction instead of two half-used 256-byte spans: the LSU data pipe was 59 % busy)
+    if ((d & 1) == 0 && d + 1 < d_end) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) held[m] = acc[m];
+    } else if ((d & 1) == 1 && d - 1 >= d_begin) {
+      if (row_ok) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          *reinterpret_cast<float2*>(masks + ((b * 4 + m) * H2 + oy) * W2 + ox - 1) = make_float2(held[m], acc[m]);
+      }
+    } else if (row_ok) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) masks[((b * 4 + m) * H2 + oy) * W2 + ox] = acc[m];
     }

@@ -258,7 +258,56 @@ inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
   return static_cast<int>(g);
 }
 
+// (H,W,3) interleaved -> three planes, mixed over the channel axis: out[c'][p] = sum_c mix[c'][c] * f(img[p][c]),
+// f = identity or square. This is the channel-axis pass of scipy.ndimage.uniform_filter on an (H,W,3) array
+// (REF saber/utils/preprocessing.py:12-13 filters every axis of what it is given).
+__global__ void __launch_bounds__(256)
+rgb_mix_planar_kernel(const float* __restrict__ img, const float* __restrict__ mix, int square, long long npix,
+                      float* __restrict__ out) {
+  float m[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = __ldg(mix + i);
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a = img[3 * p], b = img[3 * p + 1], c = img[3 * p + 2];
+    if (square) {
+      a *= a;
+      b *= b;
+      c *= c;
+    }
+    out[p] = m[0] * a + m[1] * b + m[2] * c;
+    out[npix + p] = m[3] * a + m[4] * b + m[5] * c;
+    out[2 * npix + p] = m[6] * a + m[7] * b + m[8] * c;
+  }
+}
+__global__ void __launch_bounds__(256)
+planar_to_hwc3_kernel(const float* __restrict__ planar, long long npix, float* __restrict__ out) {
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    out[3 * p] = planar[p];
+    out[3 * p + 1] = planar[npix + p];
+    out[3 * p + 2] = planar[2 * npix + p];
+  }
+}
+
 }  // namespace
+
+// img [npix,3] fp32 -> out [3,npix] fp32 = mix (3x3 row-major, device) applied over the channel axis to img or img^2.
+extern "C" int sb_rgb_mix_planar(const float* img, const float* mix, int square, long long npix, float* out,
+                                 void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(img && mix && out && npix > 0, "sb_rgb_mix_planar: bad arguments");
+  rgb_mix_planar_kernel<<<grid_for(npix), 256, 0, stream>>>(img, mix, square, npix, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+extern "C" int sb_planar_to_hwc3(const float* planar, long long npix, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(planar && out && npix > 0, "sb_planar_to_hwc3: bad arguments");
+  planar_to_hwc3_kernel<<<grid_for(npix), 256, 0, stream>>>(planar, npix, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
 
 // scipy.ndimage.uniform_filter1d(in (optionally squared), size, axis, mode='reflect') on [H, W] fp32.
 extern "C" int sb_box_filter(const float* in, float* out, int H, int W, int axis, int size, int square,

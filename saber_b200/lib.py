@@ -77,6 +77,8 @@ SIGNATURES = {
     "sb_gather_rows": [c_void_p, c_void_p, c_int, c_ll, c_void_p, c_void_p],
     "sb_box_filter": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sb_contrast_normalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p],
+    "sb_rgb_mix_planar": [c_void_p, c_void_p, c_int, c_ll, c_void_p, c_void_p],
+    "sb_planar_to_hwc3": [c_void_p, c_ll, c_void_p, c_void_p],
     "sb_resize_normalize": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, C.POINTER(c_float),
                             C.POINTER(c_float), c_void_p, c_void_p],
     "sb_upsample_bilinear": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

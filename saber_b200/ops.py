@@ -734,6 +734,39 @@ def prepare_slice(img: torch.Tensor, box: int = 500, cutoff: float = 3.0) -> tor
     return t0
 
 
+def prepare_rgb(img: torch.Tensor, channel_mix, box: int = 500, cutoff: float = 3.0) -> torch.Tensor:
+    """``prepare`` on an (H,W,3) fp32 image as the reference computes it for 3-D input (REF saber/utils/preprocessing.py:
+    4-37,67-81): box filter over ALL three axes (the channel axis = the constant 3x3 ``channel_mix``), z-score, clip,
+    global min-max. -> (H,W,3) fp32 in [0,1]."""
+    _chk_cuda(img)
+    assert img.dtype == _F32 and img.is_contiguous() and img.dim() == 3 and img.shape[2] == 3
+    H, W, _ = img.shape
+    n = H * W
+    dev = img.device
+    L = _lib.load()
+    s = _stream()
+    mix = torch.as_tensor(channel_mix, dtype=_F32).reshape(9).to(dev)
+    eye = torch.eye(3, dtype=_F32).reshape(9).to(dev)
+    planar = torch.empty((3, H, W), dtype=_F32, device=dev)
+    m0 = torch.empty_like(planar)
+    t0 = torch.empty((H, W), dtype=_F32, device=dev)
+    mean = torch.empty_like(planar)
+    sq = torch.empty_like(planar)
+    _lib.check(L.sb_rgb_mix_planar(img.data_ptr(), eye.data_ptr(), 0, n, planar.data_ptr(), s), "sb_rgb_mix_planar")
+    for square, dst in ((0, mean), (1, sq)):
+        _lib.check(L.sb_rgb_mix_planar(img.data_ptr(), mix.data_ptr(), square, n, m0.data_ptr(), s), "sb_rgb_mix_planar")
+        for c in range(3):
+            _lib.check(L.sb_box_filter(m0[c].data_ptr(), t0.data_ptr(), H, W, 0, box, 0, s), "sb_box_filter")
+            _lib.check(L.sb_box_filter(t0.data_ptr(), dst[c].data_ptr(), H, W, 1, box, 0, s), "sb_box_filter")
+    partials = torch.empty((2048,), dtype=_F32, device=dev)
+    _lib.check(L.sb_contrast_normalize(planar.data_ptr(), mean.data_ptr(), sq.data_ptr(), m0.data_ptr(), 3 * n, cutoff,
+                                       partials.data_ptr(), s), "sb_contrast_normalize")
+    out = torch.empty_like(img)
+    _lib.check(L.sb_planar_to_hwc3(m0.data_ptr(), n, out.data_ptr(), s), "sb_planar_to_hwc3")
+    _count(18)
+    return out
+
+
 _MEAN3 = (0.485, 0.456, 0.406)
 _STD3 = (0.229, 0.224, 0.225)
 

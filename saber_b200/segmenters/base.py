@@ -89,7 +89,8 @@ class saber2D:
         ``order`` lists DeviceMasks rows in the reference's final list order (area filter -> duplicate removal ->
         stable sort by area)."""
         if self.classifier is not None:
-            raise NotImplementedError("saber_b200: the expert-classifier filter is not built yet")
+            raise RuntimeError("segment_image_device is the classifier-free resident path; with an expert classifier use "
+                               "segment_image (propagationSegmenter.label_slices_device does)")
         dm, recs = self.adapter.segment_image_2d_device(image)
         recs = [r for r in recs if r["area"] >= self.min_mask_area]
         if self.remove_repeating_masks and len(recs) > 1:

@@ -37,6 +37,16 @@ class propagationSegmenter(saber3D):
         W = volume.shape[2]
         counts = []
         for ii in range(z0, z1):
+            if self.classifier is not None:
+                # expert classifier configured: the reference's per-slice list path (segment_image -> _apply_classifier,
+                # REF segmenters/base.py:159-176); the class logic is host list code fed by the device classifier
+                masks = self.segment_image(volume[ii], display=False)
+                lab = np.zeros(tuple(volume.shape[1:]), dtype=np.uint16)
+                for idx, m in enumerate(masks):
+                    lab[np.asarray(m["segmentation"], dtype=bool)] = idx + 1
+                labels[ii].copy_(torch.from_numpy(lab.view(np.int16)).to(labels.device))
+                counts.append(len(masks))
+                continue
             dm, recs = self.segment_image_device(volume[ii])
             if len(recs) == 0:
                 labels[ii].zero_()

@@ -206,3 +206,19 @@ def test_separate_masks_properties_at_baseline_size(ops):
     assert ((lab > 0) <= (vol != 0)).all()
     first = torch.stack([(lab == k).flatten().nonzero()[0, 0] for k in range(1, min(K, 8) + 1)])
     assert (first[1:] > first[:-1]).all(), "labels must be numbered in raster order of their first voxel"
+
+
+def test_prepare_rgb_input_matches_reference_semantics():
+    """REF saber/adapters/sam2/predictor.py:58-59 passes (H,W,3) images through prepare(to_rgb=False): the reference's
+    uniform_filter then also runs along the channel axis. fp32 vs the oracle (scipy on the 3-D array), 1e-4."""
+    import torch
+    from oracle import saber_ref
+    from saber_b200.utils import preprocessing as prep
+    rng = np.random.default_rng(12)
+    img = (rng.normal(size=(300, 340, 3)) + np.linspace(0, 2, 340)[None, :, None]).astype(np.float32)
+    got = prep.prepare(img, to_rgb=False, device="cuda:0")
+    want = saber_ref.prepare(img, to_rgb=False)
+    assert got.shape == (300, 340, 3) and want.shape == got.shape
+    np.testing.assert_allclose(got, want, atol=1e-4, rtol=0)
+    t = prep.prepare(torch.from_numpy(img).cuda(), to_rgb=True)  # to_rgb only repeats 2-D inputs (REF :78-80)
+    assert t.is_cuda and t.shape == (300, 340, 3)

@@ -127,3 +127,55 @@ def test_oracle_memory_modules_match_hf_golden(golden_dir):
     assert abs(float(att.std()) - float(g["att_std"])) < 1e-4
     np.testing.assert_allclose(out["vision_features"][0, ::2, ::4, ::4].numpy(), g["mm_sub"], atol=2e-5, rtol=1e-4)
     np.testing.assert_allclose(out["vision_pos_enc"][0][0, ::2, ::4, ::4].numpy(), g["mpos_sub"], atol=2e-6)
+
+
+def test_oracle_video_state_machine_matches_hf_tracking_golden(golden_dir):
+    """U6-U9 pin of the whole tracking recurrence: two objects seeded with masks on frame 1 of a 4-frame video, memory
+    encoded (binarised prompt masks), tracked forwards (frames 1-3) and backwards (1-0) with num_maskmem = 2 — per
+    frame the low-res mask logits and object scores of oracle.sam2_ref.video_predictor vs HF Sam2VideoModel on the
+    same HF-initialised weights (oracle/make_golden_hf.py). This exercises what the module-level pins cannot: which
+    stored outputs feed which memory slot, the temporal position rows, the object-pointer selection (incl. forward
+    pointers picked up by the reverse pass), mask-as-output conditioning, bf16 memory storage. fp32 recurrence with
+    bf16-stored memories on both sides: 5e-3 abs on logits of magnitude ~1e1."""
+    from transformers import Sam2VideoConfig, Sam2VideoModel
+
+    from oracle.hf_bridge import hf_to_upstream
+    from oracle.make_golden_hf import tie_shared_pe, video_inputs
+    from oracle.sam2_ref.video_predictor import SAM2VideoPredictor, empty_inference_state
+    g = np.load(os.path.join(golden_dir, "hf_video_tracking.npz"))
+    torch.manual_seed(int(g["weight_seed"]))
+    hf = Sam2VideoModel(Sam2VideoConfig(num_maskmem=2)).eval()
+    tie_shared_pe(hf)
+    sd = hf_to_upstream(hf.state_dict())
+    orc = SAM2VideoPredictor(cfg="tiny", num_maskmem=2, fill_hole_area=0, binarize_mask_from_pts_for_mem_enc=True,
+                             dynamic_multimask_via_stability=True).eval()
+    missing, unexpected = orc.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected[:5]
+    assert not [m for m in missing if not m.startswith("image_encoder.trunk.pos_embed")], missing[:5]
+    video, masks = video_inputs()
+    st = empty_inference_state(video, 1024, 1024, "cpu")
+    k = int(g["seed_frame"])
+    for obj_id, m in enumerate(masks, start=1):
+        orc.add_new_mask(st, k, obj_id, m.bool())
+
+    def low(frame, key):
+        return torch.cat([st["output_dict_per_obj"][i][key][frame]["pred_masks"] for i in range(2)])[:, 0]
+
+    def obj(frame, key):
+        return torch.cat([st["output_dict_per_obj"][i][key][frame]["object_score_logits"].reshape(-1) for i in range(2)])
+
+    def check(tag, frame, key):
+        want, got = g[f"{tag}_f{frame}"], low(frame, key)[:, ::4, ::4].numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=5e-3 * max(1.0, np.abs(want).max() / 10), err_msg=f"{tag} f{frame}")
+        np.testing.assert_allclose(obj(frame, key).numpy(), g[f"{tag}_obj_f{frame}"], rtol=0, atol=5e-3, err_msg=f"{tag} obj f{frame}")
+
+    for f, ids, logits in orc.propagate_in_video(st, start_frame_idx=k, max_frame_num_to_track=int(g["fwd"]), reverse=False):
+        assert list(ids) == [1, 2] and logits.shape == (2, 1, 1024, 1024)
+    check("cond", k, "cond_frame_outputs")
+    check("fwd", k, "cond_frame_outputs")
+    for f in (k + 1, k + 2):
+        check("fwd", f, "non_cond_frame_outputs")
+    for f, ids, logits in orc.propagate_in_video(st, start_frame_idx=k, max_frame_num_to_track=1, reverse=True):
+        pass
+    check("bwd", k, "cond_frame_outputs")
+    check("bwd", k - 1, "non_cond_frame_outputs")
