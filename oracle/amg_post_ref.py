@@ -49,10 +49,27 @@ def upsample_bilinear(planes: np.ndarray, out_hw: Tuple[int, int]) -> np.ndarray
 
 
 def mask_post(planes: np.ndarray, ious: np.ndarray, crop_box, frame_hw, pred_iou_thresh: float, mask_thresh: float,
-              stab_offset: float, stab_thresh: float, edge_atol: float = 20.0) -> Dict[str, np.ndarray]:
+              stab_offset: float, stab_thresh: float, edge_atol: float = 20.0,
+              only_iou_survivors: bool = False) -> Dict[str, np.ndarray]:
     """planes [n,S,S] fp32 low-res logits, ious [n]. Returns per-candidate keep / stability / bbox (full-frame
     xyxy, inclusive max) / area and bool masks in the full frame — the records of the kept candidates are what
-    upstream's MaskData holds after _process_batch (filters: iou > thr, stability >= thr, not near crop edge)."""
+    upstream's MaskData holds after _process_batch (filters: iou > thr, stability >= thr, not near crop edge).
+    only_iou_survivors: evaluate only the candidates that pass the predicted-IoU filter, as upstream does (it filters
+    by IoU BEFORE computing stability scores and boxes); the other rows come back with keep = False and zeros — what
+    makes the checker affordable at SABER's default AMG size (9 216 candidates per image)."""
+    if only_iou_survivors and pred_iou_thresh > 0.0:
+        n = planes.shape[0]
+        H, W = frame_hw
+        sel = np.flatnonzero(np.asarray(ious, np.float32) > f32(pred_iou_thresh))
+        out = {"keep": np.zeros(n, bool), "stability": np.zeros(n, np.float32), "bbox": np.zeros((n, 4), np.int32),
+               "area": np.zeros(n, np.int32), "masks": None, "rows": sel}
+        if sel.size:
+            r = mask_post(planes[sel], np.asarray(ious)[sel], crop_box, frame_hw, pred_iou_thresh, mask_thresh, stab_offset,
+                          stab_thresh, edge_atol)
+            for k in ("keep", "stability", "bbox", "area"):
+                out[k][sel] = r[k]
+            out["masks_rows"] = r["masks"]  # row j belongs to candidate sel[j]
+        return out
     x0, y0, x1, y1 = crop_box
     H, W = frame_hw
     n = planes.shape[0]

@@ -288,7 +288,10 @@ class SAM2Base(nn.Module):
                 to_cat_memory.append(obj_ptrs)
                 to_cat_memory_pos_embed.append(obj_pos)
                 num_obj_ptr_tokens = obj_ptrs.shape[0]
-        memory = torch.cat(to_cat_memory, dim=0)
+        # maskmem_features are stored in bf16; upstream reaches fp32 here through torch.cat's type promotion with the fp32
+        # object pointers (or runs under bf16 autocast). Without pointer tokens (a conditioning frame only in the
+        # "future") nothing promotes: make the cast explicit, the values are the same.
+        memory = torch.cat(to_cat_memory, dim=0).float()
         memory_pos_embed = torch.cat(to_cat_memory_pos_embed, dim=0)
         pix = self.memory_attention(curr=current_vision_feats[-1:], curr_pos=current_vision_pos_embeds[-1:],
                                     memory=memory, memory_pos=memory_pos_embed, num_obj_ptr_tokens=num_obj_ptr_tokens)

@@ -311,8 +311,9 @@ class SAM2Adapter(BaseAdapter):
         for frame_idx, obj_ids, mask_logits, _, _ in _frames(False):
             self._current_frame = frame_idx
             _apply(frame_idx, obj_ids, mask_logits)
-        sbdist.allreduce_max_labels(vol_masks, group)
-        nonempty = ops.slice_any(vol_masks).cpu().numpy()  # one D2H of Z bytes: which slices the forward pass filled
+        # which slices the forward pass filled ON ANY RANK: a Z-element flag vector crosses the ranks, not the label volume
+        # (round 1 all-reduced the whole volume here and again after the backward pass)
+        nonempty = sbdist.allreduce_any(ops.slice_any(vol_masks), group).cpu().numpy()  # one D2H of Z flags
         for frame_idx, obj_ids, mask_logits, _, _ in _frames(True):
             self._current_frame = frame_idx
             if not nonempty[frame_idx]:

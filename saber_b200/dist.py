@@ -69,42 +69,76 @@ def world_rank(group=None) -> Tuple[int, int]:
 
 
 def allreduce_max_labels(labels: torch.Tensor, group=None) -> torch.Tensor:
-    """Element-wise max of a uint16-payload (int16 storage) label volume over ranks, in place. 16-bit integers are not
-    collective dtypes: the payload is widened to int32 per z-chunk (<= 256 MiB in flight)."""
-    world, _ = world_rank(group)
+    """Element-wise max of a uint16-payload (int16 storage) label volume over ranks, in place ("higher object id wins";
+    SURVEY 8e Phase C). 16-bit integers are not collective dtypes, so the labels travel as BYTES:
+    NCCL: reduce-scatter by z-chunk built from all_to_all_single (every rank receives the N versions of ITS chunk, 2 B per
+          voxel), a local max, then all_gather_into_tensor — (N-1)/N x 2 B sent and received per voxel and phase instead
+          of the 4-byte widened all-reduce of round 1 (1.07 GB -> 0.47 GB per rank and phase for 300 x 928 x 960 at N = 8);
+    gloo (CPU tests): the widened int32 all-reduce (all_to_all is not a gloo collective)."""
+    world, rank = world_rank(group)
     if world == 1:
         return labels
     flat = labels.view(-1)
-    chunk = 64 * 1024 * 1024
-    for s in range(0, flat.numel(), chunk):
-        part = flat[s:s + chunk]
-        wide = part.to(torch.int32) & 0xFFFF  # uint16 payload
-        dist.all_reduce(wide, op=dist.ReduceOp.MAX, group=group)
-        part.copy_(wide.to(torch.int16))  # values < 2^16 wrap back to the same 16 bits
+    if dist.get_backend(group) != "nccl":
+        chunk = 64 * 1024 * 1024
+        for s in range(0, flat.numel(), chunk):
+            part = flat[s:s + chunk]
+            wide = part.to(torch.int32) & 0xFFFF  # uint16 payload
+            dist.all_reduce(wide, op=dist.ReduceOp.MAX, group=group)
+            part.copy_(wide.to(torch.int16))  # values < 2^16 wrap back to the same 16 bits
+        return labels
+    n = flat.numel()
+    per = (n + world - 1) // world
+    per += (-per) % 8
+    send = torch.zeros((world, per), dtype=torch.int16, device=labels.device)
+    send.view(-1)[:n] = flat
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(torch.uint8), send.view(torch.uint8), group=group)
+    # object ids are < 2^15 (SABER tracks a few hundred objects per seed slice): the signed maximum is the unsigned one
+    mine = recv.amax(dim=0).contiguous()
+    dist.all_gather_into_tensor(send.view(torch.uint8), mine.view(torch.uint8), group=group)
+    flat.copy_(send.view(-1)[:n])
     return labels
+
+
+def allreduce_any(flags: torch.Tensor, group=None) -> torch.Tensor:
+    """Logical OR of a small per-slice flag vector over ranks (int32 MAX): which z-slices any rank has already labelled."""
+    world, _ = world_rank(group)
+    if world == 1:
+        return flags
+    f = flags.to(torch.int32)
+    dist.all_reduce(f, op=dist.ReduceOp.MAX, group=group)
+    return f
 
 
 def exchange_frame_features(cached: dict, Z: int, group=None) -> None:
     """Phase A exchange: every rank holds `cached[f] = {"feat","s1","s0"}` for the frames of its z-slab; after the call
-    every rank holds all Z frames (one broadcast per slab and feature level over NVLink)."""
+    every rank holds all Z frames. ONE all_gather_into_tensor per feature level (slabs padded to the largest slab);
+    fp32 on the wire so that a sharded run is bit-identical to the single-GPU run (16 MB per frame: 4.8 GB for Z = 300,
+    7/8 of it received per rank = 6 ms at the measured 770 GB/s NVLink peer bandwidth; round 1 issued one broadcast per
+    slab and level)."""
     world, rank = world_rank(group)
     if world == 1:
         return
     some = next(iter(cached.values()))
     dev = some["feat"].device
-    for r in range(world):
-        z0, z1 = zslab_range(Z, r, world)
-        if z1 == z0:
-            continue
-        for key, width, rows in (("feat", 256, 4096), ("s1", 64, 16384), ("s0", 32, 65536)):
-            if rank == r:
-                buf = torch.stack([cached[f][key] for f in range(z0, z1)]).contiguous()
-            else:
-                buf = torch.empty((z1 - z0, rows, width), dtype=torch.float32, device=dev)
-            dist.broadcast(buf, src=r, group=group)
-            if rank != r:
-                for j, f in enumerate(range(z0, z1)):
-                    cached.setdefault(f, {})[key] = buf[j]
+    ranges = [zslab_range(Z, r, world) for r in range(world)]
+    zmax = max(z1 - z0 for z0, z1 in ranges)
+    z0, z1 = ranges[rank]
+    for key, width, rows in (("feat", 256, 4096), ("s1", 64, 16384), ("s0", 32, 65536)):
+        mine = torch.zeros((zmax, rows, width), dtype=torch.float32, device=dev)
+        for j, f in enumerate(range(z0, z1)):
+            mine[j] = cached[f][key]
+        full = torch.empty((world, zmax, rows, width), dtype=torch.float32, device=dev)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(full, mine, group=group)
+        else:
+            dist.all_gather(list(full.unbind(0)), mine, group=group)
+        for r, (a, b) in enumerate(ranges):
+            if r == rank:
+                continue
+            for j, f in enumerate(range(a, b)):
+                cached.setdefault(f, {})[key] = full[r, j]
 
 
 def merge_captured_scores(per_rank: List[dict], n_local: List[int]) -> dict:

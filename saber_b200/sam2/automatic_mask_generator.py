@@ -133,9 +133,14 @@ class SAM2AutomaticMaskGenerator:
         self.use_m2m = use_m2m
         self.multimask_output = multimask_output
         # candidates per m2m decoder call (multiple of 3 so whole prompts stay together); results do not depend on it
-        self.m2m_batch = 3 * points_per_batch
+        # Execution batch: `points_per_batch` is upstream's memory knob (64 points -> 192 m2m prompts per decoder call); the
+        # results do not depend on it, and each decoder call costs ~100 latency-bound token-side launches, so the B200 path
+        # runs SB_AMG_BATCH_MULT x points_per_batch points per call where a crop has that many (180 GB of HBM).
+        self.exec_ppb = points_per_batch * max(1, int(os.environ.get("SB_AMG_BATCH_MULT", "2")))
+        self.m2m_batch = 3 * self.exec_ppb
         # test hook: when a list, every post-processing call appends (crop, base, n, cpp, planes, ious4, sel) host copies
         self.capture: Optional[list] = None
+        self.capture_compact = False
         self.use_cuda_graph = True
         # independent prompt batches in flight (one CUDA graph instance + stream each)
         self.graph_lanes = int(os.environ.get("SB_GRAPH_LANES", "4"))
@@ -169,7 +174,7 @@ class SAM2AutomaticMaskGenerator:
             inp = inp * res
             full = pts + torch.tensor([[x0, y0]])
             n = pts.shape[0]
-            ppb = self.points_per_batch
+            ppb = self.exec_ppb
             geom = torch.tensor([[hc, wc, x0, y0, base + b0 * cpp, 0, 0, 0] for b0 in range(0, n, ppb)], dtype=_I32)
             crops.append(_CropPlan(tuple(box), layer, base, n, pts, full,
                                    inp[:, None, :].contiguous().to(dev),
@@ -223,25 +228,32 @@ class SAM2AutomaticMaskGenerator:
         if ev:
             ev[1].record()
         tok = feats.tok
-        ppb = self.points_per_batch
+        ppb = self.exec_ppb
         for k, crop in enumerate(plan.crops):
             x0, y0, x1, y1 = crop.box
             emb = tok["embed"][k * 4096:(k + 1) * 4096]
             s0 = tok["s0"][k * 65536:(k + 1) * 65536]
             s1 = tok["s1"][k * 16384:(k + 1) * 16384]
-            graph = self._batch_graph(plan, ws) if (self.use_cuda_graph and self.capture is None) else None
             main = torch.cuda.current_stream()
-            if graph is not None:
-                graph["emb"].copy_(emb)
-                graph["s0"].copy_(s0)
-                graph["s1"].copy_(s1)
-                for lane in graph["lanes"]:
-                    lane["stream"].wait_stream(main)
+            use_graph = self.use_cuda_graph and self.capture is None
+            graphs = {}  # batch size -> captured lanes whose input buffers hold this crop's features
             nb = 0
             for p0 in range(0, crop.n_points, ppb):
                 pb = min(ppb, crop.n_points - p0)
                 base = crop.base + p0 * plan.cpp
-                if graph is not None and pb == ppb:
+                graph = None
+                if use_graph and (pb == ppb or pb == self.points_per_batch):
+                    if pb not in graphs:
+                        g = self._batch_graph(plan, ws, pb)
+                        if g is not None:
+                            g["emb"].copy_(emb)
+                            g["s0"].copy_(s0)
+                            g["s1"].copy_(s1)
+                            for lane in g["lanes"]:
+                                lane["stream"].wait_stream(main)
+                        graphs[pb] = g
+                    graph = graphs[pb]
+                if graph is not None:
                     # prompt batches are independent (disjoint slot ranges): replay them round-robin on the lanes'
                     # streams so that the latency-bound token-side launches of one batch overlap the bandwidth-bound
                     # image-stream kernels of another
@@ -253,14 +265,16 @@ class SAM2AutomaticMaskGenerator:
                         lane["g"].replay()
                     ops.launch_count += lane["launches"]
                 else:
-                    if graph is not None:
-                        for lane in graph["lanes"]:
-                            main.wait_stream(lane["stream"])
+                    for g in graphs.values():
+                        if g is not None:
+                            for lane in g["lanes"]:
+                                main.wait_stream(lane["stream"])
                     self._process_batch(k, crop.in_points[p0:p0 + pb], crop.labels[p0:p0 + pb], emb, s0, s1, plan, ws,
                                         crop.box, base, None)
-            if graph is not None:
-                for lane in graph["lanes"]:
-                    main.wait_stream(lane["stream"])
+            for g in graphs.values():
+                if g is not None:
+                    for lane in g["lanes"]:
+                        main.wait_stream(lane["stream"])
             n_crop = crop.n_points * plan.cpp
             ops.compact_keep(ws["keep"], crop.base, n_crop, ws["cand"], n_cand)
             ops.nms_dev(ws["bbox"], ws["iou"], ws["cand"], n_cand, n_crop, self.box_nms_thresh, ws["order"],
@@ -315,13 +329,13 @@ class SAM2AutomaticMaskGenerator:
             sel = None if self.multimask_output else out.get("sel_idx")
             self._post(k, out["masks"], out["ious"], sel, plan.cpp, pb * plan.cpp, geom, base, geom_dev, 0)
 
-    def _batch_graph(self, plan, ws):
-        """CUDA graph of one full prompt batch (points_per_batch points): the ~250 small launches of the two decoder
-        passes are replayed with one host call; crop features, point coordinates and crop geometry are graph inputs."""
-        key = plan.hw
+    def _batch_graph(self, plan, ws, ppb):
+        """CUDA graph of one prompt batch of `ppb` points: the ~250 small launches of the two decoder passes are replayed
+        with one host call; crop features, point coordinates and crop geometry are graph inputs."""
+        key = (plan.hw, ppb)
         if key in self._graphs:
             return self._graphs[key]
-        dev, ppb = self.device, self.points_per_batch
+        dev = self.device
         if self.use_m2m and self.m2m_batch < (3 if self.multimask_output else 1) * ppb:
             self._graphs[key] = None  # m2m split into several post calls with different bases: keep it eager
             return None
@@ -360,7 +374,14 @@ class SAM2AutomaticMaskGenerator:
         assert geom_dev is None or sub_base == 0
         ops.amg_mask_post(planes, ious4, sel, cpp, n, *geom, base, geom_dev)
         if self.capture is not None:
-            self.capture.append(dict(crop=crop_idx, base=base, n=n, cpp=cpp, planes=planes.cpu().numpy(),
+            if self.capture_compact:  # only the plane post-processing reads per candidate (config-1-sized captures)
+                prompt = torch.arange(n, device=planes.device) // cpp
+                token = (sel.long()[prompt] if sel is not None else
+                         (1 + torch.arange(n, device=planes.device) % 3 if cpp == 3 else torch.zeros_like(prompt)))
+                pl = planes[prompt, token].cpu().numpy()
+            else:
+                pl = planes.cpu().numpy()
+            self.capture.append(dict(crop=crop_idx, base=base, n=n, cpp=cpp, planes=pl,
                                      ious4=ious4.cpu().numpy(), sel=None if sel is None else sel.cpu().numpy()))
 
     @staticmethod

@@ -59,7 +59,11 @@ def test_encoder_vs_oracle(cfg, tiny):
     assert rel_l2(out["s0"], vf[0].permute(1, 0, 2).reshape(-1, 32)) < REL_TOL
 
 
-def test_decoder_and_m2m_vs_oracle(tiny):
+def test_decoder_vs_oracle(tiny):
+    """First AMG decoder pass (64 point prompts, multimask): all three mask logits and IoU predictions vs the fp32 oracle.
+    The m2m pass is compared on all four tokens in tests/test_gpu_configs.py::test_m2m_decoder_float_parity_on_both_
+    branches, its discrete plane selection bit-exactly in ::test_dynamic_multimask_selection_bit_exact_on_identical_logits
+    (round 1 compared the selected plane only and tolerated 15 % of the prompts flipping)."""
     from oracle.sam2_ref.image_predictor import SAM2ImagePredictor as OraclePredictor
     orc, model, _ = tiny
     torch.manual_seed(2)
@@ -73,9 +77,6 @@ def test_decoder_and_m2m_vs_oracle(tiny):
     labels = torch.ones(P, 1, dtype=torch.int32, device="cuda")
     with torch.no_grad():
         _, ious_ref, low_ref = pred._predict(pts, labels, multimask_output=True, return_logits=True)
-        _, ious2_ref, low2_ref = pred._predict(pts.repeat_interleave(3, 0), labels.repeat_interleave(3, 0),
-                                               mask_input=low_ref.flatten(0, 1)[:, None], multimask_output=False,
-                                               return_logits=True)
     emb = pred._features["image_embed"][0].permute(1, 2, 0).reshape(4096, 256).contiguous()
     s0 = pred._features["high_res_feats"][0][0].permute(1, 2, 0).reshape(65536, 32).contiguous()
     s1 = pred._features["high_res_feats"][1][0].permute(1, 2, 0).reshape(16384, 64).contiguous()
@@ -84,19 +85,6 @@ def test_decoder_and_m2m_vs_oracle(tiny):
     out = dec.forward(emb, s0, s1, tokens, None, multimask_output=True)
     assert rel_l2(out["masks"][:, 1:], low_ref) < REL_TOL
     assert rel_l2(out["ious"][:, 1:], ious_ref) < REL_TOL
-    # m2m: the oracle's own first-pass logits are the mask prompts of both sides
-    fake = torch.zeros(P, 4, 256, 256, device="cuda")
-    fake[:, 1:] = low_ref
-    out2 = dec.forward(emb, s0, s1, tokens.repeat_interleave(3, 0), fake, multimask_output=False, mask_clamp=32.0)
-    idx = out2["sel_idx"].long()
-    sel = out2["masks"][torch.arange(3 * P, device="cuda"), idx]
-    # dynamic-multimask selection is a discrete choice on a stability score: a bf16-level perturbation may flip it
-    # for prompts whose score sits at the 0.98 threshold, so compare per prompt and allow a small flipped fraction
-    per = ((sel - low2_ref[:, 0]).flatten(1).norm(dim=1) / low2_ref[:, 0].flatten(1).norm(dim=1))
-    agree = per < REL_TOL
-    assert agree.float().mean().item() >= 0.85, per
-    assert rel_l2(sel[agree], low2_ref[:, 0][agree]) < REL_TOL
-    assert rel_l2(out2["sel_iou"][agree], ious2_ref[:, 0][agree]) < REL_TOL
 
 
 AMG_KW = dict(points_per_side=8, crop_n_layers=1, crop_n_points_downscale_factor=2, box_nms_thresh=0.95,

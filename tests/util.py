@@ -55,13 +55,15 @@ def oracle_amg_from_captures(caps, hw, *, points_per_side, crop_n_layers, crop_n
             n, cpp = c["n"], c["cpp"]
             prompt = np.arange(n) // cpp
             token = c["sel"][prompt] if c["sel"] is not None else (1 + np.arange(n) % 3 if cpp == 3 else np.zeros(n, int))
-            planes = c["planes"][prompt, token]
+            planes = c["planes"] if c["planes"].ndim == 3 else c["planes"][prompt, token]
             ious = c["ious4"][prompt, token]
             r = R.mask_post(planes, ious, cb, hw, pred_iou_thresh, mask_threshold, stability_score_offset,
-                            stability_score_thresh)
+                            stability_score_thresh, only_iou_survivors=True)
+            row_of = {int(s_): j for j, s_ in enumerate(r["rows"])} if "rows" in r else None
             for i in np.flatnonzero(r["keep"]):
                 slot = c["base"] + i
-                recs.append(dict(segmentation=r["masks"][i], area=int(r["area"][i]), bbox_xyxy=r["bbox"][i],
+                seg = r["masks"][i] if row_of is None else r["masks_rows"][row_of[int(i)]]
+                recs.append(dict(segmentation=seg, area=int(r["area"][i]), bbox_xyxy=r["bbox"][i],
                                  predicted_iou=float(ious[i]), stability_score=float(r["stability"][i]),
                                  point_coords=[pts_full[(slot - crop_base) // cpp_total].tolist()],
                                  crop_box=[x0, y0, x1 - x0, y1 - y0], crop_xyxy=cb))

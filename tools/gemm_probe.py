@@ -11,6 +11,8 @@ SHAPES = [  # M, N, K, act, res(0 none, 1 f32), out_f32, bn
     (524288, 432, 144, 0, 0, 0, 0), (8192, 4608, 1152, 1, 0, 0, 0), (8192, 8192, 8192, 0, 0, 0, 0),
     (128, 256, 64, 0, 0, 0, 256), (128, 64, 64, 0, 0, 0, 64), (512, 256, 256, 0, 0, 0, 0), (512, 2048, 256, 2, 0, 0, 0),
     (786432, 256, 256, 0, 1, 0, 0), (786432, 128, 256, 0, 1, 0, 0),
+    (86016, 2304, 576, 1, 0, 0, 0),  # 15: fc1 at the bench's encoder batch (21 crops x 4096 tokens): roofline.traffic
+    (86016, 576, 2304, 0, 1, 1, 0),  # 16: fc2 (192-wide tiles)
 ]
 R = 10
 
