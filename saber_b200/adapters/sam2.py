@@ -289,11 +289,11 @@ class SAM2Adapter(BaseAdapter):
         self._current_frame = None
         captured: Dict[Any, list] = {}
 
-        def _hook(module, inputs, output):
-            logits = output[3].detach().cpu().to(torch.float32).numpy()
-            captured.setdefault(self._current_frame, []).append(logits)
-
-        handle = p.sam_mask_decoder.register_forward_hook(_hook)
+        # The reference registers a forward hook that copies output[3] to the host on every decoder call (REF :277-284):
+        # one synchronisation per object and frame. Same bookkeeping here (scores filed under `_current_frame` at call
+        # time, incl. the off-by-one of SURVEY 3.3), but the score tensors stay on the device until both passes are done.
+        pending = []  # (frame key at call time, device tensor [B,1])
+        p.sam_mask_decoder.device_sink = lambda scores: pending.append((self._current_frame, scores.clone()))
         self.frame_metrics = {}
         vol_masks = torch.zeros((Z, H, W), dtype=torch.int16, device=self.device)
 
@@ -319,7 +319,11 @@ class SAM2Adapter(BaseAdapter):
             if not nonempty[frame_idx]:
                 _apply(frame_idx, obj_ids, mask_logits)
         sbdist.allreduce_max_labels(vol_masks, group)
-        handle.remove()
+        p.sam_mask_decoder.device_sink = None
+        for key, scores in pending:  # one D2H per call group, after the fact; per-object order as the hook would see it
+            host = scores.to(torch.float32).cpu().numpy()
+            for i in range(host.shape[0]):
+                captured.setdefault(key, []).append(host[i:i + 1])
         if world > 1:
             import torch.distributed as tdist
             logs = [None] * world

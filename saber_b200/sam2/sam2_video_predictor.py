@@ -48,6 +48,10 @@ class _DecoderModule:
     def __init__(self, exec_):
         self.exec = exec_
         self._hooks: List[Callable] = []
+        # resident alternative to a forward hook: when set to a callable it receives the DEVICE tensor of object scores
+        # [B,1] of every decoder call (no host copy, no synchronisation); SAM2Adapter.segment_volume_device uses it so
+        # that the host can run ahead of the GPU across frames. Forward hooks (the reference's interface) still work.
+        self.device_sink: Optional[Callable] = None
 
     def register_forward_hook(self, fn):
         self._hooks.append(fn)
@@ -56,6 +60,8 @@ class _DecoderModule:
     def fire(self, masks, ious, tokens, obj_scores):
         """One hook call per batch entry with upstream's output tuple (masks, iou_pred, sam_tokens_out,
         object_score_logits); the scores are brought to the host once for the whole batch."""
+        if self.device_sink is not None:
+            self.device_sink(obj_scores.detach().reshape(-1, 1))
         if not self._hooks:
             return
         host = obj_scores.detach().reshape(-1, 1).cpu()
