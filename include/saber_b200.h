@@ -33,10 +33,15 @@ int sb_require_sm100(void);             /* fails unless the current device is co
  * Replaces torch.nn.Linear / 1x1 Conv2d / ConvTranspose2d(k2,s2) (cuBLASLt / cuDNN) inside upstream sam2:
  * Hiera qkv/proj/mlp (sam2/modeling/backbones/hieradet.py), FpnNeck laterals, mask-decoder projections.
  * act: 0 none, 1 GELU(erf), 2 ReLU, 3 sigmoid. flags: bit0 out is fp32 (else bf16), bit1 residual is fp32.
- * force_bn: 0 = choose tile N automatically, else 64 / 128 / 256. */
+ * force_bn: 0 = choose the kernel and tile N automatically (products with M >= 4096 and N >= 128 run on CTA pairs:
+ * tcgen05.mma.cta_group::2 over 256 x {128,192,256} pair tiles with a TMA-store epilogue); 64 / 128 / 192 / 256 = that
+ * tile N on the single-CTA kernel; -128 / -192 / -256 = that pair-tile N. */
 int sb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
                  int K, const float* bias, int act, const void* residual, long long ldr, int res_mod, int flags,
                  float alpha, int force_bn, void* stream);
+/* Diagnostic: device array of 8 u64 clock counters that every following sb_gemm_bf16 launch adds to (NULL = off):
+ * producer / MMA / epilogue wait and work clocks summed over CTAs (see csrc/gemm_tcgen05.cu). */
+int sb_gemm_set_prof(unsigned long long* counters);
 /* out[M,N] = LayerNorm_N(A @ W^T + bias + residual) * gamma + beta in one kernel (N <= 256, N % 16 == 0): the
  * "keys = norm4(keys + cross_attn_image_to_token(...))" step of sam2/modeling/sam/transformer.py TwoWayAttentionBlock. */
 int sb_gemm_ln(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N, int K,

@@ -93,6 +93,34 @@ int sb_make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uin
   return SB_OK;
 }
 
+// 2-D row-major tensor map of 2-byte (bf16) or 4-byte (fp32) elements with a chosen swizzle (0 / 32 / 64 / 128 bytes): the
+// TMA-store side of the GEMM epilogues (box = one warp's 32 x 32 staging tile).
+int sb_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+  {
+    int rc = sb_resolve_encode();
+    if (rc != SB_OK) return rc;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sb_set_error("cuTensorMapEncodeTiled failed (%d): base=%p elem=%d rows=%llu cols=%llu ld=%llu box=%ux%u swizzle=%d",
+                 (int)r, base, elem_bytes, (unsigned long long)rows, (unsigned long long)cols,
+                 (unsigned long long)ld_elems, box_rows, box_cols, swizzle_bytes);
+    return SB_ERR_DRIVER;
+  }
+  return SB_OK;
+}
+
 int sb_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                          uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
   {

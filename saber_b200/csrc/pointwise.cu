@@ -49,47 +49,77 @@ layernorm_kernel(const void* __restrict__ in, long long ld_in, void* __restrict_
 }
 
 // Fast path for fp32 rows of up to 1536 channels (every Hiera LayerNorm): one 16-byte load per lane and 128 channels,
-// the row stays in registers for the two-pass statistics and the normalisation (the generic kernel walks the row three
-// times with 4-byte accesses: 2.6 TB/s on the [32768, 576] streams of stage 3), 8- / 16-byte stores.
-template <bool OUT_F32>
+// the row stays in registers for the two-pass statistics and the normalisation, 8- / 16-byte stores. NV = float4 per
+// lane (compile time: C <= 128 NV). Two things took the stage-3 streams ([32768, 576] fp32 -> bf16) from 2.5 TB/s up
+// (profiles/r02k_encoder_batch_launches_summary.txt: 46 us per launch, 14 % of the encoder): the loads of the warp's
+// NEXT row are issued before the current row is reduced (a warp always has a row in flight; before, load -> two
+// shuffle reductions -> store were serial per warp), and gamma / beta stay in registers across rows for NV <= 5
+// (re-reading them per row doubled the LSU wavefronts of the kernel).
+template <int NV, bool OUT_F32>
 __global__ void __launch_bounds__(256)
 layernorm_rows_f32_kernel(const float* __restrict__ in, long long ld_in, void* __restrict__ out, long long ld_out,
                           const float* __restrict__ gamma, const float* __restrict__ beta, int M, int C, float eps,
                           int act) {
-  constexpr int MAXV = 12;
+  constexpr bool GB_REGS = NV <= 5;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nv = C >> 2;  // float4 per row
   const float inv_c = 1.f / static_cast<float>(C);
-  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < M;
-       row += static_cast<long long>(gridDim.x) * warps_per_block) {
+  const long long stride = static_cast<long long>(gridDim.x) * warps_per_block;
+  long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float4 g[GB_REGS ? NV : 1], b[GB_REGS ? NV : 1];
+  if (GB_REGS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      g[i] = c4 < nv ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      b[i] = c4 < nv ? __ldg(reinterpret_cast<const float4*>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float4 nxt[NV];
+  {
     const float4* src = reinterpret_cast<const float4*>(in + row * ld_in);
-    float4 v[MAXV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      nxt[i] = c4 < nv ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (; row < M; row += stride) {
+    float4 v[NV];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c4 = lane + 32 * i;
-      v[i] = c4 < nv ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) {
+      v[i] = nxt[i];
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    if (row + stride < M) {  // warp-uniform
+      const float4* src = reinterpret_cast<const float4*>(in + (row + stride) * ld_in);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + 32 * i;
+        nxt[i] = c4 < nv ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     const float mean = sb::warp_sum(sum) * inv_c;
     float vs = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (lane + 32 * i < nv) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        vs += (a * a + b * b) + (c * c + d * d);
+        const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        vs += (a * a + bb * bb) + (c * c + d * d);
       }
     }
     const float rstd = rsqrtf(sb::warp_sum(vs) * inv_c + eps);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       if (c4 < nv) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-        float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
-        float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+        const float4 gg = GB_REGS ? g[i] : __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 be = GB_REGS ? b[i] : __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        float y0 = (v[i].x - mean) * rstd * gg.x + be.x, y1 = (v[i].y - mean) * rstd * gg.y + be.y;
+        float y2 = (v[i].z - mean) * rstd * gg.z + be.z, y3 = (v[i].w - mean) * rstd * gg.w + be.w;
         if (act == 1) {
           y0 = sb::gelu_erf(y0);
           y1 = sb::gelu_erf(y1);
@@ -104,6 +134,15 @@ layernorm_rows_f32_kernel(const float* __restrict__ in, long long ld_in, void* _
       }
     }
   }
+}
+
+template <int NV>
+void launch_ln_rows(int g, cudaStream_t stream, const float* in, long long ld_in, void* out, long long ld_out, int out_f32,
+                    const float* gamma, const float* beta, int M, int C, float eps, int act) {
+  if (out_f32)
+    layernorm_rows_f32_kernel<NV, true><<<g, 256, 0, stream>>>(in, ld_in, out, ld_out, gamma, beta, M, C, eps, act);
+  else
+    layernorm_rows_f32_kernel<NV, false><<<g, 256, 0, stream>>>(in, ld_in, out, ld_out, gamma, beta, M, C, eps, act);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -255,12 +294,14 @@ extern "C" int sb_layernorm(const void* in, long long ld_in, int in_f32, void* o
                     ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                       reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (fast) {
-    if (out_f32)
-      layernorm_rows_f32_kernel<true><<<g, 256, 0, stream>>>(static_cast<const float*>(in), ld_in, out, ld_out, gamma,
-                                                            beta, M, C, eps, act);
-    else
-      layernorm_rows_f32_kernel<false><<<g, 256, 0, stream>>>(static_cast<const float*>(in), ld_in, out, ld_out, gamma,
-                                                             beta, M, C, eps, act);
+    const float* inf = static_cast<const float*>(in);
+    const int nvl = (C / 4 + 31) / 32;  // float4 per lane
+    if (nvl <= 1) launch_ln_rows<1>(g, stream, inf, ld_in, out, ld_out, out_f32, gamma, beta, M, C, eps, act);
+    else if (nvl <= 2) launch_ln_rows<2>(g, stream, inf, ld_in, out, ld_out, out_f32, gamma, beta, M, C, eps, act);
+    else if (nvl <= 3) launch_ln_rows<3>(g, stream, inf, ld_in, out, ld_out, out_f32, gamma, beta, M, C, eps, act);
+    else if (nvl <= 5) launch_ln_rows<5>(g, stream, inf, ld_in, out, ld_out, out_f32, gamma, beta, M, C, eps, act);
+    else if (nvl <= 9) launch_ln_rows<9>(g, stream, inf, ld_in, out, ld_out, out_f32, gamma, beta, M, C, eps, act);
+    else launch_ln_rows<12>(g, stream, inf, ld_in, out, ld_out, out_f32, gamma, beta, M, C, eps, act);
     SB_CHECK_LAUNCH();
     return SB_OK;
   }

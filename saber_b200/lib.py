@@ -21,6 +21,7 @@ SIGNATURES = {
     "sb_require_sm100": [],
     "sb_gemm_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p,
                      c_int, c_void_p, c_ll, c_int, c_int, c_float, c_int, c_void_p],
+    "sb_gemm_set_prof": [c_void_p],
     "sb_gemm_ln": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_int,
                    c_int, c_void_p, c_void_p, c_float, c_void_p],
     "sb_gemm_upscale1": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p,

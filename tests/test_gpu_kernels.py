@@ -29,6 +29,17 @@ GEMM_CASES = [
     # 192-wide tiles (TMEM accumulator stages 256 columns apart): exact and ragged N, both output types
     dict(M=4096, N=576, K=576, bias=1, res=1, out_f32=1, bn=192), dict(M=1000, N=200, K=136, bias=1, act=1, bn=192),
     dict(M=8192, N=1728, K=576, bias=1, bn=192),
+    # many tiles per CTA: residual gathers pipelined across tiles, both warp sets on every tile (K >= 512) and the
+    # alternating scheme (K < 512), in-place output staging (fp32 / fp32), ragged last column tile, every tile width
+    dict(M=40000, N=576, K=576, bias=1, res=1, out_f32=1), dict(M=40000, N=576, K=576, bias=1, res=1, out_f32=1, bn=256),
+    dict(M=40000, N=576, K=1152, bias=1, res=1, out_f32=1, bn=192), dict(M=40000, N=400, K=576, bias=1, res=1, out_f32=1, bn=64),
+    dict(M=40000, N=288, K=288, bias=1, res=1, out_f32=1), dict(M=40000, N=144, K=144, bias=1, res=1, out_f32=1),
+    dict(M=30000, N=2304, K=576, bias=1, act=1), dict(M=30000, N=4608, K=128, bias=1),
+    dict(M=30001, N=272, K=640, bias=1, res=1, res_bf16=1), dict(M=30001, N=272, K=64, bias=1, res=1, res_bf16=1, out_f32=1),
+    # CTA-pair kernel (M >= 4096, N >= 128): ragged M (not a multiple of 256), ragged N, K tail, every pair-tile width
+    dict(M=5000, N=576, K=576, bias=1, res=1, out_f32=1, bn=-256), dict(M=5000, N=576, K=200, bias=1, act=1, bn=-192),
+    dict(M=4100, N=144, K=1152, bias=1, res=1, out_f32=1, bn=-128), dict(M=70000, N=1152, K=288, bias=1, act=1, bn=-256),
+    dict(M=9000, N=336, K=96, bias=1, out_f32=1, bn=-192),
 ]
 
 
@@ -43,6 +54,8 @@ def test_gemm_bf16(ops, kw):
     bias = torch.randn(N, device="cuda") if kw.get("bias") else None
     res_mod = kw.get("res_mod", 0)
     res = torch.randn(res_mod if res_mod else M, N, device="cuda") if kw.get("res") else None
+    if res is not None and kw.get("res_bf16"):
+        res = res.to(BF16)
     out = ops.gemm(a, w, bias, kw.get("act", 0), res, res_mod, F32 if kw.get("out_f32") else BF16,
                    force_bn=kw.get("bn", 0))
     ref = a.float() @ w.float().t()
@@ -50,7 +63,7 @@ def test_gemm_bf16(ops, kw):
         ref = ref + bias
     ref = {0: lambda x: x, 1: F.gelu, 2: F.relu, 3: torch.sigmoid}[kw.get("act", 0)](ref)
     if res is not None:
-        ref = ref + (res.repeat(M // res.shape[0], 1) if res_mod else res)
+        ref = ref + (res.float().repeat(M // res.shape[0], 1) if res_mod else res.float())
     err = (out.float() - ref).abs().max().item()
     tol = 2e-2 * max(1.0, ref.abs().max().item()) if out.dtype == BF16 else 1e-4 * max(1.0, ref.abs().max().item())
     assert err <= tol, (err, tol)

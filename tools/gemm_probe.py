@@ -59,6 +59,20 @@ def main():
         tiles128 = ((M + 127) // 128)
         print(f"M={M:7d} N={N:5d} K={K:5d} act={act} res={res} f32={of32} bn={bn:3d}: {us:9.1f} us  "
               f"{2.0 * M * N * K / us / 1e6:8.1f} TFLOP/s  out {M * N * (4 if of32 else 2) / us / 1e3:7.1f} GB/s")
+        if os.environ.get("SB_GEMM_PROF", "1") != "0":  # one instrumented launch: where do the warps wait?
+            from saber_b200 import lib as _lib
+            L = _lib.load()
+            cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+            L.sb_gemm_set_prof(cnt.data_ptr())
+            run()
+            torch.cuda.synchronize()
+            L.sb_gemm_set_prof(None)
+            c = cnt.tolist()
+            ctas, tot = max(c[6], 1), max(c[5], 1)
+            etiles = max(c[7], 1)
+            print(f"      per CTA (clocks, MMA-warp span {tot / ctas:9.0f}): producer waits slot {c[0] / tot:5.1%}  MMA waits operands "
+                  f"{c[1] / tot:5.1%}  MMA waits accumulator {c[2] / tot:5.1%} | epilogue set: waits {c[3] / etiles:7.0f} clk/tile, works "
+                  f"{c[4] / etiles:7.0f} clk/tile ({etiles} tiles)")
         del a, w, r, out
 
 
