@@ -1118,14 +1118,16 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     if (extra <= 0) vec_all_bytes = VEC_BYTES;
     else if (extra <= have) vec_all_bytes = need;
   }
-  // Both warp sets on every tile (see the kernel): always for the up-scaling epilogues; for STD when the main loop is a
-  // visible part of the tile (K >= split_min_k, SB_GEMM_SPLIT_MINK to override for A/B runs)
+  // Both warp sets on every tile (see the kernel): for UP1 and for STD when the main loop is a visible part of the tile
+  // (K >= split_min_k, SB_GEMM_SPLIT_MINK to override for A/B runs)
   static int split_min_k = -1;
   if (split_min_k < 0) {
     const char* e = getenv("SB_GEMM_SPLIT_MINK");
     split_min_k = e ? atoi(e) : 512;
   }
-  const int split = (EW == 8 && (EPI == EPI_UP1 || EPI == EPI_UP2 || (EPI == EPI_STD && p.K >= split_min_k))) ||
+  // UP2 (K = 64: no main loop to hide) stays on the alternating scheme: in the bench's decoder passes the split form
+  // was 25 % slower (16.2 vs 12.9 ms per slice, profiles/r02w_gemm_shapes.txt vs r02k), UP1 (K = 256) 9 % faster.
+  const int split = (EW == 8 && (EPI == EPI_UP1 || (EPI == EPI_STD && p.K >= split_min_k))) ||
                             (EW == 16 && EPI == EPI_STD) ? 1 : 0;
   const int smem_bytes = 1024 + BAR_BYTES + stages * C::STAGE_BYTES + epi_bytes(res_bufs) +
                          (vec_all_bytes > VEC_BYTES ? vec_all_bytes - VEC_BYTES : 0);
@@ -1576,9 +1578,9 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
     } else {
       const long long m_tiles = (M + BM - 1) / BM;
       long long best = -1;
-      // 192 divides Hiera-L's 576 / 1152-wide MLP outputs exactly (256 wastes a quarter of the last tile). Measured
-      // (profiles/r02d_encoder_probe.log vs r01zc): a win for the main-loop-bound K >= 1152 shapes (fc2: 605 -> 754
-      // TFLOP/s), a loss for the epilogue-bound K <= 576 ones (qkv: 935 -> 876), so it is only a candidate for large K.
+      // 192 divides Hiera-L's 576 / 1152-wide outputs exactly (256 wastes a quarter of the last tile): a candidate for
+      // every product with a residual (they all have N in {144, 288, 576, 1152}; profiles/r02u_gemm_tile_ab.log) and for
+      // K >= 1152 otherwise.
       static int min_k_192 = -1;
       if (min_k_192 < 0) {
         const char* e = getenv("SB_GEMM_192_MINK");
@@ -1587,7 +1589,7 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
       const int cands[4] = {256, 192, 128, 64};
       for (int i = 0; i < 4; ++i) {
         const int c = cands[i];
-        if (c == 192 && K < min_k_192) continue;
+        if (c == 192 && K < min_k_192 && residual == nullptr) continue;
         const long long tiles = m_tiles * ((N + c - 1) / c);
         const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
         const long long cost = waves * (c + 24);  // +24: fixed per-tile overhead proxy
@@ -1607,7 +1609,11 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
       pair_env = (e && atoi(e) == 0) ? 0 : 1;
     }
     const long long ob = ldo * (p.out_f32 ? 4 : 2), rb = ldr * (p.res_f32 ? 4 : 2);
-    const bool ok = pair_env && force_bn <= 0 && M >= 4096 && N >= 128 && (N % 16) == 0 && (ob % 16) == 0 &&
+    // Measured per shape (profiles/r02u_gemm_tile_ab.log, cold L2): the pair kernel wins for the bf16-output products
+    // without a residual (fc1 +6 %, stage-2 fc1 +9 %), the single-CTA kernel (two residual tiles, outputs staged in
+    // place) for the "+ residual" ones (proj +8 %), so a residual keeps the product on the single-CTA kernel unless
+    // the pair width is forced.
+    const bool ok = pair_env && force_bn <= 0 && (force_bn < 0 || residual == nullptr) && M >= 4096 && N >= 128 && (N % 16) == 0 && (ob % 16) == 0 &&
                     (!residual || rb % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) && (res_mod == 0 || (res_mod % 32) == 0) &&
                     (static_cast<long long>(M) * ob < (1ll << 35)) && (!residual || static_cast<long long>(M) * rb < (1ll << 35)) &&
@@ -1623,7 +1629,8 @@ extern "C" int sb_gemm_bf16(const void* A, long long lda, const void* W, long lo
           const int c = cands[i];
           const long long tiles = m_tiles2 * ((N + c - 1) / c);
           const long long waves = (tiles + g_num_sms / 2 - 1) / (g_num_sms / 2);
-          const long long cost = waves * (c + 16);
+          // bytes staged per k-block and CTA ~ 128 rows of A + c / 2 rows of B: wider tiles re-use A better
+          const long long cost = waves * (c + 256);
           if (best < 0 || cost < best) {
             best = cost;
             bn2 = c;
