@@ -50,12 +50,18 @@ int sb_gemm_ln(const void* A, long long lda, const void* W, long long ldw, void*
 /* mask_decoder.py output_upscaling[0..2]: ConvTranspose2d(256->64,k2,s2) + feat_s1 skip + LayerNorm2d + GELU, fused */
 int sb_gemm_upscale1(const void* A, long long lda, const void* W, long long ldw, int B, int gh, int gw,
                      const float* bias, const float* feat_s1, long long skip_bstride, const float* gamma,
-                     const float* beta, float eps, void* u1, void* stream);
+                     const float* beta, float eps, void* u1, const int* plist, const int* pcount, void* stream);
 /* output_upscaling[3..4] + (hyper_in @ upscaled_embedding): ConvTranspose2d(64->32,k2,s2) + feat_s0 + GELU + dot with the
  * prompt's 4 hyper-network vectors -> masks [B,4,2gh,2gw] fp32, fused */
 int sb_gemm_upscale2(const void* A, long long lda, const void* W, long long ldw, int B, int gh, int gw,
                      const float* bias, const float* feat_s0, long long skip_bstride, const float* hyper, float* masks,
-                     void* stream);
+                     const int* plist, const int* pcount, void* stream);
+/* Both up-scaling stages take an optional device-side prompt list (plist [<= B] int32, *pcount entries; NULL = all B):
+ * only the listed prompts are processed, the other prompts' rows of u1 / masks are left untouched. sb_iou_gate builds
+ * the list of the AMG m2m pass: prompts with max(ious[b][0..3]) > thresh, the only ones that can survive
+ * SAM2AutomaticMaskGenerator's pred_iou_thresh filter (sam2/automatic_mask_generator.py _process_batch), in ascending
+ * order. */
+int sb_iou_gate(const float* ious4, int B, float thresh, int* list, int* count, void* stream);
 /* Plain batched multi-head attention (mask-decoder two-way transformer: sam2/modeling/sam/transformer.py
  * Attention.forward -> F.scaled_dot_product_attention). q [batch*nq, heads*hd], k/v [batch*nk, heads*hd]. */
 int sb_attention(const void* q, long long q_ld, const void* k, long long k_ld, const void* v, long long v_ld, void* o,

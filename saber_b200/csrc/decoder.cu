@@ -294,6 +294,43 @@ upscale2_mask_kernel(const __nv_bfloat16* __restrict__ g2, const float* __restri
   }
 }
 
+// AMG m2m pass: which prompts can still pass `iou > thresh` whatever dynamic_multimask_via_stability picks? The output
+// IoU of a prompt is ious[b][0] or max(ious[b][1..3]), so max over the four is an upper bound: prompts below it are
+// discarded by SAM2AutomaticMaskGenerator's pred_iou_thresh filter without their masks ever being looked at
+// (automatic_mask_generator.py _process_batch: keep = data["iou_preds"] > pred_iou_thresh), and the up-scaling GEMMs
+// skip them. Ordered compaction (ascending prompt index) by one block; list [B], count [1].
+__global__ void __launch_bounds__(1024)
+iou_gate_kernel(const float* __restrict__ ious /*[B,4]*/, int B, float thresh, int* __restrict__ list,
+                int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    bool pass = false;
+    if (b < B) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ious) + b);
+      pass = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > thresh;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (pass) list[off + __popc(m & ((1u << lane) - 1u))] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += warp_tot[w];
+      base_s += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+
 // dynamic_multimask_via_stability (single-mask output): per prompt, stability of mask token 0 =
 // count(logit > delta) / count(logit > -delta) (1 when the union is empty); if >= thresh keep token 0
 // else the best-IoU token among 1..3 (first max). Writes the chosen token index and IoU.
@@ -440,6 +477,15 @@ extern "C" int sb_select_mask(const float* masks, const float* ious, int B, int 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(B > 0 && HW > 0, "sb_select_mask: bad sizes");
   select_mask_kernel<<<B, 1024, 0, stream>>>(masks, ious, HW, delta, thresh, sel_idx, sel_iou);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_iou_gate(const float* ious4, int B, float thresh, int* list, int* count, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(B > 0 && ious4 && list && count, "sb_iou_gate: bad arguments");
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(ious4) & 15) == 0, "sb_iou_gate: ious must be 16-byte aligned");
+  iou_gate_kernel<<<1, 1024, 0, stream>>>(ious4, B, thresh, list, count);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

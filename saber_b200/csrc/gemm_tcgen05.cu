@@ -56,6 +56,10 @@ struct GemmParams {
   const float* hyper;         // UP2: [B, 4, 32] fp32
   int gh, gw;                 // input token grid of the transposed conv (rows m = (b, y, x), y < gh, x < gw)
   unsigned long long* prof;   // optional (sb_gemm_set_prof): 8 clock counters summed over CTAs, see sb_gemm_set_prof
+  // UP1 / UP2 on a device-side prompt list: only the prompts plist[0 .. *pcount) are processed (rows of prompt b are
+  // b * gh * gw ...); the other prompts' outputs are left untouched. nullptr = all B prompts.
+  const int* plist;
+  const int* pcount;
 };
 
 template <int BN>
@@ -737,7 +741,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  // up-scaling on a prompt list: tile t -> (listed prompt t / tpp, row block t % tpp); the tile count is read on the device
+  const int tpp = ((EPI == EPI_UP1 || EPI == EPI_UP2) && p.plist != nullptr) ? (p.gh * p.gw) / BM : 0;
+  const int num_tiles = tpp > 0 ? __ldg(p.pcount) * tpp : m_tiles * n_tiles;
+  auto tile_m = [&](int tile) -> int {
+    if (tpp > 0) return __ldg(p.plist + tile / tpp) * (p.gh * p.gw) + (tile % tpp) * BM;
+    return (tile / n_tiles) * BM;
+  };
   const int num_kb = (p.K + BK - 1) / BK;
   const int last_ksteps = ((p.K - (num_kb - 1) * BK) + 15) / 16;
 
@@ -775,7 +785,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t phase = 0;
     long long prof_acc = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_idx = (tile / n_tiles) * BM;
+      const int m_idx = tile_m(tile);
       const int n_idx = (tile % n_tiles) * BN;
       if (pf_res) {
         const uint32_t bytes = static_cast<uint32_t>(min(BN, p.N - n_idx) * res_esz);
@@ -890,7 +900,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int st = it & 1;
         const uint32_t acc_phase = static_cast<uint32_t>((it >> 1) & 1);
-        const int m_idx = (tile / n_tiles) * BM;
+        const int m_idx = tile_m(tile);
         float* vec = sVec + st * VEC_FLOATS;
         es.vec = sb::smem_u32(vec);
         asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp is done with the previous tiles' vectors
@@ -987,7 +997,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (!split && (it & 1) != set) continue;
       const int st = split ? (it & 1) : set;
       if (split) acc_phase = static_cast<uint32_t>((it >> 1) & 1);
-      const int m_idx = (tile / n_tiles) * BM;
+      const int m_idx = tile_m(tile);
       const int n_idx = (tile % n_tiles) * BN;
       if (!const_vec) {
         // stage this tile's per-column vectors once per set: every read in the epilogues is a shared-memory broadcast
@@ -1719,7 +1729,8 @@ extern "C" int sb_gemm_ln(const void* A, long long lda, const void* W, long long
 // + feat_s1 (fp32 [.., 2gh*2gw, 64], batch stride skip_bstride), LayerNorm2d(64, eps), GELU -> u1 [B*2gh*2gw, 64] bf16.
 extern "C" int sb_gemm_upscale1(const void* A, long long lda, const void* W, long long ldw, int B, int gh, int gw,
                                 const float* bias, const float* feat_s1, long long skip_bstride,
-                                const float* gamma, const float* beta, float eps, void* u1, void* stream_) {
+                                const float* gamma, const float* beta, float eps, void* u1, const int* plist,
+                                const int* pcount, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(B > 0 && gh > 0 && gw > 0 && bias && feat_s1 && gamma && beta, "sb_gemm_upscale1: bad arguments");
   if (ensure_sms() != SB_OK) return SB_ERR_CUDA;
@@ -1738,6 +1749,11 @@ extern "C" int sb_gemm_upscale1(const void* A, long long lda, const void* W, lon
   p.skip_bstride = skip_bstride;
   p.gh = gh;
   p.gw = gw;
+  SB_REQUIRE((plist == nullptr) == (pcount == nullptr) && (plist == nullptr || (gh * gw) % BM == 0),
+             "sb_gemm_upscale1: prompt list needs its count and gh * gw a multiple of 128");
+  p.plist = plist;
+  p.pcount = pcount;
+  p.prof = g_prof;
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, p.M, 256, 256, 256, &tmA, &tmB);
   if (rc != SB_OK) return rc;
@@ -1757,7 +1773,7 @@ extern "C" int sb_gemm_upscale1(const void* A, long long lda, const void* W, lon
 // dot with hyper [B,4,32] -> masks [B, 4, 2gh, 2gw] fp32. gh*gw must be a multiple of 128 (a tile never spans prompts).
 extern "C" int sb_gemm_upscale2(const void* A, long long lda, const void* W, long long ldw, int B, int gh, int gw,
                                 const float* bias, const float* feat_s0, long long skip_bstride, const float* hyper,
-                                float* masks, void* stream_) {
+                                float* masks, const int* plist, const int* pcount, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(B > 0 && gh > 0 && gw > 0 && bias && feat_s0 && hyper, "sb_gemm_upscale2: bad arguments");
   if (ensure_sms() != SB_OK) return SB_ERR_CUDA;
@@ -1774,6 +1790,11 @@ extern "C" int sb_gemm_upscale2(const void* A, long long lda, const void* W, lon
   p.hyper = hyper;
   p.gh = gh;
   p.gw = gw;
+  SB_REQUIRE((plist == nullptr) == (pcount == nullptr) && (gh * gw) % BM == 0,
+             "sb_gemm_upscale2: gh * gw must be a multiple of 128 (and a prompt list needs its count)");
+  p.plist = plist;
+  p.pcount = pcount;
+  p.prof = g_prof;
   CUtensorMap tmA, tmB;
   int rc = make_maps(A, lda, W, ldw, p.M, 128, 64, 128, &tmA, &tmB);
   if (rc != SB_OK) return rc;

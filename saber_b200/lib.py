@@ -25,9 +25,10 @@ SIGNATURES = {
     "sb_gemm_ln": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_int,
                    c_int, c_void_p, c_void_p, c_float, c_void_p],
     "sb_gemm_upscale1": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p,
-                         c_void_p, c_float, c_void_p, c_void_p],
+                         c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_gemm_upscale2": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p,
-                         c_void_p, c_void_p],
+                         c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_iou_gate": [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "sb_attention": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
                      c_int, c_int, c_int, c_float, c_int, c_int, c_void_p],
     "sb_attention_kadd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,

@@ -180,9 +180,24 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resi
     return out
 
 
+def iou_gate(ious4: torch.Tensor, thresh: float):
+    """Prompts whose best predicted IoU exceeds `thresh` (ascending): (list int32 [B], count int32 [1]) on the device."""
+    _chk_cuda(ious4)
+    assert ious4.dtype == _F32 and ious4.is_contiguous() and ious4.dim() == 2 and ious4.shape[1] == 4
+    B = ious4.shape[0]
+    lst = torch.empty((B,), dtype=torch.int32, device=ious4.device)
+    cnt = torch.empty((1,), dtype=torch.int32, device=ious4.device)
+    L = _lib.load()
+    _lib.check(L.sb_iou_gate(ious4.data_ptr(), B, float(thresh), lst.data_ptr(), cnt.data_ptr(), _stream()), "sb_iou_gate")
+    _count()
+    return lst, cnt
+
+
 def gemm_upscale1(keys: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_s1: torch.Tensor, s1_bstride: int,
-                  gamma: torch.Tensor, beta: torch.Tensor, B: int, gh: int, gw: int, eps: float = 1e-6) -> torch.Tensor:
-    """keys [B*gh*gw,256] bf16 -> u1 [B*2gh*2gw, 64] bf16 (transposed conv + skip + LayerNorm2d + GELU fused)."""
+                  gamma: torch.Tensor, beta: torch.Tensor, B: int, gh: int, gw: int, eps: float = 1e-6,
+                  plist=None) -> torch.Tensor:
+    """keys [B*gh*gw,256] bf16 -> u1 [B*2gh*2gw, 64] bf16 (transposed conv + skip + LayerNorm2d + GELU fused).
+    plist = (list, count) from iou_gate: only those prompts are computed."""
     _chk_cuda(keys, w, bias, feat_s1, gamma, beta)
     assert keys.dtype == _BF16 and keys.shape == (B * gh * gw, 256) and keys.stride(1) == 1
     assert w.dtype == _BF16 and w.shape == (256, 256) and bias.numel() == 256 and feat_s1.dtype == _F32
@@ -191,7 +206,7 @@ def gemm_upscale1(keys: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_
     ev = _prof_begin()
     rc = L.sb_gemm_upscale1(keys.data_ptr(), keys.stride(0), w.data_ptr(), w.stride(0), B, gh, gw, bias.data_ptr(),
                             feat_s1.data_ptr(), s1_bstride, gamma.data_ptr(), beta.data_ptr(), eps, u1.data_ptr(),
-                            _stream())
+                            _ptr(plist[0]) if plist else None, _ptr(plist[1]) if plist else None, _stream())
     _prof_end(ev, 2.0 * B * gh * gw * 256 * 256, f"up1 M={B * gh * gw} N=256 K=256")
     _lib.check(rc, "sb_gemm_upscale1")
     _count()
@@ -199,17 +214,20 @@ def gemm_upscale1(keys: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_
 
 
 def gemm_upscale2(u1: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, feat_s0: torch.Tensor, s0_bstride: int,
-                  hyper: torch.Tensor, B: int, gh: int, gw: int) -> torch.Tensor:
-    """u1 [B*gh*gw,64] bf16 -> masks [B,4,2gh,2gw] fp32 (transposed conv + skip + GELU + hyper-network dot fused)."""
+                  hyper: torch.Tensor, B: int, gh: int, gw: int, plist=None, zero_fill: bool = False) -> torch.Tensor:
+    """u1 [B*gh*gw,64] bf16 -> masks [B,4,2gh,2gw] fp32 (transposed conv + skip + GELU + hyper-network dot fused).
+    plist = (list, count) from iou_gate: only those prompts' masks are written (the others are uninitialised, or zero
+    with zero_fill)."""
     _chk_cuda(u1, w, bias, feat_s0, hyper)
     assert u1.dtype == _BF16 and u1.shape == (B * gh * gw, 64) and (gh * gw) % 128 == 0
     assert w.dtype == _BF16 and w.shape == (128, 64) and bias.numel() == 128 and feat_s0.dtype == _F32
     assert hyper.dtype == _F32 and hyper.is_contiguous() and hyper.shape == (B, 4, 32)
-    masks = torch.empty((B, 4, 2 * gh, 2 * gw), dtype=_F32, device=u1.device)
+    masks = (torch.zeros if (plist and zero_fill) else torch.empty)((B, 4, 2 * gh, 2 * gw), dtype=_F32, device=u1.device)
     L = _lib.load()
     ev = _prof_begin()
     rc = L.sb_gemm_upscale2(u1.data_ptr(), u1.stride(0), w.data_ptr(), w.stride(0), B, gh, gw, bias.data_ptr(),
-                            feat_s0.data_ptr(), s0_bstride, hyper.data_ptr(), masks.data_ptr(), _stream())
+                            feat_s0.data_ptr(), s0_bstride, hyper.data_ptr(), masks.data_ptr(),
+                            _ptr(plist[0]) if plist else None, _ptr(plist[1]) if plist else None, _stream())
     _prof_end(ev, 2.0 * B * gh * gw * 128 * 64, f"up2 M={B * gh * gw} N=128 K=64")
     _lib.check(rc, "sb_gemm_upscale2")
     _count()

@@ -144,6 +144,9 @@ class SAM2AutomaticMaskGenerator:
         self.use_cuda_graph = True
         # independent prompt batches in flight (one CUDA graph instance + stream each)
         self.graph_lanes = int(os.environ.get("SB_GRAPH_LANES", "4"))
+        # m2m pass: skip the mask up-scaling of prompts whose predicted IoUs cannot pass pred_iou_thresh (results are
+        # identical: upstream computes those masks and then drops them unseen); SB_M2M_GATE=0 computes everything
+        self.m2m_gate = os.environ.get("SB_M2M_GATE", "1") != "0"
         self.phase_ms: Optional[Dict[str, float]] = None  # set to {} to accumulate encode / decode+post / total ms
         self._graphs: Dict[Tuple[int, int], Any] = {}
         self._plans: Dict[Tuple[int, int], _ImagePlan] = {}
@@ -321,8 +324,9 @@ class SAM2AutomaticMaskGenerator:
             for c0 in range(0, ncand, step):
                 cbn = min(step, ncand - c0)
                 mi = mask_in[c0 // 3:(c0 + cbn) // 3] if self.multimask_output else mask_in[c0:c0 + cbn]
+                gate = self.pred_iou_thresh if (self.m2m_gate and self.pred_iou_thresh > 0.0) else None
                 out2 = dec.forward(emb, s0, s1, tokens2[c0:c0 + cbn].contiguous(), mi, multimask_output=False,
-                                   mask_clamp=32.0)
+                                   mask_clamp=32.0, iou_gate=gate, zero_fill=self.capture is not None)
                 self._post(k, out2["masks"], out2["ious"], out2.get("sel_idx"), 1, cbn, geom, base + c0,
                            geom_dev, c0)
         else:

@@ -140,13 +140,17 @@ class MaskDecoder:
 
     def forward(self, image_embed: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, tokens: torch.Tensor,
                 mask_input: Optional[torch.Tensor] = None, multimask_output: bool = True,
-                mask_clamp: float = 0.0):
+                mask_clamp: float = 0.0, iou_gate: Optional[float] = None, zero_fill: bool = False):
         """image_embed [4096,256] fp32 (one image shared by the B prompts) or [B*4096,256] fp32 (one conditioned
         embedding per prompt: the video predictor's memory-attention output), s0 [65536,32] fp32, s1 [16384,64] fp32
         (one image, token-major);
         tokens [B, Nt, 256] fp32; mask_input [B, 256, 256] fp32, or a previous decoder output
         [B/3, 4, 256, 256] whose multimask tokens 1..3 are the B mask prompts (AMG m2m), or None;
         mask_clamp > 0 clamps the mask prompt to +-mask_clamp (upstream clamps low-res logits to +-32).
+
+        iou_gate (AMG m2m pass): prompts whose four predicted IoUs are all <= iou_gate cannot pass the caller's
+        ``iou > pred_iou_thresh`` filter whichever token the stability rule selects, so the up-scaling stages (a third
+        of the pass) skip them; their ``masks`` entries are uninitialised (zero with ``zero_fill``).
 
         Returns dict: masks [B,4,256,256] fp32 (all four tokens), ious [B,4], obj [B,1], hs [B,Nt,256]
         and, per upstream's output selection, ``sel`` describing which tokens are "the output":
@@ -245,16 +249,19 @@ class MaskDecoder:
             a = ops.attention_kadd(q, kv[:, 0:128], self.fa_k_add, kv[:, 128:256], B, 8, Nt, NT_IMG, kv_shared=(kb == 1))
         queries = ops.gemm(a, self.fa_o_w, self.fa_o_b, residual=queries, out_dtype=_F32)
         hs = ops.layernorm(queries, self.nf_w, self.nf_b, 1e-5, _F32)  # [B*Nt,256]
-        # ---- up-scaling + hyper-network masks
-        u1 = ops.gemm_upscale1(keys, self.up1_w, self.up1_b, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64)
+        # ---- IoU head first: it decides (iou_gate) which prompts need their masks at all
         hs16 = ops.add_cast(hs, None, _BF16).view(B, Nt * 256)
+        ious = self._mlp3(hs16[:, 256:512], self.iou_head, last_act=ops.ACT_SIGMOID)  # [B,4]
+        plist = ops.iou_gate(ious, iou_gate) if iou_gate is not None else None
+        # ---- up-scaling + hyper-network masks
+        u1 = ops.gemm_upscale1(keys, self.up1_w, self.up1_b, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64, plist=plist)
         hyper = torch.empty((B, 4, 32), dtype=_F32, device=self.device)
         hv = hyper.view(B, 128)
         for i in range(4):
             self._mlp3(hs16[:, (2 + i) * 256:(3 + i) * 256], self.hyper[i], out=hv[:, i * 32:(i + 1) * 32])
-        masks = ops.gemm_upscale2(u1, self.up2_w, self.up2_b, s0, 0, hyper, B, 128, 128)  # [B,4,256,256]
+        masks = ops.gemm_upscale2(u1, self.up2_w, self.up2_b, s0, 0, hyper, B, 128, 128, plist=plist,
+                                  zero_fill=zero_fill)  # [B,4,256,256]
         del u1
-        ious = self._mlp3(hs16[:, 256:512], self.iou_head, last_act=ops.ACT_SIGMOID)  # [B,4]
         obj = self._mlp3(hs16[:, 0:256], self.obj_head)  # [B,1]
         out = {"masks": masks, "ious": ious, "obj": obj, "hs": hs.view(B, Nt, 256)}
         if not multimask_output:

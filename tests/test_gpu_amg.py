@@ -167,3 +167,50 @@ def test_amg_cuda_graph_replay_equals_eager(tiny):
         assert built and all(g is not None for g in built)  # keyed by (image size, points per call)
         assert_mask_lists_equal(a, b)
         assert len(a) > 0
+
+
+def test_m2m_iou_gate_identical_results(tiny):
+    """The m2m pass skips the mask up-scaling of prompts whose four predicted IoUs are all <= pred_iou_thresh (they cannot
+    pass upstream's `iou_preds > pred_iou_thresh` whichever token the stability rule picks). (1) decoder level: listed
+    prompts' masks are bit-identical to the ungated call, the others untouched (zero); IoUs / selection inputs unchanged;
+    (2) AMG level: gate on == gate off, bit for bit, with a threshold that discards part of the candidates."""
+    from saber_b200 import ops, synth
+    from saber_b200.sam2.automatic_mask_generator import SAM2AutomaticMaskGenerator
+    from saber_b200.utils import preprocessing as prep
+    orc, model, _ = tiny
+    dec = model.decoder
+    torch.manual_seed(5)
+    img = torch.randn(1, 3, 1024, 1024, device="cuda")
+    f = model.forward_image(img)
+    B = 96
+    pts = torch.rand(B, 1, 2, device="cuda") * 1024
+    labels = torch.ones(B, 1, dtype=torch.int32, device="cuda")
+    tokens = dec.prompt_tokens(pts, labels)
+    feat = f["feat"]  # (no_mem_embed left out: any [4096, 256] embedding serves this test)
+    mi = (torch.randn(B, 256, 256, device="cuda") * 4).contiguous()
+    full = dec.forward(feat, f["s0"], f["s1"], tokens, mi, multimask_output=False, mask_clamp=32.0)
+    thr = float(full["ious"].max(dim=1).values.median())  # about half of the prompts below the gate
+    gated = dec.forward(feat, f["s0"], f["s1"], tokens, mi, multimask_output=False, mask_clamp=32.0, iou_gate=thr,
+                        zero_fill=True)
+    assert torch.equal(full["ious"], gated["ious"])
+    live = full["ious"].max(dim=1).values > thr
+    assert 0 < int(live.sum()) < B
+    assert torch.equal(full["masks"][live], gated["masks"][live])
+    assert float(gated["masks"][~live].abs().max()) == 0.0
+    assert torch.equal(full["sel_idx"][live], gated["sel_idx"][live])
+
+    vol = synth.make_tomogram((1, 300, 400), seed=3, n_ellipsoids=8)[0]
+    rgb = prep.prepare(vol.numpy(), to_rgb=True)
+    kw = dict(points_per_side=8, crop_n_layers=1, crop_n_points_downscale_factor=2, pred_iou_thresh=thr,
+              stability_score_thresh=0.2, stability_score_offset=0.7, box_nms_thresh=0.95, use_m2m=True,
+              multimask_output=True)
+    res = []
+    for gate in (True, False):
+        gen = SAM2AutomaticMaskGenerator(model, **kw)
+        gen.m2m_gate = gate
+        dm = gen.generate_device(rgb)
+        res.append(dm)
+    a, b = res
+    assert a.count == b.count and a.count > 0
+    for name in ("slots", "bits", "bbox", "area", "iou", "stability"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
