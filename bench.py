@@ -46,6 +46,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-propagation", action="store_true",
+                    help="skip the config-3 sub-record (3-D propagation of a 300x928x960 tomogram, z-slab relay over the ranks)")
+    ap.add_argument("--prop-frames", type=int, default=300)
+    ap.add_argument("--prop-objects", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true",
                     help="skip thresholds_open / components_3d / bandwidth / gpu_eager_baseline (N = 1 only anyway)")
     return ap.parse_args()
@@ -323,6 +327,89 @@ def measure_extras(args, seg, slab, labels, flush, dev):
     return out
 
 
+def measure_propagation(args, dev, world, rank):
+    """BASELINE configs[2]: SAM2.1 hiera-large 3-D propagation (memory attention along z) of a synthetic 300x928x960
+    tomogram, frames sharded by z-slab over the ranks (STRONG scaling: the volume is fixed). One step = set_volume
+    (normalise + resize + encode this rank's slab; no feature exchange) + segment_volume (bidirectional tracking of
+    `--prop-objects` seed masks from the middle slice as a relay: the memory-bank halo crosses each slab boundary
+    point-to-point over NCCL, label slabs are all-gathered). Reported: slices/s over the whole step (max over ranks),
+    bytes moved over NCCL per step and the CRC-32 of the label volume (identical for every N: compare the lines)."""
+    import zlib
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from saber_b200 import synth
+    from saber_b200.adapters.base import SAM2AdapterConfig, cfgAMG
+    from saber_b200.adapters.sam2 import SAM2Adapter
+
+    Z, H, W = args.prop_frames, 928, 960
+    sam_cfg = {"large": "large", "base_plus": "base", "small": "small", "tiny": "tiny"}[args.cfg]
+    ad = SAM2Adapter(SAM2AdapterConfig(cfg=sam_cfg, amg_cfg=cfgAMG(sam2_cfg=sam_cfg), num_maskmem=2, seed=0,
+                                       allow_random_init=True), device=str(dev))
+    vol = synth.make_tomogram((Z, H, W), seed=3, n_ellipsoids=10, device=dev)
+    rng = np.random.default_rng(0)
+    yy, xx = np.mgrid[0:H, 0:W]
+    seeds = []
+    for _ in range(args.prop_objects):
+        cy, cx, ry, rx = rng.uniform(200, 700), rng.uniform(200, 700), rng.uniform(30, 90), rng.uniform(30, 90)
+        seeds.append(torch.from_numpy((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1).astype(np.float32)).to(dev))
+    seeds = torch.stack(seeds)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    ad._video()
+    zw = min(Z, 16 * world)  # build + warm the kernels on a small volume (>= 15 frames per slab: the relay's minimum)
+    ad.set_volume(vol[:zw].contiguous())
+    ad.segment_volume_device(zw // 2, masks=seeds[:1], vol_shape=(zw, H, W), min_presence_score=-1e9)
+    ad.reset_state()
+    t_set, t_seg, out = [], [], None
+    for rep in range(2):
+        sync()
+        t0 = time.perf_counter()
+        ad.set_volume(vol)
+        sync()
+        t1 = time.perf_counter()
+        out = ad.segment_volume_device(Z // 2, masks=seeds, vol_shape=(Z, H, W), min_presence_score=-1e9)
+        sync()
+        t2 = time.perf_counter()
+        t_set.append(tmax(t1 - t0))
+        t_seg.append(tmax(t2 - t1))
+        ad.reset_state()
+    sent = torch.tensor([float((ad.relay_stats or {}).get("bytes_sent", 0))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sent)
+    label_bytes = (world - 1) * 2.0 * Z * H * W if world > 1 else 0.0  # all-gather of the uint16 slabs: received per rank x ranks / ... total
+    rec = None
+    if rank == 0:
+        crc = zlib.crc32(out.cpu().numpy().tobytes())
+        total = t_set[-1] + t_seg[-1]
+        rec = {"workload": f"SAM2.1 hiera-{args.cfg} 3-D propagation of a {Z}x{H}x{W} synthetic tomogram, {args.prop_objects} objects "
+                           f"seeded on slice {Z // 2} (BASELINE configs[2]), frames sharded by z-slab over {world} GPU(s)",
+               "value": Z / total, "unit": "slices/s", "scaling": "strong", "n_gpus": world,
+               "set_volume_ms": t_set[-1] * 1e3, "segment_volume_ms": t_seg[-1] * 1e3,
+               "first_rep_ms": (t_set[0] + t_seg[0]) * 1e3,
+               "nccl_bytes_per_step": {"memory_bank_halo": sent.item(), "label_slab_allgather_total": label_bytes,
+                                       "frame_features": 0.0},
+               "shard": ad.prop_shard, "label_volume_crc32": crc,
+               "labels_present": int(torch.unique(out).numel() - 1),
+               "timing": "wall clock around the public calls, device-synchronised + barrier on both sides, max over ranks; 2nd of 2 repetitions"}
+    del ad, vol, out
+    torch.cuda.empty_cache()
+    return rec
+
+
 def gpu_eager_baseline(args, dev):
     import numpy as np
     import torch
@@ -399,6 +486,7 @@ def run_b200(args):
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
         dist.init_process_group("nccl", device_id=dev)
     ops.require_b200()
 
@@ -538,6 +626,10 @@ def run_b200(args):
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         extras = measure_extras(args, seg, slabs[zs[0]], labels, flush, dev)
+    if not args.no_propagation:  # every rank takes part
+        prop = measure_propagation(args, dev, world, rank)
+        if prop is not None:
+            extras["propagation"] = prop
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -9,6 +9,8 @@ drive. Same class / method names and return types; the arithmetic underneath is 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -124,6 +126,11 @@ class SAM2Adapter(BaseAdapter):
         self._current_frame = None
         self._mask_generator = None
         self.predictor = None  # video predictor: built on first volume call
+        # multi-GPU propagation (one process per GPU): "zslab" = frames and features stay on the rank that owns the
+        # z-slab, the memory-bank halo is relayed to the neighbour (north_star); "objects" = features all-gathered,
+        # tracked objects sharded over the ranks (round-1 scheme, kept for A/B measurements)
+        self.prop_shard = os.environ.get("SB_PROP_SHARD", "zslab")
+        self.relay_stats = None
 
     # ------------------------------------------------------------------ 2-D segmentation
     def _amg(self):
@@ -207,7 +214,8 @@ class SAM2Adapter(BaseAdapter):
             p.encode_frames(state, list(range(z0, z1)))
             if 0 not in range(z0, z1):
                 state["cached_features"].pop(0, None)  # frame 0 was warmed above on every rank; slab owner is authoritative
-            sbdist.exchange_frame_features(state["cached_features"], len(images))
+            if self.prop_shard != "zslab":  # object sharding: every rank needs every frame
+                sbdist.exchange_frame_features(state["cached_features"], len(images))
         return state
 
     def _create_empty_inference_state(self, images, video_height, video_width, offload_video_to_cpu=False,
@@ -277,6 +285,9 @@ class SAM2Adapter(BaseAdapter):
         Z, H, W = vol_shape
         p = self._video()
         mask_list = self._normalize_masks(masks)
+        if world > 1 and self.prop_shard == "zslab":
+            return self._segment_volume_relay(start_frame_idx, mask_list, (Z, H, W), max_frame_num_to_track,
+                                              min_presence_score, state, group)
         k = 0  # index among the non-empty seeds (the objects that are actually tracked)
         n_local = 0
         for obj_id, mask in enumerate(mask_list, start=1):
@@ -349,6 +360,82 @@ class SAM2Adapter(BaseAdapter):
                     if ps < min_presence_score:
                         ops.erase_label_(vol_masks[fidx], mi + 1)
         return vol_masks
+
+    def _presence_filter(self, vol_masks, captured, n_masks, Z, min_presence_score):
+        """REF :300-348: per-frame object scores -> fitted presence curves -> labels below the threshold erased."""
+        from .. import ops
+        from ..filters import estimate_thickness
+        self.frame_scores = np.zeros([Z, n_masks])
+        if n_masks > 0:
+            for fidx, scores in captured.items():
+                if fidx is None:
+                    continue
+                vals = np.concatenate([np.asarray(s_, dtype=np.float32).flatten() for s_ in scores])
+                n = min(len(vals), n_masks)
+                self.frame_scores[fidx, :n] = vals[:n]
+            bounds = estimate_thickness.fit_organelle_boundaries(self.frame_scores, plot=False)
+            for fidx in range(Z):
+                self.frame_metrics[fidx] = {}
+                for mi in range(n_masks):
+                    ps = float(bounds[fidx, mi])
+                    self.frame_metrics[fidx][mi + 1] = {"presence_score": ps}
+                    if ps < min_presence_score:
+                        ops.erase_label_(vol_masks[fidx], mi + 1)
+        return vol_masks
+
+    def _segment_volume_relay(self, start, mask_list, vol_shape, max_frame_num_to_track, min_presence_score, state, group):
+        """segment_volume with the frames sharded by z-slab (saber_b200/dist.py relay_propagate): this rank holds the
+        features of its own slab only, tracks only its own frames, and the memory-bank halo (~0.5 MB per object) is
+        handed to the neighbouring rank at each slab boundary; label slabs are all-gathered at the end. Every rank
+        returns the single-GPU label volume, bit for bit."""
+        import torch.distributed as tdist
+        from .. import dist as sbdist
+        from .. import ops
+        if max_frame_num_to_track is not None:
+            raise NotImplementedError("z-slab relay tracks the whole volume (max_frame_num_to_track=None)")
+        world, rank = sbdist.world_rank(group)
+        Z, H, W = vol_shape
+        p = self._video()
+        obj_ids = [oid for oid, m in enumerate(mask_list, start=1) if float(m.max()) != 0]
+        self._current_frame = None
+        self._relay_pass = 0
+        pending = []  # (pass, frame key at call time, device scores [B,1])
+        p.sam_mask_decoder.device_sink = lambda sc: pending.append((self._relay_pass, self._current_frame, sc.clone()))
+        self.frame_metrics = {}
+        vol_masks = torch.zeros((Z, H, W), dtype=torch.int16, device=self.device)
+        nonempty = {}
+
+        def seed_fn():
+            for oid in obj_ids:
+                self.add_new_mask(frame_idx=start, obj_id=oid, mask=mask_list[oid - 1], inference_state=state)
+
+        def set_key(k, pass_id):
+            self._current_frame = k
+            self._relay_pass = pass_id
+
+        def on_frame(pass_id, frame_idx, ids, logits):
+            if pass_id == 1 and frame_idx not in nonempty:  # only the seed slice can have been filled by the forward pass
+                nonempty[frame_idx] = bool(ops.slice_any(vol_masks[frame_idx:frame_idx + 1]).item()) if frame_idx == start else False
+            if pass_id == 0 or not nonempty[frame_idx]:
+                idt = torch.tensor([int(o) for o in ids], dtype=torch.int32, device=self.device)
+                ops.stitch_objects_(logits[:, 0].contiguous(), idt, vol_masks[frame_idx])
+
+        stats = {"bytes_sent": 0, "frames": 0}
+        if obj_ids:
+            stats = sbdist.relay_propagate(p, state, obj_ids, start, Z, seed_fn, on_frame, set_key, self.device, group)
+        p.sam_mask_decoder.device_sink = None
+        sbdist.allgather_label_slabs(vol_masks, Z, group)
+        mine = [(ps, key, [float(v) for v in sc.to(torch.float32).cpu().numpy().flatten()]) for ps, key, sc in pending]
+        logs = [None] * world
+        tdist.all_gather_object(logs, mine, group=group)
+        captured: Dict[Any, list] = {}
+        for ps in (0, 1):  # single-process order: forward-pass calls first, then the backward pass; a (pass, key) pair
+            for r in range(world):  # lives on exactly one rank
+                for q, key, vals in logs[r]:
+                    if q == ps:
+                        captured.setdefault(key, []).extend(np.asarray([v], dtype=np.float32) for v in vals)
+        self.relay_stats = stats
+        return self._presence_filter(vol_masks, captured, len(mask_list), Z, min_presence_score)
 
     @torch.inference_mode()
     def segment_volume(self, start_frame_idx: int, masks=None, vol_shape=None, max_frame_num_to_track=None,

@@ -171,3 +171,229 @@ def merge_captured_scores(per_rank: List[dict], n_local: List[int]) -> dict:
                 out.append(per_rank[r][k][g * n_local[r] + li])
         merged[k] = out
     return merged
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# z-slab RELAY of the propagation (BASELINE north_star: "NCCL ... only for halo slices of the memory bank and the final
+# label gather"; SURVEY §8e Phase B). Every rank keeps the features of ITS z-slab only. The chain of a seed slice runs
+# through the slabs in order; what crosses a slab boundary is the part of the predictor's per-object memory bank the
+# next frames can still see: the conditioning frame(s) (maskmem_features [4096,64] bf16 + object pointer), the object
+# pointers of the last 15 tracked frames and the memory features of the last num_maskmem-1 frames — ~0.5 MB per object
+# and boundary, sent point-to-point to the neighbour. Stored tensors travel bit for bit, so a relayed run produces the
+# single-GPU label volume exactly.
+# ---------------------------------------------------------------------------------------------------------------------
+def owner_of_frame(frame: int, Z: int, world: int) -> int:
+    for r in range(world):
+        z0, z1 = zslab_range(Z, r, world)
+        if z0 <= frame < z1:
+            return r
+    raise ValueError(f"frame {frame} outside [0, {Z})")
+
+
+def halo_pack(state: dict, n_obj: int, ptr_frames: List[int], mem_frames: List[int]):
+    """Serialise the memory-bank halo of objects 0..n_obj-1 of a video-predictor state: all conditioning frames
+    (memory + pointer), `ptr_frames` (pointer; frames missing from the bank are skipped) and `mem_frames` (memory).
+    Returns (meta int64 [..], mem blob [n, 4096*64] in the bank's storage dtype or None, ptr blob fp32 [m, 256] or None)."""
+    per = state["output_dict_per_obj"]
+    cond_frames = sorted(per[0]["cond_frame_outputs"]) if n_obj else []
+    pf = [f for f in ptr_frames if all(f in per[i]["non_cond_frame_outputs"] for i in range(n_obj))]
+    mf = [f for f in mem_frames if f in pf]
+    mems, ptrs = [], []
+    for i in range(n_obj):
+        for f in cond_frames:
+            out = per[i]["cond_frame_outputs"][f]
+            mems.append(out["maskmem_features"].reshape(1, -1))
+            ptrs.append(out["obj_ptr"].reshape(1, -1))
+        for f in pf:
+            ptrs.append(per[i]["non_cond_frame_outputs"][f]["obj_ptr"].reshape(1, -1))
+        for f in mf:
+            mems.append(per[i]["non_cond_frame_outputs"][f]["maskmem_features"].reshape(1, -1))
+    meta = torch.tensor([n_obj, len(cond_frames), len(pf), len(mf)] + cond_frames + pf + mf, dtype=torch.int64)
+    return meta, (torch.cat(mems, 0).contiguous() if mems else None), (torch.cat(ptrs, 0).contiguous() if ptrs else None)
+
+
+def halo_unpack(meta: torch.Tensor, mem: Optional[torch.Tensor], ptr: Optional[torch.Tensor]):
+    """Inverse of halo_pack -> list over objects of {"cond": {f: out}, "non_cond": {f: out}} (out dicts in the
+    predictor's layout; entries without memory carry no "maskmem_features" key)."""
+    m = [int(v) for v in meta.tolist()]
+    n_obj, nc, npf, nmf = m[:4]
+    cond_frames, pf, mf = m[4:4 + nc], m[4 + nc:4 + nc + npf], m[4 + nc + npf:4 + nc + npf + nmf]
+    objs = []
+    mi = pi = 0
+    for _ in range(n_obj):
+        cond, non = {}, {}
+        for f in cond_frames:
+            cond[f] = {"maskmem_features": mem[mi].view(-1, 64), "maskmem_pos_enc": True, "pred_masks": None,
+                       "obj_ptr": ptr[pi].view(1, -1), "object_score_logits": None}
+            mi += 1
+            pi += 1
+        for f in pf:
+            non[f] = {"maskmem_pos_enc": True, "pred_masks": None, "obj_ptr": ptr[pi].view(1, -1),
+                      "object_score_logits": None}
+            pi += 1
+        for f in mf:
+            non[f]["maskmem_features"] = mem[mi].view(-1, 64)
+            mi += 1
+        objs.append({"cond": cond, "non_cond": non})
+    return objs
+
+
+def halo_send(dst: int, meta, mem, ptr, device, group=None) -> int:
+    """Point-to-point send of a packed halo; returns the payload bytes. 16-bit memory travels as bytes (uint8 view)."""
+    comm_dev = device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mem_b = mem.view(torch.uint8).reshape(-1) if mem is not None else torch.empty(0, dtype=torch.uint8)
+    ptr_b = ptr.reshape(-1) if ptr is not None else torch.empty(0, dtype=torch.float32)
+    head = torch.tensor([meta.numel(), mem_b.numel(), ptr_b.numel(), 0 if mem is None else mem.element_size()],
+                        dtype=torch.int64)
+    dist.send(head.to(comm_dev), dst, group=group)
+    dist.send(meta.to(comm_dev), dst, group=group)
+    if mem_b.numel():
+        dist.send(mem_b.to(comm_dev).contiguous(), dst, group=group)
+    if ptr_b.numel():
+        dist.send(ptr_b.to(comm_dev).contiguous(), dst, group=group)
+    return int(mem_b.numel() + 4 * ptr_b.numel() + 8 * meta.numel() + 32)
+
+
+def halo_recv(src: int, device, group=None):
+    comm_dev = device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    head = torch.empty(4, dtype=torch.int64, device=comm_dev)
+    dist.recv(head, src, group=group)
+    n_meta, n_mem, n_ptr, esz = [int(v) for v in head.tolist()]
+    meta = torch.empty(n_meta, dtype=torch.int64, device=comm_dev)
+    dist.recv(meta, src, group=group)
+    mem = ptr = None
+    if n_mem:
+        raw = torch.empty(n_mem, dtype=torch.uint8, device=comm_dev)
+        dist.recv(raw, src, group=group)
+        mem = raw.to(device).view(torch.bfloat16 if esz == 2 else torch.float32).view(-1, 4096 * 64)
+    if n_ptr:
+        p = torch.empty(n_ptr, dtype=torch.float32, device=comm_dev)
+        dist.recv(p, src, group=group)
+        ptr = p.to(device).view(-1, 256)
+    return meta.cpu(), mem, ptr
+
+
+def halo_install(predictor, state: dict, obj_ids: List[int], objs: List[dict]) -> None:
+    """Put an unpacked halo into a predictor state (creating the objects on first use). Existing entries are kept:
+    the receiving rank's own results are authoritative."""
+    for obj_id, h in zip(obj_ids, objs):
+        idx = predictor._obj_id_to_idx(state, obj_id)
+        od = state["output_dict_per_obj"][idx]
+        for f, out in h["cond"].items():
+            od["cond_frame_outputs"].setdefault(f, out)
+        for f, out in h["non_cond"].items():
+            if f not in od["cond_frame_outputs"]:
+                od["non_cond_frame_outputs"].setdefault(f, out)
+
+
+def allgather_label_slabs(labels: torch.Tensor, Z: int, group=None) -> torch.Tensor:
+    """Every rank holds valid labels for its z-slab of the full-size volume `labels` [Z,Y,X] (16-bit): after the call every
+    rank holds the whole volume. One all_gather of the slabs as bytes (2 B per voxel, (N-1)/N of the volume received)."""
+    world, rank = world_rank(group)
+    if world == 1:
+        return labels
+    ranges = [zslab_range(Z, r, world) for r in range(world)]
+    zmax = max(b - a for a, b in ranges)
+    z0, z1 = ranges[rank]
+    plane = labels[0].numel()
+    mine = torch.zeros((zmax * plane,), dtype=labels.dtype, device=labels.device)
+    mine[:(z1 - z0) * plane] = labels[z0:z1].reshape(-1)
+    full = torch.empty((world, zmax * plane), dtype=labels.dtype, device=labels.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), group=group)
+    else:
+        dist.all_gather(list(full.view(torch.uint8).unbind(0)), mine.view(torch.uint8), group=group)
+    for r, (a, b) in enumerate(ranges):
+        if r != rank:
+            labels[a:b] = full[r, :(b - a) * plane].view(b - a, *labels.shape[1:])
+    return labels
+
+
+def relay_propagate(predictor, state: dict, obj_ids: List[int], start: int, Z: int, seed_fn, on_frame, set_frame_key,
+                    device, group=None, n_ptr_frames: int = 15) -> dict:
+    """Bidirectional propagation of one seed slice with the frames sharded by z-slab (this rank tracks only its own
+    frames). `seed_fn()` registers the seed prompts (called on the rank that owns `start`), `on_frame(pass_id,
+    frame_idx, obj_ids, logits)` consumes a tracked frame, `set_frame_key(k, pass_id)` tells the caller which frame key
+    the single-process loop would hold at the next decoder call and which pass (0 forward, 1 backward) it belongs to
+    (SABER's hook files scores under the key). Returns {"bytes_sent": n, "frames": tracked here}.
+
+    Dependencies (upstream SAM2 memory bank): a forward frame f reads the conditioning frame, the memory of f-1 and the
+    object pointers of f-1 .. f-15; a backward frame reads f+1 and the pointers of f+1 .. f+15 — which, next to the seed
+    slice, include FORWARD frames start+1 .. start+14. Nothing in the forward pass reads a backward result once it is 15
+    frames past the seed. Schedule: the seed rank tracks forward 15 frames, then its part of the backward pass, hands the
+    backward halo down, and only then finishes its forward frames and hands the forward halo up — so the backward chain
+    (lower ranks) and the forward chain (higher ranks) run CONCURRENTLY. When the seed slab ends within 15 frames of the
+    seed, the missing forward pointers come back from the next rank first (sequential fall-back)."""
+    world, rank = world_rank(group)
+    ranges = [zslab_range(Z, r, world) for r in range(world)]
+    z0, z1 = ranges[rank]
+    r_seed = owner_of_frame(start, Z, world)
+    n_mem = max(int(getattr(predictor, "num_maskmem", 2)) - 1, 0)
+    stats = {"bytes_sent": 0, "frames": 0}
+    n_obj = len(obj_ids)
+    seed_z1 = ranges[r_seed][1]
+    need_hi = min(start + n_ptr_frames - 1, Z - 1)  # last forward frame the backward pass can see
+    overlap = need_hi + 1 <= seed_z1 - 1             # the seed slab holds them all (+1: forward must be past them)
+
+    def nonempty(r):
+        return 0 <= r < world and ranges[r][1] > ranges[r][0]
+
+    def run(first, count, reverse, pass_id, key_before):
+        if count < 0:
+            return
+        set_frame_key(key_before, pass_id)
+        for frame_idx, ids, logits in predictor.propagate_in_video(state, start_frame_idx=first,
+                                                                   max_frame_num_to_track=count, reverse=reverse):
+            set_frame_key(frame_idx, pass_id)
+            on_frame(pass_id, frame_idx, ids, logits)
+            stats["frames"] += 1
+
+    def send_up():
+        if rank >= r_seed and nonempty(rank + 1):
+            pk = halo_pack(state, n_obj, list(range(max(z1 - n_ptr_frames, 0), z1)), list(range(z1 - n_mem, z1)))
+            stats["bytes_sent"] += halo_send(rank + 1, *pk, device, group)
+
+    def send_down():
+        if rank <= r_seed and nonempty(rank - 1) and z1 > z0:
+            pk = halo_pack(state, n_obj, list(range(z0, min(z0 + n_ptr_frames, Z))), list(range(z0, min(z0 + n_mem, Z))))
+            stats["bytes_sent"] += halo_send(rank - 1, *pk, device, group)
+
+    if rank == r_seed:
+        seed_fn()
+        if overlap:
+            run(start, need_hi + 1 - start, False, 0, None)          # forward: start .. start+15
+            run(start, start - z0, True, 1, need_hi + 1)             # backward part of this slab
+            send_down()
+            run(need_hi + 2, z1 - 1 - (need_hi + 2), False, 0, need_hi + 1)  # rest of the forward frames
+            send_up()
+        else:
+            run(start, z1 - 1 - start, False, 0, None)
+            send_up()
+            if need_hi >= seed_z1 and nonempty(r_seed + 1):
+                if ranges[r_seed + 1][1] <= need_hi and nonempty(r_seed + 2):
+                    raise RuntimeError("z-slab relay needs slabs of at least 15 frames next to the seed slice")
+                objs = halo_unpack(*halo_recv(r_seed + 1, device, group))
+                for o in objs:
+                    o["cond"] = {}
+                halo_install(predictor, state, obj_ids, objs)
+            run(start, start - z0, True, 1, z1 - 1)
+            send_down()
+    elif rank > r_seed and z1 > z0:
+        halo_install(predictor, state, obj_ids, halo_unpack(*halo_recv(rank - 1, device, group)))
+        if rank == r_seed + 1 and not overlap and need_hi >= seed_z1:
+            # the seed rank waits for the forward pointers seed_z1 .. need_hi before its backward pass: track them first
+            if z1 <= need_hi and nonempty(rank + 1):
+                raise RuntimeError("z-slab relay needs slabs of at least 15 frames next to the seed slice")
+            last = min(need_hi, z1 - 1)
+            run(z0, last - z0, False, 0, z0 - 1)
+            pk = halo_pack(state, n_obj, list(range(seed_z1, last + 1)), [])
+            stats["bytes_sent"] += halo_send(r_seed, *pk, device, group)
+            run(last + 1, z1 - 1 - (last + 1), False, 0, last)
+        else:
+            run(z0, z1 - 1 - z0, False, 0, z0 - 1)
+        send_up()
+    elif rank < r_seed and z1 > z0:
+        halo_install(predictor, state, obj_ids, halo_unpack(*halo_recv(rank + 1, device, group)))
+        run(z1 - 1, z1 - 1 - z0, True, 1, z1)
+        send_down()
+    return stats

@@ -120,3 +120,154 @@ def test_label_max_merge_and_feature_exchange_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# z-slab relay of the propagation: a CPU stand-in predictor with the real state layout and the real dependency
+# structure (conditioning frames + the previous frame's memory + the last 15 object pointers; reverse pass sees
+# forward-pass pointers) so that any missing / stale / misordered halo entry changes the result.
+# ---------------------------------------------------------------------------------------------------------------------
+class _FakeVideo:
+    num_maskmem = 2
+    max_obj_ptrs = 16
+
+    def _obj_id_to_idx(self, st, obj_id):
+        if obj_id not in st["obj_id_to_idx"]:
+            idx = len(st["obj_id_to_idx"])
+            st["obj_id_to_idx"][obj_id] = idx
+            st["obj_ids"] = list(st["obj_id_to_idx"])
+            st["output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        return st["obj_id_to_idx"][obj_id]
+
+    @staticmethod
+    def new_state(Z, feats):
+        return {"num_frames": Z, "obj_id_to_idx": {}, "obj_ids": [], "output_dict_per_obj": {}, "feats": feats}
+
+    def add_seed(self, st, frame, obj_id):
+        idx = self._obj_id_to_idx(st, obj_id)
+        g = torch.Generator().manual_seed(1000 + obj_id)
+        st["output_dict_per_obj"][idx]["cond_frame_outputs"][frame] = {
+            "maskmem_features": torch.randn(4096, 64, generator=g).to(torch.bfloat16), "maskmem_pos_enc": True,
+            "pred_masks": None, "obj_ptr": torch.randn(1, 256, generator=g), "object_score_logits": None}
+
+    def propagate_in_video(self, st, start_frame_idx, max_frame_num_to_track, reverse=False):
+        Z = st["num_frames"]
+        if reverse:
+            order = range(start_frame_idx, max(start_frame_idx - max_frame_num_to_track, 0) - 1, -1)
+        else:
+            order = range(start_frame_idx, min(start_frame_idx + max_frame_num_to_track, Z - 1) + 1)
+        for f in order:
+            res = []
+            for idx in range(len(st["obj_ids"])):
+                od = st["output_dict_per_obj"][idx]
+                if f in od["cond_frame_outputs"]:
+                    res.append(torch.zeros(1))
+                    continue
+                acc = torch.zeros(256)
+                memsum = torch.zeros(64)
+                for cf, out in od["cond_frame_outputs"].items():
+                    acc = acc + out["obj_ptr"].view(-1) * 0.5
+                    memsum = memsum + out["maskmem_features"].float().mean(0)
+                prev = f + 1 if reverse else f - 1
+                out = od["non_cond_frame_outputs"].get(prev)
+                if out is not None:
+                    memsum = memsum + 2.0 * out["maskmem_features"].float().mean(0)
+                for t in range(1, self.max_obj_ptrs):
+                    tt = f + t if reverse else f - t
+                    o = od["non_cond_frame_outputs"].get(tt)
+                    if o is not None:
+                        acc = acc + o["obj_ptr"].view(-1) / (t + 1.0)
+                feat = st["feats"][f]  # KeyError if this rank does not own the frame: the relay must never ask for it
+                ptr = torch.tanh(acc + feat[:256] + memsum.sum())
+                mem = (torch.outer(torch.arange(4096, dtype=torch.float32) % 7 + 1.0, memsum) * 0.01 + ptr[:64]).to(torch.bfloat16)
+                od["non_cond_frame_outputs"][f] = {"maskmem_features": mem, "maskmem_pos_enc": True, "pred_masks": None,
+                                                   "obj_ptr": ptr.view(1, 256), "object_score_logits": None}
+                res.append(ptr.sum().view(1))
+            yield f, st["obj_ids"], torch.cat(res).view(-1, 1)
+
+
+def _relay_reference(Z, start, obj_ids, feats):
+    fv = _FakeVideo()
+    st = fv.new_state(Z, feats)
+    for o in obj_ids:
+        fv.add_seed(st, start, o)
+    out = {}
+    for f, ids, v in fv.propagate_in_video(st, start, Z, False):
+        out[(0, f)] = v.clone()
+    for f, ids, v in fv.propagate_in_video(st, start, Z, True):
+        out[(1, f)] = v.clone()
+    return out
+
+
+def _relay_worker(rank, world, port, Z, start, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    feats_all = {f: torch.randn(300, generator=g) for f in range(Z)}
+    z0, z1 = sbdist.zslab_range(Z, rank, world)
+    fv = _FakeVideo()
+    st = fv.new_state(Z, {f: feats_all[f] for f in range(z0, z1)})  # own slab only
+    obj_ids = [1, 2, 5]
+    got, keys = {}, []
+
+    def seed_fn():
+        for o in obj_ids:
+            fv.add_seed(st, start, o)
+
+    stats = sbdist.relay_propagate(fv, st, obj_ids, start, Z, seed_fn,
+                                   lambda ps, f, ids, v: got.__setitem__((ps, f), v.clone()),
+                                   lambda k, ps: keys.append((k, ps)), torch.device("cpu"))
+    allgot = [None] * world
+    dist.all_gather_object(allgot, {k: v.tolist() for k, v in got.items()})
+    if rank == 0:
+        want = _relay_reference(Z, start, obj_ids, feats_all)
+        merged = {}
+        for d in allgot:
+            for k, v in d.items():
+                assert k not in merged, "a frame was tracked on two ranks"
+                merged[k] = v
+        ok = set(merged) == set(want) and all(merged[k] == want[k].tolist() for k in want)
+        q.put((ok, stats["bytes_sent"]))
+    assert all(z0 <= f < z1 for (_, f) in got), "tracked a frame outside the own slab"
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_zslab_relay_reproduces_single_process_chain():
+    """relay_propagate over 2 and 3 gloo ranks == the single-process forward + backward chain, exactly, for seeds in the
+    middle, next to a slab boundary (the backward pass needs forward pointers owned by the next rank) and on the first
+    frame; every rank only ever touches the frames of its own slab."""
+    ctx = mp.get_context("spawn")
+    for world, Z, start in ((2, 40, 19), (2, 40, 12), (3, 60, 35), (2, 36, 0), (2, 36, 35)):
+        q = ctx.Queue()
+        port = 29500 + (os.getpid() + 17 * Z + start + world) % 2000
+        procs = [ctx.Process(target=_relay_worker, args=(r, world, port, Z, start, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        ok, sent = q.get(timeout=180)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert ok, (world, Z, start)
+
+
+def test_halo_pack_roundtrip():
+    fv = _FakeVideo()
+    st = fv.new_state(30, {f: torch.randn(300) for f in range(30)})
+    for o in (1, 2):
+        fv.add_seed(st, 10, o)
+    list(fv.propagate_in_video(st, 10, 12, False))
+    meta, mem, ptr = sbdist.halo_pack(st, 2, list(range(8, 23)), [22])
+    objs = sbdist.halo_unpack(meta, mem, ptr)
+    st2 = fv.new_state(30, {})
+    sbdist.halo_install(fv, st2, [1, 2], objs)
+    for i in range(2):
+        a, b = st["output_dict_per_obj"][i], st2["output_dict_per_obj"][i]
+        assert sorted(b["cond_frame_outputs"]) == [10]
+        assert torch.equal(a["cond_frame_outputs"][10]["maskmem_features"], b["cond_frame_outputs"][10]["maskmem_features"])
+        assert sorted(b["non_cond_frame_outputs"]) == list(range(11, 23))  # frames 8-10 were never tracked / are cond
+        for f in range(11, 23):
+            assert torch.equal(a["non_cond_frame_outputs"][f]["obj_ptr"], b["non_cond_frame_outputs"][f]["obj_ptr"])
+        assert torch.equal(a["non_cond_frame_outputs"][22]["maskmem_features"], b["non_cond_frame_outputs"][22]["maskmem_features"])
+        assert "maskmem_features" not in b["non_cond_frame_outputs"][21]

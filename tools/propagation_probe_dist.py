@@ -73,8 +73,8 @@ def main():
         if rank == 0:
             print(f"[{world} GPU] segment_volume N_obj={n_obj}: {dt * 1e3:.1f} ms for {Z} frames ({dt / Z * 1e3:.2f} ms/frame, "
                   f"{dt / max(1, (Z - 1) * n_obj) * 1e3:.2f} ms per object-frame); label volume crc32 per rank {crcs} "
-                  f"({'identical' if len(set(crcs)) == 1 else 'MISMATCH'}); labels present {sorted(set(np.unique(out).tolist()))[:10]}",
-                  flush=True)
+                  f"({'identical' if len(set(crcs)) == 1 else 'MISMATCH'}); labels present {sorted(set(np.unique(out).tolist()))[:10]}"
+                  f"; shard={ad.prop_shard} relay={ad.relay_stats}", flush=True)
     if world > 1:
         dist.destroy_process_group()
 
