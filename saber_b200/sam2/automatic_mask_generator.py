@@ -365,7 +365,10 @@ class SAM2AutomaticMaskGenerator:
             torch.cuda.synchronize()
             n0 = ops.launch_count
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread-local capture mode: SABER's GPUPool drives one GPU per THREAD of one process (REF saber/utils/
+            # parallelization.py:95-155); in the default global mode an allocation by another worker thread during this
+            # capture would invalidate it
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 body()
             lane["launches"] = ops.launch_count - n0
             ops.launch_count = n0

@@ -336,3 +336,52 @@ def test_segmenters_end_to_end_on_the_real_adapter():
     assert got.shape == vol.shape and got.dtype == np.uint32
     # single_segment = separate_masks of the union of the binarised per-seed propagations: idempotent under separate_masks
     np.testing.assert_array_equal(sutils.separate_masks((got > 0).astype(np.uint16), 0, device="cuda:0") > 0, got > 0)
+
+
+def test_gpupool_threads_tomogram_level_data_parallelism():
+    """BASELINE configs[4] (tomogram-level DP) the way the reference runs it: GPUPool keeps one model per GPU and drives
+    them from the THREADS of one process, task i -> GPU i % n (REF saber/utils/parallelization.py:139-141,155). Here:
+    one worker thread per visible GPU (two workers sharing cuda:0 on a single-GPU box), each with its own segmenter,
+    CUDA-graph capture included; every task's label volume must equal the one a single thread produces."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from saber_b200 import synth
+    from saber_b200.adapters.base import SAM2AdapterConfig, cfgAMG
+    from saber_b200.dist import tasks_for_rank
+    from saber_b200.segmenters.propagation import propagationSegmenter
+    n_dev = torch.cuda.device_count()
+    n_workers = max(2, n_dev)
+    devs = [w % n_dev for w in range(n_workers)]
+    amg = cfgAMG(sam2_cfg="tiny", points_per_side=6, crop_n_layers=0, pred_iou_thresh=0.3, stability_score_thresh=0.0)
+
+    def make(dev):
+        return propagationSegmenter(deviceID=dev, cfg=SAM2AdapterConfig(cfg="tiny", amg_cfg=amg, min_mask_area=50,
+                                                                       allow_random_init=True), min_mask_area=50)
+
+    tasks = [synth.make_tomogram((2, 200, 256), seed=20 + i, n_ellipsoids=5) for i in range(6)]
+    ref_seg = make(0)
+    want = [ref_seg.slice_by_slice_device(t.cuda(0)).cpu() for t in tasks]
+    segs = [make(d) for d in devs]
+    # CUDA graphs are captured on first use. GPUPool has one GPU per thread, so captures never share a device; on a
+    # single-GPU box the two workers share cuda:0, where a device-wide synchronize of one thread is illegal while the
+    # other captures — warm the workers one after the other, then run them concurrently
+    for w, sg in enumerate(segs):
+        torch.cuda.set_device(devs[w])
+        sg.slice_by_slice_device(tasks[0].cuda(devs[w]))
+    torch.cuda.set_device(0)
+
+    def worker(w):
+        torch.cuda.set_device(devs[w])
+        out = {}
+        for i in tasks_for_rank(len(tasks), w, n_workers):  # task i -> worker i % n
+            out[i] = segs[w].slice_by_slice_device(tasks[i].cuda(devs[w])).cpu()
+        return out
+
+    with ThreadPoolExecutor(max_workers=n_workers) as ex:
+        results = list(ex.map(worker, range(n_workers)))
+    got = {}
+    for r in results:
+        got.update(r)
+    assert sorted(got) == list(range(len(tasks)))
+    for i in range(len(tasks)):
+        assert torch.equal(got[i], want[i]), f"task {i}"

@@ -62,3 +62,59 @@ def test_gaussian_smoothing_other_axes_match_oracle(dim):
     np.testing.assert_allclose(out, saber_ref.gaussian_smoothing(vol, 3, dim=dim % 3), atol=1e-5, rtol=0)
     t = gaussian_smoothing(torch.from_numpy(vol).cuda(), 3, dim=dim)
     assert t.is_cuda and torch.equal(t.cpu(), torch.from_numpy(out))
+
+
+def test_segment_tomogram_core_smooths_and_writes_uint8(golden_dir):
+    """SURVEY §8f row 1 (REF saber/entry_points/inference_core.py:10-93): reader -> segmenter.segment -> adaptive Gaussian
+    smoothing (scale 0.05) -> uint8 -> writers.segmentation(run, mask, 'saber', name, session_id, voxel_size). In-memory
+    stand-ins for the copick run / reader / writer and the segmenter; the written volume must equal the oracle's
+    smoothing of the segmenter's label volume, cast to uint8."""
+    import numpy as np
+    from oracle import saber_ref
+    from saber_b200 import synth
+    from saber_b200.entry_points.inference_core import segment_tomogram_core
+    labels = synth.make_label_volume((24, 64, 72), seed=5, n_ellipsoids=6, rmin=6.0, rmax=14.0).numpy().view(np.uint16)
+
+    class Run:
+        name = "run_001"
+
+    class Reader:
+        @staticmethod
+        def tomogram(run, voxel_size, algorithm=None):
+            return np.zeros((24, 64, 72), dtype=np.float32) if run is not None else None
+
+    written = {}
+
+    class Writer:
+        @staticmethod
+        def segmentation(run, mask, user_id, name=None, session_id=None, voxel_size=None):
+            written.update(run=run.name, mask=mask, user=user_id, name=name, session=session_id, voxel=voxel_size)
+
+    class Segmenter:
+        inference_state = "something"
+        calls = []
+
+        def segment(self, vol, thickness, *a, **kw):
+            self.calls.append((a, kw))
+            return labels
+
+    seg = Segmenter()
+    out = segment_tomogram_core(Run(), 10.0, "wbp", "organelles", "7", 10, 1, 30, False, seg, gpu_id=0, target_class=1,
+                                reader=Reader, writer=Writer)
+    assert out is None and seg.inference_state is None
+    assert seg.calls[0][1] == {"target_class": 1, "save_run": "run_001-7", "display": False}
+    want = saber_ref.fast_3d_gaussian_smoothing(labels, scale=0.05).astype(np.uint8)
+    assert written["user"] == "saber" and written["name"] == "organelles" and written["session"] == "7"
+    assert written["voxel"] == 10.0 and written["mask"].dtype == np.uint8
+    assert np.array_equal(written["mask"], want)
+    # multi-slab call shape (REF :52-55) and the "no tomogram" / "no segmentation" early returns
+    segment_tomogram_core(Run(), 10.0, "wbp", "o", "7", 10, 3, 30, True, seg, reader=Reader, writer=Writer)
+    assert seg.calls[1][0] == (3, 30, "run_001-7", True)
+    written.clear()
+
+    class Empty(Segmenter):
+        def segment(self, *a, **kw):
+            return None
+
+    assert segment_tomogram_core(Run(), 10.0, "wbp", "o", "7", 10, 1, 30, False, Empty(), reader=Reader, writer=Writer) is None
+    assert not written
