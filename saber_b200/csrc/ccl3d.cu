@@ -42,16 +42,41 @@ __device__ __forceinline__ void uf_unite(int* P, int a, int b) {
   } while (!done);
 }
 
+// parent initialisation: a foreground voxel points at the first voxel of its foreground RUN inside the warp's 32-voxel
+// segment of the row (one ballot; runs never cross a row end), background voxels get -1. Chains start one hop from their
+// run head, and the merge pass only has to link run heads to the left (at segment boundaries).
 template <typename T>
 __global__ void __launch_bounds__(256)
-ccl_init_kernel(const T* __restrict__ vol, int* __restrict__ P, int* __restrict__ aux, long long n) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    P[i] = vol[i] != 0 ? static_cast<int>(i) : -1;
-    aux[i] = 0;
+ccl_init_kernel(const T* __restrict__ vol, int* __restrict__ P, int* __restrict__ aux, long long n, int X) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n_round = ((n + 31) / 32) * 32;
+  const int lane = threadIdx.x & 31;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool in = i < n;
+    const bool fg = in && vol[i] != 0;
+    const bool row_start = in && (i % X) == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, fg);
+    const uint32_t brk = __ballot_sync(0xffffffffu, row_start);
+    // lanes a run cannot extend across (to lower lanes): background lanes, and the lane just before a row start
+    const uint32_t stop = (~m | (brk >> 1)) & ((1u << lane) - 1u);
+    const int first = stop ? 32 - __clz(stop) : 0;  // first lane of this lane's run
+    if (in) {
+      P[i] = fg ? static_cast<int>(i - lane + first) : -1;
+      aux[i] = 0;
+    }
   }
 }
 
+// 26-connectivity merge over the 13 raster-preceding neighbours, with the redundant unions removed:
+//  * left neighbour: already linked by the initialisation unless this voxel heads its run (segment boundary);
+//  * in each of the 4 preceding rows (previous row of the plane, 3 rows of the previous plane) the cells dx = -1, 0, +1
+//    are consecutive voxels of ONE row: if the centre is foreground it is linked to both others by that row's own runs,
+//    so one union (with the centre) suffices; otherwise dx = -1 and dx = +1 are united separately;
+//  * if the left neighbour v-1 is foreground, everything at dx <= 0 is also a neighbour of v-1 (its dx <= +1) and is
+//    linked through it: only dx = +1 remains, and only when the centre is background.
+// Inside a solid object a voxel performs no union at all (the voxel-by-voxel form did 13 find/atomicMin pairs: 22 ms of
+// the 23 ms a 200 x 1024 x 1024 volume took, profiles/r02zc). Roots are component minima under any union order, so the
+// labels are unchanged (scipy's raster numbering).
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(int* __restrict__ P, int Z, int Y, int X) {
   const long long n = static_cast<long long>(Z) * Y * X;
@@ -63,30 +88,27 @@ ccl_merge_kernel(int* __restrict__ P, int Z, int Y, int X) {
     const int y = static_cast<int>((i / X) % Y);
     const int z = static_cast<int>(i / plane);
     const int v = static_cast<int>(i);
-    // same row, previous voxel
-    if (x > 0 && P[i - 1] >= 0) uf_unite(P, v, v - 1);
-    // previous row of the same plane
-    if (y > 0) {
-      const long long r = i - X;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx >= 0 && xx < X && P[r + dx] >= 0) uf_unite(P, v, static_cast<int>(r + dx));
+    const bool left = x > 0 && P[i - 1] >= 0;
+    // a run head with a foreground voxel to its left exists only at a 32-voxel segment boundary (decided from the
+    // geometry: P[v] itself may already have been lowered by another thread's union)
+    if (left && (i & 31) == 0) uf_unite(P, v, v - 1);
+    auto row = [&](long long r) {  // r = linear index of the cell above / behind v (dx = 0) in a preceding row
+      const bool c = P[r] >= 0;
+      const bool rgt = x + 1 < X && P[r + 1] >= 0;
+      if (left) {
+        if (!c && rgt) uf_unite(P, v, static_cast<int>(r + 1));
+      } else if (c) {
+        uf_unite(P, v, static_cast<int>(r));
+      } else {
+        if (x > 0 && P[r - 1] >= 0) uf_unite(P, v, static_cast<int>(r - 1));
+        if (rgt) uf_unite(P, v, static_cast<int>(r + 1));
       }
-    }
-    // previous plane: 3 x 3 neighbourhood
+    };
+    if (y > 0) row(i - X);
     if (z > 0) {
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= Y) continue;
-        const long long r = i - plane + static_cast<long long>(dy) * X;
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int xx = x + dx;
-          if (xx >= 0 && xx < X && P[r + dx] >= 0) uf_unite(P, v, static_cast<int>(r + dx));
-        }
-      }
+      if (y > 0) row(i - plane - X);
+      row(i - plane);
+      if (y + 1 < Y) row(i - plane + X);
     }
   }
 }
@@ -218,11 +240,11 @@ extern "C" int sb_ccl3d_26(const void* vol, int elem_bytes, int Z, int Y, int X,
   if (g > 148 * 16) g = 148 * 16;
   const int grid = static_cast<int>(g);
   if (elem_bytes == 1)
-    ccl_init_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char*>(vol), P, aux, n);
+    ccl_init_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char*>(vol), P, aux, n, X);
   else if (elem_bytes == 2)
-    ccl_init_kernel<unsigned short><<<grid, 256, 0, stream>>>(static_cast<const unsigned short*>(vol), P, aux, n);
+    ccl_init_kernel<unsigned short><<<grid, 256, 0, stream>>>(static_cast<const unsigned short*>(vol), P, aux, n, X);
   else
-    ccl_init_kernel<unsigned int><<<grid, 256, 0, stream>>>(static_cast<const unsigned int*>(vol), P, aux, n);
+    ccl_init_kernel<unsigned int><<<grid, 256, 0, stream>>>(static_cast<const unsigned int*>(vol), P, aux, n, X);
   SB_CHECK_LAUNCH();
   ccl_merge_kernel<<<grid, 256, 0, stream>>>(P, Z, Y, X);
   SB_CHECK_LAUNCH();
