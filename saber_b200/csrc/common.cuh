@@ -209,8 +209,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster. Default (CTA-scope) semantics on purpose: the explicit
+// .release.cluster form compiles to MEMBAR.ALL.CTA + ERRBAR in front of the arrive, which was 15 % of all warp samples
+// of the pair GEMM (profiles/r02ze: ~25 % of its epilogue). The accumulator reads this arrive publishes are ordered by
+// tcgen05.fence::before_thread_sync, which the callers issue first.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tile load issued by one CTA of a pair; the bytes complete on the mbarrier at shared::cluster address `bar_cluster`
 // (the leader CTA's barrier)

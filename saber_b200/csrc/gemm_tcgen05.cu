@@ -1181,10 +1181,10 @@ struct Cfg2 {
 };
 
 template <int BN, int ACT>
-__device__ __forceinline__ void epilogue2_std(const GemmParams& p, const CUtensorMap* tmOut, uint32_t out_stg,
-                                              uint32_t res_stg, uint32_t vec, uint32_t tmem_acc, int m_idx, int n_idx,
-                                              int q, int lane, int g_begin, int g_end, int vbase, bool& issued,
-                                              int next_m_idx, int next_n_idx) {
+__device__ __forceinline__ void epilogue2_std(const GemmParams& p, const CUtensorMap* tmOut, uint32_t out_stg0,
+                                              uint32_t out_stg1, int& ob, uint32_t res_stg, uint32_t vec,
+                                              uint32_t tmem_acc, int m_idx, int n_idx, int q, int lane, int g_begin,
+                                              int g_end, int vbase, bool& issued, int next_m_idx, int next_n_idx) {
   const int first_n = n_idx + g_begin * 32;
   if (first_n >= p.N) return;
   const int row0 = m_idx + q * 32;
@@ -1214,7 +1214,17 @@ __device__ __forceinline__ void epilogue2_std(const GemmParams& p, const CUtenso
     const int n0 = n_idx + g * 32;
     const int ncols = min(32, p.N - n0);  // 16 or 32
     if (has_res) cp_async_wait_all();
-    if (lane == 0) sb::bulk_wait_read<0>();  // the previous group's tensor store has read the output tile
+    // output tiles alternate (when the launch reserved two): the tensor store issued two groups ago has read this one —
+    // waiting for the PREVIOUS group's store here was the second largest stall of the epilogue (profiles/r02ze)
+    const bool two = out_stg1 != out_stg0;
+    const uint32_t out_stg = (two && ob) ? out_stg1 : out_stg0;
+    ob ^= 1;
+    if (lane == 0) {
+      if (two)
+        sb::bulk_wait_read<1>();
+      else
+        sb::bulk_wait_read<0>();
+    }
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -1273,7 +1283,8 @@ template <int BN, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmOut, const GemmParams p, const int stages,
-                          const int stg_out_bytes, const int stg_res_bytes, const int vec_bytes, const int vec_all) {
+                          const int stg_out_bytes, const int stg_res_bytes, const int vec_bytes, const int vec_all,
+                          const int out_bufs) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -1410,9 +1421,11 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // ===================== epilogue: both sets on every tile, set s = column half s =====================
     const int q = warp & 3;
     const int set = (warp - 4) >> 2;
-    uint8_t* mine = sEpi + (warp - 4) * (stg_out_bytes + stg_res_bytes);
-    const uint32_t out_stg = sb::smem_u32(mine);
-    const uint32_t res_stg = sb::smem_u32(mine + stg_out_bytes);
+    uint8_t* mine = sEpi + (warp - 4) * (out_bufs * stg_out_bytes + stg_res_bytes);
+    const uint32_t out_stg0 = sb::smem_u32(mine);
+    const uint32_t out_stg1 = sb::smem_u32(mine + (out_bufs - 1) * stg_out_bytes);
+    const uint32_t res_stg = sb::smem_u32(mine + out_bufs * stg_out_bytes);
+    int ob = 0;
     const uint32_t vec = sb::smem_u32(sVec);
     {  // bias: the whole vector (vec_all) or, for a single column tile, its BN entries — staged once
       const int tid256 = (warp - 4) * 32 + lane;
@@ -1452,7 +1465,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int nt = tile + num_pairs;
       const int next_m = nt < num_tiles ? (nt / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM : -1;
       const int next_n = nt < num_tiles ? (nt % n_tiles) * BN : 0;
-      epilogue2_std<BN, ACT>(p, &tmOut, out_stg, res_stg, vec, tmem_acc, m_idx, n_idx, q, lane, set * (NG / 2),
+      epilogue2_std<BN, ACT>(p, &tmOut, out_stg0, out_stg1, ob, res_stg, vec, tmem_acc, m_idx, n_idx, q, lane, set * (NG / 2),
                              (set + 1) * (NG / 2), vec_all ? 0 : n_idx, issued, next_m, next_n);
       sb::tc_fence_before();
       __syncwarp();
@@ -1500,7 +1513,8 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, con
   const int stg_out_bytes = p.out_f32 ? STG_BYTES : STG_BYTES / 2;
   const int stg_res_bytes = p.res == nullptr ? 0 : (p.res_f32 ? STG_BYTES : STG_BYTES / 2);
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int epi = NEPI_WARPS * (stg_out_bytes + stg_res_bytes);
+  const int out_bufs = p.out_f32 ? 1 : 2;  // bf16 output tiles are 2 KB: two per warp decouple the tensor stores
+  const int epi = NEPI_WARPS * (out_bufs * stg_out_bytes + stg_res_bytes);
   // bias staging: all of N when it costs no pipeline stage, else the per-tile slice is not supported here -> caller falls back
   int vec_bytes = n_tiles > 1 ? ((p.N + 255) / 256) * 1024 : 1024;
   const int vec_all = n_tiles > 1 ? 1 : 0;
@@ -1515,7 +1529,7 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, con
   int pairs = num_sms / 2;
   if (pairs > tiles) pairs = tiles;
   gemm2_bf16_tcgen05_kernel<BN, ACT><<<2 * pairs, NTHREADS, smem_bytes, stream>>>(tmA, tmB, tmOut, p, stages, stg_out_bytes,
-                                                                                 stg_res_bytes, vec_bytes, vec_all);
+                                                                                 stg_res_bytes, vec_bytes, vec_all, out_bufs);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
