@@ -82,6 +82,11 @@ class SAM2VideoPredictor(SAM2Model):
         self.sam_mask_decoder: Optional[_DecoderModule] = None
         self._const_cache: Dict[Any, Any] = {}
         self.max_encode_batch = int(os.environ.get("SB_ENCODE_BATCH", "8"))  # crops / frames per encoder pass
+        # A tracking step is ~175 launches of mostly small kernels: run eagerly it is bound by the host (25 us per launch,
+        # 4.5 ms per frame with one object). Steps whose memory layout is in steady state (all 15 object pointers present)
+        # are captured once per (layout, batch) into a CUDA graph and replayed; SB_PROP_GRAPH=0 keeps everything eager.
+        self.use_cuda_graph = os.environ.get("SB_PROP_GRAPH", "1") != "0"
+        self._step_graphs: Dict[Any, Any] = {}
         super().__init__(cfg, state_dict, device=device, dynamic_multimask_via_stability=dynamic_multimask_via_stability,
                          num_maskmem=num_maskmem)
 
@@ -304,6 +309,70 @@ class SAM2VideoPredictor(SAM2Model):
         sig = (tuple(tp for tp, _, _ in spatial), tuple(td for td, _, _ in ptrs))
         return sig, spatial, ptrs
 
+    def _assemble_memory(self, memory: torch.Tensor, objs: List[int], plans) -> None:
+        """Fill memory [B, Nk, 64] bf16: per object the spatial memories, then the object pointers (4 tokens each). Stored
+        outputs of one tracking step are views of ONE [B*4096,64] / [B,256] tensor per group (`_batch` entry), so a
+        slot that every object of this batch fills from the same earlier step is ONE copy instead of B."""
+        B = len(objs)
+        first = plans[objs[0]]
+        n_sp, n_pt = len(first[1]), len(first[2])
+        off = 0
+        for k in range(n_sp + n_pt):
+            is_sp = k < n_sp
+            outs = [plans[i][1][k][2] if is_sp else plans[i][2][k - n_sp][2] for i in objs]
+            width = NT if is_sp else 4
+            b0 = outs[0].get("_batch")
+            if b0 is not None and b0["objs"] == tuple(objs) and all(o.get("_batch") is b0 for o in outs):
+                src = b0["mem"].view(B, NT, 64) if is_sp else b0["ptr"].view(B, 4, 64)
+                memory[:, off:off + width] = src  # (fp32 pointers -> bf16 storage cast)
+            else:
+                for bi, out in enumerate(outs):
+                    memory[bi, off:off + width] = out["maskmem_features"] if is_sp else out["obj_ptr"].view(4, 64)
+            off += width
+
+    def _layout_pos(self, st, sig):
+        """Key positional term of a memory layout, per layer [Nk, 256]: spatial slots + pointer tokens (weights-only
+        constants). The pointer part depends on the temporal distances — the conditioning frame's distance changes
+        every frame — so the term lives in ONE buffer per layout STRUCTURE (which slots, how many pointers): the spatial
+        rows are written once, the 4 * n_ptr pointer rows are refreshed per call (stream-ordered before their consumer).
+        A CUDA graph of the step can therefore bake the buffer addresses."""
+        t_pos_list, t_diff_list = sig
+        ck = ("layout", tuple(t_pos_list), len(t_diff_list), st["num_frames"], self._tpos_key())
+        buf = self._const_cache.get(ck)
+        if buf is None:
+            parts = [self._spatial_key_pos(tp) for tp in t_pos_list]
+            n_sp = sum(p[0].shape[0] for p in parts)
+            n_pt = 4 * len(t_diff_list)
+            ref = parts[0][0] if parts else self._ptr_key_pos(tuple(t_diff_list), st["num_frames"])[0]
+            buf = [torch.empty((n_sp + n_pt, ref.shape[1]), dtype=ref.dtype, device=ref.device) for _ in range(4)]
+            for l in range(4):
+                off = 0
+                for p_ in parts:
+                    buf[l][off:off + p_[l].shape[0]] = p_[l]
+                    off += p_[l].shape[0]
+            self._const_cache[ck] = buf
+        if t_diff_list:
+            # pointer rows from a per-distance table on the device (built once per video length); only the rows whose
+            # distance changed since the last call are rewritten — in steady state that is the conditioning frame's
+            # pointer alone: 4 small device copies per frame, no host matmul / H2D copy on the frame path
+            table = self._ptr_pos_table(st["num_frames"])
+            last = self._const_cache.setdefault(ck + ("last",), [None] * len(t_diff_list))
+            n_sp = buf[0].shape[0] - 4 * len(t_diff_list)
+            for j, td in enumerate(t_diff_list):
+                if last[j] != td:
+                    for l in range(4):
+                        buf[l][n_sp + 4 * j:n_sp + 4 * j + 4] = table[l][td]
+                    last[j] = td
+        return buf
+
+    def _ptr_pos_table(self, num_frames: int) -> List[torch.Tensor]:
+        """Per layer [num_frames, 4, 256]: positional term of an object pointer at temporal distance t (0 .. num_frames-1)."""
+        key = ("ptr_table", num_frames)
+        if key not in self._const_cache:
+            per = self._ptr_key_pos(tuple(range(num_frames)), num_frames)  # per layer [4 * num_frames, 256]
+            self._const_cache[key] = [p_.view(num_frames, 4, -1).contiguous() for p_ in per]
+        return self._const_cache[key]
+
     def _conditioned_features(self, st, c, objs: List[int], sig, plans) -> torch.Tensor:
         """Memory attention for a batch of objects that share the memory layout `sig` (SAM2Base._prepare_memory_
         conditioned_features for a non-initial frame) -> [B*4096, 256] fp32."""
@@ -312,46 +381,97 @@ class SAM2VideoPredictor(SAM2Model):
         n_ptr_tok = 4 * len(t_diff_list)
         Nk = NT * len(t_pos_list) + n_ptr_tok
         memory = torch.empty((B, Nk, 64), dtype=_BF16, device=self.device)
-        for bi, i in enumerate(objs):
-            _, spatial, ptrs = plans[i]
-            off = 0
-            for _, _, out in spatial:
-                memory[bi, off:off + NT] = out["maskmem_features"]
-                off += NT
-            for _, _, out in ptrs:
-                memory[bi, off:off + 4] = out["obj_ptr"].view(4, 64)  # fp32 -> bf16 storage cast
-                off += 4
-        # key positional term: spatial slots + pointer tokens (weights-only constants, cached per layout)
-        ck = ("layout", sig, st["num_frames"], self._tpos_key())
-        if ck not in self._const_cache:
-            parts = [self._spatial_key_pos(tp) for tp in t_pos_list]
-            if t_diff_list:
-                parts.append(self._ptr_key_pos(tuple(t_diff_list), st["num_frames"]))
-            self._const_cache[ck] = [torch.cat([p[l] for p in parts], 0).contiguous() for l in range(4)]
-        pos_k = self._const_cache[ck]
+        self._assemble_memory(memory, objs, plans)
+        pos_k = self._layout_pos(st, sig)
         return self.mem_attn.forward(c["feat"], memory.view(B * Nk, 64), pos_k, n_ptr_tok, B)  # [B*4096,256]
+
+    def _step_body(self, feat, s0, s1, pix_proj, memory, pos_k, n_ptr_tok, B):
+        """The device work of one tracking step on given inputs (memory attention -> mask decoder -> selection ->
+        object pointer -> memory encoder -> hole filling). No host synchronisation: capturable."""
+        Nk = memory.shape[1]
+        pix = self.mem_attn.forward(feat, memory.view(B * Nk, 64), pos_k, n_ptr_tok, B)
+        dec = self.decoder
+        coords = torch.zeros((B, 1, 2), dtype=_F32, device=self.device)
+        labels = torch.full((B, 1), -1, dtype=_I32, device=self.device)
+        tokens = dec.prompt_tokens(coords, labels)
+        out = dec.forward(pix, s0, s1, tokens, None, multimask_output=True)
+        obj = out["obj"].reshape(-1).contiguous()
+        low, tok, _ = ops.track_select(out["masks"], out["ious"], obj, out["hs"].contiguous(), None, True)
+        ptr = self._obj_ptr(tok, obj)
+        mem = self.mem_enc.forward(pix_proj, low, obj, binarize=False)  # is_mask_from_pts = False
+        pred = ops.fill_holes(low, self.fill_hole_area) if self.fill_hole_area > 0 else low
+        return {"masks": out["masks"], "ious": out["ious"], "hs": out["hs"], "obj_raw": out["obj"], "obj": obj, "ptr": ptr,
+                "mem": mem, "pred": pred}
+
+    def _step_graph(self, st, sig, B):
+        """CUDA graph of `_step_body` for the steady-state layout `sig` and batch B (static input / output buffers)."""
+        key = (tuple(sig[0]), len(sig[1]), B, st["num_frames"], self._tpos_key())
+        g = self._step_graphs.get(key)
+        if g is not None:
+            return g
+        dev = self.device
+        t_pos_list, t_diff_list = sig
+        n_ptr_tok = 4 * len(t_diff_list)
+        Nk = NT * len(t_pos_list) + n_ptr_tok
+        g = {"feat": torch.zeros((NT, 256), dtype=_F32, device=dev), "s0": torch.zeros((65536, 32), dtype=_F32, device=dev),
+             "s1": torch.zeros((16384, 64), dtype=_F32, device=dev), "pix_proj": None,
+             "memory": torch.zeros((B, Nk, 64), dtype=_BF16, device=dev), "n_ptr_tok": n_ptr_tok}
+        self._step_graphs[key] = g
+        return g
 
     def _track_group(self, st, frame_idx, objs: List[int], sig, plans, reverse) -> Dict[int, Dict[str, Any]]:
         """One tracking step for a batch of objects that share the memory layout `sig`."""
         B = len(objs)
         c = self._frame(st, frame_idx)
-        pix = self._conditioned_features(st, c, objs, sig, plans)
-        dec = self.decoder
-        coords = torch.zeros((B, 1, 2), dtype=_F32, device=self.device)
-        labels = torch.full((B, 1), -1, dtype=_I32, device=self.device)
-        tokens = dec.prompt_tokens(coords, labels)
-        out = dec.forward(pix, c["s0"], c["s1"], tokens, None, multimask_output=True)
-        self.sam_mask_decoder.fire(out["masks"][:, 1:4], out["ious"][:, 1:4], out["hs"][:, 3:6], out["obj"])
-        obj = out["obj"].reshape(-1).contiguous()
-        low, tok, _ = ops.track_select(out["masks"], out["ious"], obj, out["hs"].contiguous(), None, True)
-        ptr = self._obj_ptr(tok, obj)
-        mem = self.mem_enc.forward(c["pix_proj"], low, obj, binarize=False)  # is_mask_from_pts = False
-        pred = ops.fill_holes(low, self.fill_hole_area) if self.fill_hole_area > 0 else low
+        pos_k = self._layout_pos(st, sig)
+        t_pos_list, t_diff_list = sig
+        n_ptr_tok = 4 * len(t_diff_list)
+        steady = len(t_diff_list) >= self.max_obj_ptrs_in_encoder - 1 or len(t_diff_list) >= st["num_frames"] - 2
+        use_graph = (self.use_cuda_graph and steady and not self.sam_mask_decoder._hooks
+                     and not torch.cuda.is_current_stream_capturing())
+        if use_graph:
+            g = self._step_graph(st, sig, B)
+            if g["pix_proj"] is None:
+                g["pix_proj"] = torch.zeros_like(c["pix_proj"])
+            g["feat"].copy_(c["feat"])
+            g["s0"].copy_(c["s0"])
+            g["s1"].copy_(c["s1"])
+            g["pix_proj"].copy_(c["pix_proj"])
+            self._assemble_memory(g["memory"], objs, plans)
+            if "graph" not in g:
+                args = (g["feat"], g["s0"], g["s1"], g["pix_proj"], g["memory"], pos_k, n_ptr_tok, B)
+                main = torch.cuda.current_stream()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self._step_body(*args)  # warm-up: function attributes, constant caches
+                main.wait_stream(side)
+                torch.cuda.synchronize()
+                n0 = ops.launch_count
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    g["out"] = self._step_body(*args)
+                g["launches"] = ops.launch_count - n0
+                ops.launch_count = n0
+                g["graph"] = graph
+            g["graph"].replay()
+            ops.launch_count += g["launches"]
+            o = g["out"]
+            # results are stored across frames: copy them out of the graph's static buffers (one clone per tensor)
+            r = {k: o[k].clone() for k in ("obj", "ptr", "mem", "pred")}
+            self.sam_mask_decoder.fire(o["masks"][:, 1:4], o["ious"][:, 1:4], o["hs"][:, 3:6], o["obj_raw"])
+        else:
+            memory = torch.empty((B, NT * len(t_pos_list) + n_ptr_tok, 64), dtype=_BF16, device=self.device)
+            self._assemble_memory(memory, objs, plans)
+            r = self._step_body(c["feat"], c["s0"], c["s1"], c["pix_proj"], memory, pos_k, n_ptr_tok, B)
+            self.sam_mask_decoder.fire(r["masks"][:, 1:4], r["ious"][:, 1:4], r["hs"][:, 3:6], r["obj_raw"])
+        obj, ptr, mem, pred = r["obj"], r["ptr"], r["mem"], r["pred"]
+        batch = {"objs": tuple(objs), "mem": mem, "ptr": ptr}
         res = {}
         for bi, i in enumerate(objs):
             res[i] = {"maskmem_features": mem[bi * NT:(bi + 1) * NT], "maskmem_pos_enc": True,
                       "pred_masks": pred[bi].view(1, 1, 256, 256), "obj_ptr": ptr[bi:bi + 1],
-                      "object_score_logits": obj[bi].view(1, 1)}
+                      "object_score_logits": obj[bi].view(1, 1), "_batch": batch}
         return res
 
     @torch.no_grad()

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k gemm > gpurun_out/r02zf_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02zf_tests.log
-timeout 200 python tools/gemm_probe.py 0 1 4 5 6 7 15 > /dev/null 2>&1
-timeout 200 python tools/gemm_probe.py 2>&1 > gpurun_out/r02zf_gemm_probe.log; grep -A1 "N= 2304\|N= 1728\|N= 1152 K=  288\|N= 4608\|N= 8192" gpurun_out/r02zf_gemm_probe.log | cut -c1-260
-timeout 200 python tools/encoder_probe.py > gpurun_out/r02zf_enc.log 2>&1; head -12 gpurun_out/r02zf_enc.log
+export SABER_B200_ALLOW_RANDOM_INIT=1
+timeout 900 python -m pytest tests/test_gpu_video.py tests/test_gpu_configs.py tests/test_refstack.py -m gpu -q -x > gpurun_out/r02zi_tests.log 2>&1; echo "tests rc=$?"; tail -8 gpurun_out/r02zi_tests.log
+timeout 600 python tools/propagation_probe_dist.py 64 1 8 2>&1 | grep "GPU\]" | cut -c1-330
+SB_PROP_GRAPH=0 timeout 600 python tools/propagation_probe_dist.py 64 1 8 2>&1 | grep "GPU\]" | cut -c1-330
