@@ -130,6 +130,17 @@ int sb_hiera_attention_tc_prof(const void* qkv, void* out, int batch, int H, int
 int sb_layernorm(const void* in, long long ld_in, int in_f32, void* out, long long ld_out, int out_f32,
                  const float* gamma, const float* beta, int M, int C, float eps, int act, void* stream);
 int sb_im2col_k7s4(const float* img, void* cols, int B, int Cin, int S, int Kp, void* stream); /* PatchEmbed 7x7 s4 p3 */
+
+/* ---- fp32 validation mode (SB_VALIDATE_FP32; BASELINE north_star "1e-4 in the fp32 validation mode") -------------- */
+/* x (fp32) split into three bf16 parts, K-concatenated into the operand of a 6-term split product: a GEMM of the role-0
+ * (activation: [h h h m m l]) and role-1 (weight: [h m l h m h]) outputs with K' = 6K on sb_gemm_bf16 reproduces the
+ * fp32 product to ~2^-24: the production tcgen05 kernel is the one validated. out [M, 6K] bf16, pitch ldo. */
+int sb_split3_bf16(const float* x, long long ldx, int M, int K, int role, void* out, long long ldo, void* stream);
+/* fp32 twin of sb_window_attention (hieradet.py MultiScaleAttention in torch fp32): CUDA cores, one block per query. */
+int sb_window_attention_f32(const float* qkv, const float* qkv_bias, float* o, int batch, int H, int W, int heads,
+                            int hd, int ws, int pool, float scale, void* stream);
+int sb_im2col_k7s4_f32(const float* img, float* cols, int B, int Cin, int S, int Kp, void* stream);
+int sb_gelu_exact_f32(float* x, long long n, void* stream); /* erff GELU in place (the fused epilogue form is 4e-4) */
 int sb_maxpool2x2(const void* in, void* out, int is_f32, int B, int H, int W, int C, void* stream); /* hieradet do_pool */
 int sb_add_upsample2x(float* dst, const float* src, int B, int H, int W, int C, void* stream);   /* FpnNeck top-down */
 int sb_nhwc_to_nchw(const void* in, int in_f32, void* out, int out_f32, int B, int HW, int C, const float* chan_add,

@@ -149,8 +149,9 @@ void launch_ln_rows(int g, cudaStream_t stream, const float* in, long long ld_in
 // im2col for Conv2d(k=7, stride=4, pad=3): img [B, Cin, S, S] fp32 -> cols [B*(S/4)^2, Kp] bf16,
 // column index = c*49 + ky*7 + kx, zero beyond Cin*49 (Kp is the padded pitch).
 // ------------------------------------------------------------------------------------------
+template <typename TO>
 __global__ void __launch_bounds__(256)
-im2col_k7s4_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int B, int Cin,
+im2col_k7s4_kernel(const float* __restrict__ img, TO* __restrict__ cols, int B, int Cin,
                    int S, int Kp) {
   const int T = S / 4;
   const long long total = static_cast<long long>(B) * T * T * Kp;
@@ -168,7 +169,7 @@ im2col_k7s4_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ co
       if (y >= 0 && y < S && x >= 0 && x < S)
         v = img[((static_cast<long long>(b) * Cin + c) * S + y) * S + x];
     }
-    cols[i] = __float2bfloat16(v);
+    cols[i] = static_cast<TO>(v);
   }
 }
 
@@ -322,8 +323,18 @@ extern "C" int sb_im2col_k7s4(const float* img, void* cols, int B, int Cin, int 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(S % 4 == 0 && Kp >= Cin * 49 && (Kp % 8) == 0, "sb_im2col_k7s4: bad S=%d Kp=%d", S, Kp);
   const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * Kp;
-  im2col_k7s4_kernel<<<grid_for(total), 256, 0, stream>>>(
+  im2col_k7s4_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(
       img, static_cast<__nv_bfloat16*>(cols), B, Cin, S, Kp);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// fp32 patches (validation mode)
+extern "C" int sb_im2col_k7s4_f32(const float* img, float* cols, int B, int Cin, int S, int Kp, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(S % 4 == 0 && Kp >= Cin * 49 && (Kp % 8) == 0, "sb_im2col_k7s4_f32: bad S=%d Kp=%d", S, Kp);
+  const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * Kp;
+  im2col_k7s4_kernel<float><<<grid_for(total), 256, 0, stream>>>(img, cols, B, Cin, S, Kp);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

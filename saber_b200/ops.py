@@ -4,6 +4,7 @@ arithmetic op on the hot path is one of our sm_100a kernels. No CPU / eager fall
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -97,6 +98,73 @@ def require_b200() -> None:
     _lib.check(L.sb_require_sm100(), "sb_require_sm100")
 
 
+# ---------------------------------------------------------------------------------------------
+# fp32 validation mode (BASELINE north_star: "1e-4 in the fp32 validation mode"; csrc/validate.cu). While it is on,
+# executors keep fp32 weights (`weight()`), activations stay fp32 between kernels, every GEMM runs as the 6-term
+# bf16 split product on the PRODUCTION tcgen05 kernel (K' = 6 K, fp32 accumulation in TMEM) and Hiera's attention
+# runs in fp32 on CUDA cores. Covers the image encoder (U1); the fused decoder / memory kernels exist in bf16 only.
+# ---------------------------------------------------------------------------------------------
+VALIDATE_FP32 = os.environ.get("SB_VALIDATE_FP32", "0") == "1"
+_split_w_cache: dict = {}
+
+
+class validate_fp32:
+    """Context manager: `with ops.validate_fp32(): model = build_sam2(...); model.forward_image(x)`."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global VALIDATE_FP32
+        self.prev, VALIDATE_FP32 = VALIDATE_FP32, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global VALIDATE_FP32
+        VALIDATE_FP32 = self.prev
+        _split_w_cache.clear()
+
+
+def weight(t: torch.Tensor, device) -> torch.Tensor:
+    """GEMM weight as the executors store it: bf16, or fp32 in validation mode."""
+    return t.to(device, _F32 if VALIDATE_FP32 else _BF16).contiguous()
+
+
+def act_dtype():
+    """dtype of the activations that feed GEMMs / attention: bf16, or fp32 in validation mode."""
+    return _F32 if VALIDATE_FP32 else _BF16
+
+
+def split3(x: torch.Tensor, role: int) -> torch.Tensor:
+    """fp32 [M,K] -> bf16 [M,6K] operand of the 6-term split product (role 0 activation, 1 weight)."""
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 8 == 0, (x.dtype, x.shape)
+    M, K = x.shape
+    out = torch.empty((M, 6 * K), dtype=_BF16, device=x.device)
+    L = _lib.load()
+    _lib.check(L.sb_split3_bf16(x.data_ptr(), x.stride(0), M, K, role, out.data_ptr(), out.stride(0), _stream()),
+               "sb_split3_bf16")
+    _count()
+    return out
+
+
+def _gemm_validate(a, w, bias, act, residual, res_mod, out, alpha, force_bn):
+    assert a.dtype == _F32 and w.dtype == _F32, "validation mode: fp32 activations and weights"
+    key = (w.data_ptr(), tuple(w.shape), w.stride(0))
+    w6 = _split_w_cache.get(key)
+    if w6 is None:
+        w6 = _split_w_cache[key] = split3(w, 1)
+    a6 = split3(a, 0)
+    if act == ACT_GELU:  # exact erf GELU after the product (the fused MUFU.TANH form is accurate to 4e-4 only)
+        assert residual is None
+        y = gemm(a6, w6, bias, ACT_NONE, None, 0, _F32, out=out, alpha=alpha, force_bn=force_bn)
+        L = _lib.load()
+        _lib.check(L.sb_gelu_exact_f32(y.data_ptr(), y.numel(), _stream()), "sb_gelu_exact_f32")
+        _count()
+        return y
+    return gemm(a6, w6, bias, act, residual, res_mod, _F32, out=out, alpha=alpha, force_bn=force_bn)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, res_mod: int = 0, out_dtype=_BF16,
          out: Optional[torch.Tensor] = None, alpha: float = 1.0, force_bn: int = 0) -> torch.Tensor:
@@ -106,6 +174,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     fp32 2-D. out: bf16 or fp32.
     """
     _chk_cuda(a, w, bias, residual, out)
+    if w.dtype == _F32:  # validation mode: fp32 operands through the split product (fp32 result)
+        return _gemm_validate(a, w, bias, act, residual, res_mod, out, alpha, force_bn)
     assert a.dtype == _BF16 and w.dtype == _BF16, (a.dtype, w.dtype)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -240,6 +310,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     _chk_cuda(x, gamma, beta, out)
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (_BF16, _F32)
     M, Cc = x.shape
+    if VALIDATE_FP32 and out is None:
+        out_dtype = _F32
     if out is None:
         out = torch.empty((M, Cc), dtype=out_dtype, device=x.device)
     assert gamma.dtype == _F32 and beta.dtype == _F32
@@ -434,6 +506,8 @@ def window_attention(qkv: torch.Tensor, qkv_bias: Optional[torch.Tensor], batch:
                      heads: int, ws: int, pool: int = 1, scale: Optional[float] = None) -> torch.Tensor:
     """Hiera (windowed / global, optionally q-pooled) attention over a fused qkv [B*H*W, 3*C] buffer."""
     _chk_cuda(qkv, qkv_bias)
+    if qkv.dtype == _F32:  # validation mode
+        return _window_attention_f32(qkv, qkv_bias, batch, H, W, heads, ws, pool, scale)
     assert qkv.dtype == _BF16 and qkv.is_contiguous() and qkv.shape[0] == batch * H * W
     C3 = qkv.shape[1]
     Cc = C3 // 3
@@ -448,6 +522,22 @@ def window_attention(qkv: torch.Tensor, qkv_bias: Optional[torch.Tensor], batch:
     rc = L.sb_window_attention(qkv.data_ptr(), _ptr(qkv_bias), out.data_ptr(), batch, H, W, heads, hd,
                                ws, pool, scale, _stream())
     _lib.check(rc, "sb_window_attention")
+    _count()
+    return out
+
+
+def _window_attention_f32(qkv, qkv_bias, batch, H, W, heads, ws, pool, scale):
+    assert qkv.is_contiguous() and qkv.shape[0] == batch * H * W
+    Cc = qkv.shape[1] // 3
+    hd = Cc // heads
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if ws <= 0 or ws >= max(H, W):
+        ws = max(H, W)
+    out = torch.empty((batch * (H // pool) * (W // pool), Cc), dtype=_F32, device=qkv.device)
+    L = _lib.load()
+    _lib.check(L.sb_window_attention_f32(qkv.data_ptr(), _ptr(qkv_bias), out.data_ptr(), batch, H, W, heads, hd, ws, pool,
+                                         scale, _stream()), "sb_window_attention_f32")
     _count()
     return out
 
@@ -472,9 +562,10 @@ def im2col_k7s4(img: torch.Tensor, kp: int) -> torch.Tensor:
     _chk_cuda(img)
     assert img.dtype == _F32 and img.is_contiguous() and img.dim() == 4 and img.shape[2] == img.shape[3]
     B, Cin, S, _ = img.shape
-    cols = torch.empty((B * (S // 4) ** 2, kp), dtype=_BF16, device=img.device)
+    cols = torch.empty((B * (S // 4) ** 2, kp), dtype=act_dtype(), device=img.device)
     L = _lib.load()
-    _lib.check(L.sb_im2col_k7s4(img.data_ptr(), cols.data_ptr(), B, Cin, S, kp, _stream()), "sb_im2col_k7s4")
+    fn = L.sb_im2col_k7s4_f32 if VALIDATE_FP32 else L.sb_im2col_k7s4
+    _lib.check(fn(img.data_ptr(), cols.data_ptr(), B, Cin, S, kp, _stream()), "sb_im2col_k7s4")
     _count()
     return cols
 
@@ -535,6 +626,8 @@ def add_cast(a: torch.Tensor, b: Optional[torch.Tensor] = None, out_dtype=_BF16)
     """out = a + b (b fp32, broadcast by flat index modulo b.numel()), converted to out_dtype."""
     _chk_cuda(a, b)
     assert a.is_contiguous() and a.dtype in (_BF16, _F32)
+    if VALIDATE_FP32 and out_dtype == _BF16:
+        out_dtype = _F32
     out = torch.empty(a.shape, dtype=out_dtype, device=a.device)
     b_mod = 0
     if b is not None:

@@ -28,8 +28,8 @@ class HieraEncoder:
         dev = self.device
         t = "image_encoder.trunk."
 
-        def w16(name):
-            return sd[name].to(dev, _BF16).contiguous()
+        def w16(name):  # bf16 operand of the tcgen05 GEMM (fp32 in the validation mode: ops.weight)
+            return ops.weight(sd[name], dev)
 
         def f32(name):
             return sd[name].to(dev, _F32).contiguous()
@@ -38,8 +38,8 @@ class HieraEncoder:
         E = h["embed_dim"]
         pw = sd[t + "patch_embed.proj.weight"].reshape(E, 147)
         self.kp = 160
-        self.patch_w = torch.zeros((E, self.kp), dtype=_BF16, device=dev)
-        self.patch_w[:, :147] = pw.to(dev, _BF16)
+        self.patch_w = torch.zeros((E, self.kp), dtype=ops.act_dtype(), device=dev)
+        self.patch_w[:, :147] = pw.to(dev, ops.act_dtype())
         self.patch_b = f32(t + "patch_embed.proj.bias")
         # positional embedding for the fixed 256x256 token grid (weights-only, done once at load):
         # bicubic background + tiled window embedding (hieradet.Hiera._get_pos_embed)
@@ -65,12 +65,12 @@ class HieraEncoder:
             self.blocks.append(blk)
 
         n = "image_encoder.neck.convs."
-        self.neck_w = [sd[f"{n}{i}.conv.weight"].reshape(arch.HIDDEN, -1).to(dev, _BF16).contiguous() for i in range(4)]
+        self.neck_w = [ops.weight(sd[f"{n}{i}.conv.weight"].reshape(arch.HIDDEN, -1), dev) for i in range(4)]
         self.neck_b = [f32(f"{n}{i}.conv.bias") for i in range(4)]
         md = "sam_mask_decoder."
-        self.s0_w = sd[md + "conv_s0.weight"].reshape(32, 256).to(dev, _BF16).contiguous()
+        self.s0_w = ops.weight(sd[md + "conv_s0.weight"].reshape(32, 256), dev)
         self.s0_b = f32(md + "conv_s0.bias")
-        self.s1_w = sd[md + "conv_s1.weight"].reshape(64, 256).to(dev, _BF16).contiguous()
+        self.s1_w = ops.weight(sd[md + "conv_s1.weight"].reshape(64, 256), dev)
         self.s1_b = f32(md + "conv_s1.bias")
 
     # ------------------------------------------------------------------

@@ -385,3 +385,39 @@ def test_gpupool_threads_tomogram_level_data_parallelism():
     assert sorted(got) == list(range(len(tasks)))
     for i in range(len(tasks)):
         assert torch.equal(got[i], want[i]), f"task {i}"
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "large"])
+def test_encoder_fp32_validation_mode(cfg):
+    """BASELINE north_star: embeddings within 1e-4 in the fp32 validation mode. `ops.validate_fp32()` keeps fp32 weights
+    and activations and runs every product as the 6-term bf16 split (K' = 6K) on the PRODUCTION tcgen05 GEMM kernel
+    (fp32 accumulation in TMEM), attention in fp32 on CUDA cores, exact erf GELU: same host orchestration, same layouts,
+    same window / pooling addressing as the bf16 path — what remains against the fp32 oracle is summation order.
+    tiny has ragged 14 x 14 / 7 x 7 windows (padded tokens carry the qkv bias), large the 16 x 16 and global blocks."""
+    from oracle.sam2_ref.sam2_base import SAM2Base
+    from saber_b200 import ops
+    from saber_b200.sam2 import arch
+    from saber_b200.sam2.build_sam import build_sam2
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = arch.random_state_dict(cfg, seed=0)
+    orc = SAM2Base(cfg)
+    orc.load_state_dict(sd, strict=True)
+    orc = orc.cuda().eval()
+    torch.manual_seed(1)
+    img = torch.randn(1, 3, 1024, 1024, device="cuda")
+    with torch.no_grad():
+        _, vf, _, _ = orc._prepare_backbone_features(orc.forward_image(img))
+    with ops.validate_fp32():
+        model = build_sam2(cfg, None, device="cuda", state_dict=sd)
+        out = model.forward_image(img)
+    for got, want, width in ((out["feat"], vf[2], 256), (out["s1"], vf[1], 64), (out["s0"], vf[0], 32)):
+        want = want.permute(1, 0, 2).reshape(-1, width)
+        assert got.dtype == torch.float32
+        rel = ((got - want).norm() / want.norm()).item()
+        worst = ((got - want).abs().max() / want.abs().max()).item()
+        assert rel < 1e-4 and worst < 1e-4, (cfg, width, rel, worst)
+    # and the mode is really off afterwards: the bf16 path differs from it by bf16 rounding (~0.5 %)
+    out16 = build_sam2(cfg, None, device="cuda", state_dict=sd).forward_image(img)
+    rel16 = ((out16["feat"] - out["feat"]).norm() / out["feat"].norm()).item()
+    assert 1e-4 < rel16 < 2e-2, rel16
