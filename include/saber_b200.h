@@ -140,6 +140,10 @@ int sb_split3_bf16(const float* x, long long ldx, int M, int K, int role, void* 
 int sb_window_attention_f32(const float* qkv, const float* qkv_bias, float* o, int batch, int H, int W, int heads,
                             int hd, int ws, int pool, float scale, void* stream);
 int sb_im2col_k7s4_f32(const float* img, float* cols, int B, int Cin, int S, int Kp, void* stream);
+/* fp32 twin of sb_attention / sb_attention_kadd (k_add may be NULL) */
+int sb_attention_f32(const float* q, long long q_ld, const float* k, long long k_ld, const float* k_add, long long ka_ld,
+                     const float* v, long long v_ld, float* o, long long o_ld, int batch, int heads, int hd, int nq,
+                     int nk, float scale, int q_shared, int kv_shared, void* stream);
 int sb_gelu_exact_f32(float* x, long long n, void* stream); /* erff GELU in place (the fused epilogue form is 4e-4) */
 int sb_maxpool2x2(const void* in, void* out, int is_f32, int B, int H, int W, int C, void* stream); /* hieradet do_pool */
 int sb_add_upsample2x(float* dst, const float* src, int B, int H, int W, int C, void* stream);   /* FpnNeck top-down */

@@ -174,3 +174,80 @@ extern "C" int sb_gelu_exact_f32(float* x, long long n, void* stream_) {
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
+
+namespace {
+// Generic batched multi-head attention in fp32 (CUDA cores): one block per (batch, head, query); optional additive key
+// term shared by all batch entries (scores = q (k[b] + k_add)^T). q / k / v may hold one batch entry read by all.
+__global__ void __launch_bounds__(128)
+attention_f32_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, long long k_ld,
+                     const float* __restrict__ k_add, long long ka_ld, const float* __restrict__ v, long long v_ld,
+                     float* __restrict__ o, long long o_ld, int heads, int hd, int nq, int nk, float scale, int q_shared,
+                     int kv_shared) {
+  extern __shared__ float sm[];
+  float* sq = sm;       // [hd]
+  float* ss = sm + hd;  // [nk]
+  __shared__ float red[4];
+  long long id = blockIdx.x;
+  const int qi = static_cast<int>(id % nq);
+  id /= nq;
+  const int h = static_cast<int>(id % heads);
+  const int b = static_cast<int>(id / heads);
+  const float* qrow = q + (static_cast<long long>(q_shared ? 0 : b) * nq + qi) * q_ld + h * hd;
+  const float* kb = k + static_cast<long long>(kv_shared ? 0 : b) * nk * k_ld + h * hd;
+  const float* vb = v + static_cast<long long>(kv_shared ? 0 : b) * nk * v_ld + h * hd;
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) sq[d] = qrow[d];
+  __syncthreads();
+  float mx = -FLT_MAX;
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+    const float* kr = kb + static_cast<long long>(j) * k_ld;
+    const float* ka = k_add ? k_add + static_cast<long long>(j) * ka_ld + h * hd : nullptr;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc = fmaf(sq[d], ka ? kr[d] + ka[d] : kr[d], acc);
+    acc *= scale;
+    ss[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = sb::warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+    const float e = expf(ss[j] - mx);
+    ss[j] = e;
+    sum += e;
+  }
+  sum = sb::warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  const float inv = 1.f / ((red[0] + red[1]) + (red[2] + red[3]));
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < nk; ++j) acc = fmaf(ss[j], vb[static_cast<long long>(j) * v_ld + d], acc);
+    o[(static_cast<long long>(b) * nq + qi) * o_ld + h * hd + d] = acc * inv;
+  }
+}
+}  // namespace
+
+// fp32 twin of sb_attention / sb_attention_kadd (k_add may be NULL): F.scaled_dot_product_attention in torch fp32.
+extern "C" int sb_attention_f32(const float* q, long long q_ld, const float* k, long long k_ld, const float* k_add,
+                                long long ka_ld, const float* v, long long v_ld, float* o, long long o_ld, int batch,
+                                int heads, int hd, int nq, int nk, float scale, int q_shared, int kv_shared,
+                                void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(batch > 0 && heads > 0 && hd > 0 && nq > 0 && nk > 0 && q && k && v && o, "sb_attention_f32: bad arguments");
+  const size_t smem = (static_cast<size_t>(hd) + static_cast<size_t>(nk)) * sizeof(float);
+  SB_REQUIRE(smem <= 200 * 1024, "sb_attention_f32: %d keys do not fit shared memory", nk);
+  static SbPerDeviceOnce once;
+  if (once.need()) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    once.mark();
+  }
+  const long long blocks = static_cast<long long>(batch) * heads * nq;
+  SB_REQUIRE(blocks < (1ll << 31), "sb_attention_f32: too many queries");
+  attention_f32_kernel<<<static_cast<unsigned>(blocks), 128, smem, stream>>>(q, q_ld, k, k_ld, k_add, ka_ld, v, v_ld, o, o_ld,
+                                                                            heads, hd, nq, nk, scale, q_shared, kv_shared);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

@@ -106,6 +106,7 @@ def require_b200() -> None:
 # ---------------------------------------------------------------------------------------------
 VALIDATE_FP32 = os.environ.get("SB_VALIDATE_FP32", "0") == "1"
 _split_w_cache: dict = {}
+_weight_ptrs: set = set()  # fp32 weights created by weight(): only their split operands are cached
 
 
 class validate_fp32:
@@ -123,11 +124,15 @@ class validate_fp32:
         global VALIDATE_FP32
         VALIDATE_FP32 = self.prev
         _split_w_cache.clear()
+        _weight_ptrs.clear()
 
 
 def weight(t: torch.Tensor, device) -> torch.Tensor:
     """GEMM weight as the executors store it: bf16, or fp32 in validation mode."""
-    return t.to(device, _F32 if VALIDATE_FP32 else _BF16).contiguous()
+    w = t.to(device, _F32 if VALIDATE_FP32 else _BF16).contiguous()
+    if VALIDATE_FP32:
+        _weight_ptrs.add(w.data_ptr())
+    return w
 
 
 def act_dtype():
@@ -148,12 +153,24 @@ def split3(x: torch.Tensor, role: int) -> torch.Tensor:
     return out
 
 
+def gelu_exact_(x: torch.Tensor) -> torch.Tensor:
+    """Exact erf GELU in place on an fp32 tensor (validation mode)."""
+    _chk_cuda(x)
+    assert x.dtype == _F32 and x.is_contiguous()
+    L = _lib.load()
+    _lib.check(L.sb_gelu_exact_f32(x.data_ptr(), x.numel(), _stream()), "sb_gelu_exact_f32")
+    _count()
+    return x
+
+
 def _gemm_validate(a, w, bias, act, residual, res_mod, out, alpha, force_bn):
     assert a.dtype == _F32 and w.dtype == _F32, "validation mode: fp32 activations and weights"
     key = (w.data_ptr(), tuple(w.shape), w.stride(0))
     w6 = _split_w_cache.get(key)
     if w6 is None:
-        w6 = _split_w_cache[key] = split3(w, 1)
+        w6 = split3(w, 1)
+        if key[0] in _weight_ptrs:  # a model weight (constant); activation-valued "weights" (hyper vectors) are not cached
+            _split_w_cache[key] = w6
     a6 = split3(a, 0)
     if act == ACT_GELU:  # exact erf GELU after the product (the fused MUFU.TANH form is accurate to 4e-4 only)
         assert residual is None
@@ -229,6 +246,9 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resi
             gamma: torch.Tensor, beta: torch.Tensor, eps: float, res_mod: int = 0, out_dtype=_BF16) -> torch.Tensor:
     """out = LayerNorm(a @ w^T + bias + residual[m % res_mod or m]) * gamma + beta, fused in the GEMM epilogue."""
     _chk_cuda(a, w, bias, residual, gamma, beta)
+    if w.dtype == _F32:  # validation mode: split-product GEMM, then the row LayerNorm kernel
+        y = gemm(a, w, bias, ACT_NONE, residual, res_mod, _F32)
+        return layernorm(y, gamma, beta, eps, _F32)
     assert a.dtype == _BF16 and w.dtype == _BF16 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
@@ -330,6 +350,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     """Plain batched MHA. q [batch*nq, heads*hd], k/v [batch*nk, heads*hd] (bf16, row views allowed).
     With q_shared / kv_shared the operand holds one batch entry ([nq|nk, C]) read by every batch element."""
     _chk_cuda(q, k, v, out)
+    if q.dtype == _F32:  # validation mode
+        return _attention_f32(q, k, None, v, batch, heads, nq, nk, scale, q_shared, kv_shared, out)
     assert q.dtype == _BF16 and k.dtype == _BF16 and v.dtype == _BF16
     Cc = q.shape[1]
     hd = Cc // heads
@@ -348,10 +370,30 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     return out
 
 
+def _attention_f32(q, k, k_add, v, batch, heads, nq, nk, scale, q_shared, kv_shared, out):
+    assert q.dtype == _F32 and k.dtype == _F32 and v.dtype == _F32 and (k_add is None or k_add.dtype == _F32)
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    Cc = q.shape[1]
+    hd = Cc // heads
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if out is None:
+        out = torch.empty((batch * nq, Cc), dtype=_F32, device=q.device)
+    L = _lib.load()
+    _lib.check(L.sb_attention_f32(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), _ptr(k_add),
+                                  k_add.stride(0) if k_add is not None else 0, v.data_ptr(), v.stride(0), out.data_ptr(),
+                                  out.stride(0), batch, heads, hd, nq, nk, scale, int(q_shared), int(kv_shared), _stream()),
+               "sb_attention_f32")
+    _count()
+    return out
+
+
 def attention_kadd(q: torch.Tensor, k: torch.Tensor, k_add: torch.Tensor, v: torch.Tensor, batch: int, heads: int, nq: int,
                    nk: int, kv_shared: bool = False, scale: Optional[float] = None) -> torch.Tensor:
     """attention() with scores = q (k[b] + k_add)^T; k_add [nk, heads*hd] bf16 is shared by all batch entries."""
     _chk_cuda(q, k, k_add, v)
+    if q.dtype == _F32:  # validation mode
+        return _attention_f32(q, k, k_add, v, batch, heads, nq, nk, scale, False, kv_shared, None)
     assert q.dtype == _BF16 and k.dtype == _BF16 and v.dtype == _BF16 and k_add.dtype == _BF16
     Cc = q.shape[1]
     hd = Cc // heads

@@ -44,8 +44,8 @@ class MaskDecoder:
         self.t2i_tensor_core = os.environ.get("SB_T2I_TC", "1") != "0"  # tcgen05 token->image attention (0: mma.sync)
         self.i2t_tensor_core = os.environ.get("SB_I2T_TC", "1") != "0"  # tcgen05 image->token block (0: mma.sync kernel)
 
-        def w16(t):
-            return t.to(dev, _BF16).contiguous()
+        def w16(t):  # bf16 GEMM operand (fp32 in the validation mode)
+            return ops.weight(t, dev)
 
         def f32(t):
             return t.to(dev, _F32).contiguous()
@@ -138,6 +138,26 @@ class MaskDecoder:
         h = ops.gemm(h, head[1][0], head[1][1], act=ops.ACT_RELU)
         return ops.gemm(h, head[2][0], head[2][1], act=last_act, out_dtype=_F32, out=out)
 
+    def _upscale_validate(self, keys, s0, s1, hyper, B, kb):
+        """fp32 validation route of output_upscaling + the hyper-network product, unfused: transposed convolutions as
+        split-product GEMMs (column = (dy, dx, channel)), pixel shuffle by tensor views (data movement only), skip adds,
+        LayerNorm2d and exact GELU through the stand-alone kernels, one small GEMM per prompt for the mask logits."""
+        if kb == 1:
+            keys = keys.repeat(B, 1)
+        g1 = ops.gemm(keys, self.up1_w, self.up1_b, out_dtype=_F32)  # [B*4096, 4*64]
+        u = g1.view(B, 64, 64, 2, 2, 64).permute(0, 1, 3, 2, 4, 5).reshape(B * 16384, 64).contiguous()
+        u = ops.add_cast(u, s1.contiguous(), _F32)  # + feat_s1 (broadcast over the prompts)
+        u = ops.layernorm(u, self.up_ln_w, self.up_ln_b, 1e-6, _F32)
+        u = ops.gelu_exact_(u)
+        g2 = ops.gemm(u, self.up2_w, self.up2_b, out_dtype=_F32)  # [B*16384, 4*32]
+        z = g2.view(B, 128, 128, 2, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(B * 65536, 32).contiguous()
+        z = ops.gelu_exact_(ops.add_cast(z, s0.contiguous(), _F32))
+        masks = torch.empty((B, 4, 256, 256), dtype=_F32, device=self.device)
+        for b in range(B):
+            m = ops.gemm(z[b * 65536:(b + 1) * 65536], hyper[b].contiguous(), None, out_dtype=_F32)  # [65536, 4]
+            masks[b] = m.t().reshape(4, 256, 256)
+        return masks
+
     def forward(self, image_embed: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, tokens: torch.Tensor,
                 mask_input: Optional[torch.Tensor] = None, multimask_output: bool = True,
                 mask_clamp: float = 0.0, iou_gate: Optional[float] = None, zero_fill: bool = False):
@@ -157,6 +177,11 @@ class MaskDecoder:
         multimask -> tokens 1..3; single -> token 0 or the dynamic-stability choice (sel_idx, sel_iou).
         """
         B, Nt, _ = tokens.shape
+        val = ops.VALIDATE_FP32  # fp32 validation mode: the unfused route through GEMM + generic attention + LayerNorm
+        if val and mask_input is not None:
+            raise NotImplementedError("fp32 validation mode covers point / box prompts (the mask-prompt convolutions "
+                                      "exist in bf16 only)")
+        fuse8 = Nt <= 8 and not val
         query_pe = tokens.reshape(B * Nt, 256)
         queries = query_pe
         per_prompt = image_embed.shape[0] != NT_IMG
@@ -189,7 +214,7 @@ class MaskDecoder:
             queries = ops.layernorm(queries, L["n1w"], L["n1b"], 1e-5, _F32)
             # ---- tokens attend to image
             q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), L["t2i_q_w"], L["t2i_q_b"])
-            if Nt <= 8:  # k / v projections folded onto the tokens: the image stream is read once, K|V never exist
+            if fuse8:  # k / v projections folded onto the tokens: the image stream is read once, K|V never exist
                 a = ops.t2i_fold_attention(q, keys, L["t2i_k_add"], L["t2i_kv_w"][0:128], L["t2i_kv_w"][128:256],
                                            L["t2i_v_b"], B, Nt, NT_IMG, x_shared=(kb == 1), tc=self.t2i_tensor_core)
             else:
@@ -207,7 +232,7 @@ class MaskDecoder:
             vt = ops.gemm(ops.add_cast(queries, None, _BF16), L["i2t_v_w"], L["i2t_v_b"])
             # q = keys @ Wq^T; its positional term (image_pe @ Wq^T + bq) is added inside the attention kernel, so the
             # big GEMM has no residual stream to gather
-            if Nt <= 8:
+            if fuse8:
                 # <= 8 tokens per prompt: q projection, attention, out projection, residual and norm4 in ONE pass over
                 # the image stream, with the projections folded into per-prompt operands (csrc/decoder_fused.cu)
                 if self.i2t_tensor_core:  # both GEMMs on tcgen05 (csrc/decoder_i2t_tc.cu); a stream shared by all
@@ -228,7 +253,7 @@ class MaskDecoder:
                 # call (built above from the image embedding): updated in place
                 keys_f32, kb = keys, B
                 continue
-            if Nt <= 16:
+            if Nt <= 16 and not val:
                 qi = ops.gemm(keys, L["i2t_q_w"], None)
                 a = ops.attention_few_keys(qi, L["i2t_q_res"], kt, vt, B, NT_IMG, Nt, q_shared=(kb == 1))  # [B*4096,128]
             else:  # many prompt points per object: generic flash kernel
@@ -241,7 +266,7 @@ class MaskDecoder:
             kb = B
         # ---- final token -> image attention
         q = ops.gemm(ops.add_cast(queries, query_pe, _BF16), self.fa_q_w, self.fa_q_b)
-        if Nt <= 8:
+        if fuse8:
             a = ops.t2i_fold_attention(q, keys, self.fa_k_add, self.fa_kv_w[0:128], self.fa_kv_w[128:256], self.fa_v_b, B,
                                        Nt, NT_IMG, x_shared=(kb == 1), tc=self.t2i_tensor_core)
         else:
@@ -252,16 +277,19 @@ class MaskDecoder:
         # ---- IoU head first: it decides (iou_gate) which prompts need their masks at all
         hs16 = ops.add_cast(hs, None, _BF16).view(B, Nt * 256)
         ious = self._mlp3(hs16[:, 256:512], self.iou_head, last_act=ops.ACT_SIGMOID)  # [B,4]
-        plist = ops.iou_gate(ious, iou_gate) if iou_gate is not None else None
+        plist = ops.iou_gate(ious, iou_gate) if (iou_gate is not None and not val) else None
         # ---- up-scaling + hyper-network masks
-        u1 = ops.gemm_upscale1(keys, self.up1_w, self.up1_b, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64, plist=plist)
         hyper = torch.empty((B, 4, 32), dtype=_F32, device=self.device)
         hv = hyper.view(B, 128)
         for i in range(4):
             self._mlp3(hs16[:, (2 + i) * 256:(3 + i) * 256], self.hyper[i], out=hv[:, i * 32:(i + 1) * 32])
-        masks = ops.gemm_upscale2(u1, self.up2_w, self.up2_b, s0, 0, hyper, B, 128, 128, plist=plist,
-                                  zero_fill=zero_fill)  # [B,4,256,256]
-        del u1
+        if val:
+            masks = self._upscale_validate(keys, s0, s1, hyper, B, kb)
+        else:
+            u1 = ops.gemm_upscale1(keys, self.up1_w, self.up1_b, s1, 0, self.up_ln_w, self.up_ln_b, B, 64, 64, plist=plist)
+            masks = ops.gemm_upscale2(u1, self.up2_w, self.up2_b, s0, 0, hyper, B, 128, 128, plist=plist,
+                                      zero_fill=zero_fill)  # [B,4,256,256]
+            del u1
         obj = self._mlp3(hs16[:, 0:256], self.obj_head)  # [B,1]
         out = {"masks": masks, "ious": ious, "obj": obj, "hs": hs.view(B, Nt, 256)}
         if not multimask_output:

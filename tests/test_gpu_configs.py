@@ -421,3 +421,55 @@ def test_encoder_fp32_validation_mode(cfg):
     out16 = build_sam2(cfg, None, device="cuda", state_dict=sd).forward_image(img)
     rel16 = ((out16["feat"] - out["feat"]).norm() / out["feat"].norm()).item()
     assert 1e-4 < rel16 < 2e-2, rel16
+
+
+def test_decoder_fp32_validation_mode():
+    """Prompt encoder + mask decoder in the fp32 validation mode (point prompts, multimask and single-mask output with
+    the dynamic-stability selection) against the fp32 oracle at 1e-4: the unfused route — split-product GEMMs on the
+    production tcgen05 kernel, generic fp32 attention, stand-alone LayerNorm / exact GELU, transposed convolutions as
+    GEMM + pixel shuffle — shares the host-side folding (positional terms pushed through the projections, shared
+    layer-0 image stream) with the bf16 path."""
+    from oracle.sam2_ref.image_predictor import SAM2ImagePredictor as OraclePredictor
+    from oracle.sam2_ref.sam2_base import SAM2Base
+    from saber_b200 import ops
+    from saber_b200.sam2 import arch
+    from saber_b200.sam2.build_sam import build_sam2
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = arch.random_state_dict("tiny", seed=0)
+    for k in list(sd):
+        if "output_hypernetworks_mlps" in k and ".layers.2." in k:
+            sd[k] = sd[k] * 30.0
+    orc = SAM2Base("tiny", dynamic_multimask_via_stability=True)
+    orc.load_state_dict(sd, strict=True)
+    orc = orc.cuda().eval()
+    torch.manual_seed(2)
+    img = torch.randn(1, 3, 1024, 1024, device="cuda")
+    pred = OraclePredictor(orc)
+    pred._orig_hw = [(1024, 1024)]
+    pred._set_features(img, 1)
+    pred._is_image_set = True
+    P = 6
+    pts = torch.rand(P, 2, 2, device="cuda") * 1024  # two points per prompt
+    labels = torch.tensor([[1, 1], [1, 0], [2, 3], [1, 1], [0, 1], [1, 0]], dtype=torch.int32, device="cuda")
+    emb = pred._features["image_embed"][0].permute(1, 2, 0).reshape(4096, 256).contiguous()
+    s0 = pred._features["high_res_feats"][0][0].permute(1, 2, 0).reshape(65536, 32).contiguous()
+    s1 = pred._features["high_res_feats"][1][0].permute(1, 2, 0).reshape(16384, 64).contiguous()
+    with ops.validate_fp32():
+        model = build_sam2("tiny", None, device="cuda", state_dict=sd)
+        dec = model.decoder
+        tokens = dec.prompt_tokens(pts.contiguous(), labels.contiguous())
+        for multi in (True, False):
+            with torch.no_grad():
+                _, ious_ref, low_ref = pred._predict(pts, labels, multimask_output=multi, return_logits=True)
+            out = dec.forward(emb, s0, s1, tokens, None, multimask_output=multi)
+            if multi:
+                got_m, got_i = out["masks"][:, 1:], out["ious"][:, 1:]
+            else:
+                idx = out["sel_idx"].long()
+                got_m = out["masks"][torch.arange(P, device="cuda"), idx][:, None]
+                got_i = out["ious"][torch.arange(P, device="cuda"), idx][:, None]
+            rel_m = ((got_m - low_ref).norm() / low_ref.norm()).item()
+            worst_m = ((got_m - low_ref).abs().max() / low_ref.abs().max()).item()
+            rel_i = ((got_i - ious_ref).norm() / ious_ref.norm()).item()
+            assert rel_m < 1e-4 and worst_m < 1e-4 and rel_i < 1e-4, (multi, rel_m, worst_m, rel_i)
