@@ -144,6 +144,8 @@ int sb_im2col_k7s4_f32(const float* img, float* cols, int B, int Cin, int S, int
 int sb_attention_f32(const float* q, long long q_ld, const float* k, long long k_ld, const float* k_add, long long ka_ld,
                      const float* v, long long v_ld, float* o, long long o_ld, int batch, int heads, int hd, int nq,
                      int nk, float scale, int q_shared, int kv_shared, void* stream);
+int sb_rope_apply_f32(const float* x, long long ld_in, float* out, long long ld_out, long long rows, int C,
+                      int rows_per_batch, int n_rope, int ntok, const float* cos_sin, void* stream);
 int sb_gelu_exact_f32(float* x, long long n, void* stream); /* erff GELU in place (the fused epilogue form is 4e-4) */
 int sb_maxpool2x2(const void* in, void* out, int is_f32, int B, int H, int W, int C, void* stream); /* hieradet do_pool */
 int sb_add_upsample2x(float* dst, const float* src, int B, int H, int W, int C, void* stream);   /* FpnNeck top-down */

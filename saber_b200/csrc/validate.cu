@@ -251,3 +251,43 @@ extern "C" int sb_attention_f32(const float* q, long long q_ld, const float* k, 
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
+
+namespace {
+__global__ void __launch_bounds__(256)
+rope_f32_kernel(const float* __restrict__ x, long long ld_in, float* __restrict__ out, long long ld_out, long long rows,
+                int C, int rows_per_batch, int n_rope, int ntok, const float2* __restrict__ cs) {
+  const int half = C / 2;
+  const long long total = rows * half;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(t % half);
+    const long long r = t / half;
+    const int rb = static_cast<int>(r % rows_per_batch);
+    float a = x[r * ld_in + 2 * i], b = x[r * ld_in + 2 * i + 1];
+    if (rb < n_rope) {
+      const float2 f = cs[static_cast<long long>(rb % ntok) * half + i];
+      const float ra = a * f.x - b * f.y;
+      const float rbv = a * f.y + b * f.x;
+      a = ra;
+      b = rbv;
+    }
+    out[r * ld_out + 2 * i] = a;
+    out[r * ld_out + 2 * i + 1] = b;
+  }
+}
+}  // namespace
+
+// fp32-in / fp32-out twin of sb_rope_apply (memory attention in the validation mode)
+extern "C" int sb_rope_apply_f32(const float* x, long long ld_in, float* out, long long ld_out, long long rows, int C,
+                                 int rows_per_batch, int n_rope, int ntok, const float* cos_sin, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(rows > 0 && C > 0 && (C % 2) == 0 && rows_per_batch > 0 && ntok > 0 && n_rope >= 0 &&
+                 n_rope <= rows_per_batch && (rows % rows_per_batch) == 0,
+             "sb_rope_apply_f32: bad arguments");
+  long long g = (rows * (C / 2) + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  rope_f32_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ld_in, out, ld_out, rows, C, rows_per_batch, n_rope, ntok,
+                                                           reinterpret_cast<const float2*>(cos_sin));
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sb_im2col_k7s4": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sb_im2col_k7s4_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sb_gelu_exact_f32": [c_void_p, c_ll, c_void_p],
+    "sb_rope_apply_f32": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_attention_f32": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
                          c_int, c_int, c_int, c_float, c_int, c_int, c_void_p],
     "sb_split3_bf16": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p],

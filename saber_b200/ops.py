@@ -1003,6 +1003,14 @@ def rope_apply(x: torch.Tensor, cos_sin: torch.Tensor, rows_per_batch: int, n_ro
     assert cos_sin.dtype == _F32 and cos_sin.is_contiguous() and cos_sin.shape[1:] == (Cc // 2, 2)
     if n_rope is None:
         n_rope = rows_per_batch
+    if VALIDATE_FP32 and out is None:
+        assert x.dtype == _F32
+        out = torch.empty((rows, Cc), dtype=_F32, device=x.device)
+        L = _lib.load()
+        _lib.check(L.sb_rope_apply_f32(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, Cc, rows_per_batch,
+                                       n_rope, cos_sin.shape[0], cos_sin.data_ptr(), _stream()), "sb_rope_apply_f32")
+        _count()
+        return out
     if out is None:
         out = torch.empty((rows, Cc), dtype=_BF16, device=x.device)
     L = _lib.load()

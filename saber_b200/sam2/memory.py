@@ -70,8 +70,8 @@ class MemoryAttention:
     def __init__(self, sd: Dict[str, torch.Tensor], device):
         dev = self.device = torch.device(device)
 
-        def w16(t):
-            return t.to(dev, _BF16).contiguous()
+        def w16(t):  # bf16 GEMM operand (fp32 in the validation mode)
+            return ops.weight(t, dev)
 
         def f32(t):
             return t.to(dev, _F32).contiguous()
@@ -113,6 +113,8 @@ class MemoryAttention:
         """curr [4096,256] fp32: this frame's (unconditioned) vision features, shared by the B objects.
         memory [B*Nk, 64] bf16; pos_k[l] [Nk,256] fp32: key positional term of layer l. Returns [B*4096,256] fp32."""
         assert curr.shape == (NT, 256) and memory.dtype == _BF16 and memory.shape[0] % B == 0
+        if ops.VALIDATE_FP32:  # the bank stores bf16 (as upstream): widening it is exact
+            memory = ops.add_cast(memory.contiguous(), None, _F32)
         Nk = memory.shape[0] // B
         n_rope = Nk - n_ptr_tokens
         tgt = ops.add_cast(curr, self.pos01, _F32)  # [4096,256], shared by all objects until the first cross-attention

@@ -473,3 +473,41 @@ def test_decoder_fp32_validation_mode():
             worst_m = ((got_m - low_ref).abs().max() / low_ref.abs().max()).item()
             rel_i = ((got_i - ious_ref).norm() / ious_ref.norm()).item()
             assert rel_m < 1e-4 and worst_m < 1e-4 and rel_i < 1e-4, (multi, rel_m, worst_m, rel_i)
+
+
+def test_memory_attention_fp32_validation_mode():
+    """The conditioning step of a propagation frame (SAM2 memory attention: 4 layers of RoPE self-attention over the
+    frame's 4096 tokens + RoPE cross-attention to a 2-frame memory bank with 16 object-pointer tokens, B = 2 objects
+    sharing the frame) in the fp32 validation mode vs the fp32 oracle module at 1e-4. (The memory ENCODER's convolution
+    kernels exist with bf16 inter-stage storage only and are compared at the bf16 tolerance in test_gpu_video.py.)"""
+    from oracle.sam2_ref.sam2_base import SAM2Base
+    from saber_b200 import ops
+    from saber_b200.sam2 import arch
+    from saber_b200.sam2.memory import MemoryAttention, sine_pe_2d
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = arch.random_state_dict("tiny", seed=0)
+    orc = SAM2Base("tiny")
+    orc.load_state_dict(sd, strict=True)
+    orc = orc.cuda().eval()
+    g = torch.Generator().manual_seed(11)
+    B, n_ptr = 2, 16
+    Nk = 2 * 4096 + 4 * n_ptr
+    curr = (torch.randn(4096, 256, generator=g) * 0.5).cuda()
+    memory = (torch.randn(B, Nk, 64, generator=g) * 0.5).to(torch.bfloat16)  # the bank stores bf16
+    memory_pos = torch.randn(Nk, 64, generator=g) * 0.5
+    curr_pos = sine_pe_2d(256, 64).cuda()
+    with torch.no_grad():
+        want = orc.memory_attention(curr=curr[:, None, :].expand(-1, B, -1).contiguous(),
+                                    curr_pos=curr_pos[:, None, :].expand(-1, B, -1).contiguous(),
+                                    memory=memory.float().permute(1, 0, 2).contiguous().cuda(),
+                                    memory_pos=memory_pos[:, None, :].expand(-1, B, -1).contiguous().cuda(),
+                                    num_obj_ptr_tokens=4 * n_ptr)  # [4096, B, 256]
+    want = want.permute(1, 0, 2).reshape(B * 4096, 256)
+    with ops.validate_fp32():
+        ma = MemoryAttention({k: v for k, v in sd.items()}, "cuda")
+        pos_k = ma.key_pos_term(memory_pos)
+        got = ma.forward(curr, memory.cuda().view(B * Nk, 64), pos_k, 4 * n_ptr, B)
+    rel = ((got - want).norm() / want.norm()).item()
+    worst = ((got - want).abs().max() / want.abs().max()).item()
+    assert rel < 1e-4 and worst < 1e-4, (rel, worst)
