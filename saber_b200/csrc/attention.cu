@@ -45,6 +45,13 @@ struct AttnParams {
   // broadcast-residual epilogue (mask decoder: k_add = image_pe @ Wk^T + bk).
   const __nv_bfloat16* k_add;
   long long k_add_ld;
+  // K / V staging depth: 2 (double-buffered tiles) or 1 when the whole key set is one tile — Hiera's 8x8 / 4x4 windows.
+  // With two stages those CTAs held 14-56 KB of shared memory for 16-64 keys and only 4-16 of them fit an SM: the
+  // kernels ran at 16-30 % of the HBM peak on latency alone (profiles/r02zo_win_probe.log).
+  int kv_stages;
+  // work items (q tile x window x batch x head, head fastest): CTAs walk them with a grid stride — Hiera's 4x4 windows are
+  // 32 768 one-warp items per 8 crops, and as one CTA each they were bound by the CTA launch rate (19 us per CTA)
+  long long ntasks;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -99,16 +106,24 @@ flash_attn_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + QROWS * PITCH;
-  uint8_t* sV = sK + 2 * KT * PITCH;
-  uint8_t* sR = sV + 2 * KT * PITCH;  // only allocated / touched when p.k_add != nullptr
+  uint8_t* sV = sK + p.kv_stages * KT * PITCH;
+  uint8_t* sR = sV + p.kv_stages * KT * PITCH;  // only allocated / touched when p.k_add != nullptr
   const bool has_kadd = p.k_add != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hd = p.hd;
   const int chunks = hd >> 3;  // 16-byte chunks per row
-  const int head = blockIdx.y;
-  const int qtile = blockIdx.x % p.qtiles;
-  const int bw = blockIdx.x / p.qtiles;
+  // One-warp CTAs (Hiera's 4x4 windows and 16-query pooled windows) walk the work items with a grid stride, head fastest:
+  // as one CTA per item they were bound by the CTA launch rate. Multi-warp CTAs keep one item per CTA (compile-time: the
+  // loop form cost the 4-warp instantiation occupancy — stage 1 349 -> 419-484 us — so it is not even a runtime branch).
+  constexpr bool PERSIST = NWARPS == 1;
+  long long task = blockIdx.x;
+  do {
+  const long long nbx_all = p.ntasks / p.heads;
+  const int head = PERSIST ? static_cast<int>(task % p.heads) : static_cast<int>(task / nbx_all);
+  const long long bxid = PERSIST ? task / p.heads : task % nbx_all;
+  const int qtile = static_cast<int>(bxid % p.qtiles);
+  const int bw = static_cast<int>(bxid / p.qtiles);
   int b, win, nq, nk, wq;
   if (p.mode == 0) {
     b = bw;
@@ -132,7 +147,7 @@ flash_attn_kernel(const AttnParams p) {
     constexpr int PADMAX = HDP / 8;
     const int npad = PADMAX - chunks;
     if (npad > 0) {
-      const int nrows = QROWS + (has_kadd ? 6 : 4) * KT;
+      const int nrows = QROWS + (has_kadd ? 3 : 2) * p.kv_stages * KT;
       for (int i = tid; i < nrows * npad; i += NT)
         *reinterpret_cast<uint4*>(smem + (i / npad) * PITCH + (chunks + i % npad) * 16) = make_uint4(0, 0, 0, 0);
     }
@@ -393,6 +408,8 @@ flash_attn_kernel(const AttnParams p) {
       }
     }
   }
+  if (PERSIST) __syncthreads();  // the staged tiles are free before the next item overwrites them
+  } while (PERSIST && (task += gridDim.x) < p.ntasks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -543,10 +560,13 @@ int launch_attn(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
 }
 
 template <int HDP, int NWARPS, int KT>
-int launch_attn_kt(const AttnParams& p, long long nblocks_x, cudaStream_t stream) {
+int launch_attn_kt(const AttnParams& p_in, long long nblocks_x, cudaStream_t stream) {
   constexpr int PITCH = HDP * 2 + 16;
   constexpr int SMEM_MAX_ = (16 * NWARPS + 6 * KT) * PITCH;
-  const int SMEM = (16 * NWARPS + (p.k_add ? 6 : 4) * KT) * PITCH;
+  AttnParams p = p_in;
+  const int nk_all = p.mode == 0 ? p.nk : p.ws * p.ws;
+  p.kv_stages = nk_all <= KT ? 1 : 2;
+  const int SMEM = (16 * NWARPS + (p.k_add ? 3 : 2) * p.kv_stages * KT) * PITCH;
   static SbPerDeviceOnce attr_once;
   if (attr_once.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HDP, NWARPS, KT>,
@@ -554,8 +574,20 @@ int launch_attn_kt(const AttnParams& p, long long nblocks_x, cudaStream_t stream
     attr_once.mark();
   }
   SB_REQUIRE(SMEM <= 227 * 1024, "sb_attention: k_add does not fit in shared memory at head_dim %d", p.hd);
-  dim3 grid(static_cast<unsigned>(nblocks_x), static_cast<unsigned>(p.heads), 1);
-  flash_attn_kernel<HDP, NWARPS, KT><<<grid, NWARPS * 32, SMEM, stream>>>(p);
+  p.ntasks = nblocks_x * p.heads;
+  int sms = 0, dev = 0;
+  SB_CHECK_CUDA(cudaGetDevice(&dev));
+  SB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int per_sm = (220 * 1024) / (SMEM + 1024);
+  if (per_sm > 2048 / (NWARPS * 32)) per_sm = 2048 / (NWARPS * 32);
+  if (per_sm > 32) per_sm = 32;
+  if (per_sm < 1) per_sm = 1;
+  // grid-stride only for the one-warp items (launch-rate bound as single CTAs: 154 -> 135 us for the 4x4 windows); with
+  // 4 / 8-warp CTAs the hardware scheduler overlaps items better than a serial loop (stage 1: 349 vs 414 us)
+  long long nblk = NWARPS == 1 ? static_cast<long long>(sms) * per_sm : p.ntasks;
+  if (nblk > p.ntasks) nblk = p.ntasks;
+  SB_REQUIRE(nblk < (1ll << 31), "sb_attention: grid too large");
+  flash_attn_kernel<HDP, NWARPS, KT><<<static_cast<unsigned>(nblk), NWARPS * 32, SMEM, stream>>>(p);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
