@@ -203,6 +203,11 @@ int sb_stitch_labels(const void* bits, const int* order, int m, int H, int W, vo
  * chunk_ws: ceil(Z*Y*X/2048)+1 int32 workspace whose last element receives the component count. */
 int sb_ccl3d_26(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, void* labels, int* aux,
                 int* chunk_ws, void* stream);
+/* The same with the connectivity as an argument (6 = scipy.ndimage.label's default structure, 26) and, optionally, the
+ * voxel count of every surviving component (sizes_out[id - 1]): the connected-component steps of the membrane-refinement
+ * workflow (REF saber/analysis/refine_membranes.py:136-249). */
+int sb_ccl3d(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, int conn, void* labels, int* aux,
+             int* chunk_ws, int* sizes_out, void* stream);
 
 /* ---- image-side bandwidth kernels -------------------------------------------------------------------- */
 /* scipy.ndimage.uniform_filter1d(mode='reflect') along one axis — REF saber/utils/preprocessing.py:13-14 */
@@ -289,6 +294,44 @@ int sb_label_equals(const void* vol, int elem_bytes, long long n, unsigned int l
 int sb_corr1d_zero(const float* in, int Z, int Y, int X, int axis, const float* w, int ks, float* out, void* stream);
 int sb_threshold_label(const float* sm, long long n, float thr, int label, unsigned char* result, void* stream);
 int sb_morph_ball(const unsigned char* in, int Z, int Y, int X, int r, int op, unsigned char* out, void* stream);
+/* the same with the full (2r+1)^3 cube (scipy binary_erosion(structure=ones((3,3,3))), REF refine_membranes.py:172) */
+int sb_morph_cube(const unsigned char* in, int Z, int Y, int X, int r, int op, unsigned char* out, void* stream);
+
+/* ---- Fourier-space rescale and band-pass -------------------------------------------------------------
+ * REF saber/filters/downsample.py:67-129,153-204 (FourierRescale3D / 2D) and saber/filters/tomograms.py:67-184 (Filter3D).
+ * A 3-D transform is three sb_fft_lines passes (x rows, y columns, z columns); see csrc/fft.cu. */
+int sb_fft_twiddles(int n, void* tw, void* stream);
+int sb_fft_lines(const void* in, void* out, const void* tw, int n, int m, int rows_mode, long long lines, int batch,
+                 int in_real, int out_mode, int inverse, float scale, int crop, int start, const float* bandpass, int D,
+                 int H, int W, void* stream);
+int sb_bandpass_volume(int D, int H, int W, const float* bandpass, float* out, void* stream);
+
+/* ---- organelle / membrane refinement workflow (REF saber/analysis/refine_membranes.py:120-548) ------
+ * dtype codes of label / mask volumes: 0 uint8, 1 int16, 2 uint16, 3 int32, 4 int64, 5 float32. */
+/* _trim_edges + (> 0): REF :120-135,142 (incl. the empty-slice quirks of `[t:-t]` for t == 0 and t >= size // 2) */
+int sb_trim_binarize(const void* vol, int dtype, int Z, int Y, int X, int zt, int xyt, unsigned char* out, void* stream);
+/* present[z] = any(vol[z]): REF :466 */
+int sb_z_any(const unsigned char* vol, int Z, long long plane, unsigned char* present, void* stream);
+/* table[(cap + 1) x 8] = {min z,y,x, max z,y,x, count, -} per label on slices with present[z] (nullable); table[7] != 0
+ * when a label exceeds cap. One pass instead of REF :251-272,470,489-495 (clone + nonzero per organelle, torch.unique). */
+int sb_label_bbox(const void* vol, int dtype, int Z, int Y, int X, const unsigned char* present, int cap, int* table,
+                  void* stream);
+/* out[roi] = vol == label (label < 0: vol != 0), zero on slices without present[z] (nullable): REF :363-364 */
+int sb_roi_binarize(const void* vol, int dtype, int Z, int Y, int X, int z0, int y0, int x0, int dz, int dy, int dx,
+                    long long label, const unsigned char* present, unsigned char* out, void* stream);
+/* vol[roi][mask] = value: REF :431-438 and convert_to_3d_labels :548-573 */
+int sb_roi_paste(void* vol, int dtype, int Z, int Y, int X, int z0, int y0, int x0, int dz, int dy, int dx,
+                 const unsigned char* mask, long long value, void* stream);
+/* dst[src > 0] = src[src > 0]: one step of convert_to_3d_labels, REF :548-573 */
+int sb_overlay_nonzero(void* dst, const void* src, int dtype, long long n, void* stream);
+/* op 0: a & b, 1: a | b, 2: a & ~b on {0,1} bytes */
+int sb_mask_logic(const unsigned char* a, const unsigned char* b, long long n, int op, unsigned char* out, void* stream);
+/* mode 0: labels > 0 (REF :202-222); mode 1: the largest component, first among equals (REF :224-249) */
+int sb_label_select(const int* labels, long long n, const int* sizes, const int* count, int mode, int* which,
+                    unsigned char* out, void* stream);
+/* components whose overlap with mask exceeds ratio x size: REF :160-199 */
+int sb_label_keep_ratio(const int* labels, const unsigned char* mask, long long n, const int* sizes, int* overlap,
+                        int capacity, double ratio, unsigned char* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -456,3 +456,158 @@ def morphological_opening_ball(image: np.ndarray, radius: int) -> np.ndarray:
     if image.sum() == 0:
         return image.astype(np.float32)
     return binary_dilation_ball(binary_erosion_ball((image > 0).astype(np.float32), radius), radius)
+
+
+# ---- REF saber/analysis/refine_membranes.py:120-548 (§8f row 3: the membrane-refinement workflow) ------------------------
+def _keep_components(binary: np.ndarray, min_size: int) -> np.ndarray:
+    """REF :136-158 / :202-222: components (scipy default = 6-connectivity) with at least min_size voxels."""
+    labels, n = ndi.label(binary)
+    if n == 0:
+        return np.zeros_like(binary, dtype=bool)
+    counts = np.bincount(labels.ravel())
+    keep = counts >= min_size
+    keep[0] = False
+    return keep[labels]
+
+
+def _largest_component(binary: np.ndarray) -> np.ndarray:
+    """REF :224-249: the component with the most voxels, the lowest label among equals (np.argmax)."""
+    labels, n = ndi.label(binary)
+    if n == 0:
+        return np.zeros_like(binary, dtype=bool)
+    counts = np.bincount(labels.ravel())[1:]
+    return labels == (int(np.argmax(counts)) + 1)
+
+
+def refine_membranes(organelle_seg: np.ndarray, membrane_seg: np.ndarray, ball_size: int = 3, min_membrane_area: int = 10000,
+                     edge_trim_z: int = 5, edge_trim_xy: int = 3, min_roi_relative_size: float = 0.15,
+                     keep_surface_membranes: bool = False):
+    """OrganelleMembraneFilter.run (REF :445-548) + _process_organelle_batch (REF :335-443) on binary numpy volumes.
+    Returns (organelles [n,Z,Y,X], membranes [n,Z,Y,X]) in the organelle dtype, or two zero [Z,Y,X] volumes when
+    nothing survives (REF :473-480, :515-522). Output values are label + 1 (the even / odd relabelling of REF
+    :484-485, 431-435 divided back by two at :529-530)."""
+    Z, Y, X = organelle_seg.shape
+    empty = (np.zeros_like(organelle_seg), np.zeros_like(organelle_seg))
+    # REF :120-135 — `[t:-t]` is empty for t == 0 and the assignment is skipped unless t < size // 2
+    trimmed = np.zeros((Z, Y, X), bool)
+    if 0 < edge_trim_z < Z // 2 and 0 < edge_trim_xy < Y // 2 and edge_trim_xy < X // 2:
+        zt, t = edge_trim_z, edge_trim_xy
+        trimmed[zt:-zt, t:-t, t:-t] = membrane_seg[zt:-zt, t:-t, t:-t] != 0
+    membrane = _keep_components(trimmed, min_membrane_area)                       # REF :459-462
+    present = membrane.any(axis=(1, 2))                                           # REF :466
+    filtered = organelle_seg * present[:, None, None].astype(organelle_seg.dtype)  # REF :467
+    labels = np.unique(filtered)
+    labels = labels[labels > 0]
+    if len(labels) == 0:
+        return empty
+    pad = ball_size // 2
+    out_o, out_m = [], []
+    for lab in labels:
+        org = filtered == lab
+        idx = np.argwhere(org)                                                    # REF :251-272
+        mins, maxs = idx.min(0), idx.max(0) + 1
+        if ((maxs - mins) < min_roi_relative_size * np.array([Z, Y, X])).any():
+            continue
+        mins = np.maximum(mins - pad, 0)
+        maxs = np.minimum(maxs + pad, [Z, Y, X])
+        sl = tuple(slice(int(a), int(b)) for a, b in zip(mins, maxs))
+        org_roi, mem_roi = org[sl], membrane[sl]
+        roi_shape = (maxs - mins).astype(np.float32)
+        if np.float32(roi_shape.max()) / np.float32(roi_shape.min()) > 3.0:       # REF :366-376
+            dilate_size, morph_ball = 1, max(1, ball_size // 2)
+        else:
+            dilate_size, morph_ball = 2, ball_size
+        ball_d = ball_kernel(dilate_size)
+        enhanced = ndi.binary_dilation(mem_roi, structure=ball_d) & ndi.binary_dilation(org_roi, structure=ball_d)  # :379-384
+        cleaned = enhanced & _keep_components(enhanced, 100)                      # REF :394-395
+        if keep_surface_membranes and cleaned.any():                              # REF :160-199
+            boundary = org_roi & ~ndi.binary_erosion(org_roi, structure=np.ones((3, 3, 3)))
+            lab_m, n_m = ndi.label(cleaned)
+            size = np.bincount(lab_m.ravel(), minlength=n_m + 1)
+            over = np.bincount(lab_m[boundary].ravel(), minlength=n_m + 1)
+            keep = np.zeros(n_m + 1, bool)
+            keep[1:] = over[1:] / np.maximum(size[1:], 1) > 0.1
+            cleaned = keep[lab_m]
+        if not cleaned.any():
+            continue
+        # REF :405-410 — organelle voxels carry the even label (>= 4), so `organelle - membrane` is non-zero wherever
+        # EITHER is set: the "combined" mask the opening sees is the union, not the difference.
+        comb = org_roi | cleaned
+        opened = ndi.binary_dilation(ndi.binary_erosion(comb, structure=ball_kernel(morph_ball)), structure=ball_kernel(morph_ball))
+        if not opened.any():
+            opened = comb                                                         # REF :416-418
+        comb_out = _largest_component(opened)                                     # REF :425
+        org_out = _largest_component(org_roi & comb_out)                          # REF :428-429
+        mem_out = cleaned & comb_out
+        mem_out = mem_out & _keep_components(mem_out, 50)                         # REF :432-433
+        full_o = np.zeros_like(organelle_seg)
+        full_m = np.zeros_like(organelle_seg)
+        full_o[sl][org_out] = lab + 1
+        full_m[sl][mem_out] = lab + 1
+        out_o.append(full_o)
+        out_m.append(full_m)
+    if not out_o:
+        return empty
+    return np.stack(out_o), np.stack(out_m)
+
+
+def convert_to_3d_labels(masks_4d: np.ndarray) -> np.ndarray:
+    """REF :548-573: later instances overwrite earlier ones."""
+    if masks_4d.ndim == 3:
+        return masks_4d
+    out = np.zeros(masks_4d.shape[1:], masks_4d.dtype)
+    for m in masks_4d:
+        out[m > 0] = m[m > 0]
+    return out
+
+
+# ---- REF saber/filters/downsample.py:67-129,153-204 and saber/filters/tomograms.py:67-184 (§8f row 2) --------------------
+def _crop_window(n_in: int, n_new: int):
+    n_new = n_new - (n_new % 2)                                  # REF downsample.py:117-119 / :183-184
+    return (n_in - n_new) // 2 + (n_in % 2), n_new                # REF :122-127 / :190-191
+
+
+def fourier_rescale_3d(volume: np.ndarray, input_voxel_size, output_voxel_size) -> np.ndarray:
+    """FourierRescale3D.run (REF downsample.py:67-129) in float64 numpy; returns float32 like the reference."""
+    vin = (input_voxel_size,) * 3 if np.isscalar(input_voxel_size) else input_voxel_size
+    vout = (output_voxel_size,) * 3 if np.isscalar(output_voxel_size) else output_voxel_size
+    wins = [_crop_window(n, int(round(n * i / o))) for n, i, o in zip(volume.shape, vin, vout)]
+    spec = np.fft.fftshift(np.fft.fftn(volume.astype(np.float64), norm="ortho"))
+    spec = spec[tuple(slice(s, s + m) for s, m in wins)]
+    return np.fft.ifftn(np.fft.ifftshift(spec), norm="ortho").real.astype(np.float32)
+
+
+def fourier_rescale_2d(image: np.ndarray, scale_factor: float) -> np.ndarray:
+    """FourierRescale2D._rescale (REF downsample.py:153-204): modulus of the inverse transform, default norms."""
+    h, w = image.shape
+    wins = [_crop_window(h, int(h / scale_factor)), _crop_window(w, int(w / scale_factor))]
+    spec = np.fft.fftshift(np.fft.fft2(image.astype(np.float64)))
+    spec = spec[tuple(slice(s, s + m) for s, m in wins)]
+    return np.abs(np.fft.ifft2(np.fft.ifftshift(spec))).astype(np.float32)
+
+
+def cosine_filter(sz, apix: float, lp=0, lpd=0, hp=0, hpd=0) -> np.ndarray:
+    """Filter3D.cosine_filter / construct_filter (REF tomograms.py:67-137), fp32 like the reference."""
+    D, H, W = sz
+    to_pix = lambda ang: max(sz) / (ang / apix)
+    zz, yy, xx = np.meshgrid(np.arange(D, dtype=np.float32) - D // 2, np.arange(H, dtype=np.float32) - H // 2,
+                             np.arange(W, dtype=np.float32) - W // 2, indexing="ij")
+    r = np.sqrt(xx ** 2 + yy ** 2 + zz ** 2)
+
+    def edge(freq, decay, highpass):
+        if freq == 0 and decay == 0:
+            return np.ones_like(r)
+        m = (r < np.float32(freq)).astype(np.float32)
+        if decay != 0:
+            half = decay / 2.0
+            sel = (r > np.float32(freq - half)) & (r < np.float32(freq + half))
+            m[sel] = np.float32(0.5) + np.float32(0.5) * np.cos(np.float32(np.pi) * (r[sel] - np.float32(freq - half)) / np.float32(decay))
+        return 1 - m if highpass else m
+
+    return edge(to_pix(lp) if lp > 0 else 0, lpd, False) * edge(to_pix(hp) if hp > 0 else 0, hpd, True)
+
+
+def filter3d_apply(volume: np.ndarray, filt: np.ndarray) -> np.ndarray:
+    """Filter3D.apply (REF tomograms.py:172-194)."""
+    spec = np.fft.fftshift(np.fft.fftn(volume.astype(np.float64))) * filt
+    return np.fft.ifftn(np.fft.ifftshift(spec)).real.astype(np.float32)

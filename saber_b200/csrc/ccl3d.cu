@@ -113,6 +113,27 @@ ccl_merge_kernel(int* __restrict__ P, int Z, int Y, int X) {
   }
 }
 
+// 6-connectivity (scipy.ndimage.label's default structure: face neighbours only) over the 3 raster-preceding neighbours.
+// Same run-head initialisation; the up / back union is implied when the left neighbour and ITS up / back neighbour are
+// both foreground (they are linked through the rows' own runs).
+__global__ void __launch_bounds__(256)
+ccl_merge6_kernel(int* __restrict__ P, int Z, int Y, int X) {
+  const long long n = static_cast<long long>(Z) * Y * X;
+  const long long plane = static_cast<long long>(Y) * X;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (P[i] < 0) continue;
+    const int x = static_cast<int>(i % X);
+    const int y = static_cast<int>((i / X) % Y);
+    const int z = static_cast<int>(i / plane);
+    const int v = static_cast<int>(i);
+    const bool left = x > 0 && P[i - 1] >= 0;
+    if (left && (i & 31) == 0) uf_unite(P, v, v - 1);
+    if (y > 0 && P[i - X] >= 0 && !(left && P[i - X - 1] >= 0)) uf_unite(P, v, static_cast<int>(i - X));
+    if (z > 0 && P[i - plane] >= 0 && !(left && P[i - plane - 1] >= 0)) uf_unite(P, v, static_cast<int>(i - plane));
+  }
+}
+
 // flatten + warp-aggregated size count: aux[root] += #voxels
 __global__ void __launch_bounds__(256)
 ccl_flatten_count_kernel(int* __restrict__ P, int* __restrict__ aux, long long n) {
@@ -186,7 +207,7 @@ ccl_scan_kernel(int* __restrict__ chunk_cnt, int nchunks, int* __restrict__ tota
 // aux[root] <- compact id (1-based) for surviving roots, 0 for dropped ones
 __global__ void __launch_bounds__(256)
 ccl_assign_kernel(const int* __restrict__ P, int* __restrict__ aux, long long n, int min_vol,
-                  const int* __restrict__ chunk_off) {
+                  const int* __restrict__ chunk_off, int* __restrict__ sizes_out) {
   const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
   __shared__ int warp_tot[8];
   __shared__ int running;
@@ -202,7 +223,11 @@ ccl_assign_kernel(const int* __restrict__ P, int* __restrict__ aux, long long n,
     __syncthreads();
     int off = running;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    if (is_root) aux[v] = keep ? off + __popc(bal & ((1u << lane) - 1u)) + 1 : 0;
+    if (is_root) {
+      const int id = keep ? off + __popc(bal & ((1u << lane) - 1u)) + 1 : 0;
+      if (keep && sizes_out) sizes_out[id - 1] = aux[v];  // voxel count of component `id`
+      aux[v] = id;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       int t = 0;
@@ -228,8 +253,25 @@ ccl_relabel_kernel(int* __restrict__ P, const int* __restrict__ aux, long long n
 // union-find parent array). aux: workspace of Z*Y*X int32. chunk_ws: workspace of ceil(Z*Y*X / 2048) + 1
 // int32; its last element receives the number of components kept. Components with fewer than min_vol
 // voxels are removed (min_vol <= 1 keeps everything).
+static int ccl3d_run(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, int conn, void* labels, int* aux,
+                     int* chunk_ws, int* sizes_out, void* stream_);
+
 extern "C" int sb_ccl3d_26(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, void* labels,
                            int* aux, int* chunk_ws, void* stream_) {
+  return ccl3d_run(vol, elem_bytes, Z, Y, X, min_vol, 26, labels, aux, chunk_ws, nullptr, stream_);
+}
+
+// conn: 6 (scipy.ndimage.label default) or 26. sizes_out (optional, one int per surviving component, at least as many
+// entries as components can exist: Z*Y*X / min_vol + 1 is always enough) receives the voxel count of component id at
+// sizes_out[id - 1]. REF saber/analysis/refine_membranes.py:136-249 (_remove_small_objects / _get_largest_component).
+extern "C" int sb_ccl3d(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, int conn, void* labels,
+                        int* aux, int* chunk_ws, int* sizes_out, void* stream_) {
+  SB_REQUIRE(conn == 6 || conn == 26, "sb_ccl3d: connectivity must be 6 or 26 (got %d)", conn);
+  return ccl3d_run(vol, elem_bytes, Z, Y, X, min_vol, conn, labels, aux, chunk_ws, sizes_out, stream_);
+}
+
+static int ccl3d_run(const void* vol, int elem_bytes, int Z, int Y, int X, int min_vol, int conn, void* labels, int* aux,
+                     int* chunk_ws, int* sizes_out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(Z > 0 && Y > 0 && X > 0, "sb_ccl3d_26: empty volume");
   const long long n = static_cast<long long>(Z) * Y * X;
@@ -246,7 +288,10 @@ extern "C" int sb_ccl3d_26(const void* vol, int elem_bytes, int Z, int Y, int X,
   else
     ccl_init_kernel<unsigned int><<<grid, 256, 0, stream>>>(static_cast<const unsigned int*>(vol), P, aux, n, X);
   SB_CHECK_LAUNCH();
-  ccl_merge_kernel<<<grid, 256, 0, stream>>>(P, Z, Y, X);
+  if (conn == 26)
+    ccl_merge_kernel<<<grid, 256, 0, stream>>>(P, Z, Y, X);
+  else
+    ccl_merge6_kernel<<<grid, 256, 0, stream>>>(P, Z, Y, X);
   SB_CHECK_LAUNCH();
   ccl_flatten_count_kernel<<<grid, 256, 0, stream>>>(P, aux, n);
   SB_CHECK_LAUNCH();
@@ -256,7 +301,7 @@ extern "C" int sb_ccl3d_26(const void* vol, int elem_bytes, int Z, int Y, int X,
   SB_CHECK_LAUNCH();
   ccl_scan_kernel<<<1, 1024, 0, stream>>>(chunk_ws, nchunks, chunk_ws + nchunks);
   SB_CHECK_LAUNCH();
-  ccl_assign_kernel<<<nchunks, 256, 0, stream>>>(P, aux, n, mv, chunk_ws);
+  ccl_assign_kernel<<<nchunks, 256, 0, stream>>>(P, aux, n, mv, chunk_ws, sizes_out);
   SB_CHECK_LAUNCH();
   ccl_relabel_kernel<<<grid, 256, 0, stream>>>(P, aux, n);
   SB_CHECK_LAUNCH();

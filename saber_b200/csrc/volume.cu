@@ -300,7 +300,8 @@ threshold_label_kernel(const float* __restrict__ sm, long long n, float thr, uns
 // Binary erosion (op 0: every ball voxel set; outside the volume counts as 0) / dilation (op 1: any ball voxel set) with
 // the radius-r ball {dz^2 + dy^2 + dx^2 <= r^2}: the exact outcome of the reference's conv3d >= sum / > 0 tests.
 __global__ void __launch_bounds__(256)
-morph_ball_kernel(const unsigned char* __restrict__ in, int Z, int Y, int X, int r, int op, unsigned char* __restrict__ out) {
+morph_ball_kernel(const unsigned char* __restrict__ in, int Z, int Y, int X, int r, int op, int cube,
+                  unsigned char* __restrict__ out) {
   const long long n = static_cast<long long>(Z) * Y * X;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -309,7 +310,7 @@ morph_ball_kernel(const unsigned char* __restrict__ in, int Z, int Y, int X, int
     for (int dz = -r; dz <= r && res == (op == 0); ++dz)
       for (int dy = -r; dy <= r && res == (op == 0); ++dy)
         for (int dx = -r; dx <= r; ++dx) {
-          if (dz * dz + dy * dy + dx * dx > r * r) continue;
+          if (!cube && dz * dz + dy * dy + dx * dx > r * r) continue;
           const int zz = z + dz, yy = y + dy, xx = x + dx;
           const bool inb = zz >= 0 && zz < Z && yy >= 0 && yy < Y && xx >= 0 && xx < X;
           const bool v = inb && in[(static_cast<long long>(zz) * Y + yy) * X + xx] != 0;
@@ -434,7 +435,17 @@ extern "C" int sb_threshold_label(const float* sm, long long n, float thr, int l
 extern "C" int sb_morph_ball(const unsigned char* in, int Z, int Y, int X, int r, int op, unsigned char* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(Z > 0 && Y > 0 && X > 0 && r >= 0 && (op == 0 || op == 1) && in && out, "sb_morph_ball: bad arguments");
-  morph_ball_kernel<<<grid_for(static_cast<long long>(Z) * Y * X), 256, 0, stream>>>(in, Z, Y, X, r, op, out);
+  morph_ball_kernel<<<grid_for(static_cast<long long>(Z) * Y * X), 256, 0, stream>>>(in, Z, Y, X, r, op, 0, out);
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// The same with the full (2r+1)^3 cube as the structuring element: scipy.ndimage.binary_erosion(structure=np.ones((3,3,3)))
+// of REF saber/analysis/refine_membranes.py:172 (border_value 0 = zero padding).
+extern "C" int sb_morph_cube(const unsigned char* in, int Z, int Y, int X, int r, int op, unsigned char* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SB_REQUIRE(Z > 0 && Y > 0 && X > 0 && r >= 0 && (op == 0 || op == 1) && in && out, "sb_morph_cube: bad arguments");
+  morph_ball_kernel<<<grid_for(static_cast<long long>(Z) * Y * X), 256, 0, stream>>>(in, Z, Y, X, r, op, 1, out);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

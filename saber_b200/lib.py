@@ -94,6 +94,7 @@ SIGNATURES = {
     "sb_upsample_bilinear": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_stitch_labels": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_ccl3d_26": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_ccl3d": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_rope_apply": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_conv3x3s2_ln_gelu": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                              c_int, c_float, c_float, c_void_p, c_void_p],
@@ -129,6 +130,22 @@ SIGNATURES = {
     "sb_corr1d_zero": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "sb_threshold_label": [c_void_p, c_ll, c_float, c_int, c_void_p, c_void_p],
     "sb_morph_ball": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_morph_cube": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_fft_twiddles": [c_int, c_void_p, c_void_p],
+    "sb_fft_lines": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+                     c_void_p, c_int, c_int, c_int, c_void_p],
+    "sb_bandpass_volume": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sb_trim_binarize": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sb_z_any": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
+    "sb_label_bbox": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "sb_roi_binarize": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p,
+                        c_void_p, c_void_p],
+    "sb_roi_paste": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll,
+                     c_void_p],
+    "sb_overlay_nonzero": [c_void_p, c_void_p, c_int, c_ll, c_void_p],
+    "sb_mask_logic": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p],
+    "sb_label_select": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "sb_label_keep_ratio": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p],
 }
 
 

@@ -976,6 +976,26 @@ def ccl3d_26(vol: torch.Tensor, min_vol: int):
     return labels, chunk_ws[nchunks:]
 
 
+def ccl3d(vol: torch.Tensor, min_vol: int = 1, conn: int = 6, with_sizes: bool = False):
+    """Connected components of vol != 0 with connectivity 6 (scipy.ndimage.label's default) or 26, components with fewer
+    than min_vol voxels dropped, compact labels in raster order of their first voxel. Returns (labels int32 [Z,Y,X],
+    count tensor [1], sizes int32 [capacity] or None — sizes[id - 1] = voxels of component id)."""
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.dim() == 3 and vol.element_size() in (1, 2, 4)
+    Z, Y, X = vol.shape
+    n = vol.numel()
+    labels = torch.empty((Z, Y, X), dtype=_I32, device=vol.device)
+    aux = torch.empty((n,), dtype=_I32, device=vol.device)
+    nchunks = (n + 2047) // 2048
+    chunk_ws = torch.empty((nchunks + 1,), dtype=_I32, device=vol.device)
+    sizes = torch.zeros((n // max(1, int(min_vol)) + 1,), dtype=_I32, device=vol.device) if with_sizes else None
+    L = _lib.load()
+    _lib.check(L.sb_ccl3d(vol.data_ptr(), vol.element_size(), Z, Y, X, int(min_vol), int(conn), labels.data_ptr(),
+                          aux.data_ptr(), chunk_ws.data_ptr(), _ptr(sizes), _stream()), "sb_ccl3d")
+    _count(7)
+    return labels, chunk_ws[nchunks:], sizes
+
+
 def upsample_bilinear(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
     """[..., Hi, Wi] fp32 -> [..., Ho, Wo] fp32 (F.interpolate bilinear, align_corners=False)."""
     _chk_cuda(x)
@@ -1387,5 +1407,207 @@ def morph_ball(x: torch.Tensor, radius: int, op: int) -> torch.Tensor:
     L = _lib.load()
     _lib.check(L.sb_morph_ball(x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], int(radius), int(op), out.data_ptr(),
                                _stream()), "sb_morph_ball")
+    _count()
+    return out
+
+
+def morph_cube(x: torch.Tensor, radius: int, op: int) -> torch.Tensor:
+    """morph_ball with the full (2r+1)^3 cube as the structuring element (scipy binary_erosion(structure=ones(3,3,3)))."""
+    _chk_cuda(x)
+    assert x.dtype == _U8 and x.is_contiguous() and x.dim() == 3
+    out = torch.empty_like(x)
+    L = _lib.load()
+    _lib.check(L.sb_morph_cube(x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], int(radius), int(op), out.data_ptr(),
+                               _stream()), "sb_morph_cube")
+    _count()
+    return out
+
+
+# ---- organelle / membrane refinement workflow (csrc/refine.cu; REF saber/analysis/refine_membranes.py:120-548) ----------
+_DT_CODE = {torch.uint8: 0, torch.int16: 1, torch.uint16: 2, torch.int32: 3, torch.int64: 4, torch.float32: 5}
+
+
+def _dt_code(t: torch.Tensor) -> int:
+    if t.dtype not in _DT_CODE:
+        raise TypeError(f"label / mask volumes must be one of {sorted(str(k) for k in _DT_CODE)}, got {t.dtype}")
+    return _DT_CODE[t.dtype]
+
+
+def trim_binarize(vol: torch.Tensor, z_trim: int, xy_trim: int) -> torch.Tensor:
+    """uint8 (vol != 0) inside the trimmed box, 0 outside (REF _trim_edges incl. its empty-slice quirks)."""
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.dim() == 3
+    out = torch.empty(vol.shape, dtype=_U8, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_trim_binarize(vol.data_ptr(), _dt_code(vol), *vol.shape, int(z_trim), int(xy_trim), out.data_ptr(),
+                                  _stream()), "sb_trim_binarize")
+    _count()
+    return out
+
+
+def z_any(vol: torch.Tensor) -> torch.Tensor:
+    """uint8 [Z]: slice z of a uint8 [Z,Y,X] volume has a set voxel."""
+    _chk_cuda(vol)
+    assert vol.dtype == _U8 and vol.is_contiguous() and vol.dim() == 3
+    out = torch.empty((vol.shape[0],), dtype=_U8, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_z_any(vol.data_ptr(), vol.shape[0], vol.shape[1] * vol.shape[2], out.data_ptr(), _stream()), "sb_z_any")
+    _count()
+    return out
+
+
+def label_bbox(vol: torch.Tensor, present: Optional[torch.Tensor], cap: int) -> torch.Tensor:
+    """int32 [cap + 1, 8] = (min z, y, x, max z, y, x, voxel count, -) per label value, restricted to slices with
+    present[z]; entry [0, 7] is non-zero when a label above cap was met."""
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.dim() == 3
+    table = torch.empty((int(cap) + 1, 8), dtype=_I32, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_label_bbox(vol.data_ptr(), _dt_code(vol), *vol.shape, _ptr(present), int(cap), table.data_ptr(),
+                               _stream()), "sb_label_bbox")
+    _count(2)
+    return table
+
+
+def roi_binarize(vol: torch.Tensor, roi, label: int = -1, present: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 crop vol[z0:z1, y0:y1, x0:x1] == label (label < 0: != 0), zeroed on slices without present[z]."""
+    _chk_cuda(vol)
+    assert vol.is_contiguous() and vol.dim() == 3
+    z0, y0, x0, z1, y1, x1 = (int(v) for v in roi)
+    out = torch.empty((z1 - z0, y1 - y0, x1 - x0), dtype=_U8, device=vol.device)
+    L = _lib.load()
+    _lib.check(L.sb_roi_binarize(vol.data_ptr(), _dt_code(vol), *vol.shape, z0, y0, x0, z1 - z0, y1 - y0, x1 - x0, int(label),
+                                 _ptr(present), out.data_ptr(), _stream()), "sb_roi_binarize")
+    _count()
+    return out
+
+
+def roi_paste(vol: torch.Tensor, roi, mask: torch.Tensor, value: int) -> None:
+    """vol[z0:z1, y0:y1, x0:x1][mask != 0] = value, in place."""
+    _chk_cuda(vol, mask)
+    assert vol.is_contiguous() and vol.dim() == 3 and mask.dtype == _U8 and mask.is_contiguous()
+    z0, y0, x0, z1, y1, x1 = (int(v) for v in roi)
+    assert tuple(mask.shape) == (z1 - z0, y1 - y0, x1 - x0)
+    L = _lib.load()
+    _lib.check(L.sb_roi_paste(vol.data_ptr(), _dt_code(vol), *vol.shape, z0, y0, x0, z1 - z0, y1 - y0, x1 - x0, mask.data_ptr(),
+                              int(value), _stream()), "sb_roi_paste")
+    _count()
+
+
+def mask_logic(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
+    """'and' / 'or' / 'andnot' of two uint8 {0,1} volumes."""
+    _chk_cuda(a, b)
+    assert a.dtype == _U8 and b.dtype == _U8 and a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a)
+    L = _lib.load()
+    _lib.check(L.sb_mask_logic(a.data_ptr(), b.data_ptr(), a.numel(), {"and": 0, "or": 1, "andnot": 2}[op], out.data_ptr(),
+                               _stream()), "sb_mask_logic")
+    _count()
+    return out
+
+
+def label_select(labels: torch.Tensor, sizes: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None,
+                 largest: bool = False) -> torch.Tensor:
+    """uint8 mask of the voxels with a label (largest=False) or of the largest component, the first among equals."""
+    _chk_cuda(labels)
+    assert labels.dtype == _I32 and labels.is_contiguous()
+    out = torch.empty(labels.shape, dtype=_U8, device=labels.device)
+    which = torch.empty((1,), dtype=_I32, device=labels.device) if largest else None
+    L = _lib.load()
+    _lib.check(L.sb_label_select(labels.data_ptr(), labels.numel(), _ptr(sizes), _ptr(count), 1 if largest else 0, _ptr(which),
+                                 out.data_ptr(), _stream()), "sb_label_select")
+    _count(2 if largest else 1)
+    return out
+
+
+def label_keep_ratio(labels: torch.Tensor, mask: torch.Tensor, sizes: torch.Tensor, ratio: float) -> torch.Tensor:
+    """uint8 mask of the components whose overlap with `mask` exceeds ratio x their voxel count."""
+    _chk_cuda(labels, mask, sizes)
+    assert labels.dtype == _I32 and labels.is_contiguous() and mask.dtype == _U8 and mask.is_contiguous()
+    out = torch.empty(labels.shape, dtype=_U8, device=labels.device)
+    overlap = torch.empty_like(sizes)
+    L = _lib.load()
+    _lib.check(L.sb_label_keep_ratio(labels.data_ptr(), mask.data_ptr(), labels.numel(), sizes.data_ptr(), overlap.data_ptr(),
+                                     sizes.numel(), float(ratio), out.data_ptr(), _stream()), "sb_label_keep_ratio")
+    _count(2)
+    return out
+
+
+def overlay_nonzero(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst[src > 0] = src[src > 0], in place (one step of convert_to_3d_labels)."""
+    _chk_cuda(dst, src)
+    assert dst.dtype == src.dtype and dst.shape == src.shape and dst.is_contiguous() and src.is_contiguous()
+    L = _lib.load()
+    _lib.check(L.sb_overlay_nonzero(dst.data_ptr(), src.data_ptr(), _dt_code(dst), dst.numel(), _stream()), "sb_overlay_nonzero")
+    _count()
+
+
+# ---- Fourier-space rescale / band-pass (csrc/fft.cu; REF saber/filters/downsample.py, saber/filters/tomograms.py) ----------
+_C64 = torch.complex64
+_fft_tw_cache: dict = {}
+
+
+def fft_twiddles(n: int, device) -> torch.Tensor:
+    """complex64 [n]: exp(-2 pi i k / n), evaluated in double precision on the device; cached per (device, n)."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(n))
+    tw = _fft_tw_cache.get(key)
+    if tw is None:
+        tw = torch.empty((int(n),), dtype=_C64, device=dev)
+        L = _lib.load()
+        _lib.check(L.sb_fft_twiddles(int(n), tw.data_ptr(), _stream()), "sb_fft_twiddles")
+        _count()
+        _fft_tw_cache[key] = tw
+    return tw
+
+
+def fft_lines(x: torch.Tensor, axis: int, inverse: bool = False, crop: Optional[tuple] = None, out_mode: str = "complex",
+              scale: float = 1.0, bandpass=None) -> torch.Tensor:
+    """One line pass of a complex FFT along `axis` of a 2-D / 3-D float32 (real) or complex64 array, out of place.
+    crop=(start, m): store the m-wide centre crop of the fftshift-ed spectrum (un-shifted again) instead of all n values.
+    out_mode 'complex' | 'real' | 'abs'; scale multiplies the stored values; bandpass = 8 floats (see sb_fft_lines),
+    only on the first axis of a 3-D spectrum."""
+    import ctypes as _C
+    _chk_cuda(x)
+    assert x.is_contiguous() and x.dim() in (2, 3) and x.dtype in (_F32, _C64)
+    axis = axis % x.dim()
+    shape = list(x.shape)
+    n = shape[axis]
+    start, m = crop if crop is not None else (0, n)
+    oshape = list(shape)
+    oshape[axis] = m
+    out = torch.empty(oshape, dtype=_C64 if out_mode == "complex" else _F32, device=x.device)
+    if axis == x.dim() - 1:
+        rows_mode, lines, batch = 1, x.numel() // n, 1
+    else:
+        rows_mode = 0
+        lines = 1
+        for s in shape[axis + 1:]:
+            lines *= s
+        batch = 1
+        for s in shape[:axis]:
+            batch *= s
+    bp = None
+    D = H = W = 0
+    if bandpass is not None:
+        assert x.dim() == 3 and axis == 0 and crop is None
+        bp = (_C.c_float * 8)(*[float(v) for v in bandpass])
+        D, H, W = shape
+    L = _lib.load()
+    _lib.check(L.sb_fft_lines(x.data_ptr(), out.data_ptr(), fft_twiddles(n, x.device).data_ptr(), n, m, rows_mode, lines, batch,
+                              1 if x.dtype == _F32 else 0, {"complex": 0, "real": 1, "abs": 2}[out_mode], 1 if inverse else 0,
+                              float(scale), 0 if crop is None else 1, int(start), bp, D, H, W, _stream()), "sb_fft_lines")
+    _count()
+    return out
+
+
+def bandpass_volume(shape, bandpass) -> torch.Tensor:
+    """float32 [D,H,W]: the fftshift-ed cosine band-pass volume (REF Filter3D.filter)."""
+    import ctypes as _C
+    D, H, W = (int(v) for v in shape)
+    out = torch.empty((D, H, W), dtype=_F32, device="cuda")
+    bp = (_C.c_float * 8)(*[float(v) for v in bandpass])
+    L = _lib.load()
+    _lib.check(L.sb_bandpass_volume(D, H, W, bp, out.data_ptr(), _stream()), "sb_bandpass_volume")
     _count()
     return out

@@ -66,3 +66,31 @@ def make_label_volume(shape, seed: int = 0, n_ellipsoids: int = 40, device="cpu"
         sp = (torch.rand(shape, generator=g) < speckle).to(device)
         lab[sp & (lab == 0)] = 1
     return lab
+
+
+def make_organelle_membrane(shape, seed: int = 0, n_organelles: int = 4, speckle: float = 0.002, gap: float = 0.15,
+                            blob: float = 2.0):
+    """(organelle labels int32 [Z,Y,X] with values 1..n, membrane uint8 {0,1}): ellipsoidal organelles well inside the
+    volume, each wrapped in a ~2-3 voxel shell broken by random gaps, plus speckle in both volumes — the input pair of
+    the membrane-refinement workflow (REF saber/analysis/refine_membranes.py:445)."""
+    rng = np.random.default_rng(seed)
+    Z, Y, X = shape
+    zz, yy, xx = np.meshgrid(np.arange(Z, dtype=np.float32), np.arange(Y, dtype=np.float32), np.arange(X, dtype=np.float32),
+                             indexing="ij")
+    org = np.zeros(shape, np.int32)
+    mem = np.zeros(shape, np.uint8)
+    blocks = rng.random((Z // 4 + 1, Y // 4 + 1, X // 4 + 1)) > gap  # 4^3 blocks knocked out of the shells
+    keep = np.repeat(np.repeat(np.repeat(blocks, 4, 0), 4, 1), 4, 2)[:Z, :Y, :X]
+    for k in range(n_organelles):
+        c = np.array([rng.uniform(0.3, 0.7) * Z, rng.uniform(0.2, 0.8) * Y, rng.uniform(0.2, 0.8) * X], np.float32)
+        r = np.array([rng.uniform(0.12, 0.25) * Z, rng.uniform(0.1, 0.2) * Y, rng.uniform(0.1, 0.2) * X], np.float32)
+        if k == n_organelles - 1:
+            r[2] *= 0.45  # one thin organelle
+        d = np.sqrt(((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2)
+        org[d < 1.0] = k + 1
+        t = 2.5 / float(r.min())
+        mem[(d > 1.0 - t) & (d < 1.0 + 0.5 * t) & keep] = 1
+        mem[(zz - c[0]) ** 2 + (yy - c[1]) ** 2 + (xx - c[2]) ** 2 <= blob * blob] = 1  # an internal blob (not on the surface)
+    mem[rng.random(shape) < speckle] = 1
+    org[(rng.random(shape) < speckle) & (org == 0)] = n_organelles + 1
+    return org, mem

@@ -1,0 +1,296 @@
+"""SURVEY §8f "next" rows — the membrane-refinement workflow (row 3) and the Fourier-space rescale / band-pass (row 2).
+CPU part: the oracle restatements against fixtures produced by the REFERENCE's own code (oracle/make_golden_next.py).
+GPU part (-m gpu): the device implementations against the same fixtures and against the oracle on further inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+REFINE_CASES = [
+    ("a", (40, 72, 80), 31, 4, 2.0, dict(ball_size=3, min_membrane_area=200, edge_trim_z=2, edge_trim_xy=2)),
+    ("b", (80, 96, 96), 34, 2, 3.2, dict(ball_size=3, min_membrane_area=100, edge_trim_z=2, edge_trim_xy=2,
+                                         keep_surface_membranes=True)),
+    ("c", (36, 64, 64), 32, 3, 2.0, dict(ball_size=5, min_membrane_area=100, edge_trim_z=3, edge_trim_xy=3,
+                                         min_roi_relative_size=0.1)),
+    ("d", (24, 40, 40), 33, 2, 2.0, dict(ball_size=3, min_membrane_area=100000, edge_trim_z=2, edge_trim_xy=2)),
+    ("e", (24, 40, 40), 33, 2, 2.0, dict(ball_size=3, min_membrane_area=50, edge_trim_z=0, edge_trim_xy=2)),
+]
+
+
+def _refine_inputs(case):
+    from saber_b200 import synth
+    _name, shape, seed, n_org, blob, _cfg = case
+    return synth.make_organelle_membrane(shape, seed, n_org, blob=blob)
+
+
+@pytest.mark.parametrize("case", REFINE_CASES, ids=[c[0] for c in REFINE_CASES])
+def test_oracle_refine_membranes_matches_reference_golden(case, golden_dir):
+    from oracle import saber_ref
+    g = np.load(os.path.join(golden_dir, "saber_refine_membranes.npz"))
+    org, mem = _refine_inputs(case)
+    o, m = saber_ref.refine_membranes(org, mem, **case[5])
+    np.testing.assert_array_equal(o, g[f"{case[0]}_organelles"])
+    np.testing.assert_array_equal(m, g[f"{case[0]}_membranes"])
+    if o.ndim == 4:
+        np.testing.assert_array_equal(saber_ref.convert_to_3d_labels(o), g[f"{case[0]}_organelles_3d"])
+        assert (o > 0).sum() < (org > 0).sum()  # the workflow removed something
+
+
+def test_refine_golden_exercises_the_surface_filter(golden_dir):
+    """case b differs from the same input without keep_surface_membranes (the internal blob goes away)."""
+    from oracle import saber_ref
+    case = REFINE_CASES[1]
+    org, mem = _refine_inputs(case)
+    cfg = dict(case[5])
+    _, m_on = saber_ref.refine_membranes(org, mem, **cfg)
+    cfg["keep_surface_membranes"] = False
+    _, m_off = saber_ref.refine_membranes(org, mem, **cfg)
+    assert (m_on > 0).sum() < (m_off > 0).sum()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("conn", [6, 26])
+def test_ccl3d_connectivity_and_sizes_vs_scipy(conn):
+    from scipy import ndimage as ndi
+    from saber_b200 import ops
+    rng = np.random.default_rng(5 + conn)
+    for shape, p, min_vol in [((17, 33, 45), 0.35, 1), ((9, 64, 70), 0.22, 4), ((30, 31, 29), 0.5, 10), ((1, 50, 37), 0.4, 1)]:
+        vol = (rng.random(shape) < p).astype(np.uint8)
+        structure = np.ones((3, 3, 3)) if conn == 26 else None
+        lab, n = ndi.label(vol, structure=structure)
+        counts = np.bincount(lab.ravel())
+        keep = counts >= min_vol
+        keep[0] = False
+        remap = np.zeros(n + 1, np.int32)
+        remap[keep] = np.arange(1, keep.sum() + 1)
+        want = remap[lab]
+        labels, count, sizes = ops.ccl3d(torch.from_numpy(vol).cuda(), min_vol=min_vol, conn=conn, with_sizes=True)
+        k = int(count.item())
+        assert k == int(keep.sum())
+        np.testing.assert_array_equal(labels.cpu().numpy(), want)
+        np.testing.assert_array_equal(sizes.cpu().numpy()[:k], counts[keep])
+
+
+@pytest.mark.gpu
+def test_refine_kernels_vs_numpy():
+    from scipy import ndimage as ndi
+    from saber_b200 import ops
+    rng = np.random.default_rng(11)
+    Z, Y, X = 13, 37, 41
+    lab = rng.integers(0, 6, (Z, Y, X)).astype(np.int32) * (rng.random((Z, Y, X)) < 0.3)
+    lab[:, :5] = 0
+    lab[3] = 0
+    for dt in (np.int32, np.int64, np.uint8, np.int16):
+        v = torch.from_numpy(lab.astype(dt)).cuda()
+        present = torch.from_numpy((np.arange(Z) % 4 != 1).astype(np.uint8)).cuda()
+        table = ops.label_bbox(v, present, 7).cpu().numpy()
+        assert table[0, 7] == 0
+        for k in range(1, 8):
+            idx = np.argwhere((lab == k) & (np.arange(Z) % 4 != 1)[:, None, None])
+            if len(idx) == 0:
+                assert table[k, 6] == 0
+                continue
+            assert table[k, 6] == len(idx)
+            np.testing.assert_array_equal(table[k, :3], idx.min(0))
+            np.testing.assert_array_equal(table[k, 3:6], idx.max(0))
+        assert ops.label_bbox(v, None, 3).cpu().numpy()[0, 7] != 0  # labels 4, 5 exceed the cap
+        roi = (2, 3, 4, 11, 30, 40)
+        got = ops.roi_binarize(v, roi, 2, present).cpu().numpy()
+        want = ((lab == 2) & (np.arange(Z) % 4 != 1)[:, None, None])[2:11, 3:30, 4:40]
+        np.testing.assert_array_equal(got, want.astype(np.uint8))
+        np.testing.assert_array_equal(ops.roi_binarize(v, roi, -1).cpu().numpy(), (lab != 0)[2:11, 3:30, 4:40].astype(np.uint8))
+        out = torch.zeros_like(v)
+        ops.roi_paste(out, roi, torch.from_numpy(want.astype(np.uint8)).cuda(), 9)
+        ref = np.zeros_like(lab)
+        ref[2:11, 3:30, 4:40][want] = 9
+        np.testing.assert_array_equal(out.cpu().numpy(), ref.astype(dt))
+        ops.overlay_nonzero(out, v)
+        ref[lab > 0] = lab[lab > 0]
+        np.testing.assert_array_equal(out.cpu().numpy(), ref.astype(dt))
+    a = (rng.random((Z, Y, X)) < 0.5).astype(np.uint8)
+    b = (rng.random((Z, Y, X)) < 0.5).astype(np.uint8)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    np.testing.assert_array_equal(ops.mask_logic(ta, tb, "and").cpu().numpy(), a & b)
+    np.testing.assert_array_equal(ops.mask_logic(ta, tb, "or").cpu().numpy(), a | b)
+    np.testing.assert_array_equal(ops.mask_logic(ta, tb, "andnot").cpu().numpy(), a & (1 - b))
+    np.testing.assert_array_equal(ops.z_any(torch.from_numpy((lab != 0).astype(np.uint8)).cuda()).cpu().numpy(),
+                                  (lab != 0).any(axis=(1, 2)).astype(np.uint8))
+    np.testing.assert_array_equal(ops.morph_cube(ta, 1, 0).cpu().numpy(),
+                                  ndi.binary_erosion(a, structure=np.ones((3, 3, 3))).astype(np.uint8))
+    for zt, t in [(2, 3), (0, 3), (2, 0), (7, 3), (2, 19)]:
+        want = np.zeros((Z, Y, X), np.uint8)
+        if 0 < zt < Z // 2 and 0 < t < Y // 2 and t < X // 2:
+            want[zt:-zt, t:-t, t:-t] = (lab != 0)[zt:-zt, t:-t, t:-t]
+        np.testing.assert_array_equal(ops.trim_binarize(torch.from_numpy(lab).cuda(), zt, t).cpu().numpy(), want)
+    # largest component: the first among equals
+    vol = np.zeros((4, 8, 8), np.uint8)
+    vol[0, 0, :3] = 1
+    vol[2, 4, 2:5] = 1
+    vol[3, 7, 7] = 1
+    labels, count, sizes = ops.ccl3d(torch.from_numpy(vol).cuda(), 1, 6, with_sizes=True)
+    big = ops.label_select(labels, sizes, count, largest=True).cpu().numpy()
+    want = np.zeros_like(vol)
+    want[0, 0, :3] = 1
+    np.testing.assert_array_equal(big, want)
+    np.testing.assert_array_equal(ops.label_select(labels).cpu().numpy(), vol)
+    over = ops.label_keep_ratio(labels, torch.from_numpy((vol * 0 + (np.arange(8) >= 3)[None, None, :]).astype(np.uint8)).cuda(),
+                                sizes, 0.1).cpu().numpy()
+    want = np.zeros_like(vol)
+    want[2, 4, 2:5] = 1   # 2 of 3 voxels at x >= 3
+    want[3, 7, 7] = 1
+    np.testing.assert_array_equal(over, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", REFINE_CASES, ids=[c[0] for c in REFINE_CASES])
+def test_refine_membranes_matches_reference_golden(case, golden_dir):
+    from saber_b200.analysis.refine_membranes import FilteringConfig, OrganelleMembraneFilter
+    g = np.load(os.path.join(golden_dir, "saber_refine_membranes.npz"))
+    org, mem = _refine_inputs(case)
+    f = OrganelleMembraneFilter(FilteringConfig(**case[5]))
+    res = f.run(org, mem, batch_processing=True)
+    o, m = res["organelles"], res["membranes"]
+    if g[f"{case[0]}_organelles"].ndim == 3:  # the reference returns the zero volume as a device tensor
+        assert torch.is_tensor(o) and o.shape == org.shape and int(o.abs().sum()) == 0 and int(m.abs().sum()) == 0
+        return
+    assert isinstance(o, np.ndarray) and o.dtype == org.dtype
+    np.testing.assert_array_equal(o, g[f"{case[0]}_organelles"])
+    np.testing.assert_array_equal(m, g[f"{case[0]}_membranes"])
+    np.testing.assert_array_equal(f.convert_to_3d_labels(o), g[f"{case[0]}_organelles_3d"])
+    dev = f.run_device(torch.from_numpy(org), torch.from_numpy(mem))
+    np.testing.assert_array_equal(dev["organelles"].cpu().numpy(), g[f"{case[0]}_organelles_3d"])
+    np.testing.assert_array_equal(dev["membranes"].cpu().numpy(), g[f"{case[0]}_membranes_3d"])
+
+
+@pytest.mark.gpu
+def test_refine_membranes_vs_oracle_more_inputs():
+    from oracle import saber_ref
+    from saber_b200 import synth
+    from saber_b200.analysis.refine_membranes import FilteringConfig, OrganelleMembraneFilter
+    for seed, shape, n_org, cfg, dt in [
+        (41, (48, 80, 72), 5, dict(ball_size=3, min_membrane_area=150, edge_trim_z=3, edge_trim_xy=2), np.int64),
+        (42, (56, 64, 96), 3, dict(ball_size=7, min_membrane_area=80, edge_trim_z=1, edge_trim_xy=1, min_roi_relative_size=0.05), np.uint8),
+        (43, (72, 88, 88), 2, dict(ball_size=3, min_membrane_area=100, edge_trim_z=2, edge_trim_xy=2, keep_surface_membranes=True), np.int16),
+    ]:
+        org, mem = synth.make_organelle_membrane(shape, seed, n_org, blob=3.2)
+        org = org.astype(dt)
+        want_o, want_m = saber_ref.refine_membranes(org, mem, **cfg)
+        res = OrganelleMembraneFilter(FilteringConfig(**cfg)).run(org, mem.astype(np.float32))
+        assert want_o.ndim == 4
+        np.testing.assert_array_equal(res["organelles"], want_o)
+        np.testing.assert_array_equal(res["membranes"], want_m)
+
+
+# ---- §8f row 2: Fourier-crop rescale and cosine band-pass -----------------------------------------------------------------
+RESCALE3D_CASES = [("r3a", (24, 58, 40), 51, 5.0, 10.0), ("r3b", (25, 45, 64), 52, (4.0, 5.0, 5.0), (7.0, 9.0, 12.0)),
+                   ("r3c", (20, 29, 48), 53, 3.0, 4.3)]
+RESCALE2D_CASES = [("r2a", (96, 116), 54, 2.0), ("r2b", (75, 128), 55, 3.3), ("r2c", (58, 50), 56, 1.0)]
+FILTER_CASES = [("fa", (20, 48, 58), 57, 10.0, 60.0, 6.0, 0.0, 0.0), ("fb", (24, 40, 40), 58, 10.0, 50.0, 4.0, 400.0, 2.0),
+                ("fc", (25, 45, 32), 59, 8.0, 40.0, 0.0, 0.0, 0.0), ("fd", (16, 32, 32), 60, 8.0, 0.0, 0.0, 200.0, 0.0)]
+FOURIER_TOL = 1e-5  # of the largest magnitude in the expected array: fp32 transforms on both sides
+
+
+def _close(got, want, tol=FOURIER_TOL):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+    assert err < tol, err
+
+
+def test_oracle_fourier_matches_reference_golden(golden_dir):
+    from oracle import saber_ref
+    from saber_b200 import synth
+    g = np.load(os.path.join(golden_dir, "saber_fourier.npz"))
+    for name, shape, seed, vin, vout in RESCALE3D_CASES:
+        vol = synth.make_tomogram(shape, seed=seed, n_ellipsoids=4).numpy()
+        _close(saber_ref.fourier_rescale_3d(vol, vin, vout), g[name])
+    for name, shape, seed, sf in RESCALE2D_CASES:
+        img = synth.make_tomogram((1, *shape), seed=seed, n_ellipsoids=3).numpy()[0]
+        _close(saber_ref.fourier_rescale_2d(img, sf), g[name])
+    for name, shape, seed, apix, lp, lpd, hp, hpd in FILTER_CASES:
+        vol = synth.make_tomogram(shape, seed=seed, n_ellipsoids=4).numpy()
+        filt = saber_ref.cosine_filter(shape, apix, lp, lpd, hp, hpd)
+        _close(filt, g[name + "_filter"], 1e-6)
+        _close(saber_ref.filter3d_apply(vol, filt), g[name])
+
+
+@pytest.mark.gpu
+def test_fft_lines_vs_numpy():
+    from saber_b200 import ops
+    rng = np.random.default_rng(3)
+    for shape in [(6, 20, 29), (3, 58, 12), (5, 7, 64), (4, 200, 45), (2, 9, 928)]:
+        x = rng.normal(size=shape).astype(np.float32)
+        t = torch.from_numpy(x).cuda()
+        for axis in (0, 1, 2):
+            got = ops.fft_lines(t, axis).cpu().numpy()
+            want = np.fft.fft(x.astype(np.float64), axis=axis)
+            assert np.abs(got - want).max() / np.abs(want).max() < 2e-6, (shape, axis)
+            c = torch.from_numpy(want.astype(np.complex64)).cuda()
+            back = ops.fft_lines(c, axis, inverse=True, out_mode="real", scale=1.0 / shape[axis]).cpu().numpy()
+            assert np.abs(back - x).max() < 5e-6 * np.abs(x).max(), (shape, axis)
+    img = rng.normal(size=(33, 40)).astype(np.float32)
+    got = ops.fft_lines(torch.from_numpy(img).cuda(), 1, crop=(11, 18)).cpu().numpy()
+    want = np.fft.ifftshift(np.fft.fftshift(np.fft.fft(img.astype(np.float64), axis=1), axes=1)[:, 11:29], axes=1)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+
+
+@pytest.mark.gpu
+def test_fourier_rescale_matches_reference_golden(golden_dir):
+    from saber_b200 import synth
+    from saber_b200.filters.downsample import FourierRescale2D, FourierRescale3D
+    g = np.load(os.path.join(golden_dir, "saber_fourier.npz"))
+    for name, shape, seed, vin, vout in RESCALE3D_CASES:
+        vol = synth.make_tomogram(shape, seed=seed, n_ellipsoids=4).numpy()
+        r = FourierRescale3D(vin, vout)
+        out = r.run(vol)
+        assert isinstance(out, np.ndarray) and out.dtype == np.float32
+        _close(out, g[name])
+        batched = r.run(torch.from_numpy(np.stack([vol, 2 * vol])))
+        assert torch.is_tensor(batched) and batched.device.type == "cpu"
+        _close(batched[1].numpy(), 2 * g[name])
+    with pytest.raises(ValueError):
+        FourierRescale3D(10.0, 5.0)
+    for name, shape, seed, sf in RESCALE2D_CASES:
+        img = synth.make_tomogram((1, *shape), seed=seed, n_ellipsoids=3).numpy()[0]
+        _close(FourierRescale2D.run(img, sf), g[name])
+    with pytest.raises(ValueError):
+        FourierRescale2D.run(np.zeros((8, 8), np.float32), 0.5)
+    _close(FourierRescale2D.run_resolution(synth.make_tomogram((1, 96, 116), seed=54, n_ellipsoids=3).numpy()[0], 1.5, 3.0), g["r2a"])
+
+
+@pytest.mark.gpu
+def test_filter3d_matches_reference_golden(golden_dir):
+    from saber_b200 import synth
+    from saber_b200.filters.tomograms import Filter3D
+    g = np.load(os.path.join(golden_dir, "saber_fourier.npz"))
+    for name, shape, seed, apix, lp, lpd, hp, hpd in FILTER_CASES:
+        vol = synth.make_tomogram(shape, seed=seed, n_ellipsoids=4).numpy()
+        f = Filter3D(apix, shape, lp=lp, lpd=lpd, hp=hp, hpd=hpd)
+        _close(f.filter.cpu().numpy(), g[name + "_filter"], 1e-6)
+        out = f.apply(vol)
+        assert out.is_cuda and out.dtype == torch.float32
+        _close(out.cpu().numpy(), g[name])
+    with pytest.raises(ValueError):
+        Filter3D(10.0, (8, 8, 8), lp=100.0, hp=50.0)
+
+
+@pytest.mark.gpu
+def test_fourier_full_size_properties():
+    """BASELINE-size volume (200 x 928 x 960): identity voxel size round-trips the volume; a 2x rescale preserves the mean
+    (the DC term) and halves every extent; an all-pass Filter3D is the identity."""
+    from saber_b200 import synth
+    from saber_b200.filters.downsample import FourierRescale3D
+    from saber_b200.filters.tomograms import Filter3D
+    shape = (200, 928, 960)
+    vol = synth.make_tomogram(shape, seed=7, n_ellipsoids=30, device="cuda").contiguous()
+    same = FourierRescale3D(10.0, 10.0).rescale_device(vol)
+    assert same.shape == vol.shape
+    assert float((same - vol).abs().max()) < 2e-5 * float(vol.abs().max())
+    half = FourierRescale3D(10.0, 20.0).rescale_device(vol)
+    assert tuple(half.shape) == (100, 464, 480)
+    # ortho norms: mean(out) = mean(in) * sqrt(N_in / N_out)
+    assert abs(float(half.double().mean()) - float(vol.double().mean()) * (8 ** 0.5)) < 1e-4
+    ident = Filter3D(10.0, shape).apply(vol)
+    assert float((ident - vol).abs().max()) < 2e-5 * float(vol.abs().max())
