@@ -84,3 +84,38 @@ def smooth_to_uint8(segment_mask, scale: float = 0.05, gpu_id: int = 0) -> np.nd
         vol = torch.from_numpy(arr).to(dev)
     out = mask_filters.fast_3d_gaussian_smoothing(vol, scale=scale, deviceID=gpu_id)
     return out.cpu().numpy().astype(np.uint8)
+
+
+def segment_micrograph_core(input: str, output: str, scale_factor: float, target_resolution: float, display_image: bool,
+                            use_sliding_window: bool, gpu_id, models, read_micrograph=None):
+    """REF saber/entry_points/inference_core.py:97-153 — the 2-D worker of `prep2d` / micrograph inference (SURVEY §8f rows
+    2 and 4 meet here): read -> optional Fourier-crop down-sampling (`FourierRescale2D`, csrc/fft.cu) -> `segmenter.segment`
+    -> labelled candidate stack -> one zarr group named after the file (pixel size stored in nanometres).
+    `read_micrograph(path) -> (array, pixel size in Angstroms or None)` is I/O (mrc / tiff / dm4) and is injected; without
+    it `saber.utils.io.read_micrograph` must be importable."""
+    import os
+
+    from ..filters.downsample import FourierRescale2D
+    from ..utils import zarr_writer
+    segmenter = models["segmenter"]
+    zwriter = zarr_writer.get_zarr_writer(output)
+    zwriter.set_dict_attr("amg", segmenter.adapter_cfg.amg_cfg.to_dict())
+    torch.cuda.set_device(gpu_id)
+    if read_micrograph is None:
+        from saber.utils.io import read_micrograph  # noqa: WPS433 (the reference's file readers; optional)
+    image, pixel_size = read_micrograph(input)
+    image = image.astype(np.float32)
+    if target_resolution is not None and target_resolution > pixel_size:
+        image = FourierRescale2D.run(image, target_resolution / pixel_size)
+    elif scale_factor is not None:
+        image = FourierRescale2D.run(image, scale_factor)
+    target_class = models.get("target_class", -1)
+    segmenter.segment(image, target_class=target_class, display=False, use_sliding_window=use_sliding_window)
+    if isinstance(pixel_size, np.ndarray):
+        pixel_size = pixel_size.item()
+    masks = mask_filters.masks_to_array(segmenter.masks)
+    pixel_size = pixel_size / 10 if pixel_size is not None else 1
+    out_image = segmenter.image
+    if out_image.ndim == 3:
+        out_image = out_image[:, :, 0]
+    zwriter.write(run_name=os.path.splitext(os.path.basename(input))[0], image=out_image, masks=masks, pixel_size=pixel_size)

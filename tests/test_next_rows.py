@@ -294,3 +294,136 @@ def test_fourier_full_size_properties():
     assert abs(float(half.double().mean()) - float(vol.double().mean()) * (8 ** 0.5)) < 1e-4
     ident = Filter3D(10.0, shape).apply(vol)
     assert float((ident - vol).abs().max()) < 2e-5 * float(vol.abs().max())
+
+
+# ---- §8f row 4: training-data store layout and the prep3d / prep2d workers ---------------------------------------------------
+def _read_zarr_v2(path):
+    """Minimal zarr-v2 reader (json + zlib / numcodecs) used only to check what the writer produced."""
+    import json
+    import zlib
+    meta = json.load(open(os.path.join(path, ".zarray")))
+    assert meta["zarr_format"] == 2 and meta["dimension_separator"] == "/" and meta["order"] == "C"
+    comp = meta["compressor"]
+    if comp["id"] == "zlib":
+        decode = zlib.decompress
+    else:
+        import numcodecs
+        decode = numcodecs.get_codec(comp).decode
+    shape, chunks = meta["shape"], meta["chunks"]
+    out = np.zeros(shape, np.dtype(meta["dtype"]))
+    if len(shape) >= 3:
+        for i in range(shape[0]):
+            p = os.path.join(path, str(i), *["0"] * (len(shape) - 1))
+            out[i] = np.frombuffer(decode(open(p, "rb").read()), out.dtype).reshape(chunks[1:])
+    else:
+        p = os.path.join(path, *["0"] * len(shape))
+        out[...] = np.frombuffer(decode(open(p, "rb").read()), out.dtype).reshape(shape)
+    return out
+
+
+class _Cfg:
+    class amg_cfg:  # noqa: N801
+        @staticmethod
+        def to_dict():
+            return {"npoints": 32, "pred_iou_thresh": np.float32(0.7), "sam2_cfg": "large"}
+
+
+class _SlabSegmenter:
+    adapter_cfg = _Cfg
+
+    def __init__(self):
+        self.calls = []
+
+    def segment_slab(self, vol, slab_thickness, display=False, zSlice=None):
+        self.calls.append((slab_thickness, zSlice))
+        rng = np.random.default_rng(zSlice)
+        self.image0 = vol[zSlice].astype(np.float32)
+        areas = [50, 10, 30]
+        self.masks = []
+        for a in areas:
+            m = np.zeros(vol.shape[1:], bool)
+            m.ravel()[rng.choice(m.size, a, replace=False)] = True
+            self.masks.append({"segmentation": m, "area": a})
+
+
+def test_zarr_layout_and_prep3d_worker(tmp_path, monkeypatch):
+    import json
+    from saber_b200.classifier.preprocess import tomo_prep
+    from saber_b200.utils import zarr_writer
+    monkeypatch.setattr(zarr_writer, "_zarr_writer", None)
+    out = str(tmp_path / "training.zarr")
+    vol = np.random.default_rng(0).normal(size=(30, 24, 28)).astype(np.float32)
+
+    class Run:
+        name = "TS_001"
+
+    class Reader:
+        @staticmethod
+        def tomogram(run, voxel_size, algorithm):
+            return vol if algorithm == "wbp" else None
+
+    seg = _SlabSegmenter()
+    tomo_prep.extract_sam2_candidates(Run, out, 10.0, "wbp", 4, 3, 0, {"segmenter": seg}, reader=Reader)
+    tomo_prep.extract_sam2_candidates(Run, out, 10.0, "missing", 4, 1, 0, {"segmenter": seg}, reader=Reader)  # no tomogram
+    Run.name = "TS_002"
+    tomo_prep.extract_sam2_candidates(Run, out, 10.0, "wbp", 4, 1, 0, {"segmenter": seg}, reader=Reader)
+    w = zarr_writer.get_zarr_writer(out)
+    w.finalize()
+    # REF tomo_prep.py:61-72: slabs centred on the volume, one thickness apart
+    assert seg.calls == [(4, 11), (4, 15), (4, 19), (4, 15)]
+    root = json.load(open(os.path.join(out, ".zattrs")))
+    assert root["total_runs"] == 4 and root["creation_complete"] is True
+    assert root["amg"] == {"npoints": 32, "pred_iou_thresh": pytest.approx(0.7), "sam2_cfg": "large"}
+    assert sorted(d for d in os.listdir(out) if not d.startswith(".")) == ["TS_001_1", "TS_001_2", "TS_001_3", "TS_002"]
+    for group, z in [("TS_001_1", 11), ("TS_001_3", 19), ("TS_002", 15)]:
+        g = os.path.join(out, group)
+        assert json.load(open(os.path.join(g, ".zgroup"))) == {"zarr_format": 2}
+        np.testing.assert_array_equal(_read_zarr_v2(os.path.join(g, "0")), vol[z])
+        masks = _read_zarr_v2(os.path.join(g, "labels", "0"))
+        assert masks.dtype == np.uint8 and masks.shape == (3, 24, 28)
+        assert [int((masks[j] == j + 1).sum()) for j in range(3)] == [10, 30, 50]  # sorted by area, labelled j + 1
+        ms = json.load(open(os.path.join(g, ".zattrs")))["multiscales"][0]
+        assert [a["name"] for a in ms["axes"]] == ["y", "x"] and ms["version"] == "0.4" and ms["name"] == "/"
+        assert ms["datasets"][0] == {"coordinateTransformations": [{"scale": [1.0, 1.0], "type": "scale"}], "path": "0"}
+        ml = json.load(open(os.path.join(g, "labels", ".zattrs")))["multiscales"][0]
+        assert [a["name"] for a in ml["axes"]] == ["z", "y", "x"]
+        assert ml["datasets"][0]["coordinateTransformations"][0]["scale"] == [1.0, 1.0, 1.0]
+    with pytest.raises(ValueError):
+        w.write("TS_002", vol[0], np.zeros((1, 24, 28), np.uint8))  # a run is written once
+    w.set_dict_attr("amg", {"npoints": 64, "extra": 1}, merge_missing=True)
+    assert json.load(open(os.path.join(out, ".zattrs")))["amg"]["npoints"] == 32
+    assert json.load(open(os.path.join(out, ".zattrs")))["amg"]["extra"] == 1
+
+
+@pytest.mark.gpu
+def test_segment_micrograph_core_rescales_and_writes(tmp_path, monkeypatch):
+    import json
+    from saber_b200 import synth
+    from saber_b200.entry_points.inference_core import segment_micrograph_core
+    from saber_b200.filters.downsample import FourierRescale2D
+    from saber_b200.utils import zarr_writer
+    monkeypatch.setattr(zarr_writer, "_zarr_writer", None)
+    img = synth.make_tomogram((1, 96, 116), seed=54, n_ellipsoids=3).numpy()[0]
+
+    class Seg:
+        adapter_cfg = _Cfg
+
+        def segment(self, image, target_class=-1, display=False, use_sliding_window=False):
+            self.image = image
+            self.args = (target_class, use_sliding_window)
+            m = np.zeros(image.shape, bool)
+            m[2:10, 3:9] = True
+            self.masks = [{"segmentation": m, "area": int(m.sum())}]
+
+    seg = Seg()
+    out = str(tmp_path / "micro.zarr")
+    segment_micrograph_core("/data/mic_07.mrc", out, None, 4.0, False, True, 0, {"segmenter": seg, "target_class": 2},
+                            read_micrograph=lambda f: (img.astype(np.float64), np.float32(2.0)))
+    assert seg.args == (2, True)
+    want = FourierRescale2D.run(img, 2.0)
+    np.testing.assert_array_equal(seg.image, want)
+    g = os.path.join(out, "mic_07")
+    np.testing.assert_array_equal(_read_zarr_v2(os.path.join(g, "0")), want)
+    assert _read_zarr_v2(os.path.join(g, "labels", "0")).shape == (1, 48, 58)
+    scale = json.load(open(os.path.join(g, ".zattrs")))["multiscales"][0]["datasets"][0]["coordinateTransformations"][0]["scale"]
+    assert scale == [pytest.approx(0.2), pytest.approx(0.2)]
