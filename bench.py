@@ -321,6 +321,50 @@ def measure_extras(args, seg, slab, labels, flush, dev):
     out["bandwidth"] = {"peak_gbs": peak, "peak_source": peak_src, "l2": "256 MiB flush before every timed launch",
                         "kernels": [t for t in table if t]}
 
+    # (v) SURVEY 8f rows 2 / 3 (the import step before the path and the refinement step after it) at the BASELINE volume
+    # size: FFT line passes against the HBM roofline, the whole rescale / band-pass calls, the membrane workflow
+    try:
+        from saber_b200.analysis.refine_membranes import FilteringConfig, OrganelleMembraneFilter
+        from saber_b200.filters.downsample import FourierRescale3D
+        from saber_b200.filters.tomograms import Filter3D
+        shape3 = (200, 928, 960)
+        v3 = synth.make_tomogram(shape3, seed=7, n_ellipsoids=30, device=dev).contiguous()
+        n3 = v3.numel()
+        spec = ops.fft_lines(v3, 2)
+        fft_rows = []
+        for name, fn, nbytes in [("fft x rows, real -> complex, n=960", lambda: ops.fft_lines(v3, 2), 12 * n3),
+                                 ("fft y columns, complex, n=928 (2^5 x 29)", lambda: ops.fft_lines(spec, 1), 16 * n3),
+                                 ("fft z columns, complex, n=200 (2^3 x 5^2)", lambda: ops.fft_lines(spec, 0), 16 * n3),
+                                 ("ifft x rows, complex -> real, n=960", lambda: ops.fft_lines(spec, 2, inverse=True, out_mode="real"), 12 * n3)]:
+            ms_ = _time_kernel(fn, flush, reps=3, warm=1)
+            g = nbytes / (ms_ * 1e-3) / 1e9
+            fft_rows.append({"kernel": name, "algorithmic_bytes": int(nbytes), "us": ms_ * 1e3, "gbs": g, "frac": g / peak})
+        del spec
+        rs = FourierRescale3D(10.0, 20.0)
+        ms_rs = _time_kernel(lambda: rs.rescale_device(v3), flush, reps=3, warm=1)
+        f3 = Filter3D(10.0, shape3, lp=60.0, lpd=6.0, hp=2000.0, hpd=2.0)
+        ms_bp = _time_kernel(lambda: f3.apply(v3), flush, reps=3, warm=1)
+        del v3
+        org, mem = synth.make_organelle_membrane((200, 464, 480), 71, 12, blob=3.0)
+        o_d, m_d = torch.from_numpy(org).to(dev), torch.from_numpy(mem).to(dev)
+        filt = OrganelleMembraneFilter(FilteringConfig(ball_size=3, min_membrane_area=2000), gpu_id=dev.index or 0)
+        filt.run_device(o_d, m_d)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = filt.run_device(o_d, m_d)
+        torch.cuda.synchronize()
+        ms_ref = (time.perf_counter() - t0) * 1e3
+        out["next_rows"] = {
+            "fft_passes": fft_rows, "peak_gbs": peak,
+            "fourier_rescale_3d": {"workload": "200x928x960 fp32 -> 100x464x480 (voxel 10 -> 20 A)", "ms": ms_rs},
+            "filter3d_bandpass": {"workload": "200x928x960 fp32, cosine low- + high-pass, 6 line passes", "ms": ms_bp,
+                                  "gbs": 88.0 * n3 / (ms_bp * 1e-3) / 1e9, "frac": 88.0 * n3 / (ms_bp * 1e-3) / 1e9 / peak},
+            "refine_membranes": {"workload": "200x464x480 int32 labels, 12 organelles + membrane shells, run_device (wall "
+                                             "clock incl. the host reads of component counts)", "ms": ms_ref,
+                                 "organelles_kept": int(torch.unique(res["organelles"]).numel()) - 1}}
+    except Exception as e:  # the headline must not depend on the next-row probes
+        out["next_rows"] = {"error": repr(e)}
+
     # (iv) same-box GPU bar: the oracle (plain PyTorch: cuBLASLt / cuDNN / SDPA) on this B200 for one crop encode + one
     # prompt batch (64 points + 192 m2m), extrapolated per slice like the CPU arm
     out["gpu_eager_baseline"] = gpu_eager_baseline(args, dev)

@@ -34,10 +34,18 @@ struct FftPass {
   int crop, start;   // stored q <- spectrum[(start + (q + m / 2) % m - n / 2) mod n]
   int nfac;
   int fac[MAX_FACTORS];
+  unsigned mag_ns[MAX_FACTORS];    // exact division by Ns / by Ns * R of the odd-radix stages (see fast_div)
+  unsigned mag_q[MAX_FACTORS];     // exact division by n / R
+  unsigned mag_n, mag_m;
   int filt;          // band-pass on store (column pass along z of a D x H x W spectrum)
   int D, H, W;
   float lp, lp_lo, lp_hi, lpd, hp, hp_lo, hp_hi, hpd;
 };
+
+// x / d for 0 <= x < 65536, 1 <= d < 65536 with magic = 2^32 / d + 1 (0 encodes d == 1): exact because x * d < 2^32
+__device__ __forceinline__ unsigned fast_div(unsigned x, unsigned magic) {
+  return magic ? __umulhi(x, magic) : x;
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -61,119 +69,211 @@ __device__ __forceinline__ int signed_freq(int k, int n) {  // coordinate of uns
   return (k + n / 2) % n - n / 2;
 }
 
+// ---- radix-R butterflies on registers (forward: sgn = +1, inverse: sgn = -1) ----------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// a * (-i) forward, a * (+i) inverse
+__device__ __forceinline__ float2 crot(float2 a, float sgn) { return make_float2(sgn * a.y, -sgn * a.x); }
+
+template <int R>
+__device__ __forceinline__ void butterfly(float2 (&v)[R], float sgn);
+
+template <>
+__device__ __forceinline__ void butterfly<2>(float2 (&v)[2], float) {
+  const float2 a = v[0];
+  v[0] = cadd(a, v[1]);
+  v[1] = csub(a, v[1]);
+}
+
+template <>
+__device__ __forceinline__ void butterfly<3>(float2 (&v)[3], float sgn) {
+  const float2 t = cadd(v[1], v[2]);
+  const float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
+  const float2 d = csub(v[1], v[2]);
+  const float2 r = crot(make_float2(0.86602540378443865f * d.x, 0.86602540378443865f * d.y), sgn);
+  v[0] = cadd(v[0], t);
+  v[1] = cadd(m, r);
+  v[2] = csub(m, r);
+}
+
+template <>
+__device__ __forceinline__ void butterfly<4>(float2 (&v)[4], float sgn) {
+  const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]), a2 = cadd(v[1], v[3]);
+  const float2 a3 = crot(csub(v[1], v[3]), sgn);
+  v[0] = cadd(a0, a2);
+  v[1] = cadd(a1, a3);
+  v[2] = csub(a0, a2);
+  v[3] = csub(a1, a3);
+}
+
+template <>
+__device__ __forceinline__ void butterfly<5>(float2 (&v)[5], float sgn) {
+  constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f, s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+  const float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+  const float2 m1 = make_float2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+  const float2 m2 = make_float2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+  const float2 n1 = crot(make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y), sgn);
+  const float2 n2 = crot(make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y), sgn);
+  v[0] = cadd(v[0], cadd(a1, a2));
+  v[1] = cadd(m1, n1);
+  v[4] = csub(m1, n1);
+  v[2] = cadd(m2, n2);
+  v[3] = csub(m2, n2);
+}
+
+// One Stockham stage of radix R: thread (line, j) loads its R inputs, applies the stage twiddles, runs the butterfly in
+// registers and scatters the outputs. `line` is fixed per thread, j strides by FFT_THREADS / T.
+template <int R>
+__device__ __forceinline__ void radix_stage(const float2* __restrict__ cur, float2* __restrict__ nxt,
+                                            const float2* __restrict__ tw, unsigned n, unsigned Ns, unsigned mag_ns,
+                                            bool ns_pow2, int logT, unsigned line, unsigned jbase, unsigned jstride,
+                                            float sgn) {
+  const unsigned q = n / R, tstep = q / Ns;
+#pragma unroll 2
+  for (unsigned j = jbase; j < q; j += jstride) {
+    const unsigned k = ns_pow2 ? (j & (Ns - 1)) : j - static_cast<unsigned>(fast_div(j, mag_ns)) * Ns;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = cur[((j + r * q) << logT) + line];
+    if (k) {
+      const unsigned kt = k * tstep;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        float2 w = tw[r * kt];
+        w.y *= sgn;
+        v[r] = cmul(v[r], w);
+      }
+    }
+    butterfly<R>(v, sgn);
+    const unsigned j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nxt[((j0 + r * Ns) << logT) + line] = v[r];
+  }
+}
+
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_lines_kernel(const __grid_constant__ FftPass p) {
   extern __shared__ float2 fft_smem[];
-  const int n = p.n, T = p.T, logT = p.logT;
+  const unsigned n = p.n, T = p.T;
+  const int logT = p.logT;
   float2* cur = fft_smem;
   float2* nxt = fft_smem + static_cast<size_t>(T) * n;
-  const int tid = threadIdx.x;
+  float2* tw = fft_smem + static_cast<size_t>(2) * T * n;  // the n roots of unity, staged once per CTA
+  const unsigned tid = threadIdx.x;
 
   long long l0;
-  int b = 0;
+  unsigned b = 0;
   if (p.rows_mode) {
     l0 = static_cast<long long>(blockIdx.x) * T;
   } else {
-    const long long tiles = (p.lines + T - 1) / T;
-    b = static_cast<int>(blockIdx.x / tiles);
-    l0 = (blockIdx.x % tiles) * T;
+    const unsigned tiles = static_cast<unsigned>((p.lines + T - 1) / T);
+    b = blockIdx.x / tiles;
+    l0 = static_cast<long long>(blockIdx.x - b * tiles) * T;
   }
-  const int nl = static_cast<int>(min(static_cast<long long>(T), p.lines - l0));
-  const int total = T * n;
+  const unsigned nl = static_cast<unsigned>(min(static_cast<long long>(T), p.lines - l0));
+  const unsigned total = T * n;
 
-  // ---- load: shared layout [i][line] (line fastest: conflict-free butterflies for every stride)
+  for (unsigned i = tid; i < n; i += FFT_THREADS) tw[i] = __ldg(p.tw + i);
+  // ---- load: shared layout [i][line] (line fastest: conflict-free butterfly reads for every stride)
   if (p.rows_mode) {
-    for (int idx = tid; idx < total; idx += FFT_THREADS) {
-      const int line = idx / n, i = idx - line * n;
-      float2 v = make_float2(0.f, 0.f);
-      if (line < nl) {
-        const long long g = (l0 + line) * n + i;
-        if (p.in_real) v.x = static_cast<const float*>(p.in)[g];
-        else v = static_cast<const float2*>(p.in)[g];
+    // the tile's rows are contiguous in memory: element idx of the tile is element (line = idx / n, i = idx % n)
+    const unsigned valid = nl * n;
+    if (p.in_real) {
+      const float* src = static_cast<const float*>(p.in) + l0 * n;
+#pragma unroll 4
+      for (unsigned idx = tid; idx < total; idx += FFT_THREADS) {
+        const unsigned line = fast_div(idx, p.mag_n), i = idx - line * n;
+        cur[(i << logT) + line] = make_float2(idx < valid ? src[idx] : 0.f, 0.f);
       }
-      cur[(i << logT) + line] = v;
+    } else {
+      const float2* src = static_cast<const float2*>(p.in) + l0 * n;
+#pragma unroll 4
+      for (unsigned idx = tid; idx < total; idx += FFT_THREADS) {
+        const unsigned line = fast_div(idx, p.mag_n), i = idx - line * n;
+        cur[(i << logT) + line] = idx < valid ? src[idx] : make_float2(0.f, 0.f);
+      }
     }
   } else {
-    for (int idx = tid; idx < total; idx += FFT_THREADS) {
-      const int i = idx >> logT, c = idx & (T - 1);
-      float2 v = make_float2(0.f, 0.f);
-      if (c < nl) {
-        const long long g = (static_cast<long long>(b) * n + i) * p.lines + l0 + c;
-        if (p.in_real) v.x = static_cast<const float*>(p.in)[g];
-        else v = static_cast<const float2*>(p.in)[g];
+    const size_t base = static_cast<size_t>(b) * n * p.lines + l0;
+    const size_t pitch = static_cast<size_t>(p.lines);
+    if (p.in_real) {
+      const float* src = static_cast<const float*>(p.in) + base;
+#pragma unroll 4
+      for (unsigned idx = tid; idx < total; idx += FFT_THREADS) {
+        const unsigned i = idx >> logT, c = idx & (T - 1);
+        cur[idx] = make_float2(c < nl ? src[i * pitch + c] : 0.f, 0.f);
       }
-      cur[idx] = v;
+    } else {
+      const float2* src = static_cast<const float2*>(p.in) + base;
+#pragma unroll 4
+      for (unsigned idx = tid; idx < total; idx += FFT_THREADS) {
+        const unsigned i = idx >> logT, c = idx & (T - 1);
+        cur[idx] = c < nl ? src[i * pitch + c] : make_float2(0.f, 0.f);
+      }
     }
   }
   __syncthreads();
 
   // ---- Stockham stages
   const float sgn = p.inverse ? -1.f : 1.f;  // conjugate roots for the inverse transform
-  int Ns = 1;
+  const unsigned line = tid & (T - 1), jbase = tid >> logT, jstride = FFT_THREADS >> logT;
+  unsigned Ns = 1;
   for (int f = 0; f < p.nfac; ++f) {
-    const int R = p.fac[f];
+    const unsigned R = p.fac[f];
+    const bool pow2 = (Ns & (Ns - 1)) == 0;
     if (R == 4) {
-      const int q = n >> 2, tstep = n / (Ns * 4);
-      for (int idx = tid; idx < (q << logT); idx += FFT_THREADS) {
-        const int j = idx >> logT, line = idx & (T - 1);
-        const int k = j % Ns;
-        float2 v0 = cur[(j << logT) + line];
-        float2 v1 = cur[((j + q) << logT) + line];
-        float2 v2 = cur[((j + 2 * q) << logT) + line];
-        float2 v3 = cur[((j + 3 * q) << logT) + line];
-        if (k) {
-          float2 w1 = __ldg(p.tw + k * tstep), w2 = __ldg(p.tw + 2 * k * tstep), w3 = __ldg(p.tw + 3 * k * tstep);
-          w1.y *= sgn; w2.y *= sgn; w3.y *= sgn;
-          v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
-        }
-        const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-        const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-        const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
-        const float2 a3 = make_float2(sgn * d.y, -sgn * d.x);  // (v1 - v3) * (-i) forward, * (+i) inverse
-        const int j0 = (j - k) * 4 + k;
-        nxt[(j0 << logT) + line] = make_float2(a0.x + a2.x, a0.y + a2.y);
-        nxt[((j0 + Ns) << logT) + line] = make_float2(a1.x + a3.x, a1.y + a3.y);
-        nxt[((j0 + 2 * Ns) << logT) + line] = make_float2(a0.x - a2.x, a0.y - a2.y);
-        nxt[((j0 + 3 * Ns) << logT) + line] = make_float2(a1.x - a3.x, a1.y - a3.y);
-      }
+      radix_stage<4>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
     } else if (R == 2) {
-      const int q = n >> 1, tstep = n / (Ns * 2);
-      for (int idx = tid; idx < (q << logT); idx += FFT_THREADS) {
-        const int j = idx >> logT, line = idx & (T - 1);
-        const int k = j % Ns;
-        const float2 v0 = cur[(j << logT) + line];
-        float2 v1 = cur[((j + q) << logT) + line];
-        if (k) {
-          float2 w = __ldg(p.tw + k * tstep);
-          w.y *= sgn;
-          v1 = cmul(v1, w);
-        }
-        const int j0 = (j - k) * 2 + k;
-        nxt[(j0 << logT) + line] = make_float2(v0.x + v1.x, v0.y + v1.y);
-        nxt[((j0 + Ns) << logT) + line] = make_float2(v0.x - v1.x, v0.y - v1.y);
-      }
+      radix_stage<2>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
+    } else if (R == 3) {
+      radix_stage<3>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
+    } else if (R == 5) {
+      radix_stage<5>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
     } else {
-      // odd prime factor R: every thread forms one output as an R-term DFT sum; the stage twiddle and the DFT_R root
-      // share one table index, advanced by a constant step per term
-      const int q = n / R, span = Ns * R, tstep = n / span;
-      for (int idx = tid; idx < total; idx += FFT_THREADS) {
-        const int o = idx >> logT, line = idx & (T - 1);
-        const int blk = o / span, rem = o - blk * span;
-        const int t = rem / Ns, k = rem - t * Ns;
-        const int j = blk * Ns + k;
-        const int step = (k * tstep + t * q) % n;
-        float2 acc = cur[(j << logT) + line];
-        int ti = 0;
-        for (int r = 1; r < R; ++r) {
-          ti += step;
-          if (ti >= n) ti -= n;
-          float2 w = __ldg(p.tw + ti);
+      // Any other odd prime R (928 = 2^5 x 29): stage twiddles applied in place first, then the DFT_R of every j as
+      // output PAIRS (t, R - t): with a_r = v_r + v_{R-r}, b_r = v_r - v_{R-r} (r = 1 .. h = (R-1)/2)
+      //   out_t = v_0 + sum_r a_r cos(2 pi r t / R) -+ i sum_r b_r sin(2 pi r t / R),   out_{R-t} = its mirror,
+      // so each product is used for two outputs. cos / sin come from the staged table: W_R^x = tw[x * n / R].
+      const unsigned q = n / R, tstep = q / Ns, h = (R - 1) / 2, mag_ns = p.mag_ns[f];
+      for (unsigned idx = tid; idx < total; idx += FFT_THREADS) {
+        const unsigned i = idx >> logT;
+        const unsigned r = fast_div(i, p.mag_q[f]), j = i - r * q;
+        const unsigned k = pow2 ? (j & (Ns - 1)) : j - static_cast<unsigned>(fast_div(j, mag_ns)) * Ns;
+        if (r && k) {
+          float2 w = tw[r * k * tstep];
           w.y *= sgn;
-          const float2 v = cmul(cur[((j + r * q) << logT) + line], w);
-          acc.x += v.x;
-          acc.y += v.y;
+          cur[idx] = cmul(cur[idx], w);
         }
-        nxt[idx] = acc;
+      }
+      __syncthreads();
+      const unsigned items = q * (h + 1);
+      for (unsigned it = jbase; it < items; it += jstride) {
+        const unsigned t = fast_div(it, p.mag_q[f]), j = it - t * q;  // t = 0 .. h
+        const unsigned k = pow2 ? (j & (Ns - 1)) : j - static_cast<unsigned>(fast_div(j, mag_ns)) * Ns;
+        const unsigned j0 = (j - k) * R + k;
+        const float2 v0 = cur[(j << logT) + line];
+        float2 A = v0, B = make_float2(0.f, 0.f);
+        if (t == 0) {
+          for (unsigned r = 1; r < R; ++r) A = cadd(A, cur[((j + r * q) << logT) + line]);
+          nxt[(j0 << logT) + line] = A;
+        } else {
+          unsigned x = 0;  // r * t mod R
+          for (unsigned r = 1; r <= h; ++r) {
+            x += t;
+            if (x >= R) x -= R;
+            const float2 w = tw[x * q];  // (cos, -sin) of 2 pi x / R
+            const float2 u = cur[((j + r * q) << logT) + line], z = cur[((j + (R - r) * q) << logT) + line];
+            const float2 a = cadd(u, z), d = csub(u, z);
+            A.x += a.x * w.x;
+            A.y += a.y * w.x;
+            B.x += d.x * w.y;  // accumulates -sin * b
+            B.y += d.y * w.y;
+          }
+          // forward: out_t = A - i S, S = sum b sin = -B  ->  A + i B;  inverse: A - i B
+          const float2 iB = make_float2(-sgn * B.y, sgn * B.x);
+          nxt[((j0 + t * Ns) << logT) + line] = cadd(A, iB);
+          nxt[((j0 + (R - t) * Ns) << logT) + line] = csub(A, iB);
+        }
       }
     }
     __syncthreads();
@@ -184,34 +284,39 @@ fft_lines_kernel(const __grid_constant__ FftPass p) {
   }
 
   // ---- store: shift + crop in the index, band-pass, normalisation, real part / modulus
-  const int m = p.m;
-  const int stotal = T * m;
-  for (int idx = tid; idx < stotal; idx += FFT_THREADS) {
-    int qo, line;
+  const unsigned m = p.m;
+  const unsigned stotal = T * m;
+  const size_t out_base = p.rows_mode ? static_cast<size_t>(l0) * m : static_cast<size_t>(b) * m * p.lines + l0;
+  const size_t pitch = static_cast<size_t>(p.lines);
+#pragma unroll 2
+  for (unsigned idx = tid; idx < stotal; idx += FFT_THREADS) {
+    unsigned qo, ln;
     if (p.rows_mode) {
-      line = idx / m;
-      qo = idx - line * m;
+      ln = fast_div(idx, p.mag_m);
+      qo = idx - ln * m;
     } else {
       qo = idx >> logT;
-      line = idx & (T - 1);
+      ln = idx & (T - 1);
     }
-    if (line >= nl) continue;
-    int src = qo;
-    if (p.crop) {
-      src = p.start + (qo + m / 2) % m - n / 2;
-      src %= n;
-      if (src < 0) src += n;
+    if (ln >= nl) continue;
+    unsigned src = qo;
+    if (p.crop) {  // spectrum bin (start + (qo + m/2) mod m - n/2) mod n, without divisions
+      unsigned sh = qo + m / 2;
+      if (sh >= m) sh -= m;
+      int sb = static_cast<int>(p.start + sh) - static_cast<int>(n / 2);
+      if (sb < 0) sb += n;
+      src = static_cast<unsigned>(sb);
     }
-    float2 v = cur[(src << logT) + line];
+    float2 v = cur[(src << logT) + ln];
     float s = p.scale;
     if (p.filt) {
-      const long long col = l0 + line;  // = y * W + x
+      const long long col = l0 + ln;  // = y * W + x
       const int y = static_cast<int>(col / p.W), x = static_cast<int>(col - static_cast<long long>(y) * p.W);
       s *= bandpass_at(signed_freq(qo, p.D), signed_freq(y, p.H), signed_freq(x, p.W), p);
     }
     v.x *= s;
     v.y *= s;
-    const long long g = p.rows_mode ? (l0 + line) * m + qo : (static_cast<long long>(b) * m + qo) * p.lines + l0 + line;
+    const size_t g = out_base + (p.rows_mode ? static_cast<size_t>(idx) : qo * pitch + ln);
     if (p.out_mode == 0) static_cast<float2*>(p.out)[g] = v;
     else if (p.out_mode == 1) static_cast<float*>(p.out)[g] = v.x;
     else static_cast<float*>(p.out)[g] = __fsqrt_rn(v.x * v.x + v.y * v.y);
@@ -292,13 +397,27 @@ extern "C" int sb_fft_lines(const void* in, void* out, const void* tw, int n, in
     p.filt = 1;
     set_bandpass(p, D, H, W, bandpass);
   }
-  // lines per CTA: two ping-pong buffers of T * n complex values within ~192 KB of shared memory
-  const size_t budget = 192 * 1024;
+  auto magic = [](int d) -> unsigned { return d <= 1 ? 0u : static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(d) + 1ull); };
+  {
+    int Ns = 1;
+    for (int f = 0; f < p.nfac; ++f) {
+      p.mag_ns[f] = magic(Ns);
+      p.mag_q[f] = magic(n / p.fac[f]);
+      Ns *= p.fac[f];
+    }
+    p.mag_n = magic(n);
+    p.mag_m = magic(m);
+  }
+  // lines per CTA: two ping-pong buffers of T * n complex values. ~72 KB per CTA keeps three CTAs (48 warps) on an SM so
+  // the loads of one overlap the butterflies of another; at least 4 lines (32 B sectors on the strided axes) as long as
+  // they fit at all.
   int T = 32, logT = 5;
-  while (T > 1 && static_cast<size_t>(2) * T * n * sizeof(float2) > budget) { T >>= 1; --logT; }
+  auto bytes = [&](int t) { return (static_cast<size_t>(2) * t + 1) * n * sizeof(float2); };  // + the root table
+  while (T > 4 && bytes(T) > 74 * 1024) { T >>= 1; --logT; }
+  while (T > 1 && bytes(T) > 220 * 1024) { T >>= 1; --logT; }
   while (T > 1 && (T >> 1) >= lines) { T >>= 1; --logT; }
-  const size_t smem = static_cast<size_t>(2) * T * n * sizeof(float2);
-  SB_REQUIRE(smem <= 220 * 1024, "sb_fft_lines: lines of %d values do not fit in shared memory", n);
+  const size_t smem = bytes(T);
+  SB_REQUIRE(smem <= 220 * 1024 && T * n < 65536, "sb_fft_lines: lines of %d values do not fit in shared memory", n);
   p.T = T; p.logT = logT;
   if (g_fft_attr.need()) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

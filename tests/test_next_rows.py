@@ -220,7 +220,7 @@ def test_oracle_fourier_matches_reference_golden(golden_dir):
 def test_fft_lines_vs_numpy():
     from saber_b200 import ops
     rng = np.random.default_rng(3)
-    for shape in [(6, 20, 29), (3, 58, 12), (5, 7, 64), (4, 200, 45), (2, 9, 928)]:
+    for shape in [(6, 20, 29), (3, 58, 12), (5, 7, 64), (4, 200, 45), (2, 9, 928), (3, 77, 91), (2, 1, 960), (1, 13, 1)]:
         x = rng.normal(size=shape).astype(np.float32)
         t = torch.from_numpy(x).cuda()
         for axis in (0, 1, 2):

@@ -73,9 +73,21 @@ def refine_probe():
           f"{int(torch.unique(res['organelles']).numel()) - 1}")
 
 
+def fft_once():
+    """Four launches for an ncu capture: x rows (real in), y columns, z columns, x rows inverse (real out)."""
+    vol = synth.make_tomogram((200, 928, 960), seed=7, n_ellipsoids=30, device="cuda").contiguous()
+    spec = ops.fft_lines(vol, 2)
+    a = ops.fft_lines(spec, 1)
+    b = ops.fft_lines(spec, 0)
+    c = ops.fft_lines(spec, 2, inverse=True, out_mode="real")
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["fft", "refine"]
     if "fft" in what:
         fft_probe()
+    if "fftonce" in what:
+        fft_once()
     if "refine" in what:
         refine_probe()
