@@ -122,40 +122,60 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5], float sgn) {
 }
 
 // One Stockham stage of radix R: thread (line, j) loads its R inputs, applies the stage twiddles, runs the butterfly in
-// registers and scatters the outputs. `line` is fixed per thread, j strides by FFT_THREADS / T.
-template <int R>
+// registers and scatters the outputs. `line` is fixed per thread (folded into the base pointers), j strides by
+// FFT_THREADS / T. LOGT and "Ns is a power of two" are compile-time so that every shared-memory address is base + shift.
+template <int R, int LOGT, bool POW2>
 __device__ __forceinline__ void radix_stage(const float2* __restrict__ cur, float2* __restrict__ nxt,
                                             const float2* __restrict__ tw, unsigned n, unsigned Ns, unsigned mag_ns,
-                                            bool ns_pow2, int logT, unsigned line, unsigned jbase, unsigned jstride,
-                                            float sgn) {
+                                            unsigned jbase, float sgn) {
+  constexpr unsigned jstride = FFT_THREADS >> LOGT;
   const unsigned q = n / R, tstep = q / Ns;
+  if (Ns == 1) {  // first stage: no twiddles, outputs at j * R + r
+#pragma unroll 2
+    for (unsigned j = jbase; j < q; j += jstride) {
+      float2 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = cur[(j + r * q) << LOGT];
+      butterfly<R>(v, sgn);
+#pragma unroll
+      for (int r = 0; r < R; ++r) nxt[(j * R + r) << LOGT] = v[r];
+    }
+    return;
+  }
 #pragma unroll 2
   for (unsigned j = jbase; j < q; j += jstride) {
-    const unsigned k = ns_pow2 ? (j & (Ns - 1)) : j - static_cast<unsigned>(fast_div(j, mag_ns)) * Ns;
+    const unsigned k = POW2 ? (j & (Ns - 1)) : j - fast_div(j, mag_ns) * Ns;
     float2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = cur[((j + r * q) << logT) + line];
-    if (k) {
-      const unsigned kt = k * tstep;
+    for (int r = 0; r < R; ++r) v[r] = cur[(j + r * q) << LOGT];
+    const unsigned kt = k * tstep;  // tw[0] = 1: no branch for k == 0
 #pragma unroll
-      for (int r = 1; r < R; ++r) {
-        float2 w = tw[r * kt];
-        w.y *= sgn;
-        v[r] = cmul(v[r], w);
-      }
+    for (int r = 1; r < R; ++r) {
+      float2 w = tw[r * kt];
+      w.y *= sgn;
+      v[r] = cmul(v[r], w);
     }
     butterfly<R>(v, sgn);
     const unsigned j0 = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) nxt[((j0 + r * Ns) << logT) + line] = v[r];
+    for (int r = 0; r < R; ++r) nxt[(j0 + r * Ns) << LOGT] = v[r];
   }
 }
 
+template <int R, int LOGT>
+__device__ __forceinline__ void radix_stage_any(const float2* cur, float2* nxt, const float2* tw, unsigned n, unsigned Ns,
+                                                unsigned mag_ns, bool pow2, unsigned jbase, float sgn) {
+  if (pow2) radix_stage<R, LOGT, true>(cur, nxt, tw, n, Ns, mag_ns, jbase, sgn);
+  else radix_stage<R, LOGT, false>(cur, nxt, tw, n, Ns, mag_ns, jbase, sgn);
+}
+
+template <int LOGT>
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_lines_kernel(const __grid_constant__ FftPass p) {
   extern __shared__ float2 fft_smem[];
-  const unsigned n = p.n, T = p.T;
-  const int logT = p.logT;
+  constexpr unsigned T = 1u << LOGT;
+  constexpr int logT = LOGT;
+  const unsigned n = p.n;
   float2* cur = fft_smem;
   float2* nxt = fft_smem + static_cast<size_t>(T) * n;
   float2* tw = fft_smem + static_cast<size_t>(2) * T * n;  // the n roots of unity, staged once per CTA
@@ -222,13 +242,13 @@ fft_lines_kernel(const __grid_constant__ FftPass p) {
     const unsigned R = p.fac[f];
     const bool pow2 = (Ns & (Ns - 1)) == 0;
     if (R == 4) {
-      radix_stage<4>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
+      radix_stage<4, LOGT, true>(cur + line, nxt + line, tw, n, Ns, 0u, jbase, sgn);  // radix 4 / 2 come first: Ns = 2^x
     } else if (R == 2) {
-      radix_stage<2>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
+      radix_stage<2, LOGT, true>(cur + line, nxt + line, tw, n, Ns, 0u, jbase, sgn);
     } else if (R == 3) {
-      radix_stage<3>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
+      radix_stage_any<3, LOGT>(cur + line, nxt + line, tw, n, Ns, p.mag_ns[f], pow2, jbase, sgn);
     } else if (R == 5) {
-      radix_stage<5>(cur, nxt, tw, n, Ns, p.mag_ns[f], pow2, logT, line, jbase, jstride, sgn);
+      radix_stage_any<5, LOGT>(cur + line, nxt + line, tw, n, Ns, p.mag_ns[f], pow2, jbase, sgn);
     } else {
       // Any other odd prime R (928 = 2^5 x 29): stage twiddles applied in place first, then the DFT_R of every j as
       // output PAIRS (t, R - t): with a_r = v_r + v_{R-r}, b_r = v_r - v_{R-r} (r = 1 .. h = (R-1)/2)
@@ -420,12 +440,31 @@ extern "C" int sb_fft_lines(const void* in, void* out, const void* tw, int n, in
   SB_REQUIRE(smem <= 220 * 1024 && T * n < 65536, "sb_fft_lines: lines of %d values do not fit in shared memory", n);
   p.T = T; p.logT = logT;
   if (g_fft_attr.need()) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     g_fft_attr.mark();
   }
   const long long tiles = (lines + T - 1) / T * p.batch;
   SB_REQUIRE(tiles < (1ll << 31), "sb_fft_lines: too many line tiles");
-  fft_lines_kernel<<<static_cast<unsigned>(tiles), FFT_THREADS, smem, stream>>>(p);
+  const unsigned grid = static_cast<unsigned>(tiles);
+  switch (logT) {
+    case 0: fft_lines_kernel<0><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+    case 1: fft_lines_kernel<1><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+    case 2: fft_lines_kernel<2><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+    case 3: fft_lines_kernel<3><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+    case 4: fft_lines_kernel<4><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+    default: fft_lines_kernel<5><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+  }
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
