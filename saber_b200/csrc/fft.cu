@@ -169,8 +169,10 @@ __device__ __forceinline__ void radix_stage_any(const float2* cur, float2* nxt, 
   else radix_stage<R, LOGT, false>(cur, nxt, tw, n, Ns, mag_ns, jbase, sgn);
 }
 
-template <int LOGT>
-__global__ void __launch_bounds__(FFT_THREADS)
+// BIG: the length has a prime factor other than 2, 3, 5 (the general odd-prime stage needs more registers; lengths
+// without one get the leaner kernel and three resident CTAs per SM)
+template <int LOGT, bool BIG>
+__global__ void __launch_bounds__(FFT_THREADS, BIG ? 2 : 3)
 fft_lines_kernel(const __grid_constant__ FftPass p) {
   extern __shared__ float2 fft_smem[];
   constexpr unsigned T = 1u << LOGT;
@@ -249,7 +251,7 @@ fft_lines_kernel(const __grid_constant__ FftPass p) {
       radix_stage_any<3, LOGT>(cur + line, nxt + line, tw, n, Ns, p.mag_ns[f], pow2, jbase, sgn);
     } else if (R == 5) {
       radix_stage_any<5, LOGT>(cur + line, nxt + line, tw, n, Ns, p.mag_ns[f], pow2, jbase, sgn);
-    } else {
+    } else if (BIG) {
       // Any other odd prime R (928 = 2^5 x 29): stage twiddles applied in place first, then the DFT_R of every j as
       // output PAIRS (t, R - t): with a_r = v_r + v_{R-r}, b_r = v_r - v_{R-r} (r = 1 .. h = (R-1)/2)
       //   out_t = v_0 + sum_r a_r cos(2 pi r t / R) -+ i sum_r b_r sin(2 pi r t / R),   out_{R-t} = its mirror,
@@ -266,33 +268,53 @@ fft_lines_kernel(const __grid_constant__ FftPass p) {
         }
       }
       __syncthreads();
-      const unsigned items = q * (h + 1);
+      // t = 0: the plain sum
+      for (unsigned j = jbase; j < q; j += jstride) {
+        const unsigned k = pow2 ? (j & (Ns - 1)) : j - fast_div(j, mag_ns) * Ns;
+        float2 A = cur[(j << logT) + line];
+        for (unsigned r = 1; r < R; ++r) A = cadd(A, cur[((j + r * q) << logT) + line]);
+        nxt[(((j - k) * R + k) << logT) + line] = A;
+      }
+      // t = 1 .. h in groups of four output pairs per thread: the two loads and the sum / difference of a term are
+      // shared by the group, each pair adds one root lookup and four FMAs
+      constexpr unsigned G = 4;
+      const unsigned groups = (h + G - 1) / G, items = q * groups;
       for (unsigned it = jbase; it < items; it += jstride) {
-        const unsigned t = fast_div(it, p.mag_q[f]), j = it - t * q;  // t = 0 .. h
-        const unsigned k = pow2 ? (j & (Ns - 1)) : j - static_cast<unsigned>(fast_div(j, mag_ns)) * Ns;
+        const unsigned tg = fast_div(it, p.mag_q[f]), j = it - tg * q;
+        const unsigned k = pow2 ? (j & (Ns - 1)) : j - fast_div(j, mag_ns) * Ns;
         const unsigned j0 = (j - k) * R + k;
+        unsigned t[G], x[G];
+        float2 A[G], B[G];
         const float2 v0 = cur[(j << logT) + line];
-        float2 A = v0, B = make_float2(0.f, 0.f);
-        if (t == 0) {
-          for (unsigned r = 1; r < R; ++r) A = cadd(A, cur[((j + r * q) << logT) + line]);
-          nxt[(j0 << logT) + line] = A;
-        } else {
-          unsigned x = 0;  // r * t mod R
-          for (unsigned r = 1; r <= h; ++r) {
-            x += t;
-            if (x >= R) x -= R;
-            const float2 w = tw[x * q];  // (cos, -sin) of 2 pi x / R
-            const float2 u = cur[((j + r * q) << logT) + line], z = cur[((j + (R - r) * q) << logT) + line];
-            const float2 a = cadd(u, z), d = csub(u, z);
-            A.x += a.x * w.x;
-            A.y += a.y * w.x;
-            B.x += d.x * w.y;  // accumulates -sin * b
-            B.y += d.y * w.y;
+#pragma unroll
+        for (unsigned g = 0; g < G; ++g) {
+          t[g] = 1 + tg * G + g;
+          if (t[g] > h) t[g] = 0;  // padding lane of the last group: multiplies by tw[0] = 1, never stored
+          x[g] = 0;
+          A[g] = v0;
+          B[g] = make_float2(0.f, 0.f);
+        }
+        for (unsigned r = 1; r <= h; ++r) {
+          const float2 u = cur[((j + r * q) << logT) + line], z = cur[((j + (R - r) * q) << logT) + line];
+          const float2 a = cadd(u, z), d = csub(u, z);
+#pragma unroll
+          for (unsigned g = 0; g < G; ++g) {
+            x[g] += t[g];  // r * t mod R
+            if (x[g] >= R) x[g] -= R;
+            const float2 w = tw[x[g] * q];  // (cos, -sin) of 2 pi x / R
+            A[g].x += a.x * w.x;
+            A[g].y += a.y * w.x;
+            B[g].x += d.x * w.y;  // accumulates -sin * b
+            B[g].y += d.y * w.y;
           }
+        }
+#pragma unroll
+        for (unsigned g = 0; g < G; ++g) {
+          if (t[g] == 0) continue;
           // forward: out_t = A - i S, S = sum b sin = -B  ->  A + i B;  inverse: A - i B
-          const float2 iB = make_float2(-sgn * B.y, sgn * B.x);
-          nxt[((j0 + t * Ns) << logT) + line] = cadd(A, iB);
-          nxt[((j0 + (R - t) * Ns) << logT) + line] = csub(A, iB);
+          const float2 iB = make_float2(-sgn * B[g].y, sgn * B[g].x);
+          nxt[((j0 + t[g] * Ns) << logT) + line] = cadd(A[g], iB);
+          nxt[((j0 + (R - t[g]) * Ns) << logT) + line] = csub(A[g], iB);
         }
       }
     }
@@ -439,32 +461,38 @@ extern "C" int sb_fft_lines(const void* in, void* out, const void* tw, int n, in
   const size_t smem = bytes(T);
   SB_REQUIRE(smem <= 220 * 1024 && T * n < 65536, "sb_fft_lines: lines of %d values do not fit in shared memory", n);
   p.T = T; p.logT = logT;
+  bool big = false;
+  for (int f = 0; f < p.nfac; ++f) big = big || p.fac[f] > 5;
   if (g_fft_attr.need()) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SB_CHECK_CUDA(cudaFuncSetAttribute(fft_lines_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    auto prep = [](const void* fn) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      return e != cudaSuccess ? e : cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    };
+    const void* fns[] = {(const void*)fft_lines_kernel<0, false>, (const void*)fft_lines_kernel<1, false>,
+                         (const void*)fft_lines_kernel<2, false>, (const void*)fft_lines_kernel<3, false>,
+                         (const void*)fft_lines_kernel<4, false>, (const void*)fft_lines_kernel<5, false>,
+                         (const void*)fft_lines_kernel<0, true>,  (const void*)fft_lines_kernel<1, true>,
+                         (const void*)fft_lines_kernel<2, true>,  (const void*)fft_lines_kernel<3, true>,
+                         (const void*)fft_lines_kernel<4, true>,  (const void*)fft_lines_kernel<5, true>};
+    for (const void* fn : fns) SB_CHECK_CUDA(prep(fn));
     g_fft_attr.mark();
   }
   const long long tiles = (lines + T - 1) / T * p.batch;
   SB_REQUIRE(tiles < (1ll << 31), "sb_fft_lines: too many line tiles");
   const unsigned grid = static_cast<unsigned>(tiles);
+#define SB_FFT_LAUNCH(L)                                                                  \
+  case L:                                                                                 \
+    if (big) fft_lines_kernel<L, true><<<grid, FFT_THREADS, smem, stream>>>(p);           \
+    else fft_lines_kernel<L, false><<<grid, FFT_THREADS, smem, stream>>>(p);              \
+    break;
   switch (logT) {
-    case 0: fft_lines_kernel<0><<<grid, FFT_THREADS, smem, stream>>>(p); break;
-    case 1: fft_lines_kernel<1><<<grid, FFT_THREADS, smem, stream>>>(p); break;
-    case 2: fft_lines_kernel<2><<<grid, FFT_THREADS, smem, stream>>>(p); break;
-    case 3: fft_lines_kernel<3><<<grid, FFT_THREADS, smem, stream>>>(p); break;
-    case 4: fft_lines_kernel<4><<<grid, FFT_THREADS, smem, stream>>>(p); break;
-    default: fft_lines_kernel<5><<<grid, FFT_THREADS, smem, stream>>>(p); break;
+    SB_FFT_LAUNCH(0) SB_FFT_LAUNCH(1) SB_FFT_LAUNCH(2) SB_FFT_LAUNCH(3) SB_FFT_LAUNCH(4)
+    default:
+      if (big) fft_lines_kernel<5, true><<<grid, FFT_THREADS, smem, stream>>>(p);
+      else fft_lines_kernel<5, false><<<grid, FFT_THREADS, smem, stream>>>(p);
+      break;
   }
+#undef SB_FFT_LAUNCH
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
