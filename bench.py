@@ -648,7 +648,7 @@ def run_b200(args):
                               "source": tj["source"]}
         except Exception:
             traffic_detail = None
-        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": r["tflops"], "peak": peak,
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel + gemm2_bf16_tcgen05_kernel (single-CTA and CTA-pair tcgen05 GEMMs)", "achieved": r["tflops"], "peak": peak,
                     "unit": "TFLOP/s", "frac": r["tflops"] / peak, "traffic": traffic, "traffic_detail": traffic_detail,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                     "launches": r["launches"], "gemm_ms_per_step": r["ms"], "flops_per_step": r["flops"],
@@ -663,7 +663,7 @@ def run_b200(args):
             enc_tf = enc_gf * 1e9 * n_crops / (phases["encode"] * 1e-3) / 1e12
             roofline["encoder"] = {"crops_per_slice": n_crops, "gflop_per_crop": enc_gf, "ms_per_slice": phases["encode"],
                                    "achieved": enc_tf, "unit": "TFLOP/s", "frac": enc_tf / peak,
-                                   "note": "all encoder kernels (GEMMs on tcgen05, attention on mma.sync, LayerNorm, pooling)"}
+                                   "note": "all encoder kernels (GEMMs and the stage-3 window / global attention on tcgen05, the 8x8 / 4x4 / pooled windows on mma.sync, LayerNorm, pooling)"}
         roofline["not_counted"] = ("i2t_tc_kernel / t2i_tc_kernel (fused mask-decoder attention blocks on tcgen05) are not "
                                    "GEMM launches: HBM-bound, 4 MB resp. 2 MB of image stream per prompt; see DESIGN.md section 3")
 
