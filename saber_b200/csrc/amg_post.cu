@@ -43,7 +43,10 @@ struct MaskPostParams {
                            // outputs by `base` slots (lets one captured CUDA graph serve every crop / batch)
 };
 
-__global__ void __launch_bounds__(256)
+// 1024 threads: one warp per 32-column strip of a 1024-wide frame. The row walk of a warp is a serial chain of gathers,
+// so a candidate's time is (rows walked per warp) x (latency of one row): 8 warps per candidate left an SM with 8-16
+// resident warps and took 1.29 ms per 192 candidates; 32 warps quarter the chain (profiles/r02zzf, r02zzg).
+__global__ void __launch_bounds__(1024)
 mask_post_kernel(MaskPostParams p) {
   if (p.geom) {
     p.Hc = p.geom[0];
@@ -91,7 +94,8 @@ mask_post_kernel(MaskPostParams p) {
   // (bit-exact masks); the row-major version spent ~2 M warp instructions per up-sampled candidate.
   int inter = 0, uni = 0, area = 0;
   int minx = 1 << 30, maxx = -1, miny = 1 << 30, maxy = -1;  // crop-frame coordinates
-  for (int wx = warp; wx < p.WW; wx += 8) {
+  const int nwarps = blockDim.x >> 5;
+  for (int wx = warp; wx < p.WW; wx += nwarps) {
     const int x = wx * 32 + lane;
     const int cx = x - p.x0;
     const bool col_any = (wx * 32 + 31 >= p.x0) && (wx * 32 < p.x0 + p.Wc);  // warp-uniform
@@ -101,6 +105,7 @@ mask_post_kernel(MaskPostParams p) {
     if (in_x && !same) src_index(scale_w, cx, p.S, x0i, x1i, lx0, lx1);
     bool lane_any = false;  // this lane's column has a mask pixel
     uint32_t mine = 0;      // packed word of row (yb + lane) of the current 32-row group
+#pragma unroll 4
     for (int y = 0; y < p.H; ++y) {
       const int cy = y - p.y0;
       uint32_t word = 0;
@@ -108,13 +113,14 @@ mask_post_kernel(MaskPostParams p) {
         float val = -INFINITY;
         if (in_x) {
           if (same) {
-            val = plane[cy * p.S + cx];
+            val = __ldg(plane + cy * p.S + cx);
           } else {
             int y0i, y1i;
             float ly0, ly1;
             src_index(scale_h, cy, p.S, y0i, y1i, ly0, ly1);
-            const float v00 = plane[y0i * p.S + x0i], v01 = plane[y0i * p.S + x1i];
-            const float v10 = plane[y1i * p.S + x0i], v11 = plane[y1i * p.S + x1i];
+            // read-only path: lets the compiler hoist the gathers of the unrolled rows above the packed-word stores
+            const float v00 = __ldg(plane + y0i * p.S + x0i), v01 = __ldg(plane + y0i * p.S + x1i);
+            const float v10 = __ldg(plane + y1i * p.S + x0i), v11 = __ldg(plane + y1i * p.S + x1i);
             const float t0 = __fmaf_rn(v00, lx0, __fmul_rn(v01, lx1));
             const float t1 = __fmaf_rn(v10, lx0, __fmul_rn(v11, lx1));
             val = __fmaf_rn(t0, ly0, __fmul_rn(t1, ly1));
@@ -154,7 +160,7 @@ mask_post_kernel(MaskPostParams p) {
     miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o));
     maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
   }
-  __shared__ int s_red[8][7];
+  __shared__ int s_red[32][7];
   if (lane == 0) {
     s_red[warp][0] = inter;
     s_red[warp][1] = uni;
@@ -166,7 +172,7 @@ mask_post_kernel(MaskPostParams p) {
   }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < nwarps; ++w) {
       inter += s_red[w][0];
       uni += s_red[w][1];
       area += s_red[w][2];
@@ -463,7 +469,7 @@ extern "C" int sb_amg_mask_post(const float* planes, const float* ious4, const i
   p.area = area;
   p.bits = static_cast<uint32_t*>(bits);
   p.geom = geom_dev;
-  mask_post_kernel<<<n, 256, 0, stream>>>(p);
+  mask_post_kernel<<<n, 1024, 0, stream>>>(p);
   SB_CHECK_LAUNCH();
   return SB_OK;
 }

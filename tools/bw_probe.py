@@ -53,6 +53,20 @@ def main():
         report("mean_z 20 slices", 4 * 21 * 928 * 960, timeit(lambda: ops.mean_z(v, 22, 42), flush))
         img = v[0].contiguous()
         report("prepare_slice 928x960", 8 * img.numel(), timeit(lambda: ops.prepare_slice(img, 500, 3.0), flush))
+    if what in ("post", "all"):
+        # mask_post: 192 candidates of a full-frame 1024^2 crop and of a 683x683 second-layer crop, everything kept
+        n, S, H, W = 192, 256, 1024, 1024
+        planes = (torch.randn(n, 4, S, S, device=dev) * 4).contiguous()
+        ious4 = torch.rand(n, 4, device=dev).contiguous()
+        keep = torch.empty(n, dtype=torch.uint8, device=dev)
+        stab, iou = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        bbox = torch.empty(n, 4, dtype=torch.int32, device=dev)
+        area = torch.empty(n, dtype=torch.int32, device=dev)
+        bits = torch.empty(n, H, W // 32, dtype=torch.int32, device=dev)
+        for (hc, wc), (x0, y0) in (((1024, 1024), (0, 0)), ((683, 683), (341, 341))):
+            ms = timeit(lambda: ops.amg_mask_post(planes, ious4, None, 1, n, (hc, wc), (x0, y0), (H, W), 0.0, 0.0, 1.0, 0.0,
+                                                  keep, stab, iou, bbox, area, bits, 0), flush)
+            report(f"mask_post 192 candidates crop {hc}x{wc}", n * (S * S * 4 + H * W // 8), ms)
     if what in ("ccl", "all"):
         from saber_b200.segmenters import utils as sutils
         for shape in ((200, 1024, 1024), (64, 512, 512)):
