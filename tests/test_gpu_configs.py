@@ -511,3 +511,37 @@ def test_memory_attention_fp32_validation_mode():
     rel = ((got - want).norm() / want.norm()).item()
     worst = ((got - want).abs().max() / want.abs().max()).item()
     assert rel < 1e-4 and worst < 1e-4, (rel, worst)
+
+
+def test_slice_workers_give_the_serial_result():
+    """label_slices_device deals slices to concurrent workers (own generator / workspaces / graphs / stream, one shared model):
+    same labels as the serial loop, also after the thresholds of the generator were changed in place (mirrored, graphs
+    re-captured) and for an odd number of slices."""
+    from saber_b200 import synth
+    from saber_b200.adapters.base import SAM2AdapterConfig, cfgAMG
+    from saber_b200.segmenters.propagation import propagationSegmenter
+    amg = cfgAMG(sam2_cfg="tiny", points_per_side=8, crop_n_layers=1, pred_iou_thresh=0.3, stability_score_thresh=0.0)
+    seg = propagationSegmenter(deviceID=0, cfg=SAM2AdapterConfig(cfg="tiny", amg_cfg=amg, min_mask_area=50, allow_random_init=True),
+                               min_mask_area=50)
+    assert seg.slice_workers == 2
+    vol = synth.make_tomogram((5, 200, 256), seed=31, n_ellipsoids=6, device="cuda").contiguous()
+    lab2 = torch.empty(vol.shape, dtype=torch.int16, device="cuda")
+    lab1 = torch.empty_like(lab2)
+    for _ in range(2):  # second pass: every worker replays its captured graphs
+        counts2 = seg.label_slices_device(vol, lab2)
+        torch.cuda.synchronize()
+    assert len(seg._peers) == 2 and seg._peers[1].adapter._amg().base_generator.predictor.model is \
+        seg.adapter._amg().base_generator.predictor.model
+    seg.slice_workers = 1
+    counts1 = seg.label_slices_device(vol, lab1)
+    assert counts1 == counts2 and sum(counts1) > 0
+    assert torch.equal(lab1, lab2)
+    gen = seg.adapter._amg().base_generator
+    gen.pred_iou_thresh = 0.45
+    gen._graphs.clear()
+    counts1 = seg.label_slices_device(vol, lab1)
+    seg.slice_workers = 2
+    counts2 = seg.label_slices_device(vol, lab2)
+    assert seg._peers[1].adapter._amg().base_generator.pred_iou_thresh == 0.45
+    assert counts1 == counts2 and torch.equal(lab1, lab2)
+    assert torch.equal(seg.slice_by_slice_device(vol[:3].contiguous()), seg._peers[1].slice_by_slice_device(vol[:3].contiguous()))
