@@ -1542,6 +1542,12 @@ int ensure_sms() {
     int dev = 0;
     SB_CHECK_CUDA(cudaGetDevice(&dev));
     SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // SB_GEMM_SMS: SMs the persistent GEMM kernels may occupy. With concurrent slice workers (one slice encoding while
+    // another decodes) the SMs left over keep running the other worker's non-persistent, HBM-bound decoder kernels.
+    if (const char* e = getenv("SB_GEMM_SMS")) {
+      const int lim = atoi(e);
+      if (lim >= 2 && lim < g_num_sms) g_num_sms = lim & ~1;
+    }
   }
   return SB_OK;
 }

@@ -533,6 +533,10 @@ int ha_run(const void* qkv, void* out, int batch, int H, int W, int heads, int w
     int dev = 0;
     SB_CHECK_CUDA(cudaGetDevice(&dev));
     SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_ha_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* e = getenv("SB_GEMM_SMS")) {  // same SM budget as the persistent GEMMs (see gemm_tcgen05.cu)
+      const int lim = atoi(e);
+      if (lim >= 2 && lim < g_ha_sms) g_ha_sms = lim;
+    }
   }
   const int grid = p.nitems < g_ha_sms ? p.nitems : g_ha_sms;
   if (prof) return ha_launch<true>(tm, p, grid, stream);
