@@ -626,6 +626,8 @@ def run_b200(args):
     if not args.no_roofline and rank == 0:
         gen = seg.adapter._amg().base_generator
         workers_was, seg.slice_workers = seg.slice_workers, 1  # instrumented steps run the slices one after the other
+        step_serial(args.warmup + args.steps)  # un-instrumented pass first: the serial path runs on the caller's stream, whose
+        torch.cuda.synchronize()               # allocator pool may not yet hold the encoder's transient buffers (cudaMalloc)
         gen.phase_ms = {}
         step_serial(args.warmup + args.steps)  # one more normal (graph-replay) step with phase events
         torch.cuda.synchronize()
