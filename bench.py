@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cfg", default="large")
-    ap.add_argument("--slices-per-step", type=int, default=2,
+    ap.add_argument("--slices-per-step", type=int, default=3,
                     help="slices per step; with 2 or more the slice workers overlap one slice's encoder with another's decoder")
     ap.add_argument("--thresholds", default="default", choices=["default", "open"],
                     help="'open' lowers pred_iou/stability thresholds so random-init weights exercise NMS/CC stages")

@@ -29,7 +29,7 @@ class propagationSegmenter(saber3D):
         super().__init__(deviceID=deviceID, cfg=cfg, amg_cfg=amg_cfg, min_mask_area=min_mask_area)
         self.ini_depth = 10
         # concurrent slice workers of label_slices_device (1 = the plain serial loop)
-        self.slice_workers = max(1, int(os.environ.get("SB_SLICE_WORKERS", "2")))
+        self.slice_workers = max(1, int(os.environ.get("SB_SLICE_WORKERS", "3")))
         self._peers, self._peer_streams, self._pool = [self], [torch.cuda.Stream(device=self.device)], None
 
     # ------------------------------------------------------------------
@@ -39,10 +39,10 @@ class propagationSegmenter(saber3D):
         (the body of the reference loop, REF :177-187). Returns the number of masks kept per slice.
 
         Slices are independent, and the two halves of a slice load different units: the encoder is tensor-bound, the
-        decoder streams per-prompt image features (HBM-bound). With ``slice_workers`` > 1 (default 2, ``SB_SLICE_WORKERS``)
+        decoder streams per-prompt image features (HBM-bound). With ``slice_workers`` > 1 (default 3, ``SB_SLICE_WORKERS``)
         the slices are dealt round-robin to that many worker threads, each with its own segmenter instance (own
         workspaces and CUDA graphs, same weights) on its own stream, so one slice's encoder overlaps another's decoder:
-        6.2 vs 5.8 slices/s on hiera-L at 1024^2 (profiles/r02zzj). Results are identical to the serial loop."""
+        5.8 (serial) -> 6.14 (two workers) -> 6.26 (three) slices/s on hiera-L at 1024^2 (profiles/r02zzj, r02zzr). Results are identical to the serial loop."""
         z1 = volume.shape[0] if z1 is None else z1
         nw = min(self.slice_workers, z1 - z0)
         if nw > 1 and self.classifier is None:

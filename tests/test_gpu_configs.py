@@ -523,7 +523,8 @@ def test_slice_workers_give_the_serial_result():
     amg = cfgAMG(sam2_cfg="tiny", points_per_side=8, crop_n_layers=1, pred_iou_thresh=0.3, stability_score_thresh=0.0)
     seg = propagationSegmenter(deviceID=0, cfg=SAM2AdapterConfig(cfg="tiny", amg_cfg=amg, min_mask_area=50, allow_random_init=True),
                                min_mask_area=50)
-    assert seg.slice_workers == 2
+    assert seg.slice_workers == 3
+    seg.slice_workers = 2
     vol = synth.make_tomogram((5, 200, 256), seed=31, n_ellipsoids=6, device="cuda").contiguous()
     lab2 = torch.empty(vol.shape, dtype=torch.int16, device="cuda")
     lab1 = torch.empty_like(lab2)
