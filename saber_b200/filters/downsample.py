@@ -116,6 +116,21 @@ class FourierRescale2D:
         return ops.fft_lines(spec, 1, inverse=True, out_mode="abs", scale=1.0 / (float(nh) * nw))
 
     @staticmethod
+    def rescale_stack_device(stack: torch.Tensor, scale_factor: float) -> torch.Tensor:
+        """float32 [Z,h,w] on the device -> [Z,h',w']: every slice rescaled as `rescale_device` does, in four launches for
+        the whole stack (the reference loops `FourierRescale2D.run` over the slices of a movie / FIB stack, REF
+        saber/utils/io.py:37-39). The line passes treat the leading axis as a batch."""
+        Z, h, w = stack.shape
+        sh, nh = _crop_window(h, int(h / scale_factor))
+        sw, nw = _crop_window(w, int(w / scale_factor))
+        if min(nh, nw) <= 0:
+            raise ValueError("the scale factor leaves an empty image")
+        spec = ops.fft_lines(stack, 2, crop=(sw, nw))
+        spec = ops.fft_lines(spec, 1, crop=(sh, nh))
+        spec = ops.fft_lines(spec, 1, inverse=True)
+        return ops.fft_lines(spec, 2, inverse=True, out_mode="abs", scale=1.0 / (float(nh) * nw))
+
+    @staticmethod
     def _rescale(image, scale_factor: float, device=None):
         """REF downsample.py:153-204."""
         is_numpy = isinstance(image, np.ndarray)

@@ -258,6 +258,10 @@ def test_fourier_rescale_matches_reference_golden(golden_dir):
     with pytest.raises(ValueError):
         FourierRescale2D.run(np.zeros((8, 8), np.float32), 0.5)
     _close(FourierRescale2D.run_resolution(synth.make_tomogram((1, 96, 116), seed=54, n_ellipsoids=3).numpy()[0], 1.5, 3.0), g["r2a"])
+    stack = synth.make_tomogram((5, 75, 128), seed=61, n_ellipsoids=6, device="cuda").contiguous()
+    got = FourierRescale2D.rescale_stack_device(stack, 3.3)
+    for z in range(5):
+        assert torch.equal(got[z], FourierRescale2D.rescale_device(stack[z].contiguous(), 3.3))
 
 
 @pytest.mark.gpu
@@ -427,3 +431,40 @@ def test_segment_micrograph_core_rescales_and_writes(tmp_path, monkeypatch):
     assert _read_zarr_v2(os.path.join(g, "labels", "0")).shape == (1, 48, 58)
     scale = json.load(open(os.path.join(g, ".zattrs")))["multiscales"][0]["datasets"][0]["coordinateTransformations"][0]["scale"]
     assert scale == [pytest.approx(0.2), pytest.approx(0.2)]
+
+
+@pytest.mark.gpu
+def test_prep2d_chain_loader_rescale_segment_store(tmp_path, monkeypatch, capsys):
+    """The prep2d worker end to end on the real pieces: GPUPool loader (`base_microsegmenter`) -> `cryoMicroSegmenter` ->
+    Fourier-crop down-sampling -> AMG -> candidate stack -> zarr group (REF micro_prep.py:104-133, inference_core.py:97-153)."""
+    import json
+    from saber_b200 import synth
+    from saber_b200.adapters.base import cfgAMG
+    from saber_b200.entry_points.inference_core import segment_micrograph_core
+    from saber_b200.filters.downsample import FourierRescale2D
+    from saber_b200.segmenters.loaders import base_microsegmenter
+    from saber_b200.utils import zarr_writer
+    monkeypatch.setattr(zarr_writer, "_zarr_writer", None)
+    models = base_microsegmenter(0, cfgAMG(sam2_cfg="tiny", npoints=8, crop_n_layers=0, pred_iou_thresh=0.3,
+                                           stability_score_thresh=0.0))
+    seg = models["segmenter"]
+    assert type(seg).__name__ == "cryoMicroSegmenter" and seg.max_pixels == 1280
+    img = synth.make_tomogram((1, 400, 512), seed=63, n_ellipsoids=8).numpy()[0]
+    out = str(tmp_path / "prep2d.zarr")
+    segment_micrograph_core("/data/grid_03.tif", out, 2.0, None, False, False, 0, models, read_micrograph=lambda f: (img, None))
+    small = FourierRescale2D.run(img, 2.0)
+    assert small.shape == (200, 256)
+    g = os.path.join(out, "grid_03")
+    stored = _read_zarr_v2(os.path.join(g, "0"))
+    assert stored.shape[:2] == (200, 256)
+    masks = _read_zarr_v2(os.path.join(g, "labels", "0"))
+    assert masks.ndim == 3 and masks.shape[1:] == (200, 256) and masks.shape[0] == len(seg.masks) > 0
+    for j in range(masks.shape[0]):  # labelled stack: plane j holds value j + 1 on its mask
+        np.testing.assert_array_equal(masks[j] > 0, np.asarray(seg.masks[j]["segmentation"], bool))
+        assert set(np.unique(masks[j])) <= {0, j + 1}
+    scale = json.load(open(os.path.join(g, ".zattrs")))["multiscales"][0]["datasets"][0]["coordinateTransformations"][0]["scale"]
+    assert scale == [1, 1]  # no pixel size in a tiff: REF :135-138 falls back to 1
+    assert json.load(open(os.path.join(out, ".zattrs")))["amg"]["npoints"] == 8
+    big = np.random.default_rng(0).normal(size=(1300, 64)).astype(np.float32)
+    seg.segment(big, display=False)
+    assert "Consider Downsampling" in capsys.readouterr().out
