@@ -468,3 +468,61 @@ def test_prep2d_chain_loader_rescale_segment_store(tmp_path, monkeypatch, capsys
     big = np.random.default_rng(0).normal(size=(1300, 64)).astype(np.float32)
     seg.segment(big, display=False)
     assert "Consider Downsampling" in capsys.readouterr().out
+
+
+@pytest.mark.gpu
+def test_gpupool_contract(tmp_path, monkeypatch):
+    """GPUPool (REF saber/utils/parallelization.py): task i -> GPU i % n, models from init_fn once per GPU, result dicts
+    sorted by task id, failures reported not raised; then the pool drives the prep3d worker as `prep3d` does
+    (REF tomo_prep.py:150-170: init_fn = base_tomosegmenter-like loader, func = extract_sam2_candidates)."""
+    import json
+    from saber_b200.classifier.preprocess import tomo_prep
+    from saber_b200.utils import zarr_writer
+    from saber_b200.utils.parallelization import GPUPool, gpu_map
+    n = torch.cuda.device_count()
+    loads = []
+
+    def init(gpu_id, tag, scale=1):
+        loads.append(gpu_id)
+        return {"tag": tag, "scale": scale, "dev": gpu_id}
+
+    def work(x, y=0, gpu_id=None, models=None):
+        if x == 3:
+            raise ValueError("boom")
+        assert torch.cuda.current_device() == gpu_id == models["dev"]
+        return float((torch.full((4,), float(x), device="cuda") * models["scale"]).sum()) + y
+
+    pool = GPUPool(init_fn=init, init_args=("t",), init_kwargs={"scale": 2}, verbose=False)
+    res = pool.execute(work, [0, (1,), ((2,), {"y": 5}), 3, {"x": 4, "y": 1}], task_ids=[10, 11, 12, 13, 14])
+    assert loads == list(range(n)) and [r["task_id"] for r in res] == [10, 11, 12, 13, 14]
+    assert [r["gpu_id"] for r in res] == [i % n for i in range(5)]
+    assert [r["success"] for r in res] == [True, True, True, False, True] and res[3]["error"] == "boom"
+    assert [r["result"] for r in res if r["success"]] == [0.0, 8.0, 21.0, 33.0]
+    assert pool.execute(work, []) == []
+    pool.shutdown()
+    with pytest.raises(ValueError):
+        GPUPool(approach="multiprocessing")
+    assert [r["result"] for r in gpu_map(lambda v, gpu_id=None: v * 2, [1, 2, 3], verbose=False)] == [2, 4, 6]
+
+    # the prep3d wiring with a stand-in slab segmenter
+    monkeypatch.setattr(zarr_writer, "_zarr_writer", None)
+    out = str(tmp_path / "prep3d.zarr")
+    vol = np.random.default_rng(1).normal(size=(20, 24, 28)).astype(np.float32)
+
+    class Reader:
+        @staticmethod
+        def tomogram(run, voxel_size, algorithm):
+            return vol
+
+    class Run:
+        def __init__(self, name):
+            self.name = name
+
+    runs = [Run(f"TS_{i:02d}") for i in range(5)]
+    with GPUPool(init_fn=lambda g: {"segmenter": _SlabSegmenter()}, verbose=False) as p3:
+        res = p3.execute(tomo_prep.extract_sam2_candidates,
+                         [((r, out, 10.0, "wbp", 4, 1), {"reader": Reader}) for r in runs], task_ids=[r.name for r in runs])
+    assert all(r["success"] for r in res), [r.get("error") for r in res]
+    zarr_writer.get_zarr_writer(out).finalize()
+    assert json.load(open(os.path.join(out, ".zattrs")))["total_runs"] == 5
+    assert sorted(d for d in os.listdir(out) if not d.startswith(".")) == [r.name for r in runs]
