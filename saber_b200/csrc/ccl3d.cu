@@ -62,10 +62,12 @@ __device__ __forceinline__ void uf_unite(int* P, int a, int b) {
 // run head, and the merge pass only has to link run heads to the left (at segment boundaries).
 template <typename T>
 __global__ void __launch_bounds__(256)
-ccl_init_kernel(const T* __restrict__ vol, int* __restrict__ P, int* __restrict__ aux, long long n, int X) {
+ccl_init_kernel(const T* __restrict__ vol, int* __restrict__ P, int* __restrict__ aux, long long n, int X,
+                int* __restrict__ chunk_flag) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long n_round = ((n + 31) / 32) * 32;
   const int lane = threadIdx.x & 31;
+#pragma unroll 4
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
     const bool in = i < n;
     const bool fg = in && vol[i] != 0;
@@ -77,8 +79,11 @@ ccl_init_kernel(const T* __restrict__ vol, int* __restrict__ P, int* __restrict_
     const int first = stop ? 32 - __clz(stop) : 0;  // first lane of this lane's run
     if (in) {
       P[i] = fg ? static_cast<int>(i - lane + first) : -1;
-      aux[i] = 0;
+      // sizes / ids live at roots only, and a root is always the head of its run: nothing else of aux is ever read
+      if (fg && first == lane) aux[i] = 0;
     }
+    // 2048-voxel chunks without foreground are skipped by the counting / ranking passes (a warp's 32 voxels lie in one chunk)
+    if (m != 0u && lane == 0) chunk_flag[i / CHUNK] = 1;
   }
 }
 
@@ -170,11 +175,26 @@ ccl_flatten_count_kernel(int* __restrict__ P, int* __restrict__ aux, long long n
 __global__ void __launch_bounds__(256)
 ccl_chunk_count_kernel(const int* __restrict__ P, const int* __restrict__ aux, long long n, int min_vol,
                        int* __restrict__ chunk_cnt) {
+  if (chunk_cnt[blockIdx.x] == 0) return;  // no foreground in this chunk (flag written by the init pass): count stays 0
   const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
   int c = 0;
-  for (int k = threadIdx.x; k < CHUNK; k += 256) {
-    const long long v = base + k;
-    if (v < n && P[v] == static_cast<int>(v) && aux[v] >= min_vol) ++c;
+  if (base + CHUNK <= n && (reinterpret_cast<uintptr_t>(P) & 15) == 0) {  // whole chunk: 8 parents per thread, two 128-bit loads
+    const int4* p4 = reinterpret_cast<const int4*>(P + base);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = (h * 256 + threadIdx.x) * 4;
+      const int4 q = p4[h * 256 + threadIdx.x];
+      const int v0 = static_cast<int>(base) + k;
+      if (q.x == v0 && aux[v0] >= min_vol) ++c;
+      if (q.y == v0 + 1 && aux[v0 + 1] >= min_vol) ++c;
+      if (q.z == v0 + 2 && aux[v0 + 2] >= min_vol) ++c;
+      if (q.w == v0 + 3 && aux[v0 + 3] >= min_vol) ++c;
+    }
+  } else {
+    for (int k = threadIdx.x; k < CHUNK; k += 256) {
+      const long long v = base + k;
+      if (v < n && P[v] == static_cast<int>(v) && aux[v] >= min_vol) ++c;
+    }
   }
   __shared__ int s[8];
 #pragma unroll
@@ -217,10 +237,12 @@ ccl_scan_kernel(int* __restrict__ chunk_cnt, int nchunks, int* __restrict__ tota
   if (threadIdx.x == 0) *total_out = running;
 }
 
-// aux[root] <- compact id (1-based) for surviving roots, 0 for dropped ones
+// aux[root] <- -(compact id) (1-based) for surviving roots; dropped roots keep their (positive) size, so only chunks that
+// hold a surviving root are touched at all (chunk_off[c + 1] == chunk_off[c] otherwise; chunk_off[nchunks] = total)
 __global__ void __launch_bounds__(256)
 ccl_assign_kernel(const int* __restrict__ P, int* __restrict__ aux, long long n, int min_vol,
                   const int* __restrict__ chunk_off, int* __restrict__ sizes_out) {
+  if (chunk_off[blockIdx.x + 1] == chunk_off[blockIdx.x]) return;
   const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
   __shared__ int warp_tot[8];
   __shared__ int running;
@@ -236,10 +258,10 @@ ccl_assign_kernel(const int* __restrict__ P, int* __restrict__ aux, long long n,
     __syncthreads();
     int off = running;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    if (is_root) {
-      const int id = keep ? off + __popc(bal & ((1u << lane) - 1u)) + 1 : 0;
-      if (keep && sizes_out) sizes_out[id - 1] = aux[v];  // voxel count of component `id`
-      aux[v] = id;
+    if (keep) {
+      const int id = off + __popc(bal & ((1u << lane) - 1u)) + 1;
+      if (sizes_out) sizes_out[id - 1] = aux[v];  // voxel count of component `id`
+      aux[v] = -id;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -253,10 +275,16 @@ ccl_assign_kernel(const int* __restrict__ P, int* __restrict__ aux, long long n,
 
 __global__ void __launch_bounds__(256)
 ccl_relabel_kernel(int* __restrict__ P, const int* __restrict__ aux, long long n) {
+#pragma unroll 4
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = P[i];
-    P[i] = r >= 0 ? aux[r] : 0;
+    int lab = 0;
+    if (r >= 0) {
+      const int a = aux[r];  // -(id) for a surviving root, the (positive) size of a dropped one
+      if (a < 0) lab = -a;
+    }
+    P[i] = lab;
   }
 }
 
@@ -294,12 +322,14 @@ static int ccl3d_run(const void* vol, int elem_bytes, int Z, int Y, int X, int m
   long long g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   const int grid = static_cast<int>(g);
+  const int nchunks_ = static_cast<int>((n + CHUNK - 1) / CHUNK);
+  SB_CHECK_CUDA(cudaMemsetAsync(chunk_ws, 0, sizeof(int) * (static_cast<size_t>(nchunks_) + 1), stream));
   if (elem_bytes == 1)
-    ccl_init_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char*>(vol), P, aux, n, X);
+    ccl_init_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char*>(vol), P, aux, n, X, chunk_ws);
   else if (elem_bytes == 2)
-    ccl_init_kernel<unsigned short><<<grid, 256, 0, stream>>>(static_cast<const unsigned short*>(vol), P, aux, n, X);
+    ccl_init_kernel<unsigned short><<<grid, 256, 0, stream>>>(static_cast<const unsigned short*>(vol), P, aux, n, X, chunk_ws);
   else
-    ccl_init_kernel<unsigned int><<<grid, 256, 0, stream>>>(static_cast<const unsigned int*>(vol), P, aux, n, X);
+    ccl_init_kernel<unsigned int><<<grid, 256, 0, stream>>>(static_cast<const unsigned int*>(vol), P, aux, n, X, chunk_ws);
   SB_CHECK_LAUNCH();
   // The merge pass runs slab by slab (about 32 MB of parents per launch): within one launch the CTAs drift apart (a CTA
   // full of foreground is much slower than one of background), and over the whole volume that drift made every neighbour
