@@ -9,6 +9,7 @@
 // neighbours (atomicMin hooking) | flatten | warp-aggregated component sizes | chunked prefix count of
 // surviving roots -> new ids | relabel in place. Algorithmic bytes: 2 B read + 4 B written per voxel.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -103,25 +104,22 @@ ccl_merge_kernel(int* __restrict__ P, int Z, int Y, int X, long long i0, long lo
   for (long long i = i0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < i1;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     if (P[i] < 0) continue;
-    const int x = static_cast<int>(i % X);
-    const int y = static_cast<int>((i / X) % Y);
-    const int z = static_cast<int>(i / plane);
+    const unsigned ui = static_cast<unsigned>(i), row_id = ui / static_cast<unsigned>(X);  // n < 2^31: 32-bit divisions
+    const int x = static_cast<int>(ui - row_id * static_cast<unsigned>(X));
+    const int z = static_cast<int>(row_id / static_cast<unsigned>(Y));
+    const int y = static_cast<int>(row_id - static_cast<unsigned>(z) * static_cast<unsigned>(Y));
     const int v = static_cast<int>(i);
     const bool left = x > 0 && P[i - 1] >= 0;
     // a run head with a foreground voxel to its left exists only at a 32-voxel segment boundary (decided from the
     // geometry: P[v] itself may already have been lowered by another thread's union)
     if (left && (i & 31) == 0) uf_unite(P, v, v - 1);
     auto row = [&](long long r) {  // r = linear index of the cell above / behind v (dx = 0) in a preceding row
-      const bool c = P[r] >= 0;
-      const bool rgt = x + 1 < X && P[r + 1] >= 0;
-      if (left) {
-        if (!c && rgt) uf_unite(P, v, static_cast<int>(r + 1));
-      } else if (c) {
-        uf_unite(P, v, static_cast<int>(r));
-      } else {
-        if (x > 0 && P[r - 1] >= 0) uf_unite(P, v, static_cast<int>(r - 1));
-        if (rgt) uf_unite(P, v, static_cast<int>(r + 1));
+      if (P[r] >= 0) {  // centre set: the only union that can be needed (none inside a run), and no other cell is read
+        if (!left) uf_unite(P, v, static_cast<int>(r));
+        return;
       }
+      if (!left && x > 0 && P[r - 1] >= 0) uf_unite(P, v, static_cast<int>(r - 1));
+      if (x + 1 < X && P[r + 1] >= 0) uf_unite(P, v, static_cast<int>(r + 1));
     };
     if (y > 0) row(i - X);
     if (z > 0) {
@@ -335,7 +333,8 @@ static int ccl3d_run(const void* vol, int elem_bytes, int Z, int Y, int X, int m
   // full of foreground is much slower than one of background), and over the whole volume that drift made every neighbour
   // read a DRAM miss (10 GB read for a 0.84 GB parent array, profiles/r02zzb). A slab and the plane before it stay in L2.
   {
-    const long long slab = 8ll << 20;
+    static const long long slab_mi = [] { const char* e = getenv("SB_CCL_SLAB"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    const long long slab = slab_mi << 20;  // SB_CCL_SLAB: Mi voxels per merge launch (measurement switch)
     for (long long i0 = 0; i0 < n; i0 += slab) {
       const long long i1 = i0 + slab < n ? i0 + slab : n;
       long long gl = (i1 - i0 + 255) / 256;
