@@ -526,3 +526,26 @@ def test_gpupool_contract(tmp_path, monkeypatch):
     zarr_writer.get_zarr_writer(out).finalize()
     assert json.load(open(os.path.join(out, ".zattrs")))["total_runs"] == 5
     assert sorted(d for d in os.listdir(out) if not d.startswith(".")) == [r.name for r in runs]
+
+
+def test_host_helpers_of_the_next_rows():
+    """Pure host logic (no GPU): GPUPool task forms (REF parallelization.py:143-151), the Fourier crop window
+    (REF downsample.py:117-127, 183-191) and the band-pass parameter packing (REF tomograms.py:44-52)."""
+    from saber_b200.filters.downsample import _crop_window
+    from saber_b200.utils.parallelization import _split_task
+    assert _split_task({"a": 1}) == ((), {"a": 1})
+    assert _split_task(((1, 2), {"k": 3})) == ((1, 2), {"k": 3})
+    assert _split_task([1, 2, 3]) == ((1, 2, 3), {})
+    assert _split_task((7,)) == ((7,), {})
+    assert _split_task("run") == (("run",), {})
+    for n in (64, 65, 200, 928, 929):
+        for m in (n, n - 1, n // 2, n // 2 + 1, 3, 2):
+            start, length = _crop_window(n, m)
+            assert length == m - (m % 2) and start == (n - length) // 2 + (n % 2)
+            assert 0 <= start and start + length <= n, (n, m)
+            # the kept band is centred on the zero frequency of the fftshift-ed axis (index n // 2)
+            assert start <= n // 2 < start + length or length == 0
+    import types
+    f = types.SimpleNamespace(lp_pix=12.5, lpd_pix=4, hp_pix=0, hpd_pix=0)
+    from saber_b200.filters.tomograms import Filter3D
+    assert Filter3D._bandpass(f) == [12.5, 10.5, 14.5, 4.0, 0.0, 0.0, 0.0, 0.0]
