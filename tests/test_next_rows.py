@@ -549,3 +549,72 @@ def test_host_helpers_of_the_next_rows():
     f = types.SimpleNamespace(lp_pix=12.5, lpd_pix=4, hp_pix=0, hpd_pix=0)
     from saber_b200.filters.tomograms import Filter3D
     assert Filter3D._bandpass(f) == [12.5, 10.5, 14.5, 4.0, 0.0, 0.0, 0.0, 0.0]
+
+
+def _stockham_sim(x, inverse=False):
+    """Scalar model of csrc/fft.cu's stage arithmetic (same index expressions, same root-table look-ups): radix-4 / 2 first,
+    radix-3 / 5 butterflies, and for any other odd prime R the pre-twiddle pass + output PAIRS (t, R - t) built from
+    a_r = v_r + v_{R-r}, b_r = v_r - v_{R-r}. Documents the kernel; checked against numpy's FFT below."""
+    n = len(x)
+    fac, m = [], n
+    while m % 4 == 0:
+        fac.append(4); m //= 4
+    while m % 2 == 0:
+        fac.append(2); m //= 2
+    p = 3
+    while m > 1:
+        while m % p == 0:
+            fac.append(p); m //= p
+        p += 2
+    tw = np.exp(-2j * np.pi * np.arange(n) / n)
+    sgn = -1.0 if inverse else 1.0
+    root = lambda idx: complex(tw[idx].real, tw[idx].imag * sgn)
+    cur, Ns = np.asarray(x, complex).copy(), 1
+    for R in fac:
+        q, tstep = n // R, n // R // Ns
+        nxt = np.zeros(n, complex)
+        if R in (2, 3, 4, 5):
+            W = np.exp(-2j * np.pi * sgn * np.outer(np.arange(R), np.arange(R)) / R)  # the register butterfly
+            for j in range(q):
+                k = j % Ns
+                v = np.array([cur[j + r * q] * root(r * k * tstep) for r in range(R)])
+                j0 = (j - k) * R + k
+                nxt[j0 + np.arange(R) * Ns] = W @ v
+        else:
+            h = (R - 1) // 2
+            for i in range(n):  # stage twiddles in place
+                r, j = divmod(i, q)
+                k = j % Ns
+                if r and k:
+                    cur[i] *= root(r * k * tstep)
+            for j in range(q):
+                k = j % Ns
+                j0 = (j - k) * R + k
+                nxt[j0] = sum(cur[j + r * q] for r in range(R))
+                for t in range(1, h + 1):
+                    A, B, xi = cur[j], 0j, 0
+                    for r in range(1, h + 1):
+                        xi = (xi + t) % R
+                        w = tw[xi * q]  # (cos, -sin) of 2 pi xi / R, unconjugated in both directions
+                        u, z = cur[j + r * q], cur[j + (R - r) * q]
+                        A += (u + z) * w.real
+                        B += (u - z) * w.imag
+                    iB = complex(-sgn * B.imag, sgn * B.real)
+                    nxt[j0 + t * Ns], nxt[j0 + (R - t) * Ns] = A + iB, A - iB
+        cur, Ns = nxt, Ns * R
+    return cur
+
+
+def test_fft_kernel_stage_arithmetic_model():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 12, 29, 58, 77, 200, 232, 960 // 8, 105):
+        x = rng.normal(size=n) + 1j * rng.normal(size=n)
+        assert np.abs(_stockham_sim(x) - np.fft.fft(x)).max() < 1e-10 * max(1, n)
+        assert np.abs(_stockham_sim(x, True) - np.fft.ifft(x) * n).max() < 1e-10 * max(1, n)
+    # the store index of a cropping pass: bin (start + (q + m/2) mod m - n/2) mod n == ifftshift(crop(fftshift(.)))
+    for n, m in ((40, 18), (33, 18), (29, 14), (16, 16)):
+        start = (n - m) // 2 + (n % 2)
+        spec = np.arange(n)
+        want = np.fft.ifftshift(np.fft.fftshift(spec)[start:start + m])
+        got = [(start + (qo + m // 2) % m - n // 2) % n for qo in range(m)]
+        assert list(want) == got
