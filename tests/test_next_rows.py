@@ -618,3 +618,68 @@ def test_fft_kernel_stage_arithmetic_model():
         want = np.fft.ifftshift(np.fft.fftshift(spec)[start:start + m])
         got = [(start + (qo + m // 2) % m - n // 2) % n for qo in range(m)]
         assert list(want) == got
+
+
+def _ccl_model(vol, conn):
+    """Sequential model of csrc/ccl3d.cu: parents start at the head of the foreground run inside a 32-voxel segment of the
+    row-major index space (runs never cross a row end); the merge pass performs only the unions the run structure does not
+    already imply (26: centre of each preceding row first, +-1 diagonals only when the centre is background, nothing but the
+    +1 diagonal when the left neighbour is set; 6: up / back unless the left neighbour and ITS up / back are set)."""
+    Z, Y, X = vol.shape
+    fg = (vol != 0).ravel()
+    n = fg.size
+    P = np.full(n, -1, np.int64)
+    for i in range(n):
+        if fg[i]:
+            left_ok = i % 32 != 0 and i % X != 0 and fg[i - 1]
+            P[i] = P[i - 1] if left_ok else i
+
+    def find(v):
+        while P[v] != v:
+            v = P[v]
+        return v
+
+    def unite(a, b):
+        a, b = find(a), find(b)
+        if a != b:
+            P[max(a, b)] = min(a, b)
+
+    plane = Y * X
+    for i in range(n):
+        if not fg[i]:
+            continue
+        x, y, z = i % X, (i // X) % Y, i // plane
+        left = x > 0 and fg[i - 1]
+        if left and i % 32 == 0:
+            unite(i, i - 1)
+        if conn == 6:
+            if y > 0 and fg[i - X] and not (left and fg[i - X - 1]):
+                unite(i, i - X)
+            if z > 0 and fg[i - plane] and not (left and fg[i - plane - 1]):
+                unite(i, i - plane)
+            continue
+        rows = ([i - X] if y > 0 else []) + ([i - plane - X] if z > 0 and y > 0 else []) + ([i - plane] if z > 0 else []) + \
+               ([i - plane + X] if z > 0 and y + 1 < Y else [])
+        for r in rows:
+            if fg[r]:
+                if not left:
+                    unite(i, r)
+                continue
+            if not left and x > 0 and fg[r - 1]:
+                unite(i, r - 1)
+            if x + 1 < X and fg[r + 1]:
+                unite(i, r + 1)
+    roots = np.array([find(i) if fg[i] else -1 for i in range(n)])
+    ids = {r: k + 1 for k, r in enumerate(sorted(set(roots[roots >= 0])))}  # raster order of the first voxel
+    return np.array([ids[r] if r >= 0 else 0 for r in roots]).reshape(vol.shape)
+
+
+@pytest.mark.parametrize("conn", [6, 26])
+def test_ccl_merge_rules_model_vs_scipy(conn):
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(100 + conn)
+    structure = np.ones((3, 3, 3)) if conn == 26 else None
+    for shape, p in [((3, 5, 37), 0.5), ((4, 6, 33), 0.3), ((2, 9, 70), 0.65), ((5, 4, 8), 0.4), ((1, 7, 64), 0.55)]:
+        vol = (rng.random(shape) < p).astype(np.uint8)
+        want, _ = ndi.label(vol, structure=structure)
+        np.testing.assert_array_equal(_ccl_model(vol, conn), want)
